@@ -1,0 +1,562 @@
+// gemm.cu — persistent warp-specialised bf16 GEMM for sm_100a.
+//
+//   D[M,N] = sum_k A[m,k] * B[n,k]       fp32 accumulation in TMEM
+//
+// * operands are staged by TMA (SWIZZLE_128B) into a multi-stage shared-memory ring,
+// * one elected thread issues tcgen05.mma (UMMA 128 x BN x 16) with the accumulator in TMEM,
+// * two TMEM accumulator stages let the epilogue of tile i overlap the main loop of tile i+1,
+// * four epilogue warps read TMEM with tcgen05.ld and apply the fused bi-mask epilogues.
+//
+// A and B can each be K-major (row-major [rows, K], the nn.Linear layout) or MN-major
+// (row-major [K, rows]; used by the weight-gradient GEMM whose reduction runs over tokens).
+//
+// Replaces, on the hot path of the reference: nn.Linear in MAESparseAttention.forward (layers.py:491,515),
+// MAESparseMlp.forward (layers.py:845-863), the patch-embed conv (layers.py:177), the PMIM decoder 1x1 conv
+// (vision_transformer.py:723), the head (vision_transformer.py:744) and their autograd backward (engine.py:169).
+#include "ptx.cuh"
+#include "gemm.cuh"
+#include <stdio.h>
+
+namespace ofb {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;
+static constexpr int GEMM_THREADS = 192;  // warp0 TMA, warp1 MMA (+TMEM alloc), warps2-5 epilogue
+static constexpr int SMEM_LIMIT = 232448; // 227 KB
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int SCRATCH_BYTES = 2 * 4 * BN * 4;  // two column-partial scratch arrays [4 warps][BN]
+    static constexpr int BAR_BYTES = 1024;
+    static constexpr int STAGES_RAW = (SMEM_LIMIT - 1024 - SCRATCH_BYTES - BAR_BYTES) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + SCRATCH_BYTES + BAR_BYTES;
+    static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+};
+
+// 32 values per lane -> lane L ends with the sum over lanes of v[L] (31 shuffles).
+__device__ __forceinline__ float lane_transpose_sum(float (&v)[32]) {
+    const uint32_t lane = lane_id();
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const bool upper = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < o; ++i) {
+            const float send = upper ? v[i] : v[i + o];
+            const float keep = upper ? v[i + o] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    return v[0];
+}
+
+__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32], int nvalid) {
+    if (nvalid >= 32) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint4 p;
+            p.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+            p.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+            p.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+            p.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+            reinterpret_cast<uint4*>(dst)[i] = p;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (i < nvalid) dst[i] = __float2bfloat16(v[i]);
+    }
+}
+__device__ __forceinline__ void store_f32x32(float* dst, const float (&v)[32], int nvalid) {
+    if (nvalid >= 32) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (i < nvalid) dst[i] = v[i];
+    }
+}
+__device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* src, float (&v)[32], int nvalid) {
+    if (nvalid >= 32) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint4 p = __ldg(reinterpret_cast<const uint4*>(src) + i);
+            float2 f;
+            f = unpack_bf16x2(p.x); v[8 * i + 0] = f.x; v[8 * i + 1] = f.y;
+            f = unpack_bf16x2(p.y); v[8 * i + 2] = f.x; v[8 * i + 3] = f.y;
+            f = unpack_bf16x2(p.z); v[8 * i + 4] = f.x; v[8 * i + 5] = f.y;
+            f = unpack_bf16x2(p.w); v[8 * i + 6] = f.x; v[8 * i + 7] = f.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = (i < nvalid) ? __bfloat162float(src[i]) : 0.f;
+    }
+}
+__device__ __forceinline__ void load_f32x32(const float* src, float (&v)[32], int nvalid) {
+    if (nvalid >= 32) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 p = __ldg(reinterpret_cast<const float4*>(src) + i);
+            v[4 * i] = p.x; v[4 * i + 1] = p.y; v[4 * i + 2] = p.z; v[4 * i + 3] = p.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = (i < nvalid) ? src[i] : 0.f;
+    }
+}
+
+template <int BN, int A_MN, int B_MN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmArgs g) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr uint32_t IDESC = make_idesc_bf16(BM, BN, A_MN, B_MN);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
+    float* scratch0 = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+    float* scratch1 = scratch0 + 4 * BN;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::SCRATCH_BYTES);
+    uint64_t* full_bar = bars;                   // [STAGES]
+    uint64_t* empty_bar = bars + STAGES;         // [STAGES]
+    uint64_t* tfull_bar = bars + 2 * STAGES;     // [2]
+    uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tma_a);
+        tma_prefetch_desc(&tma_b);
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(smem_u32(&full_bar[i]), 1);
+            mbar_init(smem_u32(&empty_bar[i]), 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(smem_u32(&tfull_bar[i]), 1);
+            mbar_init(smem_u32(&tempty_bar[i]), 4);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(smem_u32(tmem_slot), Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int m_tiles = (g.M + BM - 1) / BM;
+    const int n_tiles = (g.N + BN - 1) / BN;
+    const int k_blocks = (g.K + BK - 1) / BK;
+    const int splits = g.k_splits > 0 ? g.k_splits : 1;
+    const int kb_per_split = (k_blocks + splits - 1) / splits;
+    const int total_tiles = m_tiles * n_tiles * splits;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int split = t / (m_tiles * n_tiles);
+                const int mn = t % (m_tiles * n_tiles);
+                const int m_blk = mn / n_tiles, n_blk = mn % n_tiles;
+                const int kb0 = split * kb_per_split;
+                const int kb1 = min(k_blocks, kb0 + kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+                    const uint32_t fb = smem_u32(&full_bar[stage]);
+                    mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
+                    const uint32_t sa = smem_u32(smem_a + stage * Cfg::A_BYTES);
+                    const uint32_t sb = smem_u32(smem_b + stage * Cfg::B_BYTES);
+                    if (A_MN) {
+#pragma unroll
+                        for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BK * 128), &tma_a, fb, m_blk * BM + j * 64, kb * BK);
+                    } else {
+                        tma_load_2d(sa, &tma_a, fb, kb * BK, m_blk * BM);
+                    }
+                    if (B_MN) {
+#pragma unroll
+                        for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * (BK * 128), &tma_b, fb, n_blk * BN + j * 64, kb * BK);
+                    } else {
+                        tma_load_2d(sb, &tma_b, fb, kb * BK, n_blk * BN);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int it = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int split = t / (m_tiles * n_tiles);
+                const int kb0 = split * kb_per_split;
+                const int kb1 = min(k_blocks, kb0 + kb_per_split);
+                if (kb1 <= kb0) continue;
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                ++it;
+                mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(smem_u32(&full_bar[stage]), phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem_a + stage * Cfg::A_BYTES);
+                    const uint32_t sb = smem_u32(smem_b + stage * Cfg::B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        // K-major: advance 16 bf16 (32 B) inside the 128-B swizzle row.
+                        // MN-major: advance 16 k-rows of 128 B; 64-wide MN atoms are BK*128 B apart (LBO).
+                        const uint64_t da = A_MN ? make_smem_desc_sw128(sa + k * 2048, BK * 128, 1024)
+                                                 : make_smem_desc_sw128(sa + k * 32, 0, 1024);
+                        const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * 2048, BK * 128, 1024)
+                                                 : make_smem_desc_sw128(sb + k * 32, 0, 1024);
+                        umma_bf16(d_tmem, da, db, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(smem_u32(&empty_bar[stage]));
+                    if (kb == kb1 - 1) umma_commit(smem_u32(&tfull_bar[acc]));
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue warps =====================
+        const int q = warp & 3;            // TMEM lane quarter this warp may access
+        const int et = q * 32 + lane;      // row inside the tile
+        int it = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int split = t / (m_tiles * n_tiles);
+            const int mn = t % (m_tiles * n_tiles);
+            const int m_blk = mn / n_tiles, n_blk = mn % n_tiles;
+            const int kb0 = split * kb_per_split;
+            const int kb1 = min(k_blocks, kb0 + kb_per_split);
+            if (kb1 <= kb0) continue;
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            ++it;
+            mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+            tc_fence_after();
+
+            const int row = m_blk * BM + et;
+            const bool row_ok = row < g.M;
+            const int n0 = n_blk * BN;
+            float rs = 1.f;
+            if (EPI == EPI_STORE || EPI == EPI_FC2_DGRAD) {
+                if (g.rowscale != nullptr && row_ok) rs = __ldg(g.rowscale + row / g.rows_per_scale);
+            }
+            if (EPI == EPI_STORE || EPI == EPI_WGRAD) {
+                if (g.scale_ptr != nullptr) rs *= __ldg(g.scale_ptr);
+            }
+            float loss_acc = 0.f;
+
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                float v[32];
+                tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + c * 32), v);
+                tmem_ld_wait();
+                const int col0 = n0 + c * 32;
+                const int nvalid = min(32, g.N - col0);
+                if (nvalid <= 0) {
+                    if (EPI == EPI_FC2_DGRAD) {  // keep scratch defined
+                        scratch0[q * BN + c * 32 + lane] = 0.f;
+                        scratch1[q * BN + c * 32 + lane] = 0.f;
+                    }
+                    continue;
+                }
+
+                if (EPI == EPI_STORE) {
+                    if (g.bias != nullptr) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] += (i < nvalid) ? __ldg(g.bias + col0 + i) : 0.f;
+                    }
+                    if (g.colscale != nullptr) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] *= (i < nvalid) ? __ldg(g.colscale + col0 + i) : 0.f;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] *= rs;
+                    if (row_ok) {
+                        if (g.res != nullptr) {
+                            float r[32];
+                            load_bf16x32(g.res + size_t(row) * g.ldres + col0, r, nvalid);
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] += r[i];
+                        }
+                        if (g.out_fp32) store_f32x32(reinterpret_cast<float*>(g.out0) + size_t(row) * g.ld0 + col0, v, nvalid);
+                        else store_bf16x32(reinterpret_cast<__nv_bfloat16*>(g.out0) + size_t(row) * g.ld0 + col0, v, nvalid);
+                    }
+                } else if (EPI == EPI_FC1) {
+                    float h[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float b = (i < nvalid) ? __ldg(g.bias + col0 + i) : 0.f;
+                        const float gt = (i < nvalid) ? __ldg(g.colscale + col0 + i) : 0.f;
+                        v[i] += b;
+                        h[i] = gelu_erf(v[i] * gt);
+                    }
+                    if (row_ok) {
+                        store_bf16x32(reinterpret_cast<__nv_bfloat16*>(g.out0) + size_t(row) * g.ld0 + col0, v, nvalid);
+                        store_bf16x32(reinterpret_cast<__nv_bfloat16*>(g.out1) + size_t(row) * g.ld1 + col0, h, nvalid);
+                    }
+                } else if (EPI == EPI_FC2_DGRAD) {
+                    float u[32], dg[32];
+                    if (row_ok) load_bf16x32(g.aux + size_t(row) * g.ldaux + col0, u, nvalid);
+                    else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) u[i] = 0.f;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float gt = (i < nvalid) ? __ldg(g.colscale + col0 + i) : 0.f;
+                        const float dh = row_ok ? v[i] * rs : 0.f;
+                        const float gp = gelu_erf_grad(u[i] * gt);
+                        dg[i] = dh * gp * u[i];   // d gate contribution
+                        v[i] = dh * gp * gt;      // du
+                    }
+                    if (row_ok) store_bf16x32(reinterpret_cast<__nv_bfloat16*>(g.out0) + size_t(row) * g.ld0 + col0, v, nvalid);
+                    const float sdg = lane_transpose_sum(dg);
+                    const float sdu = lane_transpose_sum(v);
+                    scratch0[q * BN + c * 32 + lane] = sdg;
+                    scratch1[q * BN + c * 32 + lane] = sdu;
+                } else if (EPI == EPI_WGRAD) {
+                    if (row_ok) {
+                        float* dst = reinterpret_cast<float*>(g.out0) + size_t(row) * g.ld0 + col0;
+                        if (nvalid >= 32) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * i),
+                                             "f"(v[4 * i] * rs), "f"(v[4 * i + 1] * rs), "f"(v[4 * i + 2] * rs), "f"(v[4 * i + 3] * rs)
+                                             : "memory");
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (i < nvalid) atomicAdd(dst + i, v[i] * rs);
+                        }
+                    }
+                } else if (EPI == EPI_PATCH) {
+                    // rows are (image b, patch l); output row skips the cls slot of each image.
+                    if (row_ok) {
+                        const int b = row / g.tokens, l = row % g.tokens;
+                        const float mk = __ldg(g.rowmask + row);
+                        const float* pos = g.pos + size_t(1 + l) * g.N + col0;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            if (i < nvalid) {
+                                const float gt = __ldg(g.colscale + col0 + i);
+                                const float val = v[i] + __ldg(g.bias + col0 + i) + __ldg(pos + i);
+                                v[i] = (mk != 0.f ? __ldg(g.mask_token + col0 + i) : val) * gt;
+                            }
+                        }
+                        const size_t orow = size_t(b) * (g.tokens + 1) + 1 + l;
+                        store_bf16x32(reinterpret_cast<__nv_bfloat16*>(g.out0) + orow * g.ld0 + col0, v, nvalid);
+                    }
+                } else if (EPI == EPI_DECODER) {
+                    // rows are (image b, token t) incl. cls (t == 0, ignored). vision_transformer.py:720-729
+                    const int tk = g.tokens + 1;
+                    const int b = row / tk, tt = row % tk;
+                    const bool live = row_ok && tt > 0;
+                    float mk = 0.f;
+                    float tg[32];
+                    if (live) {
+                        const int pr = b * g.tokens + tt - 1;
+                        mk = __ldg(g.rowmask + pr);
+                        if (mk != 0.f) load_f32x32(g.target + size_t(pr) * g.N + col0, tg, nvalid);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        float s = 0.f;
+                        if (mk != 0.f && i < nvalid) {
+                            const float d = v[i] + __ldg(g.bias + col0 + i) - tg[i];
+                            loss_acc += fabsf(d);
+                            s = (d > 0.f) ? 1.f : (d < 0.f ? -1.f : 0.f);
+                        }
+                        v[i] = s;
+                    }
+                    if (row_ok) store_bf16x32(reinterpret_cast<__nv_bfloat16*>(g.out0) + size_t(row) * g.ld0 + col0, v, nvalid);
+                }
+            }
+
+            // accumulator fully drained -> hand the TMEM stage back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+
+            if (EPI == EPI_FC2_DGRAD) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int col = et; col < BN; col += 128) {
+                    if (n0 + col < g.N) {
+                        const float a = scratch0[col] + scratch0[BN + col] + scratch0[2 * BN + col] + scratch0[3 * BN + col];
+                        const float b = scratch1[col] + scratch1[BN + col] + scratch1[2 * BN + col] + scratch1[3 * BN + col];
+                        g.colpart0[size_t(m_blk) * g.N + n0 + col] = a;
+                        g.colpart1[size_t(m_blk) * g.N + n0 + col] = b;
+                    }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            if (EPI == EPI_DECODER) {
+                const float s = warp_sum(loss_acc);
+                if (lane == 0) g.colpart0[size_t(mn) * 4 + q] = s;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || p == nullptr) return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// bf16 tensor map of rank `rank`; dims/strides innermost first; strides in elements (stride[0] must be 1).
+int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                   const uint32_t* box) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (fn == nullptr) return 1001;
+    cuuint64_t gdim[5], gstride[5];
+    cuuint32_t bdim[5], estr[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bdim[i] = box[i];
+        estr[i] = 1;
+        if (i > 0) gstride[i - 1] = strides_elems[i] * 2;
+    }
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstride, bdim, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : 1002;
+}
+
+static int g_num_sms = 0;
+int num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+template <int BN, int A_MN, int B_MN, int EPI>
+static int launch_gemm_inst(const void* A, int lda, const void* B, int ldb, const GemmArgs& g, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN>;
+    static bool configured = false;
+    auto kfn = gemm_kernel<BN, A_MN, B_MN, EPI>;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return int(e);
+        configured = true;
+    }
+    CUtensorMap ta, tb;
+    {
+        // K-major: tensor [rows, K] row-major -> dims {K, rows}, box {64, 128|BN}
+        // MN-major: tensor [K, rows] row-major -> dims {rows, K}, box {64, 64}
+        uint64_t dims[2], str[2];
+        uint32_t box[2];
+        if (A_MN) { dims[0] = g.M; dims[1] = g.K; box[0] = 64; box[1] = BK; }
+        else      { dims[0] = g.K; dims[1] = g.M; box[0] = BK; box[1] = BM; }
+        str[0] = 1; str[1] = uint64_t(lda);
+        int r = make_tmap_bf16(&ta, A, 2, dims, str, box);
+        if (r) return r;
+        if (B_MN) { dims[0] = g.N; dims[1] = g.K; box[0] = 64; box[1] = BK; }
+        else      { dims[0] = g.K; dims[1] = g.N; box[0] = BK; box[1] = BN; }
+        str[1] = uint64_t(ldb);
+        r = make_tmap_bf16(&tb, B, 2, dims, str, box);
+        if (r) return r;
+    }
+    const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + BN - 1) / BN;
+    const int total = m_tiles * n_tiles * (g.k_splits > 0 ? g.k_splits : 1);
+    const int grid = total < num_sms() ? total : num_sms();
+    kfn<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, g);
+    return int(cudaGetLastError());
+}
+
+// pick the N tile: prefer exact division with the widest tile that keeps wave quantisation low
+static int pick_bn(int M, int N) {
+    const int cands[4] = {256, 192, 128, 64};
+    const int m_tiles = (M + BM - 1) / BM;
+    int best = 128; double best_cost = 1e30;
+    for (int i = 0; i < 4; ++i) {
+        const int bn = cands[i];
+        const int n_tiles = (N + bn - 1) / bn;
+        const long tiles = long(m_tiles) * n_tiles;
+        const long waves = (tiles + num_sms() - 1) / num_sms();
+        // cost ~ waves * tile work (padding waste included), small tiles pay an smem-bandwidth penalty
+        double cost = double(waves) * bn * (bn <= 64 ? 1.5 : (bn <= 128 ? 1.10 : 1.0));
+        if (cost < best_cost) { best_cost = cost; best = bn; }
+    }
+    return best;
+}
+
+template <int A_MN, int B_MN, int EPI>
+static int launch_gemm_bn(int bn, const void* A, int lda, const void* B, int ldb, const GemmArgs& g, cudaStream_t s) {
+    switch (bn) {
+        case 256: return launch_gemm_inst<256, A_MN, B_MN, EPI>(A, lda, B, ldb, g, s);
+        case 192: return launch_gemm_inst<192, A_MN, B_MN, EPI>(A, lda, B, ldb, g, s);
+        case 128: return launch_gemm_inst<128, A_MN, B_MN, EPI>(A, lda, B, ldb, g, s);
+        default:  return launch_gemm_inst<64, A_MN, B_MN, EPI>(A, lda, B, ldb, g, s);
+    }
+}
+
+int launch_gemm(int epi, int a_mn, int b_mn, int bn_hint, const void* A, int lda, const void* B, int ldb, GemmArgs g,
+                cudaStream_t stream) {
+    if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 0;
+    int bn = bn_hint > 0 ? bn_hint : pick_bn(g.M, g.N);
+    if (epi == EPI_WGRAD) {
+        if (!(a_mn && b_mn)) return 1003;
+        if (g.k_splits <= 0) {
+            const int tiles = ((g.M + BM - 1) / BM) * ((g.N + bn - 1) / bn);
+            int s = num_sms() / tiles;
+            const int kb = (g.K + BK - 1) / BK;
+            if (s < 1) s = 1;
+            if (s > kb) s = kb;
+            g.k_splits = s;
+        }
+        return launch_gemm_bn<1, 1, EPI_WGRAD>(bn, A, lda, B, ldb, g, stream);
+    }
+    if (a_mn || b_mn) return 1003;
+    g.k_splits = 1;
+    switch (epi) {
+        case EPI_STORE:     return launch_gemm_bn<0, 0, EPI_STORE>(bn, A, lda, B, ldb, g, stream);
+        case EPI_FC1:       return launch_gemm_bn<0, 0, EPI_FC1>(bn, A, lda, B, ldb, g, stream);
+        case EPI_FC2_DGRAD: return launch_gemm_bn<0, 0, EPI_FC2_DGRAD>(bn, A, lda, B, ldb, g, stream);
+        case EPI_PATCH:     return launch_gemm_bn<0, 0, EPI_PATCH>(bn, A, lda, B, ldb, g, stream);
+        case EPI_DECODER:   return launch_gemm_bn<0, 0, EPI_DECODER>(bn, A, lda, B, ldb, g, stream);
+        default: return 1004;
+    }
+}
+
+}  // namespace ofb
