@@ -41,6 +41,7 @@ typedef struct ofb_gemm_args {
     void* out0; int32_t ld0;
     void* out1; int32_t ld1;
     int32_t out_fp32;
+    int32_t bias_rowscaled;    /* STORE: out0 = (acc + rowscale*bias)*colscale + res */
     const float* bias;
     const float* colscale;
     const float* rowscale; int32_t rows_per_scale;
@@ -60,6 +61,84 @@ typedef struct ofb_gemm_args {
  * bn_hint: 0 = auto, else 64/128/192/256. */
 int ofb_gemm_bf16(int epilogue, int a_mn, int b_mn, int bn_hint, const void* A, int lda, const void* B, int ldb,
                   const ofb_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * LayerNorm (reference LayerNorm.forward, models/layers.py:96-98, eps 1e-6) — bf16 in/out, fp32 statistics.
+ * D % 8 == 0, D <= 1024. */
+int ofb_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                      int M, int D, float eps, void* stream);
+/* number of partial rows ofb_layernorm_bwd writes (size the part_* buffers as [ofb_layernorm_bwd_parts(M), D]) */
+int ofb_layernorm_bwd_parts(int M);
+/* backward + fused column partials: part_dgamma/part_dbeta always; part_dbias (may be NULL) = sum_rows
+ * rowscale[row / rows_per_scale] * dx — the bias gradient of the Linear whose output (through the DropPath-scaled
+ * residual add, vision_transformer.py:197,201) is this LayerNorm's input. */
+int ofb_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                      void* dx, float* part_dgamma, float* part_dbeta, float* part_dbias, const float* rowscale,
+                      int rows_per_scale, int M, int D, void* stream);
+/* out[col] (+)= scale * sum_r part[r,col] / (div_by ? div_by[col] : 1) */
+int ofb_reduce_partials(const float* part, int R, int N, float* out, float scale, const float* div_by, int accumulate,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * token assembly (models/layers.py:177 im2col; vision_transformer.py:586-612 PMIM mask, 646-651 cls row; timm
+ * DropPath used at vision_transformer.py:183) */
+int ofb_patchify(const float* images, void* patches_bf16, int B, int img, int patch, void* stream);
+int ofb_pmim_mask(const float* noise, float* mask, int B, int L, int keep, void* stream);
+int ofb_droppath_scale(const float* u, const float* drop_prob, float* scale, int n_rows, int B, void* stream);
+int ofb_cls_rows(const float* cls, const float* pos, const float* gate, void* x_bf16, int B, int T, int D, void* stream);
+/* backward of the embed stage: d(conv out), and [T, D] partials of d gate (sum g*x), d pos_embed, d mask_token */
+int ofb_embed_bwd(const void* g0, const void* x0, const float* gate, const float* mask, void* dconv, float* part_gx,
+                  float* part_pos, float* part_mt, int B, int T, int D, void* stream);
+/* norm_targets (vision_transformer.py:121-141, window 47) at masked patches only, patch-major [B*L, 768] fp32 */
+int ofb_norm_targets(const float* images, const float* mask, float* target, int B, int img, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * losses: timm LabelSmoothingCrossEntropy fwd+bwd (search.py:584); loss assembly of engine.py:134-144.
+ * scal[0..6] = {base, arch, decoder, total, w_dec, decoder_grad_scale, n_masked} */
+int ofb_ls_cross_entropy(const float* logits, const int64_t* labels, float* loss_rows, void* dlogits_bf16, int B, int C,
+                         float smoothing, float grad_scale, void* stream);
+int ofb_loss_finalize(const float* loss_rows, int B, const float* dec_part, int n_dec_part, const float* mask,
+                      int n_mask, const float* arch_loss, float grad_scale, float* scal, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * fused multi-segment AdamW (optim.py:56-120; groups search.py:486-559). hyper[seg*8 + {0..6}] =
+ * {lr, weight_decay, beta1, beta2, eps, 1-beta1^t, 1-beta2^t}; seg_end[] exclusive ends (multiples of 4).
+ * Writes the bf16 shadow copy used by the GEMMs and optionally zeroes the gradient. */
+int ofb_adamw(float* p, float* g, float* m, float* v, void* shadow_bf16, const float* hyper, int nseg,
+              const int64_t* seg_end, int64_t n, int zero_grad, void* stream);
+int ofb_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * bi-mask gates of all searchable modules + architecture losses, one launch each
+ * (models/layers.py:179-191, 494-509, 847-858; base_model.py:31-86; vision_transformer.py:759-783). */
+typedef struct ofb_bimask_module {
+    int32_t kind;        /* 0 embed, 1 mlp, 2 attention */
+    int32_t dim, heads, n_i, n_j;
+    int32_t switch_off, width_off, gate_off;
+    int64_t alpha_off, score_off;     /* offsets (floats) into the parameter / gradient arenas */
+    float coef, loss_w;
+} ofb_bimask_module;
+#define OFB_BIMASK_MAX_CELLS 64
+int ofb_bimask_fwd(const ofb_bimask_module* mods_dev, int nmod, int max_n, const float* params, const uint8_t* switches,
+                   const int32_t* widths, const float* w_p_dev, float* gate, int32_t* rank, float* aprob, float* wsum,
+                   float* sp_loss, void* stream);
+/* arch[0..6] = {loss_arch, l_attn, l_mlp, l_embed, l_flops, searched GFLOPs, original GFLOPs}; dwsum[nmod] */
+int ofb_arch_finalize(const ofb_bimask_module* mods_dev, int nmod, const float* wsum, const float* sp_loss, int depth,
+                      int D, int H, int d, int hidden, int L, int C, float target_flops, float w_flops, float* arch,
+                      float* dwsum, void* stream);
+int ofb_bimask_bwd(const ofb_bimask_module* mods_dev, int nmod, int max_n, const float* params, const uint8_t* switches,
+                   const int32_t* widths, const float* w_p_dev, const float* dgate, const int32_t* rank,
+                   const float* aprob, const float* dwsum, float grad_scale, float* grads, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * fused attention on gated q,k,v (models/layers.py:507-514), head_dim 64, T <= 208.
+ * qkv: bf16 [B, T, 3, H, 64] (the qkv GEMM output as is); o: bf16 [B, T, H*64] multiplied by drop_scale[b];
+ * lse: fp32 [B, H, T]. Backward writes d(pre-gate qkv) and per-image partials of d gate / d bias. */
+int ofb_attention_fwd(const void* qkv, void* o, float* lse, const float* drop_scale, int B, int T, int H, float scale,
+                      void* stream);
+int ofb_attention_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, const float* gate,
+                      const float* drop_scale, void* dqkv, float* part_gate, float* part_bias, int B, int T, int H,
+                      float scale, void* stream);
 
 #ifdef __cplusplus
 }

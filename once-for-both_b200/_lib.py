@@ -22,7 +22,7 @@ class GemmArgs(C.Structure):
         ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("k_splits", C.c_int32),
         ("out0", C.c_void_p), ("ld0", C.c_int32),
         ("out1", C.c_void_p), ("ld1", C.c_int32),
-        ("out_fp32", C.c_int32),
+        ("out_fp32", C.c_int32), ("bias_rowscaled", C.c_int32),
         ("bias", C.c_void_p), ("colscale", C.c_void_p),
         ("rowscale", C.c_void_p), ("rows_per_scale", C.c_int32),
         ("res", C.c_void_p), ("ldres", C.c_int32),
@@ -34,6 +34,44 @@ class GemmArgs(C.Structure):
     ]
 
 
+class BimaskModule(C.Structure):
+    """Mirror of ``ofb_bimask_module``."""
+    _fields_ = [
+        ("kind", C.c_int32), ("dim", C.c_int32), ("heads", C.c_int32), ("n_i", C.c_int32), ("n_j", C.c_int32),
+        ("switch_off", C.c_int32), ("width_off", C.c_int32), ("gate_off", C.c_int32),
+        ("alpha_off", C.c_int64), ("score_off", C.c_int64),
+        ("coef", C.c_float), ("loss_w", C.c_float),
+    ]
+
+
+_P, _I, _F, _L = C.c_void_p, C.c_int, C.c_float, C.c_int64
+# every symbol include/ofb_b200.h declares, with its argument types
+SIGNATURES = {
+    "ofb_version": [],
+    "ofb_num_sms": [],
+    "ofb_gemm_bf16": [_I, _I, _I, _I, _P, _I, _P, _I, _P, _P],
+    "ofb_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _F, _P],
+    "ofb_layernorm_bwd_parts": [_I],
+    "ofb_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "ofb_reduce_partials": [_P, _I, _I, _P, _F, _P, _I, _P],
+    "ofb_patchify": [_P, _P, _I, _I, _I, _P],
+    "ofb_pmim_mask": [_P, _P, _I, _I, _I, _P],
+    "ofb_droppath_scale": [_P, _P, _P, _I, _I, _P],
+    "ofb_cls_rows": [_P, _P, _P, _P, _I, _I, _I, _P],
+    "ofb_embed_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "ofb_norm_targets": [_P, _P, _P, _I, _I, _P],
+    "ofb_ls_cross_entropy": [_P, _P, _P, _P, _I, _I, _F, _F, _P],
+    "ofb_loss_finalize": [_P, _I, _P, _I, _P, _I, _P, _F, _P, _P],
+    "ofb_adamw": [_P, _P, _P, _P, _P, _P, _I, _P, _L, _I, _P],
+    "ofb_cast_bf16": [_P, _P, _L, _P],
+    "ofb_bimask_fwd": [_P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "ofb_arch_finalize": [_P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P, _P, _P],
+    "ofb_bimask_bwd": [_P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _F, _P, _P],
+    "ofb_attention_fwd": [_P, _P, _P, _P, _I, _I, _I, _F, _P],
+    "ofb_attention_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
+}
+
+
 def lib():
     """Load (once) and return the shared library; raise loudly when it has not been built."""
     global _lib
@@ -42,7 +80,12 @@ def lib():
             raise OfbError(
                 f"{LIB_PATH} not found: the CUDA extension is not built and there is no CPU fallback. "
                 "Run __graft_entry__.build().")
-        _lib = C.CDLL(LIB_PATH)
+        l = C.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(l, name)       # AttributeError here = header / library mismatch
+            fn.argtypes = args
+            fn.restype = C.c_int
+        _lib = l
     return _lib
 
 
@@ -53,9 +96,9 @@ def check(code, what):
 
 def ptr(t):
     """Device pointer of a tensor (or None)."""
-    return None if t is None else C.c_void_p(t.data_ptr())
+    return None if t is None else t.data_ptr()
 
 
 def cur_stream():
     import torch
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return torch.cuda.current_stream().cuda_stream

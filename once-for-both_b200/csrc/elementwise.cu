@@ -1,0 +1,619 @@
+// elementwise.cu — bandwidth-bound kernels of the bi-mask search step (sm_100a):
+// LayerNorm fwd/bwd (+ fused column reductions), patchify/cast, PMIM mask + DropPath scales, cls-row assembly,
+// embed backward, local 47x47 target normalisation (masked patches only), label-smoothing CE fwd+bwd,
+// loss finalisation, column-partial reduction, fused multi-segment AdamW (+ bf16 shadow weights + grad zeroing).
+// All are vectorised (16-byte accesses), warp-shuffle reduced, grid-strided over 148 SMs.
+#include "ptx.cuh"
+#include <math.h>
+
+namespace ofb {
+
+int num_sms();
+
+// =============================================================================================
+// LayerNorm forward   (reference: LayerNorm.forward layers.py:96-98, eps 1e-6; 25 per step)
+//   x, y: bf16 [M, D]; gamma/beta fp32 [D]; mean/rstd fp32 [M].  One warp per row, D % 8 == 0, D <= 1024.
+// =============================================================================================
+static constexpr int LN_MAXC = 4;  // 16-byte chunks per lane (D <= 1024)
+
+__device__ __forceinline__ void unpack8(const uint4& p, float* f) {
+    float2 t;
+    t = unpack_bf16x2(p.x); f[0] = t.x; f[1] = t.y;
+    t = unpack_bf16x2(p.y); f[2] = t.x; f[3] = t.y;
+    t = unpack_bf16x2(p.z); f[4] = t.x; f[5] = t.y;
+    t = unpack_bf16x2(p.w); f[6] = t.x; f[7] = t.y;
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+    uint4 p;
+    p.x = pack_bf16x2(f[0], f[1]); p.y = pack_bf16x2(f[2], f[3]);
+    p.z = pack_bf16x2(f[4], f[5]); p.w = pack_bf16x2(f[6], f[7]);
+    return p;
+}
+
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
+                                                     float* __restrict__ mean, float* __restrict__ rstd, int M, int D, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const int nchunk = D >> 3;
+    for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M; row += gridDim.x * warps_per_block) {
+        const uint4* xr = reinterpret_cast<const uint4*>(x + size_t(row) * D);
+        float v[LN_MAXC][8];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < LN_MAXC; ++i) {
+            const int c = lane + 32 * i;
+            if (c < nchunk) {
+                unpack8(__ldg(xr + c), v[i]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s += v[i][j];
+            }
+        }
+        const float mu = warp_sum(s) / D;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < LN_MAXC; ++i) {
+            const int c = lane + 32 * i;
+            if (c < nchunk) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mu; q += d * d; }
+            }
+        }
+        const float rs = rsqrtf(warp_sum(q) / D + eps);
+        uint4* yr = reinterpret_cast<uint4*>(y + size_t(row) * D);
+#pragma unroll
+        for (int i = 0; i < LN_MAXC; ++i) {
+            const int c = lane + 32 * i;
+            if (c < nchunk) {
+                float o[8];
+                const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c);
+                const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c + 1);
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c);
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c + 1);
+                const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mu) * rs * gg[j] + bb[j];
+                yr[c] = pack8(o);
+            }
+        }
+        if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+    }
+}
+
+// =============================================================================================
+// LayerNorm backward (autograd of layers.py:96-98) with fused column reductions:
+//   dx = rstd * (dy*gamma - mean_D(dy*gamma) - xhat * mean_D(dy*gamma*xhat))
+//   part_dgamma[blk] = sum_rows dy*xhat, part_dbeta[blk] = sum_rows dy,
+//   part_dbias[blk]  = sum_rows rowscale[row/rows_per_scale] * dx   (bias gradient of the Linear that produced x:
+//                      x = res + droppath*(.. + bias), vision_transformer.py:197,201)   [optional]
+//   partial buffers are [gridDim.x, D]; a second kernel reduces them (deterministic).
+// =============================================================================================
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                     const float* __restrict__ gamma, __nv_bfloat16* __restrict__ dx,
+                                                     float* __restrict__ part_dgamma, float* __restrict__ part_dbeta,
+                                                     float* __restrict__ part_dbias, const float* __restrict__ rowscale,
+                                                     int rows_per_scale, int M, int D) {
+    extern __shared__ float ln_smem[];  // [3][warps][D]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int warps_per_block = blockDim.x >> 5;
+    const int nchunk = D >> 3;
+    float ag[LN_MAXC][8], ab[LN_MAXC][8], ad[LN_MAXC][8];
+#pragma unroll
+    for (int i = 0; i < LN_MAXC; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ag[i][j] = ab[i][j] = ad[i][j] = 0.f;
+
+    float gam[LN_MAXC][8];
+#pragma unroll
+    for (int i = 0; i < LN_MAXC; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nchunk) {
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c);
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c + 1);
+            gam[i][0] = g0.x; gam[i][1] = g0.y; gam[i][2] = g0.z; gam[i][3] = g0.w;
+            gam[i][4] = g1.x; gam[i][5] = g1.y; gam[i][6] = g1.z; gam[i][7] = g1.w;
+        }
+    }
+
+    for (int row = blockIdx.x * warps_per_block + warp; row < M; row += gridDim.x * warps_per_block) {
+        const uint4* dyr = reinterpret_cast<const uint4*>(dy + size_t(row) * D);
+        const uint4* xr = reinterpret_cast<const uint4*>(x + size_t(row) * D);
+        const float mu = __ldg(mean + row), rs = __ldg(rstd + row);
+        float dyv[LN_MAXC][8], xh[LN_MAXC][8];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < LN_MAXC; ++i) {
+            const int c = lane + 32 * i;
+            if (c < nchunk) {
+                unpack8(__ldg(dyr + c), dyv[i]);
+                unpack8(__ldg(xr + c), xh[i]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    xh[i][j] = (xh[i][j] - mu) * rs;
+                    const float dg = dyv[i][j] * gam[i][j];
+                    s1 += dg;
+                    s2 += dg * xh[i][j];
+                    ag[i][j] += dyv[i][j] * xh[i][j];
+                    ab[i][j] += dyv[i][j];
+                }
+            }
+        }
+        s1 = warp_sum(s1) / D;
+        s2 = warp_sum(s2) / D;
+        const float rsc = (part_dbias != nullptr) ? (rowscale != nullptr ? __ldg(rowscale + row / rows_per_scale) : 1.f) : 0.f;
+        uint4* dxr = reinterpret_cast<uint4*>(dx + size_t(row) * D);
+#pragma unroll
+        for (int i = 0; i < LN_MAXC; ++i) {
+            const int c = lane + 32 * i;
+            if (c < nchunk) {
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    o[j] = rs * (dyv[i][j] * gam[i][j] - s1 - xh[i][j] * s2);
+                    ad[i][j] += rsc * o[j];
+                }
+                dxr[c] = pack8(o);
+            }
+        }
+    }
+    // cross-warp reduction of the column accumulators
+    float* sg = ln_smem;
+    float* sb = ln_smem + warps_per_block * D;
+    float* sd = ln_smem + 2 * warps_per_block * D;
+#pragma unroll
+    for (int i = 0; i < LN_MAXC; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nchunk) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                sg[warp * D + c * 8 + j] = ag[i][j];
+                sb[warp * D + c * 8 + j] = ab[i][j];
+                sd[warp * D + c * 8 + j] = ad[i][j];
+            }
+        }
+    }
+    __syncthreads();
+    for (int col = threadIdx.x; col < D; col += blockDim.x) {
+        float a = 0.f, b = 0.f, d = 0.f;
+        for (int w = 0; w < warps_per_block; ++w) {
+            a += sg[w * D + col]; b += sb[w * D + col]; d += sd[w * D + col];
+        }
+        part_dgamma[size_t(blockIdx.x) * D + col] = a;
+        part_dbeta[size_t(blockIdx.x) * D + col] = b;
+        if (part_dbias != nullptr) part_dbias[size_t(blockIdx.x) * D + col] = d;
+    }
+}
+
+// =============================================================================================
+// out[col] (+)= scale * (colscale ? 1/colscale[col] : 1) * sum_r part[r, col]      (deterministic tree per column)
+// =============================================================================================
+__global__ void reduce_partials_kernel(const float* __restrict__ part, int R, int N, float* __restrict__ out, float scale,
+                                       const float* __restrict__ inv_colscale, int accumulate) {
+    const int col = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int ty = threadIdx.x >> 5, ny = blockDim.x >> 5;
+    __shared__ float sm[32][33];
+    float s = 0.f;
+    if (col < N)
+        for (int r = ty; r < R; r += ny) s += part[size_t(r) * N + col];
+    sm[ty][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (ty == 0 && col < N) {
+        float t = 0.f;
+        for (int i = 0; i < ny; ++i) t += sm[i][threadIdx.x];
+        t *= scale;
+        if (inv_colscale != nullptr) t /= inv_colscale[col];
+        out[col] = accumulate ? out[col] + t : t;
+    }
+}
+
+// =============================================================================================
+// patchify + cast: images fp32 [B,3,224,224] -> bf16 [B*196, 768] with column c*256 + i*16 + j
+// (the im2col of the 16x16/16 conv, layers.py:177)
+// =============================================================================================
+__global__ void patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int HW, int P) {
+    // one thread = 8 consecutive pixels of one patch row
+    const int G = HW / P;                       // 14
+    const int per_img = 3 * HW * HW / 8;
+    const size_t total = size_t(B) * per_img;
+    for (size_t idx = blockIdx.x * size_t(blockDim.x) + threadIdx.x; idx < total; idx += size_t(gridDim.x) * blockDim.x) {
+        const int b = idx / per_img;
+        int r = idx % per_img;
+        const int x8 = r % (HW / 8); r /= (HW / 8);
+        const int yy = r % HW; const int c = r / HW;
+        const float4* src = reinterpret_cast<const float4*>(img + ((size_t(b) * 3 + c) * HW + yy) * HW + x8 * 8);
+        const float4 a = __ldg(src), d = __ldg(src + 1);
+        const float f[8] = {a.x, a.y, a.z, a.w, d.x, d.y, d.z, d.w};
+        const int ph = yy / P, i = yy % P, pw = (x8 * 8) / P, j = (x8 * 8) % P;
+        const size_t orow = size_t(b) * G * G + ph * G + pw;
+        *reinterpret_cast<uint4*>(out + orow * (3 * P * P) + c * P * P + i * P + j) = pack8(f);
+    }
+}
+
+// =============================================================================================
+// PMIM mask + DropPath scales from uniform randoms
+//   mask[b,l] = 1 if noise[b,l] is NOT among the `keep` smallest of its row (vision_transformer.py:597-607)
+//   drop_scale[i] = floor(keep_i + u_i) / keep_i   (timm DropPath)
+// =============================================================================================
+__global__ void pmim_mask_kernel(const float* __restrict__ noise, float* __restrict__ mask, int L, int keep) {
+    extern __shared__ float nz[];
+    const int b = blockIdx.x;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) nz[i] = noise[size_t(b) * L + i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < L; i += blockDim.x) {
+        const float v = nz[i];
+        int rank = 0;
+        for (int j = 0; j < L; ++j) rank += (nz[j] < v) || (nz[j] == v && j < i);
+        mask[size_t(b) * L + i] = rank >= keep ? 1.f : 0.f;
+    }
+}
+__global__ void droppath_scale_kernel(const float* __restrict__ u, const float* __restrict__ drop_prob, float* __restrict__ scale,
+                                      int n_layers2, int B) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < n_layers2 * B) {
+        const float p = drop_prob[idx / B];
+        const float keep = 1.f - p;
+        scale[idx] = (p > 0.f) ? floorf(keep + u[idx]) / keep : 1.f;
+    }
+}
+
+// =============================================================================================
+// cls rows of the token matrix: x[b, 0, :] = (cls + pos[0]) * gate   (vision_transformer.py:646-651)
+// =============================================================================================
+__global__ void cls_rows_kernel(const float* __restrict__ cls, const float* __restrict__ pos, const float* __restrict__ gate,
+                                __nv_bfloat16* __restrict__ x, int B, int T, int D) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < B * D) {
+        const int b = idx / D, c = idx % D;
+        x[size_t(b) * T * D + c] = __float2bfloat16((cls[c] + pos[c]) * gate[c]);
+    }
+}
+
+// =============================================================================================
+// embed backward (autograd of layers.py:179-191 + vision_transformer.py:628-651).  With
+//   x0[b,t,:] = gate * s[b,t,:],  s = cls+pos0 (t=0) | mask_token (masked) | conv+bias+pos_t (kept):
+//   dconv[b,l,:]   = g0[b,1+l,:] * gate * (1-mask)                          -> bf16 [B*L, D]
+//   part_gx[t,:]   = sum_b g0*x0            (d gate = sum_t part_gx / gate)
+//   part_pos[t,:]  = sum_b g0*gate*(t==0 ? 1 : 1-mask)   (d pos_embed; row 0 is also d cls_token)
+//   part_mt[t,:]   = sum_b g0*gate*mask                    (d mask_token, rows t >= 1)
+// grid = (T, ceil(D/128)); thread = one column, loops over the batch.
+// =============================================================================================
+__global__ void embed_bwd_kernel(const __nv_bfloat16* __restrict__ g0, const __nv_bfloat16* __restrict__ x0,
+                                 const float* __restrict__ gate, const float* __restrict__ mask, __nv_bfloat16* __restrict__ dconv,
+                                 float* __restrict__ part_gx, float* __restrict__ part_pos, float* __restrict__ part_mt, int B, int T,
+                                 int D) {
+    const int t = blockIdx.x;
+    const int col = blockIdx.y * blockDim.x + threadIdx.x;
+    if (col >= D) return;
+    const float g = gate[col];
+    const int L = T - 1;
+    float agx = 0.f, apos = 0.f, amt = 0.f;
+    for (int b = 0; b < B; ++b) {
+        const size_t off = (size_t(b) * T + t) * D + col;
+        const float gr = __bfloat162float(g0[off]);
+        const float xv = __bfloat162float(x0[off]);
+        agx += gr * xv;
+        if (t == 0) {
+            apos += gr * g;
+        } else {
+            const float mk = mask[size_t(b) * L + t - 1];
+            const float dc = gr * g * (1.f - mk);
+            apos += dc;
+            amt += gr * g * mk;
+            dconv[(size_t(b) * L + t - 1) * D + col] = __float2bfloat16(dc);
+        }
+    }
+    part_gx[size_t(t) * D + col] = agx;
+    part_pos[size_t(t) * D + col] = apos;
+    part_mt[size_t(t) * D + col] = amt;
+}
+
+// =============================================================================================
+// norm_targets (vision_transformer.py:121-141), evaluated only at masked patches, written patch-major in the
+// decoder's output order: tgt[(b*L + l), c*256 + i*16 + j].  One CTA per (patch, channel); window = 47.
+// =============================================================================================
+static constexpr int NT_P = 16, NT_K = 47, NT_R = 23, NT_W = NT_P + 2 * NT_R;  // 62
+__global__ void __launch_bounds__(256) norm_targets_kernel(const float* __restrict__ img, const float* __restrict__ mask,
+                                                           float* __restrict__ tgt, int HW) {
+    const int G = HW / NT_P;
+    const int patch = blockIdx.x;             // b*L + l
+    const int c = blockIdx.y;
+    if (mask[patch] == 0.f) return;
+    const int L = G * G;
+    const int b = patch / L, l = patch % L;
+    const int py = (l / G) * NT_P, px = (l % G) * NT_P;
+    __shared__ float win[NT_W][NT_W + 1];
+    __shared__ float h1[NT_W][NT_P + 1], h2[NT_W][NT_P + 1];
+    const float* plane = img + (size_t(b) * 3 + c) * HW * HW;
+    for (int idx = threadIdx.x; idx < NT_W * NT_W; idx += blockDim.x) {
+        const int wy = idx / NT_W, wx = idx % NT_W;
+        const int gy = py - NT_R + wy, gx = px - NT_R + wx;
+        win[wy][wx] = (gy >= 0 && gy < HW && gx >= 0 && gx < HW) ? __ldg(plane + size_t(gy) * HW + gx) : 0.f;
+    }
+    __syncthreads();
+    // horizontal box sums: for each window row, 16 outputs of width 47
+    for (int idx = threadIdx.x; idx < NT_W * NT_P; idx += blockDim.x) {
+        const int wy = idx / NT_P, j = idx % NT_P;
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+        for (int k = 0; k < NT_K; ++k) { const float v = win[wy][j + k]; s1 += v; s2 += v * v; }
+        h1[wy][j] = s1; h2[wy][j] = s2;
+    }
+    __syncthreads();
+    {
+        const int i = threadIdx.x / NT_P, j = threadIdx.x % NT_P;  // 256 threads = 16x16 outputs
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+        for (int k = 0; k < NT_K; ++k) { s1 += h1[i + k][j]; s2 += h2[i + k][j]; }
+        const int gy = py + i, gx = px + j;
+        const int cy = min(gy + NT_R, HW - 1) - max(gy - NT_R, 0) + 1;
+        const int cx = min(gx + NT_R, HW - 1) - max(gx - NT_R, 0) + 1;
+        const float cnt = float(cy * cx);
+        const float mu = s1 / cnt;
+        float var = (s2 / cnt - mu * mu) * (cnt / (cnt - 1.f));
+        var = fmaxf(var, 0.f);
+        const float xv = win[NT_R + i][NT_R + j];
+        tgt[size_t(patch) * (3 * NT_P * NT_P) + c * NT_P * NT_P + i * NT_P + j] = (xv - mu) / sqrtf(var + 1e-6f);
+    }
+}
+
+// =============================================================================================
+// label-smoothing cross entropy fwd + bwd (timm LabelSmoothingCrossEntropy, search.py:584)
+//   loss_rows[b] = (1-s)*nll + s*(-mean logp);   dlogits = (softmax - (1-s)*onehot - s/C) * gscale / B   (bf16)
+// one CTA (128 threads) per row.
+// =============================================================================================
+__global__ void __launch_bounds__(128) ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels,
+                                                 float* __restrict__ loss_rows, __nv_bfloat16* __restrict__ dlogits, int C,
+                                                 float smoothing, float gscale_over_B) {
+    const int b = blockIdx.x;
+    const float* lr = logits + size_t(b) * C;
+    __shared__ float red[4];
+    float mx = -INFINITY;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) mx = fmaxf(mx, lr[c]);
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    __syncthreads();
+    float se = 0.f, sl = 0.f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) { se += expf(lr[c] - mx); sl += lr[c]; }
+    se = warp_sum(se);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = se;
+    __syncthreads();
+    se = red[0] + red[1] + red[2] + red[3];
+    __syncthreads();
+    sl = warp_sum(sl);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sl;
+    __syncthreads();
+    sl = red[0] + red[1] + red[2] + red[3];
+    const float lse = mx + logf(se);
+    const int y = int(labels[b]);
+    if (threadIdx.x == 0) {
+        const float nll = lse - lr[y];
+        const float smooth = lse - sl / C;
+        loss_rows[b] = (1.f - smoothing) * nll + smoothing * smooth;
+    }
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float p = expf(lr[c] - lse);
+        const float t = (c == y ? (1.f - smoothing) : 0.f) + smoothing / C;
+        dlogits[size_t(b) * C + c] = __float2bfloat16((p - t) * gscale_over_B);
+    }
+}
+
+// =============================================================================================
+// loss finalisation (engine.py:134-144): one CTA.
+//   scal[0]=base CE  [1]=arch  [2]=decoder  [3]=total  [4]=w_dec=(base/dec)  [5]=decoder grad scale  [6]=#masked patches
+// =============================================================================================
+__global__ void __launch_bounds__(256) loss_finalize_kernel(const float* __restrict__ loss_rows, int B, const float* __restrict__ dec_part,
+                                                            int n_dec_part, const float* __restrict__ mask, int n_mask,
+                                                            const float* __restrict__ arch_loss, float grad_scale, float* __restrict__ scal) {
+    __shared__ float red[3][8];
+    float a = 0.f, d = 0.f, m = 0.f;
+    for (int i = threadIdx.x; i < B; i += blockDim.x) a += loss_rows[i];
+    for (int i = threadIdx.x; i < n_dec_part; i += blockDim.x) d += dec_part[i];
+    for (int i = threadIdx.x; i < n_mask; i += blockDim.x) m += mask[i];
+    a = warp_sum(a); d = warp_sum(d); m = warp_sum(m);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a; red[1][threadIdx.x >> 5] = d; red[2][threadIdx.x >> 5] = m; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a = d = m = 0.f;
+        for (int i = 0; i < 8; ++i) { a += red[0][i]; d += red[1][i]; m += red[2][i]; }
+        const float base = a / B;
+        const float denom = (m * 256.f + 1e-5f) * 3.f;
+        const float dec = d / denom;
+        const float arch = arch_loss != nullptr ? arch_loss[0] : 0.f;
+        float w_dec = 0.f, total = base + arch;
+        if (m > 0.f && dec != 0.f) { w_dec = base / dec; total += w_dec * dec; }
+        scal[0] = base; scal[1] = arch; scal[2] = dec; scal[3] = total; scal[4] = w_dec;
+        scal[5] = w_dec / denom * grad_scale;
+        scal[6] = m;
+    }
+}
+
+// =============================================================================================
+// fused multi-segment AdamW (optim.py:56-120: decay first, then Adam), bf16 shadow weights, optional grad zeroing.
+// hyper[seg] = {lr, weight_decay, beta1, beta2, eps, bias_corr1, bias_corr2, unused}; seg_end[] are exclusive
+// prefix ends (elements, multiples of 4) of the contiguous optimizer groups of the flat parameter arena.
+// =============================================================================================
+struct AdamSegs {
+    int nseg;
+    long long end[8];
+};
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                                    float* __restrict__ v, __nv_bfloat16* __restrict__ shadow,
+                                                    const float* __restrict__ hyper, AdamSegs segs, long long n4, int zero_grad) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const long long e = i * 4;
+        int s = 0;
+        while (s < segs.nseg - 1 && e >= segs.end[s]) ++s;
+        const float* h = hyper + s * 8;
+        const float lr = h[0], wd = h[1], b1 = h[2], b2 = h[3], eps = h[4], bc1 = h[5], bc2 = h[6];
+        float4 pp = reinterpret_cast<float4*>(p)[i];
+        const float4 gg = reinterpret_cast<float4*>(g)[i];
+        float4 mm = reinterpret_cast<float4*>(m)[i];
+        float4 vv = reinterpret_cast<float4*>(v)[i];
+        const float decay = 1.f - lr * wd;
+        const float step = lr / bc1;
+        const float rbc2 = 1.f / sqrtf(bc2);
+#define OFB_ADAM1(P, G, Mm, V)                         \
+        P *= decay;                                    \
+        Mm = Mm * b1 + (1.f - b1) * G;                 \
+        V = V * b2 + (1.f - b2) * G * G;               \
+        P -= step * (Mm / (sqrtf(V) * rbc2 + eps));
+        OFB_ADAM1(pp.x, gg.x, mm.x, vv.x)
+        OFB_ADAM1(pp.y, gg.y, mm.y, vv.y)
+        OFB_ADAM1(pp.z, gg.z, mm.z, vv.z)
+        OFB_ADAM1(pp.w, gg.w, mm.w, vv.w)
+#undef OFB_ADAM1
+        reinterpret_cast<float4*>(p)[i] = pp;
+        reinterpret_cast<float4*>(m)[i] = mm;
+        reinterpret_cast<float4*>(v)[i] = vv;
+        if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (shadow != nullptr) {
+            uint2 o;
+            o.x = pack_bf16x2(pp.x, pp.y);
+            o.y = pack_bf16x2(pp.z, pp.w);
+            reinterpret_cast<uint2*>(shadow)[i] = o;
+        }
+    }
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n4) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 a = reinterpret_cast<const float4*>(src)[i];
+        uint2 o;
+        o.x = pack_bf16x2(a.x, a.y);
+        o.y = pack_bf16x2(a.z, a.w);
+        reinterpret_cast<uint2*>(dst)[i] = o;
+    }
+}
+
+// =============================================================================================
+// launchers
+// =============================================================================================
+static inline int err() { return int(cudaGetLastError()); }
+
+int launch_ln_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M, int D, float eps,
+                  cudaStream_t s) {
+    if (D % 8 != 0 || D > 8 * 32 * LN_MAXC) return 1010;
+    const int wpb = 8;
+    int grid = (M + wpb - 1) / wpb;
+    const int cap = num_sms() * 8;
+    if (grid > cap) grid = cap;
+    ln_fwd_kernel<<<grid, wpb * 32, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta, reinterpret_cast<__nv_bfloat16*>(y),
+                                            mean, rstd, M, D, eps);
+    return err();
+}
+
+int ln_bwd_grid(int M) {
+    int grid = (M + 7) / 8;
+    const int cap = num_sms() * 2;
+    return grid > cap ? cap : grid;
+}
+
+int launch_ln_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx, float* part_dgamma,
+                  float* part_dbeta, float* part_dbias, const float* rowscale, int rows_per_scale, int M, int D, cudaStream_t s) {
+    if (D % 8 != 0 || D > 8 * 32 * LN_MAXC) return 1010;
+    const int wpb = 8;
+    const int grid = ln_bwd_grid(M);
+    const size_t smem = size_t(3) * wpb * D * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(ln_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 8 * 1024 * 4);
+        configured = true;
+    }
+    ln_bwd_kernel<<<grid, wpb * 32, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x), mean,
+                                               rstd, gamma, reinterpret_cast<__nv_bfloat16*>(dx), part_dgamma, part_dbeta, part_dbias,
+                                               rowscale, rows_per_scale > 0 ? rows_per_scale : 1, M, D);
+    return err();
+}
+
+int launch_reduce_partials(const float* part, int R, int N, float* out, float scale, const float* inv_colscale, int accumulate,
+                           cudaStream_t s) {
+    reduce_partials_kernel<<<(N + 31) / 32, 32 * 32, 0, s>>>(part, R, N, out, scale, inv_colscale, accumulate);
+    return err();
+}
+
+int launch_patchify(const float* img, void* out, int B, int HW, int P, cudaStream_t s) {
+    if (HW % 8 != 0 || P % 8 != 0) return 1011;
+    const size_t total = size_t(B) * 3 * HW * HW / 8;
+    int grid = int((total + 255) / 256);
+    const int cap = num_sms() * 16;
+    if (grid > cap) grid = cap;
+    patchify_kernel<<<grid, 256, 0, s>>>(img, reinterpret_cast<__nv_bfloat16*>(out), B, HW, P);
+    return err();
+}
+
+int launch_pmim_mask(const float* noise, float* mask, int B, int L, int keep, cudaStream_t s) {
+    pmim_mask_kernel<<<B, 256, L * sizeof(float), s>>>(noise, mask, L, keep);
+    return err();
+}
+
+int launch_droppath_scale(const float* u, const float* drop_prob, float* scale, int n_layers2, int B, cudaStream_t s) {
+    const int n = n_layers2 * B;
+    droppath_scale_kernel<<<(n + 255) / 256, 256, 0, s>>>(u, drop_prob, scale, n_layers2, B);
+    return err();
+}
+
+int launch_cls_rows(const float* cls, const float* pos, const float* gate, void* x, int B, int T, int D, cudaStream_t s) {
+    cls_rows_kernel<<<(B * D + 255) / 256, 256, 0, s>>>(cls, pos, gate, reinterpret_cast<__nv_bfloat16*>(x), B, T, D);
+    return err();
+}
+
+int launch_embed_bwd(const void* g0, const void* x0, const float* gate, const float* mask, void* dconv, float* part_gx, float* part_pos,
+                     float* part_mt, int B, int T, int D, cudaStream_t s) {
+    dim3 grid(T, (D + 127) / 128);
+    embed_bwd_kernel<<<grid, 128, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(g0), reinterpret_cast<const __nv_bfloat16*>(x0), gate, mask,
+                                          reinterpret_cast<__nv_bfloat16*>(dconv), part_gx, part_pos, part_mt, B, T, D);
+    return err();
+}
+
+int launch_norm_targets(const float* img, const float* mask, float* tgt, int B, int HW, cudaStream_t s) {
+    if (HW % NT_P != 0) return 1012;
+    const int L = (HW / NT_P) * (HW / NT_P);
+    dim3 grid(B * L, 3);
+    norm_targets_kernel<<<grid, 256, 0, s>>>(img, mask, tgt, HW);
+    return err();
+}
+
+int launch_ce(const float* logits, const int64_t* labels, float* loss_rows, void* dlogits, int B, int C, float smoothing, float gscale,
+              cudaStream_t s) {
+    ce_kernel<<<B, 128, 0, s>>>(logits, labels, loss_rows, reinterpret_cast<__nv_bfloat16*>(dlogits), C, smoothing, gscale / B);
+    return err();
+}
+
+int launch_loss_finalize(const float* loss_rows, int B, const float* dec_part, int n_dec_part, const float* mask, int n_mask,
+                         const float* arch_loss, float grad_scale, float* scal, cudaStream_t s) {
+    loss_finalize_kernel<<<1, 256, 0, s>>>(loss_rows, B, dec_part, n_dec_part, mask, n_mask, arch_loss, grad_scale, scal);
+    return err();
+}
+
+int launch_adamw(float* p, float* g, float* m, float* v, void* shadow, const float* hyper, int nseg, const long long* seg_end,
+                 long long n, int zero_grad, cudaStream_t s) {
+    if (nseg < 1 || nseg > 8 || n % 4 != 0) return 1013;
+    AdamSegs segs;
+    segs.nseg = nseg;
+    for (int i = 0; i < nseg; ++i) {
+        if (seg_end[i] % 4 != 0) return 1013;
+        segs.end[i] = seg_end[i];
+    }
+    const long long n4 = n / 4;
+    long long grid = (n4 + 255) / 256;
+    const long long cap = (long long)num_sms() * 16;
+    if (grid > cap) grid = cap;
+    adamw_kernel<<<int(grid), 256, 0, s>>>(p, g, m, v, reinterpret_cast<__nv_bfloat16*>(shadow), hyper, segs, n4, zero_grad);
+    return err();
+}
+
+int launch_cast_bf16(const float* src, void* dst, long long n, cudaStream_t s) {
+    if (n % 4 != 0) return 1013;
+    const long long n4 = n / 4;
+    long long grid = (n4 + 255) / 256;
+    const long long cap = (long long)num_sms() * 16;
+    if (grid > cap) grid = cap;
+    cast_bf16_kernel<<<int(grid), 256, 0, s>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n4);
+    return err();
+}
+
+}  // namespace ofb

@@ -253,11 +253,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             const bool row_ok = row < g.M;
             const int n0 = n_blk * BN;
             float rs = 1.f;
-            if (EPI == EPI_STORE || EPI == EPI_FC2_DGRAD) {
+            if (EPI == EPI_STORE || EPI == EPI_FC2_DGRAD || EPI == EPI_FC1) {
                 if (g.rowscale != nullptr && row_ok) rs = __ldg(g.rowscale + row / g.rows_per_scale);
             }
+            float gs = 1.f;   // global device scalar
             if (EPI == EPI_STORE || EPI == EPI_WGRAD) {
-                if (g.scale_ptr != nullptr) rs *= __ldg(g.scale_ptr);
+                if (g.scale_ptr != nullptr) gs = __ldg(g.scale_ptr);
             }
             float loss_acc = 0.f;
 
@@ -277,16 +278,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 }
 
                 if (EPI == EPI_STORE) {
+                    const float brs = g.bias_rowscaled ? rs : 1.f;
+                    const float ars = (g.bias_rowscaled ? 1.f : rs) * gs;
                     if (g.bias != nullptr) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] += (i < nvalid) ? __ldg(g.bias + col0 + i) : 0.f;
+                        for (int i = 0; i < 32; ++i) v[i] += (i < nvalid) ? brs * __ldg(g.bias + col0 + i) : 0.f;
                     }
                     if (g.colscale != nullptr) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] *= (i < nvalid) ? __ldg(g.colscale + col0 + i) : 0.f;
                     }
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] *= rs;
+                    for (int i = 0; i < 32; ++i) v[i] *= ars;
                     if (row_ok) {
                         if (g.res != nullptr) {
                             float r[32];
@@ -304,7 +307,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         const float b = (i < nvalid) ? __ldg(g.bias + col0 + i) : 0.f;
                         const float gt = (i < nvalid) ? __ldg(g.colscale + col0 + i) : 0.f;
                         v[i] += b;
-                        h[i] = gelu_erf(v[i] * gt);
+                        h[i] = rs * gelu_erf(v[i] * gt);
                     }
                     if (row_ok) {
                         store_bf16x32(reinterpret_cast<__nv_bfloat16*>(g.out0) + size_t(row) * g.ld0 + col0, v, nvalid);
@@ -337,13 +340,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
                                 asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * i),
-                                             "f"(v[4 * i] * rs), "f"(v[4 * i + 1] * rs), "f"(v[4 * i + 2] * rs), "f"(v[4 * i + 3] * rs)
+                                             "f"(v[4 * i] * gs), "f"(v[4 * i + 1] * gs), "f"(v[4 * i + 2] * gs), "f"(v[4 * i + 3] * gs)
                                              : "memory");
                             }
                         } else {
 #pragma unroll
                             for (int i = 0; i < 32; ++i)
-                                if (i < nvalid) atomicAdd(dst + i, v[i] * rs);
+                                if (i < nvalid) atomicAdd(dst + i, v[i] * gs);
                         }
                     }
                 } else if (EPI == EPI_PATCH) {
@@ -547,8 +550,15 @@ int launch_gemm(int epi, int a_mn, int b_mn, int bn_hint, const void* A, int lda
         }
         return launch_gemm_bn<1, 1, EPI_WGRAD>(bn, A, lda, B, ldb, g, stream);
     }
-    if (a_mn || b_mn) return 1003;
+    if (a_mn) return 1003;
     g.k_splits = 1;
+    if (b_mn) {   // data-gradient GEMMs read the nn.Linear weight [N_out, K_in] directly as an MN-major operand
+        switch (epi) {
+            case EPI_STORE:     return launch_gemm_bn<0, 1, EPI_STORE>(bn, A, lda, B, ldb, g, stream);
+            case EPI_FC2_DGRAD: return launch_gemm_bn<0, 1, EPI_FC2_DGRAD>(bn, A, lda, B, ldb, g, stream);
+            default: return 1003;
+        }
+    }
     switch (epi) {
         case EPI_STORE:     return launch_gemm_bn<0, 0, EPI_STORE>(bn, A, lda, B, ldb, g, stream);
         case EPI_FC1:       return launch_gemm_bn<0, 0, EPI_FC1>(bn, A, lda, B, ldb, g, stream);

@@ -7,7 +7,8 @@ namespace ofb {
 
 enum GemmEpilogue : int {
     EPI_STORE = 0,      // out0 = rowscale*(acc + bias)*colscale + res           (bf16 or fp32 out)
-    EPI_FC1 = 1,        // out0 = u = acc + bias ; out1 = gelu(u * colscale)       (bi-masked fc1, layers.py:845-861)
+                        //   (bias_rowscaled: out0 = (acc + rowscale*bias)*colscale + res)
+    EPI_FC1 = 1,        // out0 = u = acc + bias ; out1 = rowscale * gelu(u * colscale)       (bi-masked fc1, layers.py:845-861)
     EPI_FC2_DGRAD = 2,  // dh = rowscale*acc ; du = dh*gelu'(u*g)*g -> out0 ; column partials of dgate, dbias
     EPI_WGRAD = 3,      // out0(fp32) += scale * acc   (split-K, red.global.add)
     EPI_PATCH = 4,      // patch-embed: gate, pos-embed, PMIM mask-token select, row remap (skip cls row)
@@ -20,6 +21,7 @@ struct GemmArgs {
     void* out0; int ld0;
     void* out1; int ld1;
     int out_fp32;           // EPI_STORE: 1 -> out0 is float
+    int bias_rowscaled;     // EPI_STORE: 1 -> out0 = acc + rowscale*bias + res (input rows already carry rowscale)
     const float* bias;      // [N] or null
     const float* colscale;  // [N] or null (bi-mask gate)
     const float* rowscale;  // [ceil(M/rows_per_scale)] or null (drop-path keep/scale per sample)

@@ -21,7 +21,7 @@ def _need_cuda(*ts):
 def gemm(epi, A, B, *, M, N, K, out0=None, ld0=0, out1=None, ld1=0, out_fp32=False, bias=None, colscale=None,
          rowscale=None, rows_per_scale=1, res=None, aux=None, colpart0=None, colpart1=None, scale_ptr=None, pos=None,
          mask_token=None, rowmask=None, target=None, tokens=1, a_mn=False, b_mn=False, bn=0, k_splits=0, lda=None,
-         ldb=None):
+         ldb=None, bias_rowscaled=False):
     """D[M,N] = sum_k A[m,k] B[n,k] with a fused epilogue (see ofb_b200.h).  A/B are bf16, 2-D, last dim contiguous."""
     _need_cuda(A, B, out0)
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
@@ -30,6 +30,7 @@ def gemm(epi, A, B, *, M, N, K, out0=None, ld0=0, out1=None, ld1=0, out_fp32=Fal
     g.out0, g.ld0 = ptr(out0), ld0 or (out0.stride(0) if out0 is not None and out0.dim() == 2 else 0)
     g.out1, g.ld1 = ptr(out1), ld1 or (out1.stride(0) if out1 is not None and out1.dim() == 2 else 0)
     g.out_fp32 = 1 if out_fp32 else 0
+    g.bias_rowscaled = 1 if bias_rowscaled else 0
     g.bias, g.colscale = ptr(bias), ptr(colscale)
     g.rowscale, g.rows_per_scale = ptr(rowscale), rows_per_scale
     g.res, g.ldres = ptr(res), (res.stride(0) if res is not None else 0)
@@ -39,5 +40,121 @@ def gemm(epi, A, B, *, M, N, K, out0=None, ld0=0, out1=None, ld1=0, out_fp32=Fal
     g.tokens = tokens
     lda = lda if lda is not None else A.stride(0)
     ldb = ldb if ldb is not None else B.stride(0)
-    check(lib().ofb_gemm_bf16(epi, int(a_mn), int(b_mn), bn, ptr(A), lda, ptr(B), ldb, C.byref(g), cur_stream()),
+    check(lib().ofb_gemm_bf16(epi, int(a_mn), int(b_mn), bn, ptr(A), lda, ptr(B), ldb, C.addressof(g), cur_stream()),
           "ofb_gemm_bf16")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# LayerNorm
+# ---------------------------------------------------------------------------------------------------------------------
+def layernorm_fwd(x, gamma, beta, y, mean, rstd, eps):
+    M, D = x.shape
+    check(lib().ofb_layernorm_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(rstd), M, D, eps, cur_stream()),
+          "ofb_layernorm_fwd")
+
+
+def layernorm_bwd_parts(M):
+    return lib().ofb_layernorm_bwd_parts(M)
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dx, part_dgamma, part_dbeta, part_dbias=None, rowscale=None,
+                  rows_per_scale=1):
+    M, D = x.shape
+    check(lib().ofb_layernorm_bwd(ptr(dy), ptr(x), ptr(mean), ptr(rstd), ptr(gamma), ptr(dx), ptr(part_dgamma),
+                                  ptr(part_dbeta), ptr(part_dbias), ptr(rowscale), rows_per_scale, M, D, cur_stream()),
+          "ofb_layernorm_bwd")
+
+
+def reduce_partials(part, R, N, out, scale=1.0, div_by=None, accumulate=True):
+    check(lib().ofb_reduce_partials(ptr(part), R, N, ptr(out), scale, ptr(div_by), int(accumulate), cur_stream()),
+          "ofb_reduce_partials")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# token assembly / PMIM
+# ---------------------------------------------------------------------------------------------------------------------
+def patchify(images, patches, patch=16):
+    B, _, HW, _ = images.shape
+    check(lib().ofb_patchify(ptr(images), ptr(patches), B, HW, patch, cur_stream()), "ofb_patchify")
+
+
+def pmim_mask(noise, mask, keep):
+    B, L = noise.shape
+    check(lib().ofb_pmim_mask(ptr(noise), ptr(mask), B, L, keep, cur_stream()), "ofb_pmim_mask")
+
+
+def droppath_scale(u, drop_prob, scale):
+    n_rows, B = u.shape
+    check(lib().ofb_droppath_scale(ptr(u), ptr(drop_prob), ptr(scale), n_rows, B, cur_stream()), "ofb_droppath_scale")
+
+
+def cls_rows(cls, pos, gate, x, B, T, D):
+    check(lib().ofb_cls_rows(ptr(cls), ptr(pos), ptr(gate), ptr(x), B, T, D, cur_stream()), "ofb_cls_rows")
+
+
+def embed_bwd(g0, x0, gate, mask, dconv, part_gx, part_pos, part_mt, B, T, D):
+    check(lib().ofb_embed_bwd(ptr(g0), ptr(x0), ptr(gate), ptr(mask), ptr(dconv), ptr(part_gx), ptr(part_pos),
+                              ptr(part_mt), B, T, D, cur_stream()), "ofb_embed_bwd")
+
+
+def norm_targets(images, mask, target):
+    B, _, HW, _ = images.shape
+    check(lib().ofb_norm_targets(ptr(images), ptr(mask), ptr(target), B, HW, cur_stream()), "ofb_norm_targets")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# losses / optimizer
+# ---------------------------------------------------------------------------------------------------------------------
+def ls_cross_entropy(logits, labels, loss_rows, dlogits, smoothing, grad_scale):
+    B, Cn = logits.shape
+    check(lib().ofb_ls_cross_entropy(ptr(logits), ptr(labels), ptr(loss_rows), ptr(dlogits), B, Cn, smoothing,
+                                     grad_scale, cur_stream()), "ofb_ls_cross_entropy")
+
+
+def loss_finalize(loss_rows, dec_part, mask, arch_loss, grad_scale, scal):
+    check(lib().ofb_loss_finalize(ptr(loss_rows), loss_rows.numel(), ptr(dec_part),
+                                  dec_part.numel() if dec_part is not None else 0, ptr(mask),
+                                  mask.numel() if mask is not None else 0, ptr(arch_loss), grad_scale, ptr(scal),
+                                  cur_stream()), "ofb_loss_finalize")
+
+
+def adamw(p, g, m, v, shadow, hyper, seg_end_host, zero_grad=True):
+    """seg_end_host: ctypes int64 array of exclusive segment ends."""
+    check(lib().ofb_adamw(ptr(p), ptr(g), ptr(m), ptr(v), ptr(shadow), ptr(hyper), len(seg_end_host),
+                          C.cast(seg_end_host, C.c_void_p), p.numel(), int(zero_grad), cur_stream()), "ofb_adamw")
+
+
+def cast_bf16(src, dst):
+    check(lib().ofb_cast_bf16(ptr(src), ptr(dst), src.numel(), cur_stream()), "ofb_cast_bf16")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# bi-mask
+# ---------------------------------------------------------------------------------------------------------------------
+def bimask_fwd(mods_dev, nmod, max_n, params, switches, widths, w_p_dev, gate, rank, aprob, wsum, sp_loss):
+    check(lib().ofb_bimask_fwd(ptr(mods_dev), nmod, max_n, ptr(params), ptr(switches), ptr(widths), ptr(w_p_dev),
+                               ptr(gate), ptr(rank), ptr(aprob), ptr(wsum), ptr(sp_loss), cur_stream()), "ofb_bimask_fwd")
+
+
+def arch_finalize(mods_dev, nmod, wsum, sp_loss, depth, D, H, d, hidden, L, Cn, target_flops, w_flops, arch, dwsum):
+    check(lib().ofb_arch_finalize(ptr(mods_dev), nmod, ptr(wsum), ptr(sp_loss), depth, D, H, d, hidden, L, Cn,
+                                  target_flops, w_flops, ptr(arch), ptr(dwsum), cur_stream()), "ofb_arch_finalize")
+
+
+def bimask_bwd(mods_dev, nmod, max_n, params, switches, widths, w_p_dev, dgate, rank, aprob, dwsum, grad_scale, grads):
+    check(lib().ofb_bimask_bwd(ptr(mods_dev), nmod, max_n, ptr(params), ptr(switches), ptr(widths), ptr(w_p_dev),
+                               ptr(dgate), ptr(rank), ptr(aprob), ptr(dwsum), grad_scale, ptr(grads), cur_stream()),
+          "ofb_bimask_bwd")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# attention
+# ---------------------------------------------------------------------------------------------------------------------
+def attention_fwd(qkv, o, lse, drop_scale, B, T, H, scale):
+    check(lib().ofb_attention_fwd(ptr(qkv), ptr(o), ptr(lse), ptr(drop_scale), B, T, H, scale, cur_stream()),
+          "ofb_attention_fwd")
+
+
+def attention_bwd(qkv, o, d_o, lse, gate, drop_scale, dqkv, part_gate, part_bias, B, T, H, scale):
+    check(lib().ofb_attention_bwd(ptr(qkv), ptr(o), ptr(d_o), ptr(lse), ptr(gate), ptr(drop_scale), ptr(dqkv),
+                                  ptr(part_gate), ptr(part_bias), B, T, H, scale, cur_stream()), "ofb_attention_bwd")
