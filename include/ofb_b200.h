@@ -43,7 +43,7 @@ typedef struct ofb_gemm_args {
     int32_t out_fp32;
     int32_t bias_rowscaled;    /* STORE: out0 = (acc + rowscale*bias)*colscale + res */
     const float* bias;
-    const float* colscale;
+    const float* colscale; int32_t colscale_period;   /* >0: gate index = col % period (multiple of 32) */
     const float* rowscale; int32_t rows_per_scale;
     const void* res; int32_t ldres;       /* bf16 */
     const void* aux; int32_t ldaux;       /* bf16 */
@@ -107,6 +107,8 @@ int ofb_loss_finalize(const float* loss_rows, int B, const float* dec_part, int 
 int ofb_adamw(float* p, float* g, float* m, float* v, void* shadow_bf16, const float* hyper, int nseg,
               const int64_t* seg_end, int64_t n, int zero_grad, void* stream);
 int ofb_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
+/* out[col] += scale * (scale_dev ? *scale_dev : 1) * sum_rows x[row, col]  (bias gradients of head / decoder) */
+int ofb_colsum_bf16(const void* x, int ld, int R, int N, float* out, float scale, const float* scale_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * bi-mask gates of all searchable modules + architecture losses, one launch each

@@ -23,7 +23,7 @@ class GemmArgs(C.Structure):
         ("out0", C.c_void_p), ("ld0", C.c_int32),
         ("out1", C.c_void_p), ("ld1", C.c_int32),
         ("out_fp32", C.c_int32), ("bias_rowscaled", C.c_int32),
-        ("bias", C.c_void_p), ("colscale", C.c_void_p),
+        ("bias", C.c_void_p), ("colscale", C.c_void_p), ("colscale_period", C.c_int32),
         ("rowscale", C.c_void_p), ("rows_per_scale", C.c_int32),
         ("res", C.c_void_p), ("ldres", C.c_int32),
         ("aux", C.c_void_p), ("ldaux", C.c_int32),
@@ -64,6 +64,7 @@ SIGNATURES = {
     "ofb_loss_finalize": [_P, _I, _P, _I, _P, _I, _P, _F, _P, _P],
     "ofb_adamw": [_P, _P, _P, _P, _P, _P, _I, _P, _L, _I, _P],
     "ofb_cast_bf16": [_P, _P, _L, _P],
+    "ofb_colsum_bf16": [_P, _I, _I, _I, _P, _F, _P, _P],
     "ofb_bimask_fwd": [_P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "ofb_arch_finalize": [_P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P, _P, _P],
     "ofb_bimask_bwd": [_P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _F, _P, _P],

@@ -22,6 +22,7 @@ int launch_ce(const float*, const int64_t*, float*, void*, int, int, float, floa
 int launch_loss_finalize(const float*, int, const float*, int, const float*, int, const float*, float, float*, cudaStream_t);
 int launch_adamw(float*, float*, float*, float*, void*, const float*, int, const long long*, long long, int, cudaStream_t);
 int launch_cast_bf16(const float*, void*, long long, cudaStream_t);
+int launch_colsum_bf16(const void*, int, int, int, float*, float, const float*, cudaStream_t);
 int launch_bimask_fwd(const void*, int, int, const float*, const uint8_t*, const int*, const float*, float*, int*, float*, float*, float*,
                       cudaStream_t);
 int launch_arch_finalize(const void*, int, const float*, const float*, int, int, int, int, int, int, int, float, float, float*, float*,
@@ -46,7 +47,7 @@ int ofb_gemm_bf16(int epilogue, int a_mn, int b_mn, int bn_hint, const void* A, 
     ofb::GemmArgs g;
     g.M = a->M; g.N = a->N; g.K = a->K; g.k_splits = a->k_splits;
     g.out0 = a->out0; g.ld0 = a->ld0; g.out1 = a->out1; g.ld1 = a->ld1; g.out_fp32 = a->out_fp32; g.bias_rowscaled = a->bias_rowscaled;
-    g.bias = a->bias; g.colscale = a->colscale; g.rowscale = a->rowscale;
+    g.bias = a->bias; g.colscale = a->colscale; g.colscale_period = a->colscale_period; g.rowscale = a->rowscale;
     g.rows_per_scale = a->rows_per_scale > 0 ? a->rows_per_scale : 1;
     g.res = reinterpret_cast<const __nv_bfloat16*>(a->res); g.ldres = a->ldres;
     g.aux = reinterpret_cast<const __nv_bfloat16*>(a->aux); g.ldaux = a->ldaux;
@@ -105,6 +106,9 @@ int ofb_adamw(float* p, float* g, float* m, float* v, void* shadow, const float*
     return ofb::launch_adamw(p, g, m, v, shadow, hyper, nseg, ends, n, zero_grad, ST(stream));
 }
 int ofb_cast_bf16(const float* src, void* dst, int64_t n, void* stream) { return ofb::launch_cast_bf16(src, dst, n, ST(stream)); }
+int ofb_colsum_bf16(const void* x, int ld, int R, int N, float* out, float scale, const float* scale_dev, void* stream) {
+    return ofb::launch_colsum_bf16(x, ld, R, N, out, scale, scale_dev, ST(stream));
+}
 
 int ofb_bimask_fwd(const ofb_bimask_module* mods, int nmod, int max_n, const float* params, const uint8_t* switches,
                    const int32_t* widths, const float* w_p, float* gate, int32_t* rank, float* aprob, float* wsum, float* sp_loss,

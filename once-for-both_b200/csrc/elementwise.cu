@@ -9,6 +9,7 @@
 namespace ofb {
 
 int num_sms();
+static inline int err() { return int(cudaGetLastError()); }
 
 // =============================================================================================
 // LayerNorm forward   (reference: LayerNorm.forward layers.py:96-98, eps 1e-6; 25 per step)
@@ -490,9 +491,42 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
 }
 
 // =============================================================================================
+// out[col] += scale * sum_rows x[row, col]   (x bf16 [R, N], N even).  grid (ceil(N/64), row splits), block (32, 8)
+// =============================================================================================
+__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int ld, int R, int N, float* __restrict__ out, float scale,
+                                   const float* __restrict__ scale_dev) {
+    __shared__ float2 sm[8][32];
+    const int col = (blockIdx.x * 32 + threadIdx.x) * 2;
+    float2 acc = make_float2(0.f, 0.f);
+    if (col < N) {
+        for (int r = blockIdx.y * 8 + threadIdx.y; r < R; r += gridDim.y * 8) {
+            const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + size_t(r) * ld + col));
+            acc.x += v.x; acc.y += v.y;
+        }
+    }
+    sm[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && col < N) {
+        for (int i = 1; i < 8; ++i) { acc.x += sm[i][threadIdx.x].x; acc.y += sm[i][threadIdx.x].y; }
+        const float s = scale * (scale_dev != nullptr ? *scale_dev : 1.f);
+        atomicAdd(out + col, acc.x * s);
+        if (col + 1 < N) atomicAdd(out + col + 1, acc.y * s);
+    }
+}
+
+// =============================================================================================
 // launchers
 // =============================================================================================
-static inline int err() { return int(cudaGetLastError()); }
+int launch_colsum_bf16(const void* x, int ld, int R, int N, float* out, float scale, const float* scale_dev, cudaStream_t s) {
+    if (N % 2 != 0 || ld % 2 != 0) return 1014;
+    int splits = (R + 255) / 256;
+    if (splits > 64) splits = 64;
+    if (splits < 1) splits = 1;
+    dim3 grid((N + 63) / 64, splits), block(32, 8);
+    colsum_bf16_kernel<<<grid, block, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, R, N, out, scale, scale_dev);
+    return int(cudaGetLastError());
+}
+
 
 int launch_ln_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M, int D, float eps,
                   cudaStream_t s) {

@@ -285,8 +285,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         for (int i = 0; i < 32; ++i) v[i] += (i < nvalid) ? brs * __ldg(g.bias + col0 + i) : 0.f;
                     }
                     if (g.colscale != nullptr) {
+                        // col0 is a multiple of 32 and the period a multiple of 32 -> one modulo per chunk
+                        const float* cs = g.colscale + (g.colscale_period > 0 ? col0 % g.colscale_period : col0);
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] *= (i < nvalid) ? __ldg(g.colscale + col0 + i) : 0.f;
+                        for (int i = 0; i < 32; ++i) v[i] *= (i < nvalid) ? __ldg(cs + i) : 0.f;
                     }
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] *= ars;

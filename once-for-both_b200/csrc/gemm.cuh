@@ -24,6 +24,7 @@ struct GemmArgs {
     int bias_rowscaled;     // EPI_STORE: 1 -> out0 = acc + rowscale*bias + res (input rows already carry rowscale)
     const float* bias;      // [N] or null
     const float* colscale;  // [N] or null (bi-mask gate)
+    int colscale_period;    // >0: gate index = col % period (q,k,v share one [H*d] gate, layers.py:507-509)
     const float* rowscale;  // [ceil(M/rows_per_scale)] or null (drop-path keep/scale per sample)
     int rows_per_scale;
     const __nv_bfloat16* res; int ldres;   // residual or null

@@ -1,0 +1,532 @@
+"""SearchStepEngine — one bi-mask DeiT *search training step* (forward, losses, backward, 3x AdamW, optional DP
+all-reduce) as an explicit sequence of sm_100a kernels on a flat parameter arena.
+
+Reference step: engine.search_one_epoch loop body (engine.py:95-198) =
+  MIMVisionTransformer.forward (vision_transformer.py:614-669, 717-745) -> OFBSearchLOSS (losses.py:80-106) ->
+  decoder-loss weighting (engine.py:134-144) -> backward (engine.py:169) -> optimizer_param/arch/decoder.step()
+  (optim.py:56-120) [-> DDP all-reduce, search.py:619].
+
+HBM layout
+  * parameters, gradients, Adam m / v: four fp32 arenas with identical layout, tensors ordered by optimizer group
+    [param no-decay | param decay | decoder no-decay | decoder decay | arch] (search.py:486-559) so one fused AdamW
+    launch covers everything; a bf16 shadow arena (same offsets) feeds the GEMMs.
+  * activations: bf16, token-major [B*197, C]; per block the backward keeps x_in, LN stats, x1, qkv, lse, o, x2, x3, u, h.
+  * nn.Linear weights are used as stored ([out, in]) by forward (K-major B operand), data-gradient (MN-major B operand)
+    and weight-gradient GEMMs (MN-major A/B operands) - no transposed copies exist.
+There is no CPU path: every op goes through the C ABI in libofb_b200.so.
+"""
+import ctypes as C
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+from ._lib import BimaskModule
+
+T_PAD = 8   # arena tensors start at multiples of 8 elements (16 B in bf16, 32 B in fp32)
+
+NO_DECAY_KEYS = ("pos_embed", "cls_token", "dist_token", "scale_weight", "mask_token", "score")
+GROUPS = ("param_nd", "param_d", "dec_nd", "dec_d", "arch")
+
+
+def param_group(name: str, shape) -> str:
+    """Optimizer group of a parameter, exactly as search.py:489-508 splits them."""
+    if len(shape) == 1 or name.endswith(".bias") or any(k in name for k in NO_DECAY_KEYS):
+        return "dec_nd" if "decoder" in name else "param_nd"
+    if "alpha" in name:
+        return "arch"
+    return "dec_d" if "decoder" in name else "param_d"
+
+
+# ---- search space (layers.py:143-152, 425-462, 813-821) ----
+def embed_widths(D):
+    return [int((i / D) * D) for i in range(D // 2, D + 1, min(D // 32, 12))]
+
+
+def head_counts(H):
+    return list(range(2, H + 1, 2))
+
+
+def head_channel_widths(d):
+    return [int(d * (i / d)) for i in range(d // 4, d + 1, max(d // 8, 1))]
+
+
+def hidden_widths(h):
+    return [int((i / h) * h) for i in range(h // 4, h + 1, h // 8)]
+
+
+def flops_polynomial(D, H, d, hid, L, Cn, depth, ae, sd_list, sm_list):
+    """(original, searched) FLOPs of MIMVisionTransformer.get_flops (vision_transformer.py:759-783) as a function of
+    the weighted-mask sums; works on floats or tensors."""
+    n = float(L)
+    f_ori = L * D * 768.
+    f_s = L * ae * 768.
+    for l in range(depth):
+        sd, sm = sd_list[l], sm_list[l]
+        f_ori += 2 * D * n
+        f_s = f_s + 2 * D * n
+        f_ori += n * (D * 3 * D) + 3 * n * D + H * n * d * n + H * n * n + 5 * H * n * n + H * n * n * d + n * D * D + n * D
+        f_s = f_s + n * (ae * 3 * sd) + 3 * n * sd + n * n * sd + H * n * n + 5 * H * n * n + n * n * sd \
+            + n * (sd * ae) + n * ae
+        f_ori += (2 * D * hid + D + hid) * n
+        f_s = f_s + (ae * sm * 2 + ae + sm) * n
+    f_ori += D * Cn
+    f_s = f_s + ae * Cn
+    return f_ori, f_s
+
+
+class BimaskTable:
+    """Device-side description of every searchable module (order: patch_embed, then attn / mlp per block) plus the
+    buffers of the fused bimask_prepare kernels."""
+
+    def __init__(self, D, H, depth, hidden, switches: Dict[str, torch.Tensor], *, w_attn=0.5, w_mlp=0.5, w_embed=0.5,
+                 w_flops=5.0, target_flops=1.0, num_classes=1000, num_patches=196):
+        self.D, self.H, self.depth, self.hidden = D, H, depth, hidden
+        self.d = D // H
+        self.L, self.C = num_patches, num_classes
+        self.target_flops, self.w_flops = target_flops, w_flops
+        self.modules: List[dict] = []
+        sw_bytes, widths, gate_off = [], [], 0
+
+        def add(prefix, kind, dim, heads, wj, ni, coef, loss_w):
+            nonlocal gate_off
+            sw = switches[prefix].to(torch.bool).reshape(len(ni) if kind == 2 else 1, len(wj))
+            self.modules.append(dict(prefix=prefix, kind=kind, dim=dim, heads=heads, n_i=sw.shape[0], n_j=sw.shape[1],
+                                     switch_off=len(sw_bytes), width_off=len(widths), gate_off=gate_off, coef=coef,
+                                     loss_w=loss_w))
+            sw_bytes.extend(int(x) for x in sw.reshape(-1).tolist())
+            widths.extend(wj)
+            widths.extend(ni)
+            gate_off += heads * dim
+
+        add("patch_embed", 0, D, 1, embed_widths(D), [], 1e-4, w_embed)
+        for l in range(depth):
+            add(f"blocks.{l}.attn", 2, self.d, H, head_channel_widths(self.d), head_counts(H), 4e-4, w_attn)
+            add(f"blocks.{l}.mlp", 1, hidden, 1, hidden_widths(hidden), [], 1e-4, w_mlp)
+        self.total_gate = gate_off
+        self._sw_bytes, self._widths = sw_bytes, widths
+        self.max_n = max(m["heads"] * m["dim"] for m in self.modules)
+
+    def bind(self, offsets: Dict[str, int], device):
+        """offsets: arena offset (in floats) of '<prefix>.alpha' / '<prefix>.score'."""
+        n = len(self.modules)
+        arr = (BimaskModule * n)()
+        for i, m in enumerate(self.modules):
+            a = arr[i]
+            a.kind, a.dim, a.heads, a.n_i, a.n_j = m["kind"], m["dim"], m["heads"], m["n_i"], m["n_j"]
+            a.switch_off, a.width_off, a.gate_off = m["switch_off"], m["width_off"], m["gate_off"]
+            a.alpha_off, a.score_off = offsets[m["prefix"] + ".alpha"], offsets[m["prefix"] + ".score"]
+            a.coef, a.loss_w = m["coef"], m["loss_w"]
+        raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        self.mods_dev = raw.to(device)
+        self.switches_dev = torch.tensor(self._sw_bytes, dtype=torch.uint8, device=device)
+        self.widths_dev = torch.tensor(self._widths, dtype=torch.int32, device=device)
+        f32 = dict(dtype=torch.float32, device=device)
+        self.gate = torch.zeros(self.total_gate, **f32)
+        self.rank = torch.zeros(self.total_gate, dtype=torch.int32, device=device)
+        self.aprob = torch.zeros(n * 64, **f32)
+        self.wsum = torch.zeros(n, **f32)
+        self.sp_loss = torch.zeros(n, **f32)
+        self.arch = torch.zeros(8, **f32)
+        self.dwsum = torch.zeros(n, **f32)
+        return self
+
+    def gate_of(self, i):
+        m = self.modules[i]
+        return self.gate[m["gate_off"]:m["gate_off"] + m["heads"] * m["dim"]]
+
+    def forward(self, params, w_p_dev):
+        n = len(self.modules)
+        ops.bimask_fwd(self.mods_dev, n, self.max_n, params, self.switches_dev, self.widths_dev, w_p_dev, self.gate,
+                       self.rank, self.aprob, self.wsum, self.sp_loss)
+        ops.arch_finalize(self.mods_dev, n, self.wsum, self.sp_loss, self.depth, self.D, self.H, self.d, self.hidden,
+                          self.L, self.C, self.target_flops, self.w_flops, self.arch, self.dwsum)
+
+    def backward(self, params, w_p_dev, dgate, grad_scale, grads):
+        ops.bimask_bwd(self.mods_dev, len(self.modules), self.max_n, params, self.switches_dev, self.widths_dev, w_p_dev,
+                       dgate, self.rank, self.aprob, self.dwsum, grad_scale, grads)
+
+
+class SearchStepEngine:
+    def __init__(self, embed_dim=384, num_heads=6, depth=12, batch=256, *, mlp_ratio=4, num_classes=1000, img=224,
+                 patch=16, drop_path_rate=0.1, lr=1e-3, weight_decay=1e-3, eps_ln=1e-6, smoothing=0.1, w_attn=0.5,
+                 w_mlp=0.5, w_embed=0.5, w_flops=5.0, target_flops=1.0, accum_iter=1, warmup_epochs=20, max_ratio=0.95,
+                 min_ratio=0.75, device="cuda", switches=None, process_group=None):
+        assert embed_dim % num_heads == 0 and embed_dim // num_heads == 64, "attention kernel is built for head_dim 64"
+        self.D, self.H, self.depth, self.B = embed_dim, num_heads, depth, batch
+        self.d = 64
+        self.hid = embed_dim * mlp_ratio
+        self.C, self.img, self.P = num_classes, img, patch
+        self.L = (img // patch) ** 2
+        self.T = self.L + 1
+        self.M, self.ML = batch * self.T, batch * self.L
+        self.dev = torch.device(device)
+        self.lr, self.wd, self.eps_ln, self.smoothing = lr, weight_decay, eps_ln, smoothing
+        self.accum_iter = accum_iter
+        self.warmup_epochs, self.max_ratio, self.min_ratio = warmup_epochs, max_ratio, min_ratio
+        self.scale = float(self.d) ** -0.5
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        self.step_count = 0
+        self.w_p, self.keep_ratio = 0.99, max_ratio
+        self.drop_path_rate = drop_path_rate
+
+        # ---- parameter arenas ----
+        shapes = self._param_shapes()
+        order = sorted(shapes, key=lambda k: GROUPS.index(param_group(k, shapes[k])))   # stable: keeps model order
+        self.offsets, self.shapes, off = {}, shapes, 0
+        seg_end, cur = [], GROUPS[0]
+        for k in order:
+            gname = param_group(k, shapes[k])
+            if gname != cur:
+                while GROUPS[len(seg_end)] != gname:
+                    seg_end.append(off)
+                cur = gname
+            self.offsets[k] = off
+            off += (math.prod(shapes[k]) + T_PAD - 1) // T_PAD * T_PAD
+        while len(seg_end) < len(GROUPS):
+            seg_end.append(off)
+        self.n_arena = off
+        self.seg_end = seg_end
+        self._seg_end_c = (C.c_int64 * len(GROUPS))(*seg_end)
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        bf = dict(dtype=torch.bfloat16, device=self.dev)
+        self.params = torch.zeros(off, **f32)
+        self.grads = torch.zeros(off, **f32)
+        self.adam_m = torch.zeros(off, **f32)
+        self.adam_v = torch.zeros(off, **f32)
+        self.shadow = torch.zeros(off, **bf)
+        self.alpha_patch = torch.ones(1, 1, **f32)          # frozen when --patch_search is off
+        self.hyper_host = torch.zeros(len(GROUPS) * 8 + 8, dtype=torch.float32).pin_memory() \
+            if self.dev.type == "cuda" else torch.zeros(len(GROUPS) * 8 + 8)
+        self.hyper = torch.zeros(len(GROUPS) * 8 + 8, **f32)   # [..., w_p] at index 40
+
+        # ---- bi-mask ----
+        if switches is None:
+            switches = {"patch_embed": torch.ones(1, len(embed_widths(self.D)), dtype=torch.bool)}
+            for l in range(depth):
+                switches[f"blocks.{l}.attn"] = torch.ones(len(head_counts(self.H)), len(head_channel_widths(self.d)),
+                                                          dtype=torch.bool)
+                switches[f"blocks.{l}.mlp"] = torch.ones(1, len(hidden_widths(self.hid)), dtype=torch.bool)
+        self.switches = switches
+        self.bimask = BimaskTable(self.D, self.H, depth, self.hid, switches, w_attn=w_attn, w_mlp=w_mlp, w_embed=w_embed,
+                                  w_flops=w_flops, target_flops=target_flops, num_classes=num_classes,
+                                  num_patches=self.L).bind(self.offsets, self.dev)
+        self.dgate = torch.zeros(self.bimask.total_gate, **f32)
+
+        # ---- activations ----
+        M, ML, D, hid, B, T, H = self.M, self.ML, self.D, self.hid, self.B, self.T, self.H
+        self.patches = torch.empty(ML, 3 * patch * patch, **bf)
+        self.mask = torch.zeros(B, self.L, **f32)
+        self.tgt = torch.zeros(ML, 768, **f32)
+        dpr = torch.linspace(0, drop_path_rate, depth).repeat_interleave(2)
+        self.drop_prob = dpr.to(self.dev)
+        self.drop_scale = torch.ones(depth * 2, B, **f32)
+        self.xs = [torch.zeros(M, D, **bf) for _ in range(depth + 1)]      # xs[l] = input of block l; xs[depth] = output
+        self.blk = []
+        for _ in range(depth):
+            self.blk.append(dict(
+                mean1=torch.empty(M, **f32), rstd1=torch.empty(M, **f32), x1=torch.empty(M, D, **bf),
+                qkv=torch.empty(M, 3 * D, **bf), lse=torch.empty(B, H, T, **f32), o=torch.empty(M, D, **bf),
+                x2=torch.empty(M, D, **bf), mean2=torch.empty(M, **f32), rstd2=torch.empty(M, **f32),
+                x3=torch.empty(M, D, **bf), u=torch.empty(M, hid, **bf), h=torch.empty(M, hid, **bf)))
+        self.meanf, self.rstdf = torch.empty(M, **f32), torch.empty(M, **f32)
+        self.latent = torch.empty(M, D, **bf)
+        self.logits = torch.empty(B, self.C, **f32)
+        self.loss_rows = torch.empty(B, **f32)
+        self.dlogits = torch.empty(B, self.C, **bf)
+        self.sgn = torch.zeros(M, 768, **bf)
+        self.dec_bn = 256
+        self.dec_part = torch.zeros(((M + 127) // 128) * (768 // self.dec_bn) * 4, **f32)
+        self.scal = torch.zeros(8, **f32)
+        # backward scratch
+        self.gA, self.gB, self.gC = (torch.empty(M, D, **bf) for _ in range(3))
+        self.du = torch.empty(M, hid, **bf)
+        self.dqkv = torch.empty(M, 3 * D, **bf)
+        self.dconv = torch.empty(ML, D, **bf)
+        self.ln_parts = ops.layernorm_bwd_parts(M)
+        self.pg_, self.pb_, self.pd_ = (torch.empty(self.ln_parts, D, **f32) for _ in range(3))
+        mt = (M + 127) // 128
+        self.cp0, self.cp1 = torch.empty(mt, hid, **f32), torch.empty(mt, hid, **f32)
+        self.att_pg, self.att_pb = torch.empty(B, D, **f32), torch.empty(B, 3 * D, **f32)
+        self.e_gx, self.e_pos, self.e_mt = (torch.empty(T, D, **f32) for _ in range(3))
+        self.rand_u = torch.empty(B * self.L + depth * 2 * B, **f32)
+        self._graph = None
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _param_shapes(self):
+        D, hid, L, Cn, H, d = self.D, self.hid, self.L, self.C, self.H, self.d
+        s = {"cls_token": (1, 1, D), "pos_embed": (1, L + 1, D), "mask_token": (1, 1, D),
+             "patch_embed.alpha": (1, len(embed_widths(D))), "patch_embed.score": (1, D),
+             "patch_embed.proj.weight": (D, 3, self.P, self.P), "patch_embed.proj.bias": (D,)}
+        for l in range(self.depth):
+            p = f"blocks.{l}."
+            s[p + "norm1.weight"] = (D,); s[p + "norm1.bias"] = (D,)
+            s[p + "attn.alpha"] = (len(head_counts(H)), len(head_channel_widths(d)))
+            s[p + "attn.score"] = (H, d)
+            s[p + "attn.qkv.weight"] = (3 * D, D); s[p + "attn.qkv.bias"] = (3 * D,)
+            s[p + "attn.proj.weight"] = (D, D); s[p + "attn.proj.bias"] = (D,)
+            s[p + "norm2.weight"] = (D,); s[p + "norm2.bias"] = (D,)
+            s[p + "mlp.alpha"] = (1, len(hidden_widths(hid))); s[p + "mlp.score"] = (1, hid)
+            s[p + "mlp.fc1.weight"] = (hid, D); s[p + "mlp.fc1.bias"] = (hid,)
+            s[p + "mlp.fc2.weight"] = (D, hid); s[p + "mlp.fc2.bias"] = (D,)
+        s["norm.weight"] = (D,); s["norm.bias"] = (D,)
+        s["head.weight"] = (Cn, D); s["head.bias"] = (Cn,)
+        s["decoder.0.weight"] = (768, D, 1, 1); s["decoder.0.bias"] = (768,)
+        return s
+
+    def _view(self, arena, name):
+        o, shp = self.offsets[name], self.shapes[name]
+        return arena[o:o + math.prod(shp)].view(shp)
+
+    def p(self, name):
+        return self._view(self.params, name)
+
+    def g(self, name):
+        return self._view(self.grads, name)
+
+    def w(self, name):
+        """bf16 shadow weight as a 2-D [out, in] matrix."""
+        v = self._view(self.shadow, name)
+        return v.reshape(v.shape[0], -1)
+
+    def named_parameters(self):
+        return {k: self.p(k) for k in self.offsets}
+
+    def named_grads(self):
+        return {k: self.g(k) for k in self.offsets}
+
+    def load_params(self, named: Dict[str, torch.Tensor]):
+        for k in self.offsets:
+            self.p(k).copy_(named[k].to(self.dev))
+        self.sync_shadow()
+
+    def init_params(self, seed=0):
+        """Reference-style initialisation (trunc-normal .02 weights, zero biases, alpha~U(0,1), score~trunc-normal .2:
+        vision_transformer.py:497-519, layers.py:147-155, 455-467, 817-824)."""
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        for k, shp in self.shapes.items():
+            t = torch.zeros(shp)
+            if k.endswith("alpha"):
+                t = torch.rand(shp, generator=g)
+            elif k.endswith("score"):
+                t = (torch.randn(shp, generator=g) * .2).clamp_(-2, 2)
+            elif k.endswith("norm1.weight") or k.endswith("norm2.weight") or k == "norm.weight":
+                t = torch.ones(shp)
+            elif k.endswith(".bias"):
+                t = torch.zeros(shp)
+            elif k == "patch_embed.proj.weight":
+                bound = math.sqrt(6.0 / (768 + self.D))
+                t = (torch.rand(shp, generator=g) * 2 - 1) * bound
+            else:
+                t = (torch.randn(shp, generator=g) * .02).clamp_(-2, 2)
+            self.p(k).copy_(t)
+        self.sync_shadow()
+
+    def sync_shadow(self):
+        ops.cast_bf16(self.params, self.shadow)
+
+    # ------------------------------------------------------------------------------------------------------------
+    def set_schedule(self, epoch_frac: float):
+        """update_w (layers.py:484-486) and adjust_masking_ratio (vision_transformer.py:521-523)."""
+        e = min(epoch_frac, self.warmup_epochs)
+        self.w_p = (0.1 - 0.99) / self.warmup_epochs * e + 0.99
+        self.keep_ratio = self.max_ratio - (self.max_ratio - self.min_ratio) * e / self.warmup_epochs
+
+    def _fill_hyper(self, lrs=None):
+        t = self.step_count + 1
+        lrs = lrs or {}
+        h = self.hyper_host
+        for i, gname in enumerate(GROUPS):
+            b1, b2 = (0.5, 0.999) if gname == "arch" else (0.9, 0.999)
+            lr = lrs.get(gname, self.lr)
+            wd = 0.0 if gname.endswith("_nd") else self.wd
+            h[i * 8:i * 8 + 7] = torch.tensor([lr, wd, b1, b2, 1e-8, 1 - b1 ** t, 1 - b2 ** t])
+        h[40] = self.w_p
+
+    # ------------------------------------------------------------------------------------------------------------
+    def forward(self, images, labels, noise=None, drop_u=None):
+        """Forward + losses. images fp32 [B,3,224,224] (device), labels int64 [B]."""
+        B, D, H, T, L, M, ML, hid = self.B, self.D, self.H, self.T, self.L, self.M, self.ML, self.hid
+        bm = self.bimask
+        w_p_dev = self.hyper[40:41]
+        bm.forward(self.params, w_p_dev)
+        # random draws stay in PyTorch (RNG parity with the reference's torch.rand), masks are built by our kernels
+        if noise is None:
+            noise = torch.rand(B, L, device=self.dev)
+        if drop_u is None:
+            drop_u = torch.rand(self.depth * 2, B, device=self.dev)
+        keep = int(L * self.keep_ratio)
+        ops.pmim_mask(noise, self.mask, keep)
+        ops.droppath_scale(drop_u, self.drop_prob, self.drop_scale)
+        ops.patchify(images, self.patches, self.P)
+        ops.norm_targets(images, self.mask, self.tgt)
+        g_e = bm.gate_of(0)
+        x0 = self.xs[0]
+        ops.gemm(ops.EPI_PATCH, self.patches, self.w("patch_embed.proj.weight"), M=ML, N=D, K=768, out0=x0,
+                 bias=self.p("patch_embed.proj.bias"), colscale=g_e, pos=self.p("pos_embed"),
+                 mask_token=self.p("mask_token"), rowmask=self.mask, tokens=L)
+        ops.cls_rows(self.p("cls_token"), self.p("pos_embed"), g_e, x0, B, T, D)
+        for l in range(self.depth):
+            pre, a = f"blocks.{l}.", self.blk[l]
+            g_a, g_m = bm.gate_of(1 + 2 * l), bm.gate_of(2 + 2 * l)
+            dp1, dp2 = self.drop_scale[2 * l], self.drop_scale[2 * l + 1]
+            ops.layernorm_fwd(self.xs[l], self.p(pre + "norm1.weight"), self.p(pre + "norm1.bias"), a["x1"], a["mean1"],
+                              a["rstd1"], self.eps_ln)
+            ops.gemm(ops.EPI_STORE, a["x1"], self.w(pre + "attn.qkv.weight"), M=M, N=3 * D, K=D, out0=a["qkv"],
+                     bias=self.p(pre + "attn.qkv.bias"), colscale=g_a, colscale_period=D)
+            ops.attention_fwd(a["qkv"], a["o"], a["lse"], dp1, B, T, H, self.scale)
+            ops.gemm(ops.EPI_STORE, a["o"], self.w(pre + "attn.proj.weight"), M=M, N=D, K=D, out0=a["x2"],
+                     bias=self.p(pre + "attn.proj.bias"), rowscale=dp1, rows_per_scale=T, bias_rowscaled=True,
+                     res=a["x1"])
+            ops.layernorm_fwd(a["x2"], self.p(pre + "norm2.weight"), self.p(pre + "norm2.bias"), a["x3"], a["mean2"],
+                              a["rstd2"], self.eps_ln)
+            ops.gemm(ops.EPI_FC1, a["x3"], self.w(pre + "mlp.fc1.weight"), M=M, N=hid, K=D, out0=a["u"], out1=a["h"],
+                     bias=self.p(pre + "mlp.fc1.bias"), colscale=g_m, rowscale=dp2, rows_per_scale=T)
+            ops.gemm(ops.EPI_STORE, a["h"], self.w(pre + "mlp.fc2.weight"), M=M, N=D, K=hid, out0=self.xs[l + 1],
+                     bias=self.p(pre + "mlp.fc2.bias"), rowscale=dp2, rows_per_scale=T, bias_rowscaled=True,
+                     res=a["x3"])
+        ops.layernorm_fwd(self.xs[self.depth], self.p("norm.weight"), self.p("norm.bias"), self.latent, self.meanf,
+                          self.rstdf, self.eps_ln)
+        # head on the cls rows (row stride T*D), label-smoothing CE
+        ops.gemm(ops.EPI_STORE, self.latent, self.w("head.weight"), M=B, N=self.C, K=D, out0=self.logits, out_fp32=True,
+                 bias=self.p("head.bias"), lda=T * D)
+        gs = 1.0 / self.accum_iter
+        ops.ls_cross_entropy(self.logits, labels, self.loss_rows, self.dlogits, self.smoothing, gs)
+        # PMIM decoder + masked L1 against the locally normalised pixels
+        ops.gemm(ops.EPI_DECODER, self.latent, self.w("decoder.0.weight"), M=M, N=768, K=D, out0=self.sgn,
+                 bias=self.p("decoder.0.bias"), rowmask=self.mask, target=self.tgt, tokens=L, colpart0=self.dec_part,
+                 bn=self.dec_bn)
+        ops.loss_finalize(self.loss_rows, self.dec_part, self.mask, bm.arch, gs, self.scal)
+        return self.scal
+
+    # ------------------------------------------------------------------------------------------------------------
+    def backward(self):
+        B, D, H, T, L, M, ML, hid = self.B, self.D, self.H, self.T, self.L, self.M, self.ML, self.hid
+        bm = self.bimask
+        gs = 1.0 / self.accum_iter
+        dec_scale = self.scal[5:6]
+        R = self.ln_parts
+        mt = (M + 127) // 128
+
+        # ---- decoder + head ----
+        dlat = self.gA
+        ops.gemm(ops.EPI_STORE, self.sgn, self.w("decoder.0.weight"), M=M, N=D, K=768, out0=dlat, b_mn=True,
+                 scale_ptr=dec_scale)
+        ops.gemm(ops.EPI_STORE, self.dlogits, self.w("head.weight"), M=B, N=D, K=self.C, out0=dlat, ld0=T * D, b_mn=True)
+        ops.gemm(ops.EPI_WGRAD, self.sgn, self.latent, M=768, N=D, K=M, out0=self.g("decoder.0.weight").view(768, D),
+                 a_mn=True, b_mn=True, scale_ptr=dec_scale)
+        ops.colsum_bf16(self.sgn, M, 768, self.g("decoder.0.bias"), scale_dev=dec_scale)
+        ops.gemm(ops.EPI_WGRAD, self.dlogits, self.latent, M=self.C, N=D, K=B, out0=self.g("head.weight"), a_mn=True,
+                 b_mn=True, ldb=T * D)
+        ops.colsum_bf16(self.dlogits, B, self.C, self.g("head.bias"))
+
+        # ---- final LayerNorm ----
+        last_dp2 = self.drop_scale[2 * self.depth - 1]
+        G = self.gB
+        ops.layernorm_bwd(dlat, self.xs[self.depth], self.meanf, self.rstdf, self.p("norm.weight"), G, self.pg_,
+                          self.pb_, self.pd_, last_dp2, T)
+        ops.reduce_partials(self.pg_, R, D, self.g("norm.weight"))
+        ops.reduce_partials(self.pb_, R, D, self.g("norm.bias"))
+        ops.reduce_partials(self.pd_, R, D, self.g(f"blocks.{self.depth - 1}.mlp.fc2.bias"))
+        spare = [self.gA, self.gC]
+
+        for l in reversed(range(self.depth)):
+            pre, a = f"blocks.{l}.", self.blk[l]
+            i_a, i_m = 1 + 2 * l, 2 + 2 * l
+            g_a, g_m = bm.gate_of(i_a), bm.gate_of(i_m)
+            dp1, dp2 = self.drop_scale[2 * l], self.drop_scale[2 * l + 1]
+            G4 = G
+            # fc2: weight grad (h already carries DropPath), data grad fused with GELU' / gate / column partials
+            ops.gemm(ops.EPI_WGRAD, G4, a["h"], M=D, N=hid, K=M, out0=self.g(pre + "mlp.fc2.weight"), a_mn=True, b_mn=True)
+            ops.gemm(ops.EPI_FC2_DGRAD, G4, self.w(pre + "mlp.fc2.weight"), M=M, N=hid, K=D, out0=self.du, aux=a["u"],
+                     colscale=g_m, rowscale=dp2, rows_per_scale=T, colpart0=self.cp0, colpart1=self.cp1, b_mn=True)
+            m_off = bm.modules[i_m]["gate_off"]
+            ops.reduce_partials(self.cp0, mt, hid, self.dgate[m_off:m_off + hid], accumulate=False)
+            ops.reduce_partials(self.cp1, mt, hid, self.g(pre + "mlp.fc1.bias"))
+            ops.gemm(ops.EPI_WGRAD, self.du, a["x3"], M=hid, N=D, K=M, out0=self.g(pre + "mlp.fc1.weight"), a_mn=True,
+                     b_mn=True)
+            G3 = spare.pop()
+            ops.gemm(ops.EPI_STORE, self.du, self.w(pre + "mlp.fc1.weight"), M=M, N=D, K=hid, out0=G3, b_mn=True, res=G4)
+            spare.append(G4)
+            # LayerNorm 2 (+ proj bias grad)
+            G2 = spare.pop()
+            ops.layernorm_bwd(G3, a["x2"], a["mean2"], a["rstd2"], self.p(pre + "norm2.weight"), G2, self.pg_, self.pb_,
+                              self.pd_, dp1, T)
+            spare.append(G3)
+            ops.reduce_partials(self.pg_, R, D, self.g(pre + "norm2.weight"))
+            ops.reduce_partials(self.pb_, R, D, self.g(pre + "norm2.bias"))
+            ops.reduce_partials(self.pd_, R, D, self.g(pre + "attn.proj.bias"))
+            # proj
+            ops.gemm(ops.EPI_WGRAD, G2, a["o"], M=D, N=D, K=M, out0=self.g(pre + "attn.proj.weight"), a_mn=True, b_mn=True)
+            dO = spare.pop()
+            ops.gemm(ops.EPI_STORE, G2, self.w(pre + "attn.proj.weight"), M=M, N=D, K=D, out0=dO, b_mn=True, rowscale=dp1,
+                     rows_per_scale=T)
+            # attention
+            ops.attention_bwd(a["qkv"], a["o"], dO, a["lse"], g_a, dp1, self.dqkv, self.att_pg, self.att_pb, B, T, H,
+                              self.scale)
+            spare.append(dO)
+            a_off = bm.modules[i_a]["gate_off"]
+            ops.reduce_partials(self.att_pg, B, D, self.dgate[a_off:a_off + D], div_by=g_a, accumulate=False)
+            ops.reduce_partials(self.att_pb, B, 3 * D, self.g(pre + "attn.qkv.bias"))
+            ops.gemm(ops.EPI_WGRAD, self.dqkv, a["x1"], M=3 * D, N=D, K=M, out0=self.g(pre + "attn.qkv.weight"), a_mn=True,
+                     b_mn=True)
+            G1 = spare.pop()
+            ops.gemm(ops.EPI_STORE, self.dqkv, self.w(pre + "attn.qkv.weight"), M=M, N=D, K=3 * D, out0=G1, b_mn=True,
+                     res=G2)
+            spare.append(G2)
+            # LayerNorm 1 (+ previous block's fc2 bias grad)
+            G0 = spare.pop()
+            has_prev = l > 0
+            ops.layernorm_bwd(G1, self.xs[l], a["mean1"], a["rstd1"], self.p(pre + "norm1.weight"), G0, self.pg_,
+                              self.pb_, self.pd_ if has_prev else None,
+                              self.drop_scale[2 * l - 1] if has_prev else None, T)
+            spare.append(G1)
+            ops.reduce_partials(self.pg_, R, D, self.g(pre + "norm1.weight"))
+            ops.reduce_partials(self.pb_, R, D, self.g(pre + "norm1.bias"))
+            if has_prev:
+                ops.reduce_partials(self.pd_, R, D, self.g(f"blocks.{l - 1}.mlp.fc2.bias"))
+            G = G0
+
+        # ---- embed stage ----
+        g_e = bm.gate_of(0)
+        ops.embed_bwd(G, self.xs[0], g_e, self.mask, self.dconv, self.e_gx, self.e_pos, self.e_mt, B, T, D)
+        ops.reduce_partials(self.e_gx, T, D, self.dgate[0:D], div_by=g_e, accumulate=False)
+        ops.reduce_partials(self.e_pos, 1, T * D, self.g("pos_embed"))
+        ops.reduce_partials(self.e_pos, 1, D, self.g("cls_token"))
+        ops.reduce_partials(self.e_mt, T, D, self.g("mask_token"))
+        ops.reduce_partials(self.e_pos[1:], L, D, self.g("patch_embed.proj.bias"))
+        ops.gemm(ops.EPI_WGRAD, self.dconv, self.patches, M=D, N=768, K=ML,
+                 out0=self.g("patch_embed.proj.weight").view(D, 768), a_mn=True, b_mn=True)
+        # ---- bi-mask: d gate (+ FLOPs / sparsity losses) -> d score, d alpha ----
+        bm.backward(self.params, self.hyper[40:41], self.dgate, gs, self.grads)
+
+    # ------------------------------------------------------------------------------------------------------------
+    def allreduce_grads(self):
+        """Data-parallel mean of every gradient (DDP, search.py:619): one NCCL all-reduce per optimizer-group slab of the
+        flat gradient arena."""
+        if self.world <= 1:
+            return
+        lo = 0
+        for hi in self.seg_end:
+            if hi > lo:
+                torch.distributed.all_reduce(self.grads[lo:hi], group=self.pg)
+            lo = hi
+        self.grads.mul_(1.0 / self.world)
+
+    def optimizer_step(self):
+        ops.adamw(self.params, self.grads, self.adam_m, self.adam_v, self.shadow, self.hyper, self._seg_end_c,
+                  zero_grad=True)
+        self.step_count += 1
+
+    def step(self, images, labels, noise=None, drop_u=None, update=True, lrs=None):
+        """One full search step; returns the device tensor scal = [base, arch, decoder, total, w_dec, ...]."""
+        self._fill_hyper(lrs)
+        self.hyper.copy_(self.hyper_host, non_blocking=True)
+        self.forward(images, labels, noise, drop_u)
+        self.backward()
+        if update:
+            self.allreduce_grads()
+            self.optimizer_step()
+        return self.scal

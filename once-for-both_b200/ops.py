@@ -21,7 +21,7 @@ def _need_cuda(*ts):
 def gemm(epi, A, B, *, M, N, K, out0=None, ld0=0, out1=None, ld1=0, out_fp32=False, bias=None, colscale=None,
          rowscale=None, rows_per_scale=1, res=None, aux=None, colpart0=None, colpart1=None, scale_ptr=None, pos=None,
          mask_token=None, rowmask=None, target=None, tokens=1, a_mn=False, b_mn=False, bn=0, k_splits=0, lda=None,
-         ldb=None, bias_rowscaled=False):
+         ldb=None, bias_rowscaled=False, colscale_period=0):
     """D[M,N] = sum_k A[m,k] B[n,k] with a fused epilogue (see ofb_b200.h).  A/B are bf16, 2-D, last dim contiguous."""
     _need_cuda(A, B, out0)
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
@@ -31,7 +31,7 @@ def gemm(epi, A, B, *, M, N, K, out0=None, ld0=0, out1=None, ld1=0, out_fp32=Fal
     g.out1, g.ld1 = ptr(out1), ld1 or (out1.stride(0) if out1 is not None and out1.dim() == 2 else 0)
     g.out_fp32 = 1 if out_fp32 else 0
     g.bias_rowscaled = 1 if bias_rowscaled else 0
-    g.bias, g.colscale = ptr(bias), ptr(colscale)
+    g.bias, g.colscale, g.colscale_period = ptr(bias), ptr(colscale), colscale_period
     g.rowscale, g.rows_per_scale = ptr(rowscale), rows_per_scale
     g.res, g.ldres = ptr(res), (res.stride(0) if res is not None else 0)
     g.aux, g.ldaux = ptr(aux), (aux.stride(0) if aux is not None else 0)
@@ -122,6 +122,11 @@ def adamw(p, g, m, v, shadow, hyper, seg_end_host, zero_grad=True):
     """seg_end_host: ctypes int64 array of exclusive segment ends."""
     check(lib().ofb_adamw(ptr(p), ptr(g), ptr(m), ptr(v), ptr(shadow), ptr(hyper), len(seg_end_host),
                           C.cast(seg_end_host, C.c_void_p), p.numel(), int(zero_grad), cur_stream()), "ofb_adamw")
+
+
+def colsum_bf16(x, R, N, out, scale=1.0, scale_dev=None, ld=None):
+    check(lib().ofb_colsum_bf16(ptr(x), ld if ld is not None else x.stride(0), R, N, ptr(out), scale, ptr(scale_dev),
+                                cur_stream()), "ofb_colsum_bf16")
 
 
 def cast_bf16(src, dst):

@@ -1,0 +1,93 @@
+"""TEST INFRASTRUCTURE — run one full search step on the GPU engine and on the CPU oracle with identical seeded
+parameters, inputs and random draws, and compare logits, every loss term, every gradient and the AdamW update.
+
+Tolerance (written here once, used by tests and smoke): the GPU path computes in bf16 with fp32 accumulation, the
+oracle in fp32 -> rel 2e-2 (BASELINE.json north_star, "bf16 rel 2e-2"), measured as max|a-b| / max|b| per tensor.
+Loss scalars are reductions over many elements and are held to 5e-3; the pure-fp32 pieces (gates, AdamW) to 1e-4."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+BF16_TOL = 2e-2
+LOSS_TOL = 5e-3
+FP32_TOL = 1e-4
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def compare_step_with_oracle(embed_dim=192, num_heads=3, depth=2, batch=2, epoch_frac=0.0, drop_path_rate=0.1, lr=1e-3,
+                             switches=None, verbose=False):
+    import ofb_b200  # noqa: F401
+    from fixtures import make_inputs, make_params
+    from ofb_b200.engine import GROUPS, SearchStepEngine, param_group
+    from ofb_oracle import ModelCfg, adamw_step, default_switches, group_hparams, train_step
+
+    cfg = ModelCfg(embed_dim=embed_dim, num_heads=num_heads, depth=depth)
+    P = make_params(cfg, seed=0)
+    inp = make_inputs(cfg, batch, seed=1, epoch_frac=epoch_frac, drop_path_rate=drop_path_rate)
+    sw = switches or default_switches(cfg)
+
+    eng = SearchStepEngine(embed_dim, num_heads, depth, batch, drop_path_rate=drop_path_rate, lr=lr, switches=sw)
+    eng.load_params(P)
+    eng.set_schedule(epoch_frac)
+    assert abs(eng.w_p - inp.w_p) < 1e-9 and abs(eng.keep_ratio - inp.keep_ratio) < 1e-9
+    # the oracle takes DropPath multipliers; the engine takes the uniform draws -> invert: u = scale>0 ? 1 : 0 works
+    # because floor(keep+u) is 1 iff u >= p; feed u = 1-eps (kept) or 0 (dropped)
+    drop_u = (inp.drop_scale > 0).float().reshape(depth * 2, batch) * 0.999
+    scal = eng.step(inp.images.cuda(), inp.labels.cuda(), noise=inp.noise.cuda(), drop_u=drop_u.cuda(), update=False)
+    torch.cuda.synchronize()
+    scal = scal.cpu()
+
+    Pc = {k: v.clone() for k, v in P.items()}
+    out, grads = train_step(Pc, {}, inp, cfg, lr=lr, step=1, switches=sw)
+
+    errs = {}
+    errs["mask"] = float((eng.mask.cpu() - out.mask).abs().max())
+    errs["logits"] = rel(eng.logits, out.logits)
+    errs["loss_base"] = rel(scal[0], out.loss_base)
+    errs["loss_arch"] = rel(scal[1], out.loss_arch)
+    errs["loss_decoder"] = rel(scal[2], out.loss_decoder)
+    errs["loss_total"] = rel(scal[3], out.loss_total)
+    for i, m in enumerate(eng.bimask.modules):
+        errs["gate:" + m["prefix"]] = rel(eng.bimask.gate_of(i), out.gates[m["prefix"]].reshape(-1))
+    gerrs = {}
+    for k, g in grads.items():
+        if g is None:
+            continue
+        gerrs[k] = rel(eng.g(k), g)
+    # AdamW: apply the fused kernel to the engine's own gradients and the oracle's AdamW to the same gradients
+    g_engine = {k: eng.g(k).detach().cpu().clone() for k in eng.offsets}
+    p_before = {k: eng.p(k).detach().cpu().clone() for k in eng.offsets}
+    eng.optimizer_step()
+    torch.cuda.synchronize()
+    aerrs = {}
+    for k in eng.offsets:
+        pk, mk, vk = p_before[k].clone(), torch.zeros_like(p_before[k]), torch.zeros_like(p_before[k])
+        adamw_step(pk, g_engine[k], mk, vk, 1, **group_hparams(param_group(k, tuple(pk.shape)), lr))
+        aerrs[k] = rel(eng.p(k), pk)
+    grads_zeroed = float(eng.grads.abs().max()) == 0.0
+
+    worst_g = max(gerrs.items(), key=lambda kv: kv[1])
+    worst_a = max(aerrs.items(), key=lambda kv: kv[1])
+    gate_worst = max(v for k, v in errs.items() if k.startswith("gate:"))
+    ok = (errs["mask"] == 0 and errs["logits"] < BF16_TOL and errs["loss_base"] < LOSS_TOL
+          and errs["loss_arch"] < FP32_TOL * 10 and errs["loss_decoder"] < LOSS_TOL and errs["loss_total"] < LOSS_TOL
+          and gate_worst < FP32_TOL and worst_g[1] < BF16_TOL and worst_a[1] < FP32_TOL and grads_zeroed)
+    summary = (f"D{embed_dim} H{num_heads} depth{depth} B{batch} e{epoch_frac}: logits {errs['logits']:.2e} "
+               f"base {errs['loss_base']:.2e} arch {errs['loss_arch']:.2e} dec {errs['loss_decoder']:.2e} "
+               f"total {errs['loss_total']:.2e} gate {gate_worst:.2e} worst-grad {worst_g[0]} {worst_g[1]:.2e} "
+               f"worst-adamw {worst_a[0]} {worst_a[1]:.2e} mask_exact {errs['mask'] == 0} ok={ok}")
+    if verbose:
+        for k, v in sorted(gerrs.items(), key=lambda kv: -kv[1])[:25]:
+            print(f"   grad {k}: {v:.3e}")
+    return dict(ok=ok, summary=summary, errs=errs, grad_errs=gerrs, adamw_errs=aerrs,
+                losses=dict(base=float(scal[0]), arch=float(scal[1]), dec=float(scal[2]), total=float(scal[3])))

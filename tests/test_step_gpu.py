@@ -1,0 +1,68 @@
+"""Whole-step parity on the GPU: ofb_b200.engine.SearchStepEngine (CUDA kernels through the C ABI) against the CPU
+oracle and against the golden vectors of the unmodified reference (tests/golden/*.npz)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from step_compare import BF16_TOL, LOSS_TOL, compare_step_with_oracle
+
+pytestmark = pytest.mark.gpu
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz")))
+
+
+@pytest.mark.parametrize("D,H,depth,B,ef,dpr", [(192, 3, 2, 2, 0.0, 0.1), (192, 3, 12, 4, 10.0, 0.1),
+                                                (384, 6, 3, 3, 5.0, 0.1), (768, 12, 2, 2, 20.0, 0.0)])
+def test_step_matches_oracle(cuda_dev, D, H, depth, B, ef, dpr):
+    res = compare_step_with_oracle(D, H, depth, B, epoch_frac=ef, drop_path_rate=dpr, verbose=True)
+    print(res["summary"])
+    assert res["ok"], res["summary"]
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+def test_step_matches_reference_golden(cuda_dev, path):
+    """Same seeded parameters / inputs as oracle/make_golden.py fed to the engine; compare with the reference's own
+    outputs stored in the fixture (logits, losses, gradient fingerprints)."""
+    from fixtures import make_inputs, make_params, summarize
+    from ofb_b200.engine import SearchStepEngine
+    from ofb_oracle import ModelCfg, default_switches
+    g = np.load(path)
+    D, H, depth, B = (int(x) for x in g["cfg"])
+    cfg = ModelCfg(embed_dim=D, num_heads=H, depth=depth)
+    P = make_params(cfg, seed=0)
+    inp = make_inputs(cfg, B, seed=1, epoch_frac=float(g["epoch_frac"]), drop_path_rate=float(g["dpr"]))
+    sw = default_switches(cfg)
+    for k in sw:
+        sw[k] = torch.from_numpy(g["switch:" + k])
+    eng = SearchStepEngine(D, H, depth, B, drop_path_rate=float(g["dpr"]), lr=float(g["lr"]), switches=sw)
+    eng.load_params(P)
+    eng.set_schedule(float(g["epoch_frac"]))
+    drop_u = (inp.drop_scale > 0).float().reshape(depth * 2, B) * 0.999
+    scal = eng.step(inp.images.cuda(), inp.labels.cuda(), noise=inp.noise.cuda(), drop_u=drop_u.cuda(), update=False)
+    torch.cuda.synchronize()
+    scal = scal.cpu().numpy()
+
+    def rel(a, b):
+        a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+        return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+    assert rel(eng.logits.cpu().numpy(), g["logits"]) < BF16_TOL
+    assert rel(scal[0], g["loss_base"]) < LOSS_TOL
+    assert rel(scal[1], g["loss_arch"]) < 1e-3
+    assert rel(scal[2], g["loss_decoder"]) < LOSS_TOL
+    assert rel(scal[3], g["loss_total"]) < LOSS_TOL
+    worst = ("", 0.0)
+    for key in g.files:
+        if key.startswith("gate:"):
+            i = [m["prefix"] for m in eng.bimask.modules].index(key[5:])
+            assert rel(eng.bimask.gate_of(i).cpu().numpy(), g[key]) < 1e-4, key
+        if key.startswith("gsum:"):
+            got = summarize(eng.g(key[5:]).cpu()).numpy()
+            # strided samples of the gradient, relative to the gradient's max-norm scale (l2 / sqrt(n) is too lenient)
+            e = float(np.abs(got[3:] - g[key][3:]).max() / (np.abs(g[key][3:]).max() + 1e-30))
+            worst = max(worst, (key, e), key=lambda kv: kv[1])
+            assert abs(got[2] - g[key][2]) / (g[key][2] + 1e-30) < BF16_TOL, key     # l2 norm
+    print("worst sampled gradient error:", worst)
+    assert worst[1] < 2.5 * BF16_TOL
