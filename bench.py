@@ -1,0 +1,280 @@
+"""bench.py — images/s of the DeiT-S bi-mask search step (fwd + bwd + 3x AdamW, PMIM on), the BASELINE.json metric.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--model small|tiny|base] [--batch B]
+  torchrun launches it with one rank per GPU for N > 1 (weak scaling: 256 images per GPU, NCCL gradient all-reduce).
+
+One JSON line on rank 0:
+  value      whole-job images/s with the batch already resident in HBM (device-timed, max over ranks)
+  e2e        same metric through the engine's public step() with HOST (pinned) images/labels: H2D copy of every step's
+             inputs and a D2H read of the step's loss vector inside the timed region
+  roofline   dominant kernel = ofb::gemm_kernel (tcgen05 GEMM, all instantiations): achieved = algorithmic FLOPs of the
+             GEMM launches of the timed steps / their CUDA-event durations, against the measured bf16 peak
+  cpu_baseline / --impl reference: the CPU oracle port of the reference step (oracle/ofb_oracle.py) on the host cores,
+             bounded sample of the same workload (the Python reference itself cannot travel to the GPU box).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODELS = {"tiny": (192, 3), "small": (384, 6), "base": (768, 12)}
+# algorithmic GFLOP / image of one search step: tiny 7.64, small 27.82, base 105.85
+STEP_GFLOP = {"tiny": 7.64, "small": 27.82, "base": 105.85}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ofb", choices=["ofb", "reference"])
+    ap.add_argument("--model", default="small", choices=list(MODELS))
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--depth", type=int, default=12)
+    ap.add_argument("--cpu-sample-batch", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(tflops=float(p.get("bf16_tflops_sustained", p.get("bf16_tflops", 1590.0))), hbm=float(p.get("hbm_gbs", 6650.0)),
+                    src="measured (MEASURED_PEAKS.json, sustained)")
+    return dict(tflops=1590.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = sorted(int(r[1]) for r in self.rows if len(r) > 8 and r[1].isdigit())
+        mx = [int(r[2]) for r in self.rows if len(r) > 8 and r[2].isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) > 8:
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_oracle_rate(model, depth, sample_batch, steps=1, warmup=1):
+    """images/s of the CPU oracle port (reference step restated, fp32, all host threads) on a bounded sample."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    from fixtures import make_inputs, make_params
+    from ofb_oracle import ModelCfg, train_step
+    D, H = MODELS[model]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = ModelCfg(embed_dim=D, num_heads=H, depth=depth)
+    P = make_params(cfg, seed=0)
+    inp = make_inputs(cfg, sample_batch, seed=1, epoch_frac=0.0, drop_path_rate=0.1)
+    state = {}
+    for i in range(warmup):
+        train_step(P, state, inp, cfg, lr=1e-3, step=i + 1)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        train_step(P, state, inp, cfg, lr=1e-3, step=warmup + i + 1)
+    dt = (time.perf_counter() - t0) / steps
+    return sample_batch / dt, cores, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    D, H = MODELS[args.model]
+    rate, cores, dt = cpu_oracle_rate(args.model, args.depth, args.cpu_sample_batch, steps=max(1, min(args.steps, 3)),
+                                      warmup=max(1, min(args.warmup, 1)))
+    sample = f"{args.cpu_sample_batch} images / step of the same DeiT-{args.model} search step, fp32, {cores} threads"
+    line = {
+        "impl": "reference", "metric": "images/sec DeiT-S bi-mask search step (fwd+bwd+update, PMIM on)", "value": rate,
+        "unit": "images/s", "n_gpus": args.gpus, "steps": max(1, min(args.steps, 3)), "warmup": 1, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"DeiT-{args.model} bi-mask search + PMIM step, depth {args.depth}, 224px, CPU sample"},
+        "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import ofb_b200  # noqa: F401
+    from ofb_b200 import ops
+    from ofb_b200.engine import SearchStepEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        pg = dist.group.WORLD
+    dev = torch.device("cuda", local)
+    D, H = MODELS[args.model]
+    B = args.batch
+    eff = B * world
+    lr = 2.5e-4 * eff / 256                     # search.py:509-518
+    eng = SearchStepEngine(D, H, args.depth, B, drop_path_rate=0.1, lr=lr, device=dev, process_group=pg)
+    eng.init_params(seed=0)                     # same initial weights on every rank (DDP broadcast equivalent)
+    eng.set_schedule(0.0)
+
+    g = torch.Generator(device="cpu").manual_seed(1 + rank)
+    n_host = 2
+    host_img = [torch.randn(B, 3, 224, 224, generator=g).pin_memory() for _ in range(n_host)]
+    host_lab = [torch.randint(0, 1000, (B,), generator=g).pin_memory() for _ in range(n_host)]
+    dev_img = [h.to(dev) for h in host_img]
+    dev_lab = [h.to(dev) for h in host_lab]
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---------------- device-resident measurement ----------------
+    for i in range(args.warmup):
+        eng.step(dev_img[i % n_host], dev_lab[i % n_host])
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.GEMM_TIMING = []
+    launches0 = ops.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        eng.step(dev_img[i % n_host], dev_lab[i % n_host])
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = ops.LAUNCHES - launches0
+    gemm_t = ops.GEMM_TIMING
+    ops.GEMM_TIMING = None
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = eff * args.steps / (ms / 1e3)
+    gemm_ms = sum(a.elapsed_time(b) for a, b, _, _ in gemm_t)
+    gemm_flops = sum(f for _, _, f, _ in gemm_t)
+    scal = eng.scal.cpu().tolist()
+
+    # ---------------- end to end: host buffers -> step -> loss on host ----------------
+    copy_stream = torch.cuda.Stream(device=dev)
+    stage_img = [torch.empty_like(dev_img[0]) for _ in range(2)]
+    stage_lab = [torch.empty_like(dev_lab[0]) for _ in range(2)]
+    loss_host = torch.zeros(8).pin_memory()
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(i):
+        s = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[s])
+            stage_img[s].copy_(host_img[i % n_host], non_blocking=True)
+            stage_lab[s].copy_(host_lab[i % n_host], non_blocking=True)
+            ready[s].record(copy_stream)
+
+    def e2e_loop(n):
+        for s in range(2):
+            consumed[s].record()
+        prefetch(0)
+        for i in range(n):
+            if i + 1 < n:
+                prefetch(i + 1)
+            s = i % 2
+            torch.cuda.current_stream().wait_event(ready[s])
+            eng.step(stage_img[s], stage_lab[s])
+            consumed[s].record()
+            loss_host.copy_(eng.scal, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_loop(max(2, min(args.warmup, 3)))
+    sync_all()
+    e0.record()
+    e2e_loop(args.steps)
+    e1.record()
+    sync_all()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = eff * args.steps / (float(t.item()) / 1e3)
+    h2d = host_img[0].numel() * 4 + host_lab[0].numel() * 8
+
+    if rank == 0:
+        pk = peaks()
+        achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+        line = {
+            "metric": "images/sec DeiT-S bi-mask search step (fwd+bwd+update, PMIM on)",
+            "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"DeiT-{args.model} bi-mask search + PMIM step, depth {args.depth}, batch {B}/GPU, 224px "
+                                   f"(BASELINE.json configs[1])", "global_batch": eff, "parallelism": f"dp{world}",
+                       "l2": "activations per step (>7 GB) exceed the 126 MB L2; no explicit flush",
+                       "step_gflop_per_image": STEP_GFLOP.get(args.model)},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "ofb::gemm_kernel (tcgen05, all epilogues)", "achieved": achieved,
+                         "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": None,
+                         "peak_source": pk["src"], "launches_per_step": len(gemm_t) / max(args.steps, 1),
+                         "share_of_step": gemm_ms / ms if ms > 0 else None,
+                         "step_tflops": STEP_GFLOP.get(args.model, 0) * value / 1e3 / world},
+            "losses": {"base": scal[0], "arch": scal[1], "decoder": scal[2], "total": scal[3]},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            rate, cores, dt = cpu_oracle_rate(args.model, args.depth, args.cpu_sample_batch)
+            line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
+                                    "sample": f"{args.cpu_sample_batch} images / step of the same DeiT-{args.model} search "
+                                              f"step (oracle port, fp32, {cores} threads, {dt:.1f} s/step)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -7,9 +7,24 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import GemmArgs, check, cur_stream, lib, ptr
+from ._lib import GemmArgs, check as _check, cur_stream, lib, ptr
 
 EPI_STORE, EPI_FC1, EPI_FC2_DGRAD, EPI_WGRAD, EPI_PATCH, EPI_DECODER = range(6)
+
+# launch accounting (bench.py): every wrapper below is exactly one kernel launch of this library unless noted
+LAUNCHES = 0
+# optional per-launch GEMM timing: set to a list -> gemm() appends (start_event, end_event, flops)
+GEMM_TIMING = None
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def check(code, what):
+    _check(code, what)
+    _count()
 
 
 def _need_cuda(*ts):
@@ -40,8 +55,14 @@ def gemm(epi, A, B, *, M, N, K, out0=None, ld0=0, out1=None, ld1=0, out_fp32=Fal
     g.tokens = tokens
     lda = lda if lda is not None else A.stride(0)
     ldb = ldb if ldb is not None else B.stride(0)
+    if GEMM_TIMING is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(lib().ofb_gemm_bf16(epi, int(a_mn), int(b_mn), bn, ptr(A), lda, ptr(B), ldb, C.addressof(g), cur_stream()),
           "ofb_gemm_bf16")
+    if GEMM_TIMING is not None:
+        e1.record()
+        GEMM_TIMING.append((e0, e1, 2.0 * M * N * K, epi))
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -173,7 +173,9 @@ def test_attention_fwd_bwd(cuda_dev, B, H, T):
     dqkv = torch.empty_like(qkv)
     pg = torch.zeros(B, D, device="cuda")
     pb = torch.zeros(B, 3 * D, device="cuda")
-    ops.attention_bwd(qkv, o, d_o, lse, gate, ds, dqkv, pg, pb, B, T, H, scale)
+    # contract: d_o is the gradient w.r.t. the un-scaled attention output (the proj data-gradient GEMM applies DropPath)
+    d_o_in = (d_o.float() * ds.view(B, 1, 1)).to(torch.bfloat16)
+    ops.attention_bwd(qkv, o, d_o_in, lse, gate, ds, dqkv, pg, pb, B, T, H, scale)
     g = qf.grad                                             # grad w.r.t. the gated q,k,v  [B,T,3,H,d]
     gview = gate.view(1, 1, 1, H, d)
     assert rel(dqkv, g * gview) < BF16_TOL                  # d pre-gate

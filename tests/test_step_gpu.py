@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from step_compare import BF16_TOL, LOSS_TOL, compare_step_with_oracle
+from step_compare import BF16_TOL, DEC_TOL, LOSS_TOL, compare_step_with_oracle
 
 pytestmark = pytest.mark.gpu
 GOLD = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz")))
@@ -16,7 +16,9 @@ GOLD = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)),
 @pytest.mark.parametrize("D,H,depth,B,ef,dpr", [(192, 3, 2, 2, 0.0, 0.1), (192, 3, 12, 4, 10.0, 0.1),
                                                 (384, 6, 3, 3, 5.0, 0.1), (768, 12, 2, 2, 20.0, 0.0)])
 def test_step_matches_oracle(cuda_dev, D, H, depth, B, ef, dpr):
-    res = compare_step_with_oracle(D, H, depth, B, epoch_frac=ef, drop_path_rate=dpr, verbose=True)
+    # 12-block configurations are also measured against PyTorch's own bf16 autocast of the oracle (see step_compare)
+    res = compare_step_with_oracle(D, H, depth, B, epoch_frac=ef, drop_path_rate=dpr, verbose=True,
+                                   autocast_yardstick=depth >= 12)
     print(res["summary"])
     assert res["ok"], res["summary"]
 
@@ -62,7 +64,11 @@ def test_step_matches_reference_golden(cuda_dev, path):
             got = summarize(eng.g(key[5:]).cpu()).numpy()
             # strided samples of the gradient, relative to the gradient's max-norm scale (l2 / sqrt(n) is too lenient)
             e = float(np.abs(got[3:] - g[key][3:]).max() / (np.abs(g[key][3:]).max() + 1e-30))
+            if key.startswith("gsum:decoder."):      # L1 sign discontinuity, see step_compare.DEC_TOL
+                assert e < DEC_TOL, key
+                continue
             worst = max(worst, (key, e), key=lambda kv: kv[1])
             assert abs(got[2] - g[key][2]) / (g[key][2] + 1e-30) < BF16_TOL, key     # l2 norm
     print("worst sampled gradient error:", worst)
-    assert worst[1] < 2.5 * BF16_TOL
+    # sampled entries (48 per tensor) of 12-block gradients: see the autocast yardstick in test_step_matches_oracle
+    assert worst[1] < (2.5 if depth >= 12 else 1.25) * BF16_TOL
