@@ -21,20 +21,29 @@ namespace ofb {
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;
-static constexpr int GEMM_THREADS = 192;  // warp0 TMA, warp1 MMA (+TMEM alloc), warps2-5 epilogue
-static constexpr int SMEM_LIMIT = 232448; // 227 KB
+static constexpr int EPI_WARPS = 8;                       // two groups of four (one warp per TMEM lane quarter each)
+static constexpr int EPI_THREADS = EPI_WARPS * 32;
+static constexpr int GEMM_THREADS = 64 + EPI_THREADS;     // warp0 TMA, warp1 MMA (+TMEM alloc), warps2-9 epilogue
+static constexpr int SMEM_LIMIT = 232448;                 // 227 KB
+static constexpr int PANEL_BYTES = BM * 128;              // one [128 rows][64 bf16] SWIZZLE_128B output panel
 
-template <int BN>
+template <int BN, int EPI, int TMA_OUT>
 struct GemmCfg {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int SCRATCH_BYTES = 2 * 4 * BN * 4;  // two column-partial scratch arrays [4 warps][BN]
-    static constexpr int BAR_BYTES = 1024;
-    static constexpr int STAGES_RAW = (SMEM_LIMIT - 1024 - SCRATCH_BYTES - BAR_BYTES) / STAGE_BYTES;
+    static constexpr int NOUT = (EPI == EPI_FC1) ? 2 : 1;
+    static constexpr int STAGING_BYTES = TMA_OUT ? 2 * NOUT * PANEL_BYTES : 0;          // two slots
+    static constexpr int SCRATCH_BYTES = (EPI == EPI_FC2_DGRAD) ? 2 * 4 * BN * 4 : 0;   // column partials [4 quarters][BN] x2
+    static constexpr int VEC_BYTES = 2 * 2 * BN * 4;        // per-column epilogue vectors, double-buffered by tile parity
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int FIXED = STAGING_BYTES + SCRATCH_BYTES + VEC_BYTES + BAR_BYTES;
+    static constexpr int STAGES_RAW = (SMEM_LIMIT - FIXED) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + SCRATCH_BYTES + BAR_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED;
     static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+    static_assert(STAGES >= 3, "pipeline too shallow");
+    static_assert((2 * STAGES + 4) * 8 + 8 <= BAR_BYTES, "barrier block too small");
 };
 
 // 32 values per lane -> lane L ends with the sum over lanes of v[L] (31 shuffles).
@@ -81,22 +90,6 @@ __device__ __forceinline__ void store_f32x32(float* dst, const float (&v)[32], i
             if (i < nvalid) dst[i] = v[i];
     }
 }
-__device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* src, float (&v)[32], int nvalid) {
-    if (nvalid >= 32) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint4 p = __ldg(reinterpret_cast<const uint4*>(src) + i);
-            float2 f;
-            f = unpack_bf16x2(p.x); v[8 * i + 0] = f.x; v[8 * i + 1] = f.y;
-            f = unpack_bf16x2(p.y); v[8 * i + 2] = f.x; v[8 * i + 3] = f.y;
-            f = unpack_bf16x2(p.z); v[8 * i + 4] = f.x; v[8 * i + 5] = f.y;
-            f = unpack_bf16x2(p.w); v[8 * i + 6] = f.x; v[8 * i + 7] = f.y;
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = (i < nvalid) ? __bfloat162float(src[i]) : 0.f;
-    }
-}
 __device__ __forceinline__ void load_f32x32(const float* src, float (&v)[32], int nvalid) {
     if (nvalid >= 32) {
 #pragma unroll
@@ -109,24 +102,66 @@ __device__ __forceinline__ void load_f32x32(const float* src, float (&v)[32], in
         for (int i = 0; i < 32; ++i) v[i] = (i < nvalid) ? src[i] : 0.f;
     }
 }
+// 32 bf16 of one row as four packed 16-byte registers (zero-filled when the row / columns are out of range)
+struct Packed32 { uint4 p[4]; };
+__device__ __forceinline__ Packed32 load_packed32(const __nv_bfloat16* src, bool row_ok, int nvalid) {
+    Packed32 r;
+    if (row_ok && nvalid >= 32) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r.p[i] = __ldg(reinterpret_cast<const uint4*>(src) + i);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r.p[i] = make_uint4(0, 0, 0, 0);
+        if (row_ok) {
+            __nv_bfloat16* e = reinterpret_cast<__nv_bfloat16*>(&r);
+            for (int i = 0; i < nvalid; ++i) e[i] = src[i];
+        }
+    }
+    return r;
+}
+__device__ __forceinline__ void unpack32(const Packed32& r, float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 f;
+        f = unpack_bf16x2(r.p[i].x); v[8 * i + 0] = f.x; v[8 * i + 1] = f.y;
+        f = unpack_bf16x2(r.p[i].y); v[8 * i + 2] = f.x; v[8 * i + 3] = f.y;
+        f = unpack_bf16x2(r.p[i].z); v[8 * i + 4] = f.x; v[8 * i + 5] = f.y;
+        f = unpack_bf16x2(r.p[i].w); v[8 * i + 6] = f.x; v[8 * i + 7] = f.y;
+    }
+}
+// 32 fp32 of one row -> bf16 -> the row's 64-byte slice (chunk parity `half`) of a swizzled [128][64] output panel
+__device__ __forceinline__ void stage_bf16x32(uint32_t panel, int row, int half, const float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t a = panel + sw128_offset(row, half * 4 + i);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf16x2(v[8 * i + 0], v[8 * i + 1])),
+                     "r"(pack_bf16x2(v[8 * i + 2], v[8 * i + 3])), "r"(pack_bf16x2(v[8 * i + 4], v[8 * i + 5])),
+                     "r"(pack_bf16x2(v[8 * i + 6], v[8 * i + 7]))
+                     : "memory");
+    }
+}
 
-template <int BN, int A_MN, int B_MN, int EPI>
+template <int BN, int A_MN, int B_MN, int EPI, int TMA_OUT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmArgs g) {
-    using Cfg = GemmCfg<BN>;
+gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+            const __grid_constant__ CUtensorMap tma_o0, const __grid_constant__ CUtensorMap tma_o1, const GemmArgs g) {
+    using Cfg = GemmCfg<BN, EPI, TMA_OUT>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr uint32_t IDESC = make_idesc_bf16(BM, BN, A_MN, B_MN);
+    constexpr int NCHUNK = BN / 32;          // 32-column chunks per tile; group g handles chunks c = g, g+2, ...
+    constexpr int NPANEL = BN / 64;
 
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
-    float* scratch0 = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;                       // 1024-aligned (stage sizes are multiples of 8 KB)
+    float* scratch0 = reinterpret_cast<float*>(staging + Cfg::STAGING_BYTES);
     float* scratch1 = scratch0 + 4 * BN;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::SCRATCH_BYTES);
-    uint64_t* full_bar = bars;                   // [STAGES]
-    uint64_t* empty_bar = bars + STAGES;         // [STAGES]
-    uint64_t* tfull_bar = bars + 2 * STAGES;     // [2]
+    float* vecs = reinterpret_cast<float*>(staging + Cfg::STAGING_BYTES + Cfg::SCRATCH_BYTES);   // [2 parities][2][BN]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES + Cfg::SCRATCH_BYTES + Cfg::VEC_BYTES);
+    uint64_t* full_bar = bars;                    // [STAGES]
+    uint64_t* empty_bar = bars + STAGES;          // [STAGES]
+    uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]
     uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
@@ -134,15 +169,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     const int lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
+        if ((smem_u32(smem) & 1023u) != 0) { printf("ofb: dynamic smem base not 1024-aligned\n"); __trap(); }
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
+        if (TMA_OUT) { tma_prefetch_desc(&tma_o0); if (Cfg::NOUT == 2) tma_prefetch_desc(&tma_o1); }
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(smem_u32(&full_bar[i]), 1);
             mbar_init(smem_u32(&empty_bar[i]), 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&tfull_bar[i]), 1);
-            mbar_init(smem_u32(&tempty_bar[i]), 4);
+            mbar_init(smem_u32(&tempty_bar[i]), EPI_WARPS);
         }
         mbar_fence_init();
     }
@@ -233,9 +270,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         }
     } else {
         // ===================== epilogue warps =====================
+        const int ew = warp - 2;           // 0..7
         const int q = warp & 3;            // TMEM lane quarter this warp may access
+        const int grp = ew >> 2;           // column-chunk parity handled by this warp
         const int et = q * 32 + lane;      // row inside the tile
+        const int etid = ew * 32 + lane;   // 0..255
+        const bool elected = (etid == 0);
         int it = 0;
+        uint32_t panel_ctr = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const int split = t / (m_tiles * n_tiles);
             const int mn = t % (m_tiles * n_tiles);
@@ -246,12 +288,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             ++it;
-            mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
-            tc_fence_after();
 
             const int row = m_blk * BM + et;
             const bool row_ok = row < g.M;
             const int n0 = n_blk * BN;
+
+            // ---- per-column epilogue vectors of this tile -> smem (while the MMAs of the tile are still running) ----
+            float* vb = vecs + acc * 2 * BN;     // bias-like vector
+            float* vs = vb + BN;                 // scale-like vector
+            if (EPI == EPI_STORE || EPI == EPI_FC1 || EPI == EPI_FC2_DGRAD || EPI == EPI_PATCH || EPI == EPI_DECODER) {
+                for (int i = etid; i < BN; i += EPI_THREADS) {
+                    const int col = n0 + i;
+                    const bool ok = col < g.N;
+                    float s = 1.f, b = 0.f;
+                    if (g.colscale != nullptr) s = ok ? __ldg(g.colscale + (g.colscale_period > 0 ? col % g.colscale_period : col)) : 0.f;
+                    if (g.bias != nullptr) b = ok ? __ldg(g.bias + col) : 0.f;
+                    if (EPI == EPI_STORE) b *= s;          // out = ars*(acc*cs + brs*bias*cs) + res
+                    vb[i] = b; vs[i] = s;
+                }
+            }
             float rs = 1.f;
             if (EPI == EPI_STORE || EPI == EPI_FC2_DGRAD || EPI == EPI_FC1) {
                 if (g.rowscale != nullptr && row_ok) rs = __ldg(g.rowscale + row / g.rows_per_scale);
@@ -260,45 +315,60 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             if (EPI == EPI_STORE || EPI == EPI_WGRAD) {
                 if (g.scale_ptr != nullptr) gs = __ldg(g.scale_ptr);
             }
-            float loss_acc = 0.f;
+            // ---- prefetch this thread's residual / saved-activation slices (latency hides behind the tfull wait) ----
+            Packed32 pre[(EPI == EPI_STORE || EPI == EPI_FC2_DGRAD) ? NCHUNK / 2 : 1];
+            if (EPI == EPI_STORE) {
+                if (g.res != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < NCHUNK / 2; ++j) {
+                        const int col0 = n0 + (2 * j + grp) * 32;
+                        pre[j] = load_packed32(g.res + size_t(row) * g.ldres + col0, row_ok, min(32, g.N - col0));
+                    }
+                }
+            } else if (EPI == EPI_FC2_DGRAD) {
+#pragma unroll
+                for (int j = 0; j < NCHUNK / 2; ++j) {
+                    const int col0 = n0 + (2 * j + grp) * 32;
+                    pre[j] = load_packed32(g.aux + size_t(row) * g.ldaux + col0, row_ok, min(32, g.N - col0));
+                }
+            }
+            named_bar_sync(1, EPI_THREADS);       // epilogue vectors visible
+            mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+            tc_fence_after();
 
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            float loss_acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < NCHUNK / 2; ++j) {
+                const int c = 2 * j + grp;
                 float v[32];
                 tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + c * 32), v);
                 tmem_ld_wait();
+                if (j == NCHUNK / 2 - 1) {
+                    // this warp's last TMEM read of the tile: hand the accumulator stage back to the MMA warp early
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+                }
                 const int col0 = n0 + c * 32;
                 const int nvalid = min(32, g.N - col0);
-                if (nvalid <= 0) {
-                    if (EPI == EPI_FC2_DGRAD) {  // keep scratch defined
-                        scratch0[q * BN + c * 32 + lane] = 0.f;
-                        scratch1[q * BN + c * 32 + lane] = 0.f;
-                    }
-                    continue;
-                }
+                const float* cb = vb + c * 32;
+                const float* cs = vs + c * 32;
+                const uint32_t slot = panel_ctr & 1u;
+                const uint32_t panel0 = smem_u32(staging) + slot * (Cfg::NOUT * PANEL_BYTES);
 
                 if (EPI == EPI_STORE) {
                     const float brs = g.bias_rowscaled ? rs : 1.f;
                     const float ars = (g.bias_rowscaled ? 1.f : rs) * gs;
-                    if (g.bias != nullptr) {
+                    float r[32];
+                    if (g.res != nullptr) unpack32(pre[j], r);
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] += (i < nvalid) ? brs * __ldg(g.bias + col0 + i) : 0.f;
+                    for (int i = 0; i < 32; ++i) {
+                        const float tt = fmaf(v[i], cs[i], brs * cb[i]);
+                        v[i] = (g.res != nullptr) ? fmaf(ars, tt, r[i]) : ars * tt;
                     }
-                    if (g.colscale != nullptr) {
-                        // col0 is a multiple of 32 and the period a multiple of 32 -> one modulo per chunk
-                        const float* cs = g.colscale + (g.colscale_period > 0 ? col0 % g.colscale_period : col0);
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] *= (i < nvalid) ? __ldg(cs + i) : 0.f;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] *= ars;
-                    if (row_ok) {
-                        if (g.res != nullptr) {
-                            float r[32];
-                            load_bf16x32(g.res + size_t(row) * g.ldres + col0, r, nvalid);
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] += r[i];
-                        }
+                    if (TMA_OUT) {
+                        stage_bf16x32(panel0, et, c & 1, v);
+                    } else if (row_ok && nvalid > 0) {
                         if (g.out_fp32) store_f32x32(reinterpret_cast<float*>(g.out0) + size_t(row) * g.ld0 + col0, v, nvalid);
                         else store_bf16x32(reinterpret_cast<__nv_bfloat16*>(g.out0) + size_t(row) * g.ld0 + col0, v, nvalid);
                     }
@@ -306,37 +376,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     float h[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
-                        const float b = (i < nvalid) ? __ldg(g.bias + col0 + i) : 0.f;
-                        const float gt = (i < nvalid) ? __ldg(g.colscale + col0 + i) : 0.f;
-                        v[i] += b;
-                        h[i] = rs * gelu_erf(v[i] * gt);
+                        v[i] += cb[i];
+                        const float z = v[i] * cs[i];
+                        h[i] = rs * z * gelu_cdf(z);
                     }
-                    if (row_ok) {
-                        store_bf16x32(reinterpret_cast<__nv_bfloat16*>(g.out0) + size_t(row) * g.ld0 + col0, v, nvalid);
-                        store_bf16x32(reinterpret_cast<__nv_bfloat16*>(g.out1) + size_t(row) * g.ld1 + col0, h, nvalid);
-                    }
+                    stage_bf16x32(panel0, et, c & 1, v);
+                    stage_bf16x32(panel0 + PANEL_BYTES, et, c & 1, h);
                 } else if (EPI == EPI_FC2_DGRAD) {
-                    float u[32], dg[32];
-                    if (row_ok) load_bf16x32(g.aux + size_t(row) * g.ldaux + col0, u, nvalid);
-                    else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) u[i] = 0.f;
-                    }
+                    float u[32];
+                    unpack32(pre[j], u);           // zero for rows / columns out of range
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
-                        const float gt = (i < nvalid) ? __ldg(g.colscale + col0 + i) : 0.f;
-                        const float dh = row_ok ? v[i] * rs : 0.f;
-                        const float gp = gelu_erf_grad(u[i] * gt);
-                        dg[i] = dh * gp * u[i];   // d gate contribution
-                        v[i] = dh * gp * gt;      // du
+                        const float gt = cs[i];
+                        float Phi, zphi;
+                        gelu_terms(u[i] * gt, Phi, zphi);
+                        const float tt = (row_ok ? v[i] * rs : 0.f) * (Phi + zphi);
+                        u[i] = tt * u[i];          // d gate contribution
+                        v[i] = tt * gt;            // du
                     }
-                    if (row_ok) store_bf16x32(reinterpret_cast<__nv_bfloat16*>(g.out0) + size_t(row) * g.ld0 + col0, v, nvalid);
-                    const float sdg = lane_transpose_sum(dg);
+                    stage_bf16x32(panel0, et, c & 1, v);
+                    const float sdg = lane_transpose_sum(u);
                     const float sdu = lane_transpose_sum(v);
                     scratch0[q * BN + c * 32 + lane] = sdg;
                     scratch1[q * BN + c * 32 + lane] = sdu;
                 } else if (EPI == EPI_WGRAD) {
-                    if (row_ok) {
+                    if (row_ok && nvalid > 0) {
                         float* dst = reinterpret_cast<float*>(g.out0) + size_t(row) * g.ld0 + col0;
                         if (nvalid >= 32) {
 #pragma unroll
@@ -353,16 +417,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     }
                 } else if (EPI == EPI_PATCH) {
                     // rows are (image b, patch l); output row skips the cls slot of each image.
-                    if (row_ok) {
+                    if (row_ok && nvalid > 0) {
                         const int b = row / g.tokens, l = row % g.tokens;
                         const float mk = __ldg(g.rowmask + row);
                         const float* pos = g.pos + size_t(1 + l) * g.N + col0;
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
                             if (i < nvalid) {
-                                const float gt = __ldg(g.colscale + col0 + i);
-                                const float val = v[i] + __ldg(g.bias + col0 + i) + __ldg(pos + i);
-                                v[i] = (mk != 0.f ? __ldg(g.mask_token + col0 + i) : val) * gt;
+                                const float val = v[i] + cb[i] + __ldg(pos + i);
+                                v[i] = (mk != 0.f ? __ldg(g.mask_token + col0 + i) : val) * cs[i];
                             }
                         }
                         const size_t orow = size_t(b) * (g.tokens + 1) + 1 + l;
@@ -372,7 +435,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     // rows are (image b, token t) incl. cls (t == 0, ignored). vision_transformer.py:720-729
                     const int tk = g.tokens + 1;
                     const int b = row / tk, tt = row % tk;
-                    const bool live = row_ok && tt > 0;
+                    const bool live = row_ok && tt > 0 && nvalid > 0;
                     float mk = 0.f;
                     float tg[32];
                     if (live) {
@@ -384,24 +447,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     for (int i = 0; i < 32; ++i) {
                         float s = 0.f;
                         if (mk != 0.f && i < nvalid) {
-                            const float d = v[i] + __ldg(g.bias + col0 + i) - tg[i];
+                            const float d = v[i] + cb[i] - tg[i];
                             loss_acc += fabsf(d);
                             s = (d > 0.f) ? 1.f : (d < 0.f ? -1.f : 0.f);
                         }
                         v[i] = s;
                     }
-                    if (row_ok) store_bf16x32(reinterpret_cast<__nv_bfloat16*>(g.out0) + size_t(row) * g.ld0 + col0, v, nvalid);
+                    if (row_ok && nvalid > 0) store_bf16x32(reinterpret_cast<__nv_bfloat16*>(g.out0) + size_t(row) * g.ld0 + col0, v, nvalid);
+                }
+
+                if (TMA_OUT) {
+                    // panel j of this tile (chunks 2j, 2j+1) is complete once both groups have staged their chunk
+                    fence_proxy_async_smem();
+                    if (elected) bulk_wait_read<0>();          // the other slot's previous store has been read out
+                    named_bar_sync(2, EPI_THREADS);
+                    if (elected && n0 + j * 64 < g.N) {
+                        tma_store_2d(&tma_o0, panel0, n0 + j * 64, m_blk * BM);
+                        if (Cfg::NOUT == 2) tma_store_2d(&tma_o1, panel0 + PANEL_BYTES, n0 + j * 64, m_blk * BM);
+                        bulk_commit();
+                    }
+                    ++panel_ctr;
                 }
             }
 
-            // accumulator fully drained -> hand the TMEM stage back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
-
             if (EPI == EPI_FC2_DGRAD) {
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                for (int col = et; col < BN; col += 128) {
+                named_bar_sync(3, EPI_THREADS);
+                for (int col = etid; col < BN; col += EPI_THREADS) {
                     if (n0 + col < g.N) {
                         const float a = scratch0[col] + scratch0[BN + col] + scratch0[2 * BN + col] + scratch0[3 * BN + col];
                         const float b = scratch1[col] + scratch1[BN + col] + scratch1[2 * BN + col] + scratch1[3 * BN + col];
@@ -409,13 +480,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         g.colpart1[size_t(m_blk) * g.N + n0 + col] = b;
                     }
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                // the next tile's scratch writes happen after its named barrier 1, which every thread reaches after this loop
             }
             if (EPI == EPI_DECODER) {
                 const float s = warp_sum(loss_acc);
-                if (lane == 0) g.colpart0[size_t(mn) * 4 + q] = s;
+                if (lane == 0) g.colpart0[size_t(mn) * EPI_WARPS + ew] = s;
             }
         }
+        if (TMA_OUT && elected) bulk_wait<0>();    // all output panels fully written before the CTA retires
     }
 
     tc_fence_before();
@@ -475,17 +547,17 @@ int num_sms() {
     return g_num_sms;
 }
 
-template <int BN, int A_MN, int B_MN, int EPI>
+template <int BN, int A_MN, int B_MN, int EPI, int TMA_OUT>
 static int launch_gemm_inst(const void* A, int lda, const void* B, int ldb, const GemmArgs& g, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, EPI, TMA_OUT>;
     static bool configured = false;
-    auto kfn = gemm_kernel<BN, A_MN, B_MN, EPI>;
+    auto kfn = gemm_kernel<BN, A_MN, B_MN, EPI, TMA_OUT>;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return int(e);
         configured = true;
     }
-    CUtensorMap ta, tb;
+    CUtensorMap ta, tb, to0, to1;
     {
         // K-major: tensor [rows, K] row-major -> dims {K, rows}, box {64, 128|BN}
         // MN-major: tensor [K, rows] row-major -> dims {rows, K}, box {64, 64}
@@ -501,16 +573,30 @@ static int launch_gemm_inst(const void* A, int lda, const void* B, int ldb, cons
         str[1] = uint64_t(ldb);
         r = make_tmap_bf16(&tb, B, 2, dims, str, box);
         if (r) return r;
+        to0 = ta; to1 = ta;
+        if (TMA_OUT) {
+            // bf16 output [M, N] with row pitch ld: box = one swizzled [128 rows][64 cols] panel; the hardware clips
+            // rows >= M and columns >= N
+            dims[0] = g.N; dims[1] = g.M; box[0] = 64; box[1] = BM;
+            str[1] = uint64_t(g.ld0);
+            r = make_tmap_bf16(&to0, g.out0, 2, dims, str, box);
+            if (r) return r;
+            if (Cfg::NOUT == 2) {
+                str[1] = uint64_t(g.ld1);
+                r = make_tmap_bf16(&to1, g.out1, 2, dims, str, box);
+                if (r) return r;
+            }
+        }
     }
     const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + BN - 1) / BN;
     const int total = m_tiles * n_tiles * (g.k_splits > 0 ? g.k_splits : 1);
     const int grid = total < num_sms() ? total : num_sms();
-    kfn<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, g);
+    kfn<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, to0, to1, g);
     return int(cudaGetLastError());
 }
 
-// pick the N tile: prefer exact division with the widest tile that keeps wave quantisation low
-static int pick_bn(int M, int N) {
+// pick the N tile: fewest (waves x tile width) with a penalty for narrow tiles (shared-memory bandwidth per MMA)
+static int pick_bn(int M, int N, int splits_ok) {
     const int cands[4] = {256, 192, 128, 64};
     const int m_tiles = (M + BM - 1) / BM;
     int best = 128; double best_cost = 1e30;
@@ -518,28 +604,36 @@ static int pick_bn(int M, int N) {
         const int bn = cands[i];
         const int n_tiles = (N + bn - 1) / bn;
         const long tiles = long(m_tiles) * n_tiles;
-        const long waves = (tiles + num_sms() - 1) / num_sms();
-        // cost ~ waves * tile work (padding waste included), small tiles pay an smem-bandwidth penalty
-        double cost = double(waves) * bn * (bn <= 64 ? 1.5 : (bn <= 128 ? 1.10 : 1.0));
+        double cost;
+        if (splits_ok) {
+            // split-K fills the machine whatever the tile count: cost = padded work, narrow tiles are smem-bound
+            cost = double(tiles) * bn * (bn <= 64 ? 2.0 : (bn <= 128 ? 1.25 : 1.0));
+            if (tiles > num_sms()) cost *= double((tiles + num_sms() - 1) / num_sms()) * num_sms() / tiles;
+        } else {
+            const long waves = (tiles + num_sms() - 1) / num_sms();
+            cost = double(waves) * bn * (bn <= 64 ? 1.5 : (bn <= 128 ? 1.10 : 1.0));
+        }
         if (cost < best_cost) { best_cost = cost; best = bn; }
     }
     return best;
 }
 
-template <int A_MN, int B_MN, int EPI>
+template <int A_MN, int B_MN, int EPI, int TMA_OUT>
 static int launch_gemm_bn(int bn, const void* A, int lda, const void* B, int ldb, const GemmArgs& g, cudaStream_t s) {
     switch (bn) {
-        case 256: return launch_gemm_inst<256, A_MN, B_MN, EPI>(A, lda, B, ldb, g, s);
-        case 192: return launch_gemm_inst<192, A_MN, B_MN, EPI>(A, lda, B, ldb, g, s);
-        case 128: return launch_gemm_inst<128, A_MN, B_MN, EPI>(A, lda, B, ldb, g, s);
-        default:  return launch_gemm_inst<64, A_MN, B_MN, EPI>(A, lda, B, ldb, g, s);
+        case 256: return launch_gemm_inst<256, A_MN, B_MN, EPI, TMA_OUT>(A, lda, B, ldb, g, s);
+        case 192: return launch_gemm_inst<192, A_MN, B_MN, EPI, TMA_OUT>(A, lda, B, ldb, g, s);
+        case 128: return launch_gemm_inst<128, A_MN, B_MN, EPI, TMA_OUT>(A, lda, B, ldb, g, s);
+        default:  return launch_gemm_inst<64, A_MN, B_MN, EPI, TMA_OUT>(A, lda, B, ldb, g, s);
     }
 }
+
+static bool tma_out_ok(const void* p, int ld) { return p != nullptr && (reinterpret_cast<uintptr_t>(p) & 15u) == 0 && ld % 8 == 0; }
 
 int launch_gemm(int epi, int a_mn, int b_mn, int bn_hint, const void* A, int lda, const void* B, int ldb, GemmArgs g,
                 cudaStream_t stream) {
     if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 0;
-    int bn = bn_hint > 0 ? bn_hint : pick_bn(g.M, g.N);
+    int bn = bn_hint > 0 ? bn_hint : pick_bn(g.M, g.N, epi == EPI_WGRAD);
     if (epi == EPI_WGRAD) {
         if (!(a_mn && b_mn)) return 1003;
         if (g.k_splits <= 0) {
@@ -550,23 +644,31 @@ int launch_gemm(int epi, int a_mn, int b_mn, int bn_hint, const void* A, int lda
             if (s > kb) s = kb;
             g.k_splits = s;
         }
-        return launch_gemm_bn<1, 1, EPI_WGRAD>(bn, A, lda, B, ldb, g, stream);
+        return launch_gemm_bn<1, 1, EPI_WGRAD, 0>(bn, A, lda, B, ldb, g, stream);
     }
     if (a_mn) return 1003;
     g.k_splits = 1;
+    const bool tma_out = !g.out_fp32 && tma_out_ok(g.out0, g.ld0);
     if (b_mn) {   // data-gradient GEMMs read the nn.Linear weight [N_out, K_in] directly as an MN-major operand
         switch (epi) {
-            case EPI_STORE:     return launch_gemm_bn<0, 1, EPI_STORE>(bn, A, lda, B, ldb, g, stream);
-            case EPI_FC2_DGRAD: return launch_gemm_bn<0, 1, EPI_FC2_DGRAD>(bn, A, lda, B, ldb, g, stream);
+            case EPI_STORE:
+                return tma_out ? launch_gemm_bn<0, 1, EPI_STORE, 1>(bn, A, lda, B, ldb, g, stream)
+                               : launch_gemm_bn<0, 1, EPI_STORE, 0>(bn, A, lda, B, ldb, g, stream);
+            case EPI_FC2_DGRAD:
+                if (!tma_out) return 1005;
+                return launch_gemm_bn<0, 1, EPI_FC2_DGRAD, 1>(bn, A, lda, B, ldb, g, stream);
             default: return 1003;
         }
     }
     switch (epi) {
-        case EPI_STORE:     return launch_gemm_bn<0, 0, EPI_STORE>(bn, A, lda, B, ldb, g, stream);
-        case EPI_FC1:       return launch_gemm_bn<0, 0, EPI_FC1>(bn, A, lda, B, ldb, g, stream);
-        case EPI_FC2_DGRAD: return launch_gemm_bn<0, 0, EPI_FC2_DGRAD>(bn, A, lda, B, ldb, g, stream);
-        case EPI_PATCH:     return launch_gemm_bn<0, 0, EPI_PATCH>(bn, A, lda, B, ldb, g, stream);
-        case EPI_DECODER:   return launch_gemm_bn<0, 0, EPI_DECODER>(bn, A, lda, B, ldb, g, stream);
+        case EPI_STORE:
+            return tma_out ? launch_gemm_bn<0, 0, EPI_STORE, 1>(bn, A, lda, B, ldb, g, stream)
+                           : launch_gemm_bn<0, 0, EPI_STORE, 0>(bn, A, lda, B, ldb, g, stream);
+        case EPI_FC1:
+            if (!tma_out || !tma_out_ok(g.out1, g.ld1)) return 1005;
+            return launch_gemm_bn<0, 0, EPI_FC1, 1>(bn, A, lda, B, ldb, g, stream);
+        case EPI_PATCH:     return launch_gemm_bn<0, 0, EPI_PATCH, 0>(bn, A, lda, B, ldb, g, stream);
+        case EPI_DECODER:   return launch_gemm_bn<0, 0, EPI_DECODER, 0>(bn, A, lda, B, ldb, g, stream);
         default: return 1004;
     }
 }

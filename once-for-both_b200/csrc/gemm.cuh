@@ -29,7 +29,7 @@ struct GemmArgs {
     int rows_per_scale;
     const __nv_bfloat16* res; int ldres;   // residual or null
     const __nv_bfloat16* aux; int ldaux;   // EPI_FC2_DGRAD: saved pre-gate fc1 output u
-    float* colpart0;        // [m_tiles][N] column partial sums (dgate)  / EPI_DECODER: [tiles*4] loss partials
+    float* colpart0;        // [m_tiles][N] column partial sums (dgate)  / EPI_DECODER: [tiles*8] loss partials (one per epilogue warp)
     float* colpart1;        // [m_tiles][N] column partial sums (dbias)
     const float* scale_ptr; // EPI_WGRAD / EPI_STORE: optional device scalar multiplied into acc
     // EPI_PATCH / EPI_DECODER

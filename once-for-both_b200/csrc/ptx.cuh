@@ -97,6 +97,23 @@ __device__ __forceinline__ void tma_load_5d(uint32_t smem_dst, const CUtensorMap
         : "memory");
 }
 
+// 2-D tiled store smem -> global (bulk async group); out-of-bounds parts of the box are clipped by the hardware.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until the smem sources of all but the N most recent bulk groups have been read
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+// named barrier over `nthreads` threads (id 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ---------------------------------------------------------------------------------------------
@@ -198,6 +215,35 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
     const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
     const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
     return cdf + x * pdf;
+}
+__device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// Phi(z) (standard normal CDF) and z*phi(z) via Abramowitz-Stegun 7.1.26 (|erf error| < 2e-7; one rcp + one ex2).
+// gelu(z) = z*Phi, gelu'(z) = Phi + z*phi.  Replaces erff() in the GEMM epilogues, where ALU issue is the bound.
+__device__ __forceinline__ void gelu_terms(float z, float& Phi, float& zphi) {
+    const float x = fabsf(z) * 0.70710678118654752440f;
+    const float t = fast_rcp(fmaf(0.3275911f, x, 1.0f));
+    const float E = fast_ex2(x * x * -1.4426950408889634f);
+    float p = fmaf(t, 1.061405429f, -1.453152027f);
+    p = fmaf(t, p, 1.421413741f);
+    p = fmaf(t, p, -0.284496736f);
+    p = fmaf(t, p, 0.254829592f);
+    const float y = 0.5f * p * t * E;            // erfc(x) / 2
+    Phi = z >= 0.f ? 1.0f - y : y;
+    zphi = z * E * 0.39894228040143267794f;
+}
+// Phi(z) alone via Abramowitz-Stegun 7.1.28 (one rcp, no ex2)
+__device__ __forceinline__ float gelu_cdf(float z) {
+    const float x = fabsf(z) * 0.70710678118654752440f;
+    float p = fmaf(x, 0.0000430638f, 0.0002765672f);
+    p = fmaf(x, p, 0.0001520143f);
+    p = fmaf(x, p, 0.0092705272f);
+    p = fmaf(x, p, 0.0422820123f);
+    p = fmaf(x, p, 0.0705230784f);
+    p = fmaf(x, p, 1.0f);
+    p *= p; p *= p; p *= p; p *= p;
+    const float y = 0.5f * fast_rcp(p);         // erfc(x) / 2  (p may overflow to inf -> rcp = 0)
+    return z >= 0.f ? 1.0f - y : y;
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -238,7 +238,7 @@ class SearchStepEngine:
         self.dlogits = torch.empty(B, self.C, **bf)
         self.sgn = torch.zeros(M, 768, **bf)
         self.dec_bn = 256
-        self.dec_part = torch.zeros(((M + 127) // 128) * (768 // self.dec_bn) * 4, **f32)
+        self.dec_part = torch.zeros(((M + 127) // 128) * (768 // self.dec_bn) * 8, **f32)   # one partial per epilogue warp
         self.scal = torch.zeros(8, **f32)
         # backward scratch
         self.gA, self.gB, self.gC = (torch.empty(M, D, **bf) for _ in range(3))

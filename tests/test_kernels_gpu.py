@@ -269,7 +269,7 @@ def test_decoder_epilogue(cuda_dev):
     tgt = torch.randn(B * L, 768, device="cuda")
     sgn = torch.empty(B * T, 768, device="cuda", dtype=torch.bfloat16)
     bn = 256
-    parts = torch.zeros(((B * T + 127) // 128) * (768 // bn) * 4, device="cuda")
+    parts = torch.zeros(((B * T + 127) // 128) * (768 // bn) * 8, device="cuda")
     ops.gemm(ops.EPI_DECODER, lat, W, M=B * T, N=768, K=D, out0=sgn, bias=bias, rowmask=mask, target=tgt, tokens=L,
              colpart0=parts, bn=bn)
     rec = (lat.float() @ W.float().t() + bias).view(B, T, 768)[:, 1:]
