@@ -18,6 +18,7 @@
 
 namespace ofb {
 
+int num_sms();
 int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
                    const uint32_t* box);
 
@@ -60,101 +61,175 @@ __device__ __forceinline__ uint32_t pbuf_addr(uint32_t base, int r, int idx16) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// forward
+// forward: persistent, warp-specialised.  One CTA per SM loops over (image, head) items; the two 128-row q tiles of an
+// item are two independent "slots" (own TMEM half, own P buffer, own 8 compute warps), so the S / PV MMAs of one slot
+// and the TMA loads of the next item overlap the softmax of the other slot.
+//   warps 0-7  : slot 0 (q rows 0..127)      warp w: TMEM lane quarter w&3, kv-column half (w>>2)&1
+//   warps 8-15 : slot 1 (q rows 128..255)
+//   warp 16    : TMA producer (Q0,Q1,K then V of the next item as soon as the MMAs that read them have retired)
+//   warp 17    : MMA issuer (+ TMEM allocation)
+// TMEM: slot s owns columns [256 s, 256 s + 208) for S; O (64 columns) overlays S once P has been written out.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+static constexpr int FWD_CW = 16;                         // compute warps
+static constexpr int FWD_THREADS = (FWD_CW + 2) * 32;     // 576
+static constexpr int KV_SPLIT = 112;                      // kv columns [0,112) -> half 0, [112,208) -> half 1
+
+__device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(FWD_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, const AttnArgs a) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sQ = smem_u32(smem);                       // 2 tiles
     const uint32_t sK = sQ + 2 * TILE_B;
     const uint32_t sV = sK + KV_B;
-    const uint32_t sP = sV + KV_B;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * TILE_B + 2 * KV_B + PBUF_B);
-    const uint32_t ld_bar = smem_u32(&bars[0]), s_bar = smem_u32(&bars[1]), p_bar = smem_u32(&bars[2]), o_bar = smem_u32(&bars[3]);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[4]);
+    const uint32_t sP = sV + KV_B;                            // 2 slots x PBUF_B
+    const uint32_t sX = sP + 2 * PBUF_B;                      // exchange: [max|sum][slot][half][128] floats
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * TILE_B + 2 * KV_B + 2 * PBUF_B + 4096);
+    const uint32_t qk_full = smem_u32(&bars[0]), qk_empty = smem_u32(&bars[1]), v_full = smem_u32(&bars[2]), v_empty = smem_u32(&bars[3]);
+    // per slot: s_full, p_full, o_full, o_empty
+    auto slot_bar = [&](int s, int k) { return smem_u32(&bars[4 + s * 4 + k]); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[12]);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
+    const int n_items = a.B * a.H;
 
     if (threadIdx.x == 0) {
-        mbar_init(ld_bar, 1); mbar_init(s_bar, 1); mbar_init(p_bar, 128); mbar_init(o_bar, 1);
+        if ((sQ & 1023u) != 0) { printf("ofb: dynamic smem base not 1024-aligned\n"); __trap(); }
+        mbar_init(qk_full, 1); mbar_init(qk_empty, 1); mbar_init(v_full, 1); mbar_init(v_empty, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(slot_bar(s, 0), 1); mbar_init(slot_bar(s, 1), 8); mbar_init(slot_bar(s, 2), 1); mbar_init(slot_bar(s, 3), 8);
+        }
         mbar_fence_init();
     }
-    if (warp == 4) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
+    if (warp == FWD_CW + 1) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tS = tmem, tO = tmem + 256;
     constexpr uint32_t IDESC_S = make_idesc_bf16(128, KVP, 0, 0);
     constexpr uint32_t IDESC_O = make_idesc_bf16(128, HD, 0, 1);
 
-    if (warp == 4) {
+    if (warp == FWD_CW) {
+        // ===================== TMA producer =====================
         if (lane == 0) {
-            mbar_arrive_expect_tx(ld_bar, 2 * TILE_B + 2 * KV_B);
-            tma_load_5d(sQ, &tm_q, ld_bar, 0, 0, h, 0, b);
-            tma_load_5d(sQ + TILE_B, &tm_q, ld_bar, 0, QT, h, 0, b);
-            tma_load_5d(sK, &tm_kv, ld_bar, 0, 0, h, 1, b);
-            tma_load_5d(sV, &tm_kv, ld_bar, 0, 0, h, 2, b);
-            mbar_wait(ld_bar, 0);
-            tc_fence_after();
-            auto issue_s = [&](int i) {
+            tma_prefetch_desc(&tm_q);
+            tma_prefetch_desc(&tm_kv);
+            int it = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const int b = item / a.H, h = item % a.H;
+                const uint32_t ph = it & 1;
+                mbar_wait(qk_empty, ph ^ 1);
+                mbar_arrive_expect_tx(qk_full, 2 * TILE_B + KV_B);
+                tma_load_5d(sQ, &tm_q, qk_full, 0, 0, h, 0, b);
+                tma_load_5d(sQ + TILE_B, &tm_q, qk_full, 0, QT, h, 0, b);
+                tma_load_5d(sK, &tm_kv, qk_full, 0, 0, h, 1, b);
+                mbar_wait(v_empty, ph ^ 1);
+                mbar_arrive_expect_tx(v_full, KV_B);
+                tma_load_5d(sV, &tm_kv, v_full, 0, 0, h, 2, b);
+            }
+        }
+    } else if (warp == FWD_CW + 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int it = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const uint32_t ph = it & 1;
+                mbar_wait(qk_full, ph);
+                for (int s = 0; s < 2; ++s) {
+                    mbar_wait(slot_bar(s, 3), ph ^ 1);          // slot's TMEM free (previous item's O read out)
+                    tc_fence_after();
 #pragma unroll
-                for (int k = 0; k < HD / 16; ++k)
-                    umma_bf16(tS, make_smem_desc_sw128(sQ + i * TILE_B + k * 32, 0, 1024), make_smem_desc_sw128(sK + k * 32, 0, 1024),
-                              IDESC_S, k > 0);
-                umma_commit(s_bar);
-            };
-            issue_s(0);
-            for (int i = 0; i < 2; ++i) {
-                mbar_wait(p_bar, i);
-                tc_fence_after();
+                    for (int k = 0; k < HD / 16; ++k)
+                        umma_bf16(tmem + s * 256, make_smem_desc_sw128(sQ + s * TILE_B + k * 32, 0, 1024),
+                                  make_smem_desc_sw128(sK + k * 32, 0, 1024), IDESC_S, k > 0);
+                    umma_commit(slot_bar(s, 0));
+                }
+                umma_commit(qk_empty);                          // Q / K may be overwritten by the next item's loads
+                mbar_wait(v_full, ph);
+                for (int s = 0; s < 2; ++s) {
+                    mbar_wait(slot_bar(s, 1), ph);              // P of this slot is in shared memory, S fully consumed
+                    tc_fence_after();
 #pragma unroll
-                for (int k = 0; k < KVP / 16; ++k)
-                    umma_bf16(tO, make_smem_desc_sw128(sP + (k >> 2) * TILE_B + (k & 3) * 32, 0, 1024),
-                              make_smem_desc_sw128(sV + k * 2048, 0, 1024), IDESC_O, k > 0);
-                umma_commit(o_bar);
-                if (i == 0) issue_s(1);
+                    for (int k = 0; k < KVP / 16; ++k)
+                        umma_bf16(tmem + s * 256, make_smem_desc_sw128(sP + s * PBUF_B + (k >> 2) * TILE_B + (k & 3) * 32, 0, 1024),
+                                  make_smem_desc_sw128(sV + k * 2048, 0, 1024), IDESC_O, k > 0);
+                    umma_commit(slot_bar(s, 2));
+                }
+                umma_commit(v_empty);
             }
         }
     } else {
-        const int r = warp * 32 + lane;
-        const uint32_t lane_base = uint32_t(warp * 32) << 16;
+        // ===================== softmax / epilogue warps =====================
+        const int s = warp >> 3;                 // slot = q tile
+        const int q = warp & 3;                  // TMEM lane quarter
+        const int hf = (warp >> 2) & 1;          // kv-column half
+        const int r = q * 32 + lane;             // row inside the tile
+        const uint32_t tS = tmem + s * 256 + (uint32_t(q * 32) << 16);
+        const uint32_t pS = sP + s * PBUF_B;
+        const uint32_t x_mine = sX + ((s * 2 + hf) * 128 + r) * 4, x_other = sX + ((s * 2 + (hf ^ 1)) * 128 + r) * 4;
+        const int pair_bar = 1 + s * 4 + q;      // named barrier shared by the two warps that own this row quarter
         const float sl2 = a.scale * 1.4426950408889634f;
-        const float dps = a.drop_scale != nullptr ? a.drop_scale[b] : 1.f;
-        for (int i = 0; i < 2; ++i) {
-            const int t = i * QT + r;
-            mbar_wait(s_bar, i);
+        const int c_begin = hf ? KV_SPLIT : 0;
+        const int n32 = 3;                       // both halves: three 32-column chunks (+ one 16-column chunk in half 0)
+        const int t = s * QT + r;
+        int it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const int b = item / a.H, h = item % a.H;
+            const uint32_t ph = it & 1;
+            const float dps = a.drop_scale != nullptr ? __ldg(a.drop_scale + b) : 1.f;
+            mbar_wait(slot_bar(s, 0), ph);
             tc_fence_after();
             float v[32];
+            // ---- pass 1: row maximum over this warp's columns ----
             float mx = -INFINITY;
 #pragma unroll 1
-            for (int c = 0; c < 6; ++c) {
-                tmem_ld32(tS + lane_base + c * 32, v);
+            for (int c = 0; c < n32; ++c) {
+                const int col = c_begin + c * 32;
+                tmem_ld32(tS + col, v);
+                tmem_ld_wait();
+                if (col + 32 <= a.T) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, v[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, col + j < a.T ? v[j] : -INFINITY);
+                }
+            }
+            if (hf == 0) {
+                tmem_ld16(tS + 96, v);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) mx = fmaxf(mx, v[j]);   // columns < 192 are always valid tokens
+                for (int j = 0; j < 16; ++j) mx = fmaxf(mx, 96 + j < a.T ? v[j] : -INFINITY);
             }
-            tmem_ld16(tS + lane_base + 192, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-                if (192 + j < a.T) mx = fmaxf(mx, v[j]);
+            st_shared_f32(x_mine, mx);
+            named_bar_sync(pair_bar, 64);
+            mx = fmaxf(mx, ld_shared_f32(x_other));
+            const float mxs = mx * sl2;
+            // ---- pass 2: P = exp(S*scale - max), row sums, P -> shared memory (bf16, swizzled K-major A operand) ----
             float sum = 0.f;
 #pragma unroll 1
-            for (int c = 0; c < 7; ++c) {
-                if (c < 6) tmem_ld32(tS + lane_base + c * 32, v);
-                else tmem_ld16(tS + lane_base + 192, v);
+            for (int c = 0; c < n32 + 1; ++c) {
+                const int col = c_begin + c * 32;
+                const int nj = c < n32 ? 32 : (hf == 0 ? 16 : 0);
+                if (nj == 0) break;
+                if (nj == 32) tmem_ld32(tS + col, v);
+                else tmem_ld16(tS + col, v);
                 tmem_ld_wait();
-                const int nj = c < 6 ? 32 : 16;
+                if (col + nj <= a.T) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if (j < nj) {
-                        const float p = (c * 32 + j < a.T) ? exp2f((v[j] - mx) * sl2) : 0.f;
-                        v[j] = p;
-                        sum += p;
-                    }
+                    for (int j = 0; j < 32; ++j)
+                        if (j < nj) { v[j] = fast_ex2(fmaf(v[j], sl2, -mxs)); sum += v[j]; }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < nj) { v[j] = col + j < a.T ? fast_ex2(fmaf(v[j], sl2, -mxs)) : 0.f; sum += v[j]; }
                 }
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) {
@@ -162,56 +237,111 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                         uint4 pk;
                         pk.x = pack_bf16x2(v[q4 * 8 + 0], v[q4 * 8 + 1]); pk.y = pack_bf16x2(v[q4 * 8 + 2], v[q4 * 8 + 3]);
                         pk.z = pack_bf16x2(v[q4 * 8 + 4], v[q4 * 8 + 5]); pk.w = pack_bf16x2(v[q4 * 8 + 6], v[q4 * 8 + 7]);
-                        st_shared_v4(pbuf_addr(sP, r, c * 4 + q4), pk);
+                        st_shared_v4(pbuf_addr(pS, r, (col >> 3) + q4), pk);
                     }
                 }
             }
+            st_shared_f32(x_mine + 2048, sum);
             fence_proxy_async_smem();
             tc_fence_before();
-            mbar_arrive(p_bar);
-
-            mbar_wait(o_bar, i);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(slot_bar(s, 1));
+            named_bar_sync(pair_bar, 64);
+            sum += ld_shared_f32(x_other + 2048);
+            // ---- epilogue: O / rowsum * droppath; this warp owns head-dim columns [32 hf, 32 hf + 32) ----
+            mbar_wait(slot_bar(s, 2), ph);
             tc_fence_after();
-            const float inv = dps / sum;
-            float o0[32], o1[32];
-            tmem_ld32(tO + lane_base, o0);
-            tmem_ld32(tO + lane_base + 32, o1);
+            tmem_ld32(tS + hf * 32, v);
             tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(slot_bar(s, 3));
             if (t < a.T) {
-                uint4* dst = reinterpret_cast<uint4*>(a.o + (size_t(b) * a.T + t) * (a.H * HD) + h * HD);
+                const float inv = dps / sum;
+                uint4* dst = reinterpret_cast<uint4*>(a.o + (size_t(b) * a.T + t) * (a.H * HD) + h * HD + hf * 32);
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) {
                     uint4 pk;
-                    pk.x = pack_bf16x2(o0[q4 * 8 + 0] * inv, o0[q4 * 8 + 1] * inv); pk.y = pack_bf16x2(o0[q4 * 8 + 2] * inv, o0[q4 * 8 + 3] * inv);
-                    pk.z = pack_bf16x2(o0[q4 * 8 + 4] * inv, o0[q4 * 8 + 5] * inv); pk.w = pack_bf16x2(o0[q4 * 8 + 6] * inv, o0[q4 * 8 + 7] * inv);
+                    pk.x = pack_bf16x2(v[q4 * 8 + 0] * inv, v[q4 * 8 + 1] * inv); pk.y = pack_bf16x2(v[q4 * 8 + 2] * inv, v[q4 * 8 + 3] * inv);
+                    pk.z = pack_bf16x2(v[q4 * 8 + 4] * inv, v[q4 * 8 + 5] * inv); pk.w = pack_bf16x2(v[q4 * 8 + 6] * inv, v[q4 * 8 + 7] * inv);
                     dst[q4] = pk;
                 }
-#pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                    uint4 pk;
-                    pk.x = pack_bf16x2(o1[q4 * 8 + 0] * inv, o1[q4 * 8 + 1] * inv); pk.y = pack_bf16x2(o1[q4 * 8 + 2] * inv, o1[q4 * 8 + 3] * inv);
-                    pk.z = pack_bf16x2(o1[q4 * 8 + 4] * inv, o1[q4 * 8 + 5] * inv); pk.w = pack_bf16x2(o1[q4 * 8 + 6] * inv, o1[q4 * 8 + 7] * inv);
-                    dst[4 + q4] = pk;
-                }
-                a.lse[(size_t(b) * a.H + h) * a.T + t] = mx * a.scale + logf(sum);
+                if (hf == 0) a.lse[(size_t(b) * a.H + h) * a.T + t] = mx * a.scale + logf(sum);
             }
-            tc_fence_before();   // order the O reads before the next tile's MMA (signalled through p_bar)
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem, 512); }
+    if (warp == FWD_CW + 1) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward
-// ---------------------------------------------------------------------------------------------
+// backward: persistent, warp-specialised; one CTA per SM loops over (image, head) items, two q tiles per item.
+//   warps 0-15 : compute.  warp w: TMEM lane quarter w&3, column group w>>2
+//                (kv columns [0,64) [64,112) [112,160) [160,208) of S / dP; head-dim columns 16 cg .. 16 cg + 15 of dQ / dK / dV)
+//   warp 16    : TMA producer        warp 17 : MMA issuer (+ TMEM allocation)
 // TMEM columns: [0,208) S then dP then (first 64) dQ ; [256,384) dK (2 kv tiles x 64) ; [384,512) dV (2 kv tiles x 64)
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+// ---------------------------------------------------------------------------------------------
+static constexpr int BWD_CW = 16;
+static constexpr int BWD_THREADS = (BWD_CW + 2) * 32;     // 576
+static constexpr int BWD_CT = BWD_CW * 32;                // compute threads
+
+// 16 values per lane -> lanes with even index end with the sum over all 32 lanes of column (lane >> 1) & 15
+__device__ __forceinline__ float bfly16(float (&v)[16]) {
+    const uint32_t lane = lane_id();
+#pragma unroll
+    for (int cnt = 8, o = 16; cnt >= 1; cnt >>= 1, o >>= 1) {
+        const bool upper = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < cnt; ++i) {
+            const float send = upper ? v[i] : v[i + cnt];
+            const float keep = upper ? v[i + cnt] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+// epilogue of one 16-column slice of dQ / dK / dV for one token row: multiply by the gate (d pre-gate), store, and add
+// the row's contributions to the gate / bias column sums (shared-memory accumulators).
+__device__ __forceinline__ void dqkv_slice_epilogue(float (&v)[16], bool ok, const __nv_bfloat16* y, __nv_bfloat16* dy,
+                                                    const float* gate16, float* cs_gate, float* cs_bias) {
+    float gy[16];
+    if (ok) {
+        const uint4 x0 = __ldg(reinterpret_cast<const uint4*>(y)), x1 = __ldg(reinterpret_cast<const uint4*>(y) + 1);
+        float2 f;
+        f = unpack_bf16x2(x0.x); gy[0] = f.x * v[0]; gy[1] = f.y * v[1];
+        f = unpack_bf16x2(x0.y); gy[2] = f.x * v[2]; gy[3] = f.y * v[3];
+        f = unpack_bf16x2(x0.z); gy[4] = f.x * v[4]; gy[5] = f.y * v[5];
+        f = unpack_bf16x2(x0.w); gy[6] = f.x * v[6]; gy[7] = f.y * v[7];
+        f = unpack_bf16x2(x1.x); gy[8] = f.x * v[8]; gy[9] = f.y * v[9];
+        f = unpack_bf16x2(x1.y); gy[10] = f.x * v[10]; gy[11] = f.y * v[11];
+        f = unpack_bf16x2(x1.z); gy[12] = f.x * v[12]; gy[13] = f.y * v[13];
+        f = unpack_bf16x2(x1.w); gy[14] = f.x * v[14]; gy[15] = f.y * v[15];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] *= gate16[j];
+        uint4 p0, p1;
+        p0.x = pack_bf16x2(v[0], v[1]); p0.y = pack_bf16x2(v[2], v[3]); p0.z = pack_bf16x2(v[4], v[5]); p0.w = pack_bf16x2(v[6], v[7]);
+        p1.x = pack_bf16x2(v[8], v[9]); p1.y = pack_bf16x2(v[10], v[11]); p1.z = pack_bf16x2(v[12], v[13]); p1.w = pack_bf16x2(v[14], v[15]);
+        reinterpret_cast<uint4*>(dy)[0] = p0;
+        reinterpret_cast<uint4*>(dy)[1] = p1;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { gy[j] = 0.f; v[j] = 0.f; }
+    }
+    const float sg = bfly16(gy);
+    const float sb = bfly16(v);
+    const uint32_t lane = lane_id();
+    if ((lane & 1u) == 0) {
+        atomicAdd(cs_gate + (lane >> 1), sg);
+        atomicAdd(cs_bias + (lane >> 1), sb);
+    }
+}
+
+__global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                 const __grid_constant__ CUtensorMap tm_do, const AttnArgs a) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sQ = smem_u32(smem);
     const uint32_t sDO = sQ + TILE_B;
     const uint32_t sK = sDO + TILE_B;
@@ -219,26 +349,28 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const uint32_t sP = sV + KV_B;
     const uint32_t sDS = sP + PBUF_B;
     uint8_t* tail = smem + 2 * TILE_B + 2 * KV_B + 2 * PBUF_B;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
-    const uint32_t ld_bar = smem_u32(&bars[0]), s_bar = smem_u32(&bars[1]), p_bar = smem_u32(&bars[2]), dp_bar = smem_u32(&bars[3]),
-                   ds_bar = smem_u32(&bars[4]), dq_bar = smem_u32(&bars[5]), dqr_bar = smem_u32(&bars[6]), tile_bar = smem_u32(&bars[7]);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[8]);
-    float* cs_gate = reinterpret_cast<float*>(tail + 128);   // [64]   sum dY*Y over q,k,v
-    float* cs_bias = cs_gate + 64;                            // [3][64] sum d(pre-gate)
+    float* cs = reinterpret_cast<float*>(tail);                 // [2 parities][256]: gate[64] | bias q,k,v [3][64]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 2048);
+    enum { KV_FULL = 0, KV_EMPTY, QDO_FULL, QDO_EMPTY, S_FULL, P_FULL, DP_FULL, DS_FULL, DQ_FULL, A_EMPTY, ACC_FULL, ACC_EMPTY, NBAR };
+    auto bar = [&](int k) { return smem_u32(&bars[k]); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[NBAR]);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
+    const int n_items = a.B * a.H;
     const int D = a.H * HD;
 
     if (threadIdx.x == 0) {
-        mbar_init(ld_bar, 1); mbar_init(s_bar, 1); mbar_init(p_bar, 128); mbar_init(dp_bar, 1);
-        mbar_init(ds_bar, 128); mbar_init(dq_bar, 1); mbar_init(dqr_bar, 128); mbar_init(tile_bar, 1);
+        if ((sQ & 1023u) != 0) { printf("ofb: dynamic smem base not 1024-aligned\n"); __trap(); }
+        mbar_init(bar(KV_FULL), 1); mbar_init(bar(KV_EMPTY), 1); mbar_init(bar(QDO_FULL), 1); mbar_init(bar(QDO_EMPTY), 1);
+        mbar_init(bar(S_FULL), 1); mbar_init(bar(P_FULL), BWD_CW); mbar_init(bar(DP_FULL), 1); mbar_init(bar(DS_FULL), BWD_CW);
+        mbar_init(bar(DQ_FULL), 1); mbar_init(bar(A_EMPTY), BWD_CW); mbar_init(bar(ACC_FULL), 1); mbar_init(bar(ACC_EMPTY), BWD_CW);
         mbar_fence_init();
     }
-    if (warp == 4) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
-    // zero the P / dS buffers once: kv columns >= 208 (and anything not rewritten) must read as 0 for the MN-major MMAs
-    for (int i = threadIdx.x; i < 2 * PBUF_B / 16; i += ATT_THREADS) st_shared_v4(sP + i * 16, make_uint4(0, 0, 0, 0));
-    for (int i = threadIdx.x; i < 256; i += ATT_THREADS) cs_gate[i] = 0.f;
+    if (warp == BWD_CW + 1) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
+    // kv columns >= 208 of the P / dS buffers are never written; they only feed accumulator rows that are never read, but
+    // keep them finite
+    for (int i = threadIdx.x; i < 2 * PBUF_B / 16; i += BWD_THREADS) st_shared_v4(sP + i * 16, make_uint4(0, 0, 0, 0));
+    for (int i = threadIdx.x; i < 512; i += BWD_THREADS) cs[i] = 0.f;
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -249,267 +381,230 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     constexpr uint32_t IDESC_DQ = make_idesc_bf16(128, HD, 0, 1);     // dQ     : dS K-major, K MN-major
     constexpr uint32_t IDESC_KV = make_idesc_bf16(128, HD, 1, 1);     // dK, dV : MN-major x MN-major
 
-    if (warp == 4) {
+    if (warp == BWD_CW) {
+        // ===================== TMA producer =====================
         if (lane == 0) {
-            mbar_arrive_expect_tx(ld_bar, 2 * TILE_B + 2 * KV_B);
-            tma_load_5d(sQ, &tm_q, ld_bar, 0, 0, h, 0, b);
-            tma_load_4d(sDO, &tm_do, ld_bar, h * HD, 0, b, 0);
-            tma_load_5d(sK, &tm_kv, ld_bar, 0, 0, h, 1, b);
-            tma_load_5d(sV, &tm_kv, ld_bar, 0, 0, h, 2, b);
-            for (int i = 0; i < 2; ++i) {
-                mbar_wait(ld_bar, i);
-                if (i > 0) mbar_wait(dqr_bar, 0);      // dQ(0) drained from TMEM region A
-                tc_fence_after();
-                // S = Q K^T
+            tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_kv); tma_prefetch_desc(&tm_do);
+            int it = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const int b = item / a.H, h = item % a.H;
+                mbar_wait(bar(KV_EMPTY), (it & 1) ^ 1);
+                mbar_arrive_expect_tx(bar(KV_FULL), 2 * KV_B);
+                tma_load_5d(sK, &tm_kv, bar(KV_FULL), 0, 0, h, 1, b);
+                tma_load_5d(sV, &tm_kv, bar(KV_FULL), 0, 0, h, 2, b);
+                for (int i = 0; i < 2; ++i) {
+                    mbar_wait(bar(QDO_EMPTY), i ^ 1);            // tile counter 2*it + i -> parity i
+                    mbar_arrive_expect_tx(bar(QDO_FULL), 2 * TILE_B);
+                    tma_load_5d(sQ, &tm_q, bar(QDO_FULL), 0, i * QT, h, 0, b);
+                    tma_load_4d(sDO, &tm_do, bar(QDO_FULL), h * HD, i * QT, b, 0);
+                }
+            }
+        }
+    } else if (warp == BWD_CW + 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int it = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const uint32_t pi = it & 1;
+                mbar_wait(bar(KV_FULL), pi);
+                for (int i = 0; i < 2; ++i) {
+                    mbar_wait(bar(QDO_FULL), i);
+                    mbar_wait(bar(A_EMPTY), i ^ 1);              // dQ of the previous tile drained from region A
+                    tc_fence_after();
+                    // S = Q K^T
 #pragma unroll
-                for (int k = 0; k < HD / 16; ++k)
-                    umma_bf16(tA, make_smem_desc_sw128(sQ + k * 32, 0, 1024), make_smem_desc_sw128(sK + k * 32, 0, 1024), IDESC_S, k > 0);
-                umma_commit(s_bar);
-                mbar_wait(p_bar, i);
-                tc_fence_after();
-                // dP = dO V^T  (region A again: S fully consumed once p_bar completes)
+                    for (int k = 0; k < HD / 16; ++k)
+                        umma_bf16(tA, make_smem_desc_sw128(sQ + k * 32, 0, 1024), make_smem_desc_sw128(sK + k * 32, 0, 1024), IDESC_S, k > 0);
+                    umma_commit(bar(S_FULL));
+                    mbar_wait(bar(P_FULL), i);
+                    tc_fence_after();
+                    // dP = dO V^T  (region A again: S fully consumed once P_FULL completes)
 #pragma unroll
-                for (int k = 0; k < HD / 16; ++k)
-                    umma_bf16(tA, make_smem_desc_sw128(sDO + k * 32, 0, 1024), make_smem_desc_sw128(sV + k * 32, 0, 1024), IDESC_S, k > 0);
-                umma_commit(dp_bar);
-                // dV[kv tile m] += P^T dO      (M = kv, K = q rows of this tile)
+                    for (int k = 0; k < HD / 16; ++k)
+                        umma_bf16(tA, make_smem_desc_sw128(sDO + k * 32, 0, 1024), make_smem_desc_sw128(sV + k * 32, 0, 1024), IDESC_S, k > 0);
+                    umma_commit(bar(DP_FULL));
+                    if (i == 0) { mbar_wait(bar(ACC_EMPTY), pi ^ 1); tc_fence_after(); }   // previous item's dK / dV read out
+                    // dV[kv tile m] += P^T dO      (M = kv, K = q rows of this tile)
 #pragma unroll
-                for (int m = 0; m < 2; ++m)
+                    for (int m = 0; m < 2; ++m)
 #pragma unroll
-                    for (int k = 0; k < QT / 16; ++k)
-                        umma_bf16(tDV + m * HD, make_smem_desc_sw128(sP + (2 * m) * TILE_B + k * 2048, TILE_B, 1024),
-                                  make_smem_desc_sw128(sDO + k * 2048, 0, 1024), IDESC_KV, (i > 0 || k > 0) ? 1u : 0u);
-                mbar_wait(ds_bar, i);
-                tc_fence_after();
-                // dQ = dS K   (K = kv)
+                        for (int k = 0; k < QT / 16; ++k)
+                            umma_bf16(tDV + m * HD, make_smem_desc_sw128(sP + (2 * m) * TILE_B + k * 2048, TILE_B, 1024),
+                                      make_smem_desc_sw128(sDO + k * 2048, 0, 1024), IDESC_KV, (i > 0 || k > 0) ? 1u : 0u);
+                    mbar_wait(bar(DS_FULL), i);
+                    tc_fence_after();
+                    // dQ = dS K   (K = kv)
 #pragma unroll
-                for (int k = 0; k < KVP / 16; ++k)
-                    umma_bf16(tA, make_smem_desc_sw128(sDS + (k >> 2) * TILE_B + (k & 3) * 32, 0, 1024),
-                              make_smem_desc_sw128(sK + k * 2048, 0, 1024), IDESC_DQ, k > 0);
-                umma_commit(dq_bar);
-                // dK[kv tile m] += dS^T Q
+                    for (int k = 0; k < KVP / 16; ++k)
+                        umma_bf16(tA, make_smem_desc_sw128(sDS + (k >> 2) * TILE_B + (k & 3) * 32, 0, 1024),
+                                  make_smem_desc_sw128(sK + k * 2048, 0, 1024), IDESC_DQ, k > 0);
+                    umma_commit(bar(DQ_FULL));
+                    // dK[kv tile m] += dS^T Q
 #pragma unroll
-                for (int m = 0; m < 2; ++m)
+                    for (int m = 0; m < 2; ++m)
 #pragma unroll
-                    for (int k = 0; k < QT / 16; ++k)
-                        umma_bf16(tDK + m * HD, make_smem_desc_sw128(sDS + (2 * m) * TILE_B + k * 2048, TILE_B, 1024),
-                                  make_smem_desc_sw128(sQ + k * 2048, 0, 1024), IDESC_KV, (i > 0 || k > 0) ? 1u : 0u);
-                umma_commit(tile_bar);
-                if (i == 0) {
-                    mbar_wait(tile_bar, 0);            // every MMA reading Q0 / dO0 / P / dS has completed
-                    mbar_arrive_expect_tx(ld_bar, 2 * TILE_B);
-                    tma_load_5d(sQ, &tm_q, ld_bar, 0, QT, h, 0, b);
-                    tma_load_4d(sDO, &tm_do, ld_bar, h * HD, QT, b, 0);
+                        for (int k = 0; k < QT / 16; ++k)
+                            umma_bf16(tDK + m * HD, make_smem_desc_sw128(sDS + (2 * m) * TILE_B + k * 2048, TILE_B, 1024),
+                                      make_smem_desc_sw128(sQ + k * 2048, 0, 1024), IDESC_KV, (i > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(bar(QDO_EMPTY));                 // every MMA reading Q_i / dO_i has been issued before this commit
+                    if (i == 1) { umma_commit(bar(KV_EMPTY)); umma_commit(bar(ACC_FULL)); }
                 }
             }
         }
     } else {
-        const int r = warp * 32 + lane;
-        const uint32_t lane_base = uint32_t(warp * 32) << 16;
-        const float dps = a.drop_scale != nullptr ? a.drop_scale[b] : 1.f;
-        const float inv_dps = dps != 0.f ? 1.f / dps : 0.f;
-        const float* gate = a.gate + h * HD;
+        // ===================== compute warps =====================
+        const int q = warp & 3, cg = warp >> 2;
+        const int r = q * 32 + lane;
+        const uint32_t lane_base = uint32_t(q * 32) << 16;
+        const int cbase = cg == 0 ? 0 : 16 + 48 * cg;           // 0, 64, 112, 160
+        const int n1 = cg == 0 ? 32 : 16;                        // second piece width
+        const float* gate16 = a.gate;                            // + h*HD + cg*16 per item
         float v[32];
-        for (int i = 0; i < 2; ++i) {
-            const int t = i * QT + r;
-            const bool t_ok = t < a.T;
-            // per-row scalars: LSE and delta = rowsum(dO * O)
-            float lse = 0.f, delta = 0.f;
-            if (t_ok) {
-                lse = a.lse[(size_t(b) * a.H + h) * a.T + t];
-                const uint4* po = reinterpret_cast<const uint4*>(a.o_in + (size_t(b) * a.T + t) * D + h * HD);
-                const uint4* pd = reinterpret_cast<const uint4*>(a.d_o + (size_t(b) * a.T + t) * D + h * HD);
+        int it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const int b = item / a.H, h = item % a.H;
+            const uint32_t pi = it & 1;
+            float* cs_gate = cs + pi * 256 + cg * 16;
+            float* cs_bias = cs + pi * 256 + 64 + cg * 16;
+            const float dps = a.drop_scale != nullptr ? __ldg(a.drop_scale + b) : 1.f;
+            const float inv_dps = dps != 0.f ? 1.f / dps : 0.f;
+            float g16[16];
 #pragma unroll
-                for (int q4 = 0; q4 < 8; ++q4) {
-                    const uint4 x = __ldg(po + q4), y = __ldg(pd + q4);
-                    float2 f, g;
-                    f = unpack_bf16x2(x.x); g = unpack_bf16x2(y.x); delta += f.x * g.x + f.y * g.y;
-                    f = unpack_bf16x2(x.y); g = unpack_bf16x2(y.y); delta += f.x * g.x + f.y * g.y;
-                    f = unpack_bf16x2(x.z); g = unpack_bf16x2(y.z); delta += f.x * g.x + f.y * g.y;
-                    f = unpack_bf16x2(x.w); g = unpack_bf16x2(y.w); delta += f.x * g.x + f.y * g.y;
-                }
-                delta *= inv_dps;   // stored O carries the DropPath factor
-            }
-            // ---- P = exp(S*scale - LSE) ----
-            mbar_wait(s_bar, i);
-            tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < 7; ++c) {
-                if (c < 6) tmem_ld32(tA + lane_base + c * 32, v);
-                else tmem_ld16(tA + lane_base + 192, v);
-                tmem_ld_wait();
-                const int nj = c < 6 ? 32 : 16;
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (j < nj) v[j] = (t_ok && c * 32 + j < a.T) ? __expf(v[j] * a.scale - lse) : 0.f;
-#pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                    if (q4 * 8 < nj) {
-                        uint4 pk;
-                        pk.x = pack_bf16x2(v[q4 * 8 + 0], v[q4 * 8 + 1]); pk.y = pack_bf16x2(v[q4 * 8 + 2], v[q4 * 8 + 3]);
-                        pk.z = pack_bf16x2(v[q4 * 8 + 4], v[q4 * 8 + 5]); pk.w = pack_bf16x2(v[q4 * 8 + 6], v[q4 * 8 + 7]);
-                        st_shared_v4(pbuf_addr(sP, r, c * 4 + q4), pk);
-                    }
-                }
-            }
-            fence_proxy_async_smem();
-            tc_fence_before();
-            mbar_arrive(p_bar);
-            // ---- dS = scale * P * (dP - delta) ----
-            mbar_wait(dp_bar, i);
-            tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < 7; ++c) {
-                if (c < 6) tmem_ld32(tA + lane_base + c * 32, v);
-                else tmem_ld16(tA + lane_base + 192, v);
-                tmem_ld_wait();
-                const int nj = c < 6 ? 32 : 16;
-#pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                    if (q4 * 8 < nj) {
-                        const uint4 pp = ld_shared_v4(pbuf_addr(sP, r, c * 4 + q4));
-                        float2 p0 = unpack_bf16x2(pp.x), p1 = unpack_bf16x2(pp.y), p2 = unpack_bf16x2(pp.z), p3 = unpack_bf16x2(pp.w);
-                        const float* w = v + q4 * 8;
-                        uint4 pk;
-                        pk.x = pack_bf16x2(a.scale * p0.x * (w[0] - delta), a.scale * p0.y * (w[1] - delta));
-                        pk.y = pack_bf16x2(a.scale * p1.x * (w[2] - delta), a.scale * p1.y * (w[3] - delta));
-                        pk.z = pack_bf16x2(a.scale * p2.x * (w[4] - delta), a.scale * p2.y * (w[5] - delta));
-                        pk.w = pack_bf16x2(a.scale * p3.x * (w[6] - delta), a.scale * p3.y * (w[7] - delta));
-                        st_shared_v4(pbuf_addr(sDS, r, c * 4 + q4), pk);
-                    }
-                }
-            }
-            fence_proxy_async_smem();
-            tc_fence_before();
-            mbar_arrive(ds_bar);
-            // ---- dQ epilogue ----
-            mbar_wait(dq_bar, i);
-            tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
-                tmem_ld32(tA + lane_base + c * 32, v);
-                tmem_ld_wait();
-                float gy[32];
+            for (int j = 0; j < 16; ++j) g16[j] = __ldg(gate16 + h * HD + cg * 16 + j);
+            for (int i = 0; i < 2; ++i) {
+                const int t = i * QT + r;
+                const bool t_ok = t < a.T;
+                // per-row scalars: LSE and delta = rowsum(dO * O)
+                float lse = 0.f, delta = 0.f;
                 if (t_ok) {
-                    const size_t off = ((size_t(b) * a.T + t) * 3 + 0) * D + h * HD + c * 32;
-                    const uint4* pq = reinterpret_cast<const uint4*>(a.qkv + off);
-                    uint4* pdq = reinterpret_cast<uint4*>(a.dqkv + off);
+                    lse = a.lse[(size_t(b) * a.H + h) * a.T + t];
+                    const uint4* po = reinterpret_cast<const uint4*>(a.o_in + (size_t(b) * a.T + t) * D + h * HD);
+                    const uint4* pd = reinterpret_cast<const uint4*>(a.d_o + (size_t(b) * a.T + t) * D + h * HD);
 #pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) {
-                        const uint4 x = __ldg(pq + q4);
-                        float2 f;
-                        f = unpack_bf16x2(x.x); gy[q4 * 8 + 0] = f.x * v[q4 * 8 + 0]; gy[q4 * 8 + 1] = f.y * v[q4 * 8 + 1];
-                        f = unpack_bf16x2(x.y); gy[q4 * 8 + 2] = f.x * v[q4 * 8 + 2]; gy[q4 * 8 + 3] = f.y * v[q4 * 8 + 3];
-                        f = unpack_bf16x2(x.z); gy[q4 * 8 + 4] = f.x * v[q4 * 8 + 4]; gy[q4 * 8 + 5] = f.y * v[q4 * 8 + 5];
-                        f = unpack_bf16x2(x.w); gy[q4 * 8 + 6] = f.x * v[q4 * 8 + 6]; gy[q4 * 8 + 7] = f.y * v[q4 * 8 + 7];
+                    for (int q4 = 0; q4 < 8; ++q4) {
+                        const uint4 x = __ldg(po + q4), y = __ldg(pd + q4);
+                        float2 f, g;
+                        f = unpack_bf16x2(x.x); g = unpack_bf16x2(y.x); delta += f.x * g.x + f.y * g.y;
+                        f = unpack_bf16x2(x.y); g = unpack_bf16x2(y.y); delta += f.x * g.x + f.y * g.y;
+                        f = unpack_bf16x2(x.z); g = unpack_bf16x2(y.z); delta += f.x * g.x + f.y * g.y;
+                        f = unpack_bf16x2(x.w); g = unpack_bf16x2(y.w); delta += f.x * g.x + f.y * g.y;
                     }
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] *= __ldg(gate + c * 32 + j);
-#pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) {
-                        uint4 pk;
-                        pk.x = pack_bf16x2(v[q4 * 8 + 0], v[q4 * 8 + 1]); pk.y = pack_bf16x2(v[q4 * 8 + 2], v[q4 * 8 + 3]);
-                        pk.z = pack_bf16x2(v[q4 * 8 + 4], v[q4 * 8 + 5]); pk.w = pack_bf16x2(v[q4 * 8 + 6], v[q4 * 8 + 7]);
-                        pdq[q4] = pk;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) { gy[j] = 0.f; v[j] = 0.f; }
+                    delta *= inv_dps;   // stored O carries the DropPath factor
                 }
-                // column sums over the 32 rows of this warp, then across warps / tiles in shared memory
-                float sg, sb;
-                {
-                    // butterfly transpose-reduce (31 shuffles each)
+                const float sl2 = a.scale * 1.4426950408889634f, lse2 = lse * 1.4426950408889634f;
+                // ---- P = exp(S*scale - LSE) over this warp's kv columns ----
+                mbar_wait(bar(S_FULL), i);
+                tc_fence_after();
 #pragma unroll
-                    for (int o = 16; o >= 1; o >>= 1) {
-                        const bool upper = (lane & o) != 0;
-#pragma unroll
-                        for (int j = 0; j < o; ++j) {
-                            const float s0 = upper ? gy[j] : gy[j + o], k0 = upper ? gy[j + o] : gy[j];
-                            gy[j] = k0 + __shfl_xor_sync(0xffffffffu, s0, o);
-                            const float s1 = upper ? v[j] : v[j + o], k1 = upper ? v[j + o] : v[j];
-                            v[j] = k1 + __shfl_xor_sync(0xffffffffu, s1, o);
-                        }
-                    }
-                    sg = gy[0]; sb = v[0];
-                }
-                atomicAdd(&cs_gate[c * 32 + lane], sg);
-                atomicAdd(&cs_bias[0 * 64 + c * 32 + lane], sb);
-            }
-            tc_fence_before();
-            mbar_arrive(dqr_bar);
-        }
-        // ---- dK / dV epilogue (kv rows: tile m covers kv = m*128 + r) ----
-        mbar_wait(tile_bar, 1);
-        tc_fence_after();
-#pragma unroll 1
-        for (int which = 1; which <= 2; ++which) {
-            const uint32_t tbase = which == 1 ? tDK : tDV;
-#pragma unroll 1
-            for (int m = 0; m < 2; ++m) {
-                const int kv = m * QT + r;
-                const bool kv_ok = kv < a.T;
-#pragma unroll 1
-                for (int c = 0; c < 2; ++c) {
-                    tmem_ld32(tbase + lane_base + m * HD + c * 32, v);
+                for (int pc = 0; pc < 2; ++pc) {
+                    const int col = cbase + pc * 32;
+                    const int nj = pc == 0 ? 32 : n1;
+                    if (nj == 32) tmem_ld32(tA + lane_base + col, v);
+                    else tmem_ld16(tA + lane_base + col, v);
                     tmem_ld_wait();
-                    float gy[32];
-                    if (kv_ok) {
-                        const size_t off = ((size_t(b) * a.T + kv) * 3 + which) * D + h * HD + c * 32;
-                        const uint4* px = reinterpret_cast<const uint4*>(a.qkv + off);
-                        uint4* pd = reinterpret_cast<uint4*>(a.dqkv + off);
 #pragma unroll
-                        for (int q4 = 0; q4 < 4; ++q4) {
-                            const uint4 x = __ldg(px + q4);
-                            float2 f;
-                            f = unpack_bf16x2(x.x); gy[q4 * 8 + 0] = f.x * v[q4 * 8 + 0]; gy[q4 * 8 + 1] = f.y * v[q4 * 8 + 1];
-                            f = unpack_bf16x2(x.y); gy[q4 * 8 + 2] = f.x * v[q4 * 8 + 2]; gy[q4 * 8 + 3] = f.y * v[q4 * 8 + 3];
-                            f = unpack_bf16x2(x.z); gy[q4 * 8 + 4] = f.x * v[q4 * 8 + 4]; gy[q4 * 8 + 5] = f.y * v[q4 * 8 + 5];
-                            f = unpack_bf16x2(x.w); gy[q4 * 8 + 6] = f.x * v[q4 * 8 + 6]; gy[q4 * 8 + 7] = f.y * v[q4 * 8 + 7];
-                        }
+                    for (int j = 0; j < 32; ++j)
+                        if (j < nj) v[j] = (t_ok && col + j < a.T) ? fast_ex2(fmaf(v[j], sl2, -lse2)) : 0.f;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] *= __ldg(gate + c * 32 + j);
-#pragma unroll
-                        for (int q4 = 0; q4 < 4; ++q4) {
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        if (q4 * 8 < nj) {
                             uint4 pk;
                             pk.x = pack_bf16x2(v[q4 * 8 + 0], v[q4 * 8 + 1]); pk.y = pack_bf16x2(v[q4 * 8 + 2], v[q4 * 8 + 3]);
                             pk.z = pack_bf16x2(v[q4 * 8 + 4], v[q4 * 8 + 5]); pk.w = pack_bf16x2(v[q4 * 8 + 6], v[q4 * 8 + 7]);
-                            pd[q4] = pk;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) { gy[j] = 0.f; v[j] = 0.f; }
-                    }
-#pragma unroll
-                    for (int o = 16; o >= 1; o >>= 1) {
-                        const bool upper = (lane & o) != 0;
-#pragma unroll
-                        for (int j = 0; j < o; ++j) {
-                            const float s0 = upper ? gy[j] : gy[j + o], k0 = upper ? gy[j + o] : gy[j];
-                            gy[j] = k0 + __shfl_xor_sync(0xffffffffu, s0, o);
-                            const float s1 = upper ? v[j] : v[j + o], k1 = upper ? v[j + o] : v[j];
-                            v[j] = k1 + __shfl_xor_sync(0xffffffffu, s1, o);
+                            st_shared_v4(pbuf_addr(sP, r, (col >> 3) + q4), pk);
                         }
                     }
-                    atomicAdd(&cs_gate[c * 32 + lane], gy[0]);
-                    atomicAdd(&cs_bias[which * 64 + c * 32 + lane], v[0]);
+                }
+                fence_proxy_async_smem();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(P_FULL));
+                // ---- dS = scale * P * (dP - delta) ----
+                mbar_wait(bar(DP_FULL), i);
+                tc_fence_after();
+#pragma unroll
+                for (int pc = 0; pc < 2; ++pc) {
+                    const int col = cbase + pc * 32;
+                    const int nj = pc == 0 ? 32 : n1;
+                    if (nj == 32) tmem_ld32(tA + lane_base + col, v);
+                    else tmem_ld16(tA + lane_base + col, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        if (q4 * 8 < nj) {
+                            const uint4 pp = ld_shared_v4(pbuf_addr(sP, r, (col >> 3) + q4));
+                            float2 p0 = unpack_bf16x2(pp.x), p1 = unpack_bf16x2(pp.y), p2 = unpack_bf16x2(pp.z), p3 = unpack_bf16x2(pp.w);
+                            const float* w = v + q4 * 8;
+                            uint4 pk;
+                            pk.x = pack_bf16x2(a.scale * p0.x * (w[0] - delta), a.scale * p0.y * (w[1] - delta));
+                            pk.y = pack_bf16x2(a.scale * p1.x * (w[2] - delta), a.scale * p1.y * (w[3] - delta));
+                            pk.z = pack_bf16x2(a.scale * p2.x * (w[4] - delta), a.scale * p2.y * (w[5] - delta));
+                            pk.w = pack_bf16x2(a.scale * p3.x * (w[6] - delta), a.scale * p3.y * (w[7] - delta));
+                            st_shared_v4(pbuf_addr(sDS, r, (col >> 3) + q4), pk);
+                        }
+                    }
+                }
+                fence_proxy_async_smem();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(DS_FULL));
+                // ---- dQ epilogue: head-dim columns [16 cg, 16 cg + 16) ----
+                mbar_wait(bar(DQ_FULL), i);
+                tc_fence_after();
+                float w16[16];
+                tmem_ld16(tA + lane_base + cg * 16, w16);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(A_EMPTY));
+                {
+                    const size_t off = ((size_t(b) * a.T + (t_ok ? t : 0)) * 3 + 0) * D + h * HD + cg * 16;
+                    dqkv_slice_epilogue(w16, t_ok, a.qkv + off, a.dqkv + off, g16, cs_gate, cs_bias);
+                }
+            }
+            // ---- dK / dV epilogue (kv rows: tile m covers kv = m*128 + r) ----
+            mbar_wait(bar(ACC_FULL), pi);
+            tc_fence_after();
+#pragma unroll 1
+            for (int idx = 0; idx < 4; ++idx) {
+                const int which = 1 + (idx >> 1), m = idx & 1;
+                const int kv = m * QT + r;
+                const bool kv_ok = kv < a.T;
+                float w16[16];
+                tmem_ld16((which == 1 ? tDK : tDV) + lane_base + m * HD + cg * 16, w16);
+                tmem_ld_wait();
+                if (idx == 3) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar(ACC_EMPTY));
+                }
+                const size_t off = ((size_t(b) * a.T + (kv_ok ? kv : 0)) * 3 + which) * D + h * HD + cg * 16;
+                dqkv_slice_epilogue(w16, kv_ok, a.qkv + off, a.dqkv + off, g16, cs_gate, cs_bias + which * 64);
+            }
+            // ---- per-item column sums -> global partials; the accumulator of this parity is re-zeroed for item it+2 ----
+            named_bar_sync(1, BWD_CT);
+            {
+                const int tid = threadIdx.x;   // 0..511
+                if (tid < 256) {
+                    float* src = cs + pi * 256 + tid;
+                    const float val = *src;
+                    *src = 0.f;
+                    if (tid < 64) a.part_gate[size_t(b) * D + h * HD + tid] = val;
+                    else a.part_bias[size_t(b) * 3 * D + ((tid - 64) / 64) * D + h * HD + ((tid - 64) % 64)] = val;
                 }
             }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (r < 64) a.part_gate[size_t(b) * D + h * HD + r] = cs_gate[r];
-        for (int i = r; i < 192; i += 128) a.part_bias[size_t(b) * 3 * D + (i / 64) * D + h * HD + (i % 64)] = cs_bias[i];
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem, 512); }
+    if (warp == BWD_CW + 1) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
 // ---------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------
-static constexpr int FWD_SMEM = 1024 + 2 * TILE_B + 2 * KV_B + PBUF_B + 256;
-static constexpr int BWD_SMEM = 1024 + 2 * TILE_B + 2 * KV_B + 2 * PBUF_B + 128 + 1024 + 64;
+static constexpr int FWD_SMEM = 2 * TILE_B + 2 * KV_B + 2 * PBUF_B + 4096 + 256;
+static constexpr int BWD_SMEM = 2 * TILE_B + 2 * KV_B + 2 * PBUF_B + 2048 + 256;
 
 static int make_qkv_maps(const void* qkv, int B, int T, int H, CUtensorMap* tq, CUtensorMap* tkv) {
     const uint64_t D = uint64_t(H) * HD;
@@ -535,7 +630,9 @@ int launch_attn_fwd(const void* qkv, void* o, float* lse, const float* drop_scal
     AttnArgs a{};
     a.B = B; a.T = T; a.H = H; a.scale = scale; a.drop_scale = drop_scale;
     a.o = reinterpret_cast<__nv_bfloat16*>(o); a.lse = lse;
-    attn_fwd_kernel<<<B * H, ATT_THREADS, FWD_SMEM, s>>>(tq, tkv, a);
+    const int items = B * H;
+    const int grid = items < num_sms() ? items : num_sms();
+    attn_fwd_kernel<<<grid, FWD_THREADS, FWD_SMEM, s>>>(tq, tkv, a);
     return int(cudaGetLastError());
 }
 
@@ -568,7 +665,9 @@ int launch_attn_bwd(const void* qkv, const void* o, const void* d_o, const float
     a.gate = gate;
     a.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
     a.part_gate = part_gate; a.part_bias = part_bias;
-    attn_bwd_kernel<<<B * H, ATT_THREADS, BWD_SMEM, s>>>(tq, tkv, tdo, a);
+    const int items = B * H;
+    const int grid = items < num_sms() ? items : num_sms();
+    attn_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM, s>>>(tq, tkv, tdo, a);
     return int(cudaGetLastError());
 }
 

@@ -15,7 +15,8 @@ static inline int err() { return int(cudaGetLastError()); }
 // LayerNorm forward   (reference: LayerNorm.forward layers.py:96-98, eps 1e-6; 25 per step)
 //   x, y: bf16 [M, D]; gamma/beta fp32 [D]; mean/rstd fp32 [M].  One warp per row, D % 8 == 0, D <= 1024.
 // =============================================================================================
-static constexpr int LN_MAXC = 4;  // 16-byte chunks per lane (D <= 1024)
+// LN_MAXC = 16-byte chunks per lane, a template parameter (1..4 <-> D <= 256, 512, 768, 1024) so that narrow models
+// do not pay registers (and occupancy) for columns they do not have.
 
 __device__ __forceinline__ void unpack8(const uint4& p, float* f) {
     float2 t;
@@ -31,6 +32,7 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
     return p;
 }
 
+template <int LN_MAXC>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
                                                      float* __restrict__ mean, float* __restrict__ rstd, int M, int D, float eps) {
@@ -90,6 +92,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const __nv_bfloat16* __rest
 //                      x = res + droppath*(.. + bias), vision_transformer.py:197,201)   [optional]
 //   partial buffers are [gridDim.x, D]; a second kernel reduces them (deterministic).
 // =============================================================================================
+template <int LN_MAXC>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                                      const float* __restrict__ gamma, __nv_bfloat16* __restrict__ dx,
@@ -528,39 +531,61 @@ int launch_colsum_bf16(const void* x, int ld, int R, int N, float* out, float sc
 }
 
 
-int launch_ln_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M, int D, float eps,
-                  cudaStream_t s) {
-    if (D % 8 != 0 || D > 8 * 32 * LN_MAXC) return 1010;
+template <int MAXC>
+static int ln_fwd_inst(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M, int D, float eps,
+                       cudaStream_t s) {
     const int wpb = 8;
     int grid = (M + wpb - 1) / wpb;
     const int cap = num_sms() * 8;
     if (grid > cap) grid = cap;
-    ln_fwd_kernel<<<grid, wpb * 32, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta, reinterpret_cast<__nv_bfloat16*>(y),
-                                            mean, rstd, M, D, eps);
+    ln_fwd_kernel<MAXC><<<grid, wpb * 32, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta,
+                                                  reinterpret_cast<__nv_bfloat16*>(y), mean, rstd, M, D, eps);
     return err();
 }
+int launch_ln_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M, int D, float eps,
+                  cudaStream_t s) {
+    if (D % 8 != 0 || D > 1024) return 1010;
+    switch ((D + 255) / 256) {
+        case 1: return ln_fwd_inst<1>(x, gamma, beta, y, mean, rstd, M, D, eps, s);
+        case 2: return ln_fwd_inst<2>(x, gamma, beta, y, mean, rstd, M, D, eps, s);
+        case 3: return ln_fwd_inst<3>(x, gamma, beta, y, mean, rstd, M, D, eps, s);
+        default: return ln_fwd_inst<4>(x, gamma, beta, y, mean, rstd, M, D, eps, s);
+    }
+}
 
+// number of CTAs (= rows of the partial buffers) of the backward kernel
 int ln_bwd_grid(int M) {
     int grid = (M + 7) / 8;
-    const int cap = num_sms() * 2;
+    const int cap = num_sms() * 4;
     return grid > cap ? cap : grid;
 }
 
-int launch_ln_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx, float* part_dgamma,
-                  float* part_dbeta, float* part_dbias, const float* rowscale, int rows_per_scale, int M, int D, cudaStream_t s) {
-    if (D % 8 != 0 || D > 8 * 32 * LN_MAXC) return 1010;
+template <int MAXC>
+static int ln_bwd_inst(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
+                       float* part_dgamma, float* part_dbeta, float* part_dbias, const float* rowscale, int rows_per_scale, int M, int D,
+                       cudaStream_t s) {
     const int wpb = 8;
     const int grid = ln_bwd_grid(M);
     const size_t smem = size_t(3) * wpb * D * sizeof(float);
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(ln_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 8 * 1024 * 4);
+        cudaFuncSetAttribute(ln_bwd_kernel<MAXC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 8 * 256 * MAXC * 4);
         configured = true;
     }
-    ln_bwd_kernel<<<grid, wpb * 32, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x), mean,
-                                               rstd, gamma, reinterpret_cast<__nv_bfloat16*>(dx), part_dgamma, part_dbeta, part_dbias,
-                                               rowscale, rows_per_scale > 0 ? rows_per_scale : 1, M, D);
+    ln_bwd_kernel<MAXC><<<grid, wpb * 32, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x),
+                                                     mean, rstd, gamma, reinterpret_cast<__nv_bfloat16*>(dx), part_dgamma, part_dbeta,
+                                                     part_dbias, rowscale, rows_per_scale > 0 ? rows_per_scale : 1, M, D);
     return err();
+}
+int launch_ln_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx, float* part_dgamma,
+                  float* part_dbeta, float* part_dbias, const float* rowscale, int rows_per_scale, int M, int D, cudaStream_t s) {
+    if (D % 8 != 0 || D > 1024) return 1010;
+    switch ((D + 255) / 256) {
+        case 1: return ln_bwd_inst<1>(dy, x, mean, rstd, gamma, dx, part_dgamma, part_dbeta, part_dbias, rowscale, rows_per_scale, M, D, s);
+        case 2: return ln_bwd_inst<2>(dy, x, mean, rstd, gamma, dx, part_dgamma, part_dbeta, part_dbias, rowscale, rows_per_scale, M, D, s);
+        case 3: return ln_bwd_inst<3>(dy, x, mean, rstd, gamma, dx, part_dgamma, part_dbeta, part_dbias, rowscale, rows_per_scale, M, D, s);
+        default: return ln_bwd_inst<4>(dy, x, mean, rstd, gamma, dx, part_dgamma, part_dbeta, part_dbias, rowscale, rows_per_scale, M, D, s);
+    }
 }
 
 int launch_reduce_partials(const float* part, int R, int N, float* out, float scale, const float* inv_colscale, int accumulate,
