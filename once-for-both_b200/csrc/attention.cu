@@ -303,12 +303,12 @@ __device__ __forceinline__ float bfly16(float (&v)[16]) {
 }
 
 // epilogue of one 16-column slice of dQ / dK / dV for one token row: multiply by the gate (d pre-gate), store, and add
-// the row's contributions to the gate / bias column sums (shared-memory accumulators).
-__device__ __forceinline__ void dqkv_slice_epilogue(float (&v)[16], bool ok, const __nv_bfloat16* y, __nv_bfloat16* dy,
-                                                    const float* gate16, float* cs_gate, float* cs_bias) {
+// the row's contributions to the gate / bias column sums (shared-memory accumulators). x0/x1 = the row's 16 gated
+// q/k/v values (prefetched by the caller so the global-load latency overlaps the MMAs).
+__device__ __forceinline__ void dqkv_slice_epilogue(float (&v)[16], bool ok, const uint4& x0, const uint4& x1, __nv_bfloat16* dy,
+                                                    const float (&gate16)[16], float* cs_gate, float* cs_bias) {
     float gy[16];
     if (ok) {
-        const uint4 x0 = __ldg(reinterpret_cast<const uint4*>(y)), x1 = __ldg(reinterpret_cast<const uint4*>(y) + 1);
         float2 f;
         f = unpack_bf16x2(x0.x); gy[0] = f.x * v[0]; gy[1] = f.y * v[1];
         f = unpack_bf16x2(x0.y); gy[2] = f.x * v[2]; gy[3] = f.y * v[3];
@@ -337,6 +337,15 @@ __device__ __forceinline__ void dqkv_slice_epilogue(float (&v)[16], bool ok, con
         atomicAdd(cs_bias + (lane >> 1), sb);
     }
 }
+__device__ __forceinline__ float dot8(const uint4& x, const uint4& y) {
+    float2 f, g;
+    float d = 0.f;
+    f = unpack_bf16x2(x.x); g = unpack_bf16x2(y.x); d = fmaf(f.x, g.x, fmaf(f.y, g.y, d));
+    f = unpack_bf16x2(x.y); g = unpack_bf16x2(y.y); d = fmaf(f.x, g.x, fmaf(f.y, g.y, d));
+    f = unpack_bf16x2(x.z); g = unpack_bf16x2(y.z); d = fmaf(f.x, g.x, fmaf(f.y, g.y, d));
+    f = unpack_bf16x2(x.w); g = unpack_bf16x2(y.w); d = fmaf(f.x, g.x, fmaf(f.y, g.y, d));
+    return d;
+}
 
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
@@ -350,7 +359,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const uint32_t sDS = sP + PBUF_B;
     uint8_t* tail = smem + 2 * TILE_B + 2 * KV_B + 2 * PBUF_B;
     float* cs = reinterpret_cast<float*>(tail);                 // [2 parities][256]: gate[64] | bias q,k,v [3][64]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 2048);
+    const uint32_t sXD = smem_u32(tail + 2048);                 // [4 column groups][128 rows] delta partials
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 4096);
     enum { KV_FULL = 0, KV_EMPTY, QDO_FULL, QDO_EMPTY, S_FULL, P_FULL, DP_FULL, DS_FULL, DQ_FULL, A_EMPTY, ACC_FULL, ACC_EMPTY, NBAR };
     auto bar = [&](int k) { return smem_u32(&bars[k]); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[NBAR]);
@@ -458,7 +468,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const uint32_t lane_base = uint32_t(q * 32) << 16;
         const int cbase = cg == 0 ? 0 : 16 + 48 * cg;           // 0, 64, 112, 160
         const int n1 = cg == 0 ? 32 : 16;                        // second piece width
-        const float* gate16 = a.gate;                            // + h*HD + cg*16 per item
+        const uint32_t xd_mine = sXD + (cg * 128 + r) * 4;       // delta partial of this warp's 16 head-dim columns
+        const float sl2 = a.scale * 1.4426950408889634f;
         float v[32];
         int it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
@@ -470,28 +481,32 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             const float inv_dps = dps != 0.f ? 1.f / dps : 0.f;
             float g16[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) g16[j] = __ldg(gate16 + h * HD + cg * 16 + j);
+            for (int j = 0; j < 16; ++j) g16[j] = __ldg(a.gate + h * HD + cg * 16 + j);
             for (int i = 0; i < 2; ++i) {
                 const int t = i * QT + r;
                 const bool t_ok = t < a.T;
-                // per-row scalars: LSE and delta = rowsum(dO * O)
-                float lse = 0.f, delta = 0.f;
+                // ---- early global loads (consumed after the S / dQ MMAs): LSE, this warp's 16-column slices of O and q ----
+                float lse = INFINITY;                            // rows >= T: exp2(-inf) = 0 everywhere
+                uint4 o0 = make_uint4(0, 0, 0, 0), o1 = o0, y0 = o0, y1 = o0;
+                const size_t qoff = ((size_t(b) * a.T + (t_ok ? t : 0)) * 3 + 0) * D + h * HD + cg * 16;
                 if (t_ok) {
-                    lse = a.lse[(size_t(b) * a.H + h) * a.T + t];
-                    const uint4* po = reinterpret_cast<const uint4*>(a.o_in + (size_t(b) * a.T + t) * D + h * HD);
-                    const uint4* pd = reinterpret_cast<const uint4*>(a.d_o + (size_t(b) * a.T + t) * D + h * HD);
-#pragma unroll
-                    for (int q4 = 0; q4 < 8; ++q4) {
-                        const uint4 x = __ldg(po + q4), y = __ldg(pd + q4);
-                        float2 f, g;
-                        f = unpack_bf16x2(x.x); g = unpack_bf16x2(y.x); delta += f.x * g.x + f.y * g.y;
-                        f = unpack_bf16x2(x.y); g = unpack_bf16x2(y.y); delta += f.x * g.x + f.y * g.y;
-                        f = unpack_bf16x2(x.z); g = unpack_bf16x2(y.z); delta += f.x * g.x + f.y * g.y;
-                        f = unpack_bf16x2(x.w); g = unpack_bf16x2(y.w); delta += f.x * g.x + f.y * g.y;
-                    }
-                    delta *= inv_dps;   // stored O carries the DropPath factor
+                    lse = __ldg(a.lse + (size_t(b) * a.H + h) * a.T + t);
+                    const uint4* po = reinterpret_cast<const uint4*>(a.o_in + (size_t(b) * a.T + t) * D + h * HD + cg * 16);
+                    o0 = __ldg(po); o1 = __ldg(po + 1);
+                    const uint4* py = reinterpret_cast<const uint4*>(a.qkv + qoff);
+                    y0 = __ldg(py); y1 = __ldg(py + 1);
                 }
-                const float sl2 = a.scale * 1.4426950408889634f, lse2 = lse * 1.4426950408889634f;
+                // ---- delta = rowsum(dO * O) / droppath: dO slice from the TMA-loaded tile, partials exchanged through smem ----
+                mbar_wait(bar(QDO_FULL), i);
+                {
+                    const uint4 d0 = ld_shared_v4(sDO + sw128_offset(r, cg * 2)), d1 = ld_shared_v4(sDO + sw128_offset(r, cg * 2 + 1));
+                    st_shared_f32(xd_mine, (dot8(o0, d0) + dot8(o1, d1)) * inv_dps);
+                }
+                named_bar_sync(2 + q, 128);
+                const float delta = (ld_shared_f32(sXD + r * 4) + ld_shared_f32(sXD + (128 + r) * 4)) +
+                                    (ld_shared_f32(sXD + (256 + r) * 4) + ld_shared_f32(sXD + (384 + r) * 4));
+                const float lse2 = lse * 1.4426950408889634f;
+                const float dsc = delta * a.scale;
                 // ---- P = exp(S*scale - LSE) over this warp's kv columns ----
                 mbar_wait(bar(S_FULL), i);
                 tc_fence_after();
@@ -502,9 +517,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     if (nj == 32) tmem_ld32(tA + lane_base + col, v);
                     else tmem_ld16(tA + lane_base + col, v);
                     tmem_ld_wait();
+                    if (col + nj <= a.T) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < nj) v[j] = (t_ok && col + j < a.T) ? fast_ex2(fmaf(v[j], sl2, -lse2)) : 0.f;
+                        for (int j = 0; j < 32; ++j) v[j] = fast_ex2(fmaf(v[j], sl2, -lse2));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = (col + j < a.T) ? fast_ex2(fmaf(v[j], sl2, -lse2)) : 0.f;
+                    }
 #pragma unroll
                     for (int q4 = 0; q4 < 4; ++q4) {
                         if (q4 * 8 < nj) {
@@ -536,10 +555,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                             float2 p0 = unpack_bf16x2(pp.x), p1 = unpack_bf16x2(pp.y), p2 = unpack_bf16x2(pp.z), p3 = unpack_bf16x2(pp.w);
                             const float* w = v + q4 * 8;
                             uint4 pk;
-                            pk.x = pack_bf16x2(a.scale * p0.x * (w[0] - delta), a.scale * p0.y * (w[1] - delta));
-                            pk.y = pack_bf16x2(a.scale * p1.x * (w[2] - delta), a.scale * p1.y * (w[3] - delta));
-                            pk.z = pack_bf16x2(a.scale * p2.x * (w[4] - delta), a.scale * p2.y * (w[5] - delta));
-                            pk.w = pack_bf16x2(a.scale * p3.x * (w[6] - delta), a.scale * p3.y * (w[7] - delta));
+                            pk.x = pack_bf16x2(p0.x * fmaf(w[0], a.scale, -dsc), p0.y * fmaf(w[1], a.scale, -dsc));
+                            pk.y = pack_bf16x2(p1.x * fmaf(w[2], a.scale, -dsc), p1.y * fmaf(w[3], a.scale, -dsc));
+                            pk.z = pack_bf16x2(p2.x * fmaf(w[4], a.scale, -dsc), p2.y * fmaf(w[5], a.scale, -dsc));
+                            pk.w = pack_bf16x2(p3.x * fmaf(w[6], a.scale, -dsc), p3.y * fmaf(w[7], a.scale, -dsc));
                             st_shared_v4(pbuf_addr(sDS, r, (col >> 3) + q4), pk);
                         }
                     }
@@ -557,19 +576,26 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar(A_EMPTY));
-                {
-                    const size_t off = ((size_t(b) * a.T + (t_ok ? t : 0)) * 3 + 0) * D + h * HD + cg * 16;
-                    dqkv_slice_epilogue(w16, t_ok, a.qkv + off, a.dqkv + off, g16, cs_gate, cs_bias);
-                }
+                dqkv_slice_epilogue(w16, t_ok, y0, y1, a.dqkv + qoff, g16, cs_gate, cs_bias);
             }
-            // ---- dK / dV epilogue (kv rows: tile m covers kv = m*128 + r) ----
+            // ---- dK / dV epilogue (kv rows: tile m covers kv = m*128 + r); the gated k / v slices are prefetched one ahead ----
+            auto slice_off = [&](int idx) {
+                const int which = 1 + (idx >> 1), kv = (idx & 1) * QT + r;
+                return ((size_t(b) * a.T + (kv < a.T ? kv : 0)) * 3 + which) * D + h * HD + cg * 16;
+            };
+            uint4 n0 = __ldg(reinterpret_cast<const uint4*>(a.qkv + slice_off(0))),
+                  n1v = __ldg(reinterpret_cast<const uint4*>(a.qkv + slice_off(0)) + 1);
             mbar_wait(bar(ACC_FULL), pi);
             tc_fence_after();
-#pragma unroll 1
+#pragma unroll
             for (int idx = 0; idx < 4; ++idx) {
                 const int which = 1 + (idx >> 1), m = idx & 1;
-                const int kv = m * QT + r;
-                const bool kv_ok = kv < a.T;
+                const bool kv_ok = m * QT + r < a.T;
+                const uint4 x0 = n0, x1 = n1v;
+                if (idx < 3) {
+                    n0 = __ldg(reinterpret_cast<const uint4*>(a.qkv + slice_off(idx + 1)));
+                    n1v = __ldg(reinterpret_cast<const uint4*>(a.qkv + slice_off(idx + 1)) + 1);
+                }
                 float w16[16];
                 tmem_ld16((which == 1 ? tDK : tDV) + lane_base + m * HD + cg * 16, w16);
                 tmem_ld_wait();
@@ -578,8 +604,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar(ACC_EMPTY));
                 }
-                const size_t off = ((size_t(b) * a.T + (kv_ok ? kv : 0)) * 3 + which) * D + h * HD + cg * 16;
-                dqkv_slice_epilogue(w16, kv_ok, a.qkv + off, a.dqkv + off, g16, cs_gate, cs_bias + which * 64);
+                dqkv_slice_epilogue(w16, kv_ok, x0, x1, a.dqkv + slice_off(idx), g16, cs_gate, cs_bias + which * 64);
             }
             // ---- per-item column sums -> global partials; the accumulator of this parity is re-zeroed for item it+2 ----
             named_bar_sync(1, BWD_CT);
@@ -604,7 +629,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 // host
 // ---------------------------------------------------------------------------------------------
 static constexpr int FWD_SMEM = 2 * TILE_B + 2 * KV_B + 2 * PBUF_B + 4096 + 256;
-static constexpr int BWD_SMEM = 2 * TILE_B + 2 * KV_B + 2 * PBUF_B + 2048 + 256;
+static constexpr int BWD_SMEM = 2 * TILE_B + 2 * KV_B + 2 * PBUF_B + 4096 + 256;
 
 static int make_qkv_maps(const void* qkv, int B, int T, int H, CUtensorMap* tq, CUtensorMap* tkv) {
     const uint64_t D = uint64_t(H) * HD;
