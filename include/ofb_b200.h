@@ -78,6 +78,16 @@ int ofb_layernorm_bwd(const void* dy, const void* x, const float* mean, const fl
 /* out[col] (+)= scale * sum_r part[r,col] / (div_by ? div_by[col] : 1) */
 int ofb_reduce_partials(const float* part, int R, int N, float* out, float scale, const float* div_by, int accumulate,
                         void* stream);
+/* up to 8 such reductions in one launch (the gradient pieces that fall out of one backward kernel) */
+typedef struct ofb_reduce_job {
+    const float* part;
+    float* out;
+    const float* div_by;
+    int32_t R, N;
+    float scale;
+    int32_t accumulate;
+} ofb_reduce_job;
+int ofb_reduce_partials_multi(const ofb_reduce_job* jobs, int njobs, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * token assembly (models/layers.py:177 im2col; vision_transformer.py:586-612 PMIM mask, 646-651 cls row; timm

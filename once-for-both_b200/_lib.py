@@ -44,6 +44,12 @@ class BimaskModule(C.Structure):
     ]
 
 
+class ReduceJob(C.Structure):
+    """Mirror of ``ofb_reduce_job``."""
+    _fields_ = [("part", C.c_void_p), ("out", C.c_void_p), ("div_by", C.c_void_p), ("R", C.c_int32), ("N", C.c_int32),
+                ("scale", C.c_float), ("accumulate", C.c_int32)]
+
+
 _P, _I, _F, _L = C.c_void_p, C.c_int, C.c_float, C.c_int64
 # every symbol include/ofb_b200.h declares, with its argument types
 SIGNATURES = {
@@ -54,6 +60,7 @@ SIGNATURES = {
     "ofb_layernorm_bwd_parts": [_I],
     "ofb_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "ofb_reduce_partials": [_P, _I, _I, _P, _F, _P, _I, _P],
+    "ofb_reduce_partials_multi": [_P, _I, _P],
     "ofb_patchify": [_P, _P, _I, _I, _I, _P],
     "ofb_pmim_mask": [_P, _P, _I, _I, _I, _P],
     "ofb_droppath_scale": [_P, _P, _P, _I, _I, _P],

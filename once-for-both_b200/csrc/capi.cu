@@ -12,6 +12,7 @@ int ln_bwd_grid(int M);
 int launch_ln_bwd(const void*, const void*, const float*, const float*, const float*, void*, float*, float*, float*, const float*, int,
                   int, int, cudaStream_t);
 int launch_reduce_partials(const float*, int, int, float*, float, const float*, int, cudaStream_t);
+int launch_reduce_partials_multi(const void*, int, cudaStream_t);
 int launch_patchify(const float*, void*, int, int, int, cudaStream_t);
 int launch_pmim_mask(const float*, float*, int, int, int, cudaStream_t);
 int launch_droppath_scale(const float*, const float*, float*, int, int, cudaStream_t);
@@ -70,6 +71,11 @@ int ofb_layernorm_bwd(const void* dy, const void* x, const float* mean, const fl
 }
 int ofb_reduce_partials(const float* part, int R, int N, float* out, float scale, const float* div_by, int accumulate, void* stream) {
     return ofb::launch_reduce_partials(part, R, N, out, scale, div_by, accumulate, ST(stream));
+}
+int ofb_reduce_partials_multi(const ofb_reduce_job* jobs, int njobs, void* stream) {
+    static_assert(sizeof(ofb_reduce_job) == 40, "ofb_reduce_job layout");
+    if (jobs == nullptr) return 1000;
+    return ofb::launch_reduce_partials_multi(jobs, njobs, ST(stream));
 }
 int ofb_patchify(const float* images, void* patches, int B, int img, int patch, void* stream) {
     return ofb::launch_patchify(images, patches, B, img, patch, ST(stream));

@@ -5,6 +5,7 @@
 // All are vectorised (16-byte accesses), warp-shuffle reduced, grid-strided over 148 SMs.
 #include "ptx.cuh"
 #include <math.h>
+#include <string.h>
 
 namespace ofb {
 
@@ -92,6 +93,14 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const __nv_bfloat16* __rest
 //                      x = res + droppath*(.. + bias), vision_transformer.py:197,201)   [optional]
 //   partial buffers are [gridDim.x, D]; a second kernel reduces them (deterministic).
 // =============================================================================================
+// Rows are staged by 1-D bulk async copies (cp.async.bulk + mbarrier) into a per-warp ring of LN_STAGES rows, so every warp
+// keeps LN_STAGES x 2 row loads in flight without holding them in registers.
+static constexpr int LN_STAGES = 4;
+__device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(bar)
+                 : "memory");
+}
 template <int LN_MAXC>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -99,16 +108,29 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
                                                      float* __restrict__ part_dgamma, float* __restrict__ part_dbeta,
                                                      float* __restrict__ part_dbias, const float* __restrict__ rowscale,
                                                      int rows_per_scale, int M, int D) {
-    extern __shared__ float ln_smem[];  // [3][warps][D]
+    extern __shared__ __align__(128) uint8_t ln_smem_raw[];
+    // layout: ring [8 warps][LN_STAGES][2][D bf16] | barriers [8][LN_STAGES]; the ring is reused as float [3][8][D] at the end
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int warps_per_block = blockDim.x >> 5;
+    constexpr int WPB = 8;
     const int nchunk = D >> 3;
+    const uint32_t row_bytes = uint32_t(D) * 2u;
+    const uint32_t ring_bytes = WPB * LN_STAGES * 2 * row_bytes;
+    const uint32_t red_bytes = 3u * WPB * uint32_t(D) * 4u;
+    const uint32_t bar_off = (ring_bytes > red_bytes ? ring_bytes : red_bytes);
+    uint8_t* my_ring = ln_smem_raw + size_t(warp) * LN_STAGES * 2 * row_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem_raw + bar_off) + warp * LN_STAGES;
+
+    if (lane == 0) {
+        for (int sidx = 0; sidx < LN_STAGES; ++sidx) mbar_init(smem_u32(&bars[sidx]), 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+
     float ag[LN_MAXC][8], ab[LN_MAXC][8], ad[LN_MAXC][8];
 #pragma unroll
     for (int i = 0; i < LN_MAXC; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) ag[i][j] = ab[i][j] = ad[i][j] = 0.f;
-
     float gam[LN_MAXC][8];
 #pragma unroll
     for (int i = 0; i < LN_MAXC; ++i) {
@@ -121,18 +143,50 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
         }
     }
 
-    for (int row = blockIdx.x * warps_per_block + warp; row < M; row += gridDim.x * warps_per_block) {
-        const uint4* dyr = reinterpret_cast<const uint4*>(dy + size_t(row) * D);
-        const uint4* xr = reinterpret_cast<const uint4*>(x + size_t(row) * D);
+    const int row_stride = gridDim.x * WPB;
+    const int first = blockIdx.x * WPB + warp;
+    auto issue = [&](int row, int stage) {
+        const uint32_t b = smem_u32(&bars[stage]);
+        const uint32_t dst = smem_u32(my_ring + size_t(stage) * 2 * row_bytes);
+        mbar_arrive_expect_tx(b, 2 * row_bytes);
+        bulk_load_1d(dst, dy + size_t(row) * D, row_bytes, b);
+        bulk_load_1d(dst + row_bytes, x + size_t(row) * D, row_bytes, b);
+    };
+    if (lane == 0) {
+        for (int sidx = 0; sidx < LN_STAGES; ++sidx) {
+            const int row = first + sidx * row_stride;
+            if (row < M) issue(row, sidx);
+        }
+    }
+    int k = 0;
+    for (int row = first; row < M; row += row_stride, ++k) {
+        const int stage = k % LN_STAGES;
+        const uint32_t parity = (k / LN_STAGES) & 1;
         const float mu = __ldg(mean + row), rs = __ldg(rstd + row);
+        const float rsc = (part_dbias != nullptr) ? (rowscale != nullptr ? __ldg(rowscale + row / rows_per_scale) : 1.f) : 0.f;
+        mbar_wait(smem_u32(&bars[stage]), parity);
+        const uint4* sdy = reinterpret_cast<const uint4*>(my_ring + size_t(stage) * 2 * row_bytes);
+        const uint4* sx = reinterpret_cast<const uint4*>(my_ring + size_t(stage) * 2 * row_bytes + row_bytes);
         float dyv[LN_MAXC][8], xh[LN_MAXC][8];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < LN_MAXC; ++i) {
             const int c = lane + 32 * i;
             if (c < nchunk) {
-                unpack8(__ldg(dyr + c), dyv[i]);
-                unpack8(__ldg(xr + c), xh[i]);
+                unpack8(sdy[c], dyv[i]);
+                unpack8(sx[c], xh[i]);
+            }
+        }
+        // the stage is consumed (values are in registers): refill it with the row LN_STAGES iterations ahead
+        __syncwarp();
+        if (lane == 0) {
+            const int nxt = row + LN_STAGES * row_stride;
+            if (nxt < M) { fence_proxy_async_smem(); issue(nxt, stage); }
+        }
+#pragma unroll
+        for (int i = 0; i < LN_MAXC; ++i) {
+            const int c = lane + 32 * i;
+            if (c < nchunk) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     xh[i][j] = (xh[i][j] - mu) * rs;
@@ -146,7 +200,6 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
         }
         s1 = warp_sum(s1) / D;
         s2 = warp_sum(s2) / D;
-        const float rsc = (part_dbias != nullptr) ? (rowscale != nullptr ? __ldg(rowscale + row / rows_per_scale) : 1.f) : 0.f;
         uint4* dxr = reinterpret_cast<uint4*>(dx + size_t(row) * D);
 #pragma unroll
         for (int i = 0; i < LN_MAXC; ++i) {
@@ -162,10 +215,11 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
             }
         }
     }
-    // cross-warp reduction of the column accumulators
-    float* sg = ln_smem;
-    float* sb = ln_smem + warps_per_block * D;
-    float* sd = ln_smem + 2 * warps_per_block * D;
+    // cross-warp reduction of the column accumulators (the ring is idle now: every issued copy has been consumed)
+    __syncthreads();
+    float* sg = reinterpret_cast<float*>(ln_smem_raw);
+    float* sb = sg + WPB * D;
+    float* sd = sg + 2 * WPB * D;
 #pragma unroll
     for (int i = 0; i < LN_MAXC; ++i) {
         const int c = lane + 32 * i;
@@ -181,7 +235,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
     __syncthreads();
     for (int col = threadIdx.x; col < D; col += blockDim.x) {
         float a = 0.f, b = 0.f, d = 0.f;
-        for (int w = 0; w < warps_per_block; ++w) {
+        for (int w = 0; w < WPB; ++w) {
             a += sg[w * D + col]; b += sb[w * D + col]; d += sd[w * D + col];
         }
         part_dgamma[size_t(blockIdx.x) * D + col] = a;
@@ -209,6 +263,30 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, int R, in
         t *= scale;
         if (inv_colscale != nullptr) t /= inv_colscale[col];
         out[col] = accumulate ? out[col] + t : t;
+    }
+}
+
+// several independent reductions in one launch (blockIdx.y = job): the gradient pieces that fall out of one backward
+// kernel (LayerNorm: d gamma, d beta, d bias; fc2 dgrad: d gate, d bias; ...) are finished together.
+struct ReduceJob { const float* part; float* out; const float* div_by; int R, N; float scale; int accumulate; };
+struct ReduceJobs { ReduceJob j[8]; };
+__global__ void reduce_partials_multi_kernel(const ReduceJobs jobs) {
+    const ReduceJob jb = jobs.j[blockIdx.y];
+    const int col = blockIdx.x * 32 + (threadIdx.x & 31);
+    if (blockIdx.x * 32 >= jb.N) return;
+    const int ty = threadIdx.x >> 5, ny = blockDim.x >> 5;
+    __shared__ float sm[32][33];
+    float s = 0.f;
+    if (col < jb.N)
+        for (int r = ty; r < jb.R; r += ny) s += jb.part[size_t(r) * jb.N + col];
+    sm[ty][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (ty == 0 && col < jb.N) {
+        float t = 0.f;
+        for (int i = 0; i < ny; ++i) t += sm[i][threadIdx.x];
+        t *= jb.scale;
+        if (jb.div_by != nullptr) t /= jb.div_by[col];
+        jb.out[col] = jb.accumulate ? jb.out[col] + t : t;
     }
 }
 
@@ -556,7 +634,7 @@ int launch_ln_fwd(const void* x, const float* gamma, const float* beta, void* y,
 // number of CTAs (= rows of the partial buffers) of the backward kernel
 int ln_bwd_grid(int M) {
     int grid = (M + 7) / 8;
-    const int cap = num_sms() * 4;
+    const int cap = num_sms() * 2;      // two resident CTAs per SM at D <= 512 (128 registers, 48 KB ring each): one wave
     return grid > cap ? cap : grid;
 }
 
@@ -566,10 +644,14 @@ static int ln_bwd_inst(const void* dy, const void* x, const float* mean, const f
                        cudaStream_t s) {
     const int wpb = 8;
     const int grid = ln_bwd_grid(M);
-    const size_t smem = size_t(3) * wpb * D * sizeof(float);
+    const size_t ring = size_t(wpb) * LN_STAGES * 2 * D * 2, red = size_t(3) * wpb * D * sizeof(float);
+    const size_t smem = (ring > red ? ring : red) + wpb * LN_STAGES * 8;
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(ln_bwd_kernel<MAXC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 8 * 256 * MAXC * 4);
+        const int dmax = 256 * MAXC;
+        const size_t ring_max = size_t(wpb) * LN_STAGES * 2 * dmax * 2, red_max = size_t(3) * wpb * dmax * sizeof(float);
+        cudaFuncSetAttribute(ln_bwd_kernel<MAXC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             int((ring_max > red_max ? ring_max : red_max) + wpb * LN_STAGES * 8));
         configured = true;
     }
     ln_bwd_kernel<MAXC><<<grid, wpb * 32, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x),
@@ -591,6 +673,18 @@ int launch_ln_bwd(const void* dy, const void* x, const float* mean, const float*
 int launch_reduce_partials(const float* part, int R, int N, float* out, float scale, const float* inv_colscale, int accumulate,
                            cudaStream_t s) {
     reduce_partials_kernel<<<(N + 31) / 32, 32 * 32, 0, s>>>(part, R, N, out, scale, inv_colscale, accumulate);
+    return err();
+}
+
+int launch_reduce_partials_multi(const void* jobs_host, int njobs, cudaStream_t s) {
+    if (njobs < 1 || njobs > 8) return 1015;
+    ReduceJobs jobs;
+    memset(&jobs, 0, sizeof(jobs));
+    const ReduceJob* src = reinterpret_cast<const ReduceJob*>(jobs_host);
+    int maxn = 0;
+    for (int i = 0; i < njobs; ++i) { jobs.j[i] = src[i]; if (src[i].N > maxn) maxn = src[i].N; }
+    dim3 grid((maxn + 31) / 32, njobs);
+    reduce_partials_multi_kernel<<<grid, 32 * 32, 0, s>>>(jobs);
     return err();
 }
 

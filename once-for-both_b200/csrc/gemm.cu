@@ -110,12 +110,16 @@ __device__ __forceinline__ Packed32 load_packed32(const __nv_bfloat16* src, bool
 #pragma unroll
         for (int i = 0; i < 4; ++i) r.p[i] = __ldg(reinterpret_cast<const uint4*>(src) + i);
     } else {
+        // ragged tail: compile-time indexed so that the struct stays in registers (no local-memory round trip)
+        uint32_t w[16];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) r.p[i] = make_uint4(0, 0, 0, 0);
-        if (row_ok) {
-            __nv_bfloat16* e = reinterpret_cast<__nv_bfloat16*>(&r);
-            for (int i = 0; i < nvalid; ++i) e[i] = src[i];
+        for (int i = 0; i < 16; ++i) {
+            const uint32_t lo = (row_ok && 2 * i < nvalid) ? uint32_t(__bfloat16_as_ushort(src[2 * i])) : 0u;
+            const uint32_t hi = (row_ok && 2 * i + 1 < nvalid) ? uint32_t(__bfloat16_as_ushort(src[2 * i + 1])) : 0u;
+            w[i] = lo | (hi << 16);
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r.p[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
     }
     return r;
 }

@@ -427,9 +427,8 @@ class SearchStepEngine:
         G = self.gB
         ops.layernorm_bwd(dlat, self.xs[self.depth], self.meanf, self.rstdf, self.p("norm.weight"), G, self.pg_,
                           self.pb_, self.pd_, last_dp2, T)
-        ops.reduce_partials(self.pg_, R, D, self.g("norm.weight"))
-        ops.reduce_partials(self.pb_, R, D, self.g("norm.bias"))
-        ops.reduce_partials(self.pd_, R, D, self.g(f"blocks.{self.depth - 1}.mlp.fc2.bias"))
+        ops.reduce_partials_multi([(self.pg_, R, D, self.g("norm.weight")), (self.pb_, R, D, self.g("norm.bias")),
+                                   (self.pd_, R, D, self.g(f"blocks.{self.depth - 1}.mlp.fc2.bias"))])
         spare = [self.gA, self.gC]
 
         for l in reversed(range(self.depth)):
@@ -443,8 +442,8 @@ class SearchStepEngine:
             ops.gemm(ops.EPI_FC2_DGRAD, G4, self.w(pre + "mlp.fc2.weight"), M=M, N=hid, K=D, out0=self.du, aux=a["u"],
                      colscale=g_m, rowscale=dp2, rows_per_scale=T, colpart0=self.cp0, colpart1=self.cp1, b_mn=True)
             m_off = bm.modules[i_m]["gate_off"]
-            ops.reduce_partials(self.cp0, mt, hid, self.dgate[m_off:m_off + hid], accumulate=False)
-            ops.reduce_partials(self.cp1, mt, hid, self.g(pre + "mlp.fc1.bias"))
+            mlp_jobs = [dict(part=self.cp0, R=mt, N=hid, out=self.dgate[m_off:m_off + hid], accumulate=False),
+                        dict(part=self.cp1, R=mt, N=hid, out=self.g(pre + "mlp.fc1.bias"))]
             ops.gemm(ops.EPI_WGRAD, self.du, a["x3"], M=hid, N=D, K=M, out0=self.g(pre + "mlp.fc1.weight"), a_mn=True,
                      b_mn=True)
             G3 = spare.pop()
@@ -455,9 +454,10 @@ class SearchStepEngine:
             ops.layernorm_bwd(G3, a["x2"], a["mean2"], a["rstd2"], self.p(pre + "norm2.weight"), G2, self.pg_, self.pb_,
                               self.pd_, dp1, T)
             spare.append(G3)
-            ops.reduce_partials(self.pg_, R, D, self.g(pre + "norm2.weight"))
-            ops.reduce_partials(self.pb_, R, D, self.g(pre + "norm2.bias"))
-            ops.reduce_partials(self.pd_, R, D, self.g(pre + "attn.proj.bias"))
+            # one launch finishes the column partials of the fc2 data-gradient GEMM and of this LayerNorm
+            ops.reduce_partials_multi(mlp_jobs + [(self.pg_, R, D, self.g(pre + "norm2.weight")),
+                                                  (self.pb_, R, D, self.g(pre + "norm2.bias")),
+                                                  (self.pd_, R, D, self.g(pre + "attn.proj.bias"))])
             # proj
             ops.gemm(ops.EPI_WGRAD, G2, a["o"], M=D, N=D, K=M, out0=self.g(pre + "attn.proj.weight"), a_mn=True, b_mn=True)
             dO = spare.pop()
@@ -468,8 +468,8 @@ class SearchStepEngine:
                               self.scale)
             spare.append(dO)
             a_off = bm.modules[i_a]["gate_off"]
-            ops.reduce_partials(self.att_pg, B, D, self.dgate[a_off:a_off + D], div_by=g_a, accumulate=False)
-            ops.reduce_partials(self.att_pb, B, 3 * D, self.g(pre + "attn.qkv.bias"))
+            attn_jobs = [dict(part=self.att_pg, R=B, N=D, out=self.dgate[a_off:a_off + D], div_by=g_a, accumulate=False),
+                         dict(part=self.att_pb, R=B, N=3 * D, out=self.g(pre + "attn.qkv.bias"))]
             ops.gemm(ops.EPI_WGRAD, self.dqkv, a["x1"], M=3 * D, N=D, K=M, out0=self.g(pre + "attn.qkv.weight"), a_mn=True,
                      b_mn=True)
             G1 = spare.pop()
@@ -483,20 +483,19 @@ class SearchStepEngine:
                               self.pb_, self.pd_ if has_prev else None,
                               self.drop_scale[2 * l - 1] if has_prev else None, T)
             spare.append(G1)
-            ops.reduce_partials(self.pg_, R, D, self.g(pre + "norm1.weight"))
-            ops.reduce_partials(self.pb_, R, D, self.g(pre + "norm1.bias"))
+            ln1_jobs = [(self.pg_, R, D, self.g(pre + "norm1.weight")), (self.pb_, R, D, self.g(pre + "norm1.bias"))]
             if has_prev:
-                ops.reduce_partials(self.pd_, R, D, self.g(f"blocks.{l - 1}.mlp.fc2.bias"))
+                ln1_jobs.append((self.pd_, R, D, self.g(f"blocks.{l - 1}.mlp.fc2.bias")))
+            ops.reduce_partials_multi(attn_jobs + ln1_jobs)
             G = G0
 
         # ---- embed stage ----
         g_e = bm.gate_of(0)
         ops.embed_bwd(G, self.xs[0], g_e, self.mask, self.dconv, self.e_gx, self.e_pos, self.e_mt, B, T, D)
-        ops.reduce_partials(self.e_gx, T, D, self.dgate[0:D], div_by=g_e, accumulate=False)
-        ops.reduce_partials(self.e_pos, 1, T * D, self.g("pos_embed"))
-        ops.reduce_partials(self.e_pos, 1, D, self.g("cls_token"))
-        ops.reduce_partials(self.e_mt, T, D, self.g("mask_token"))
-        ops.reduce_partials(self.e_pos[1:], L, D, self.g("patch_embed.proj.bias"))
+        ops.reduce_partials_multi([
+            dict(part=self.e_gx, R=T, N=D, out=self.dgate[0:D], div_by=g_e, accumulate=False),
+            (self.e_pos, 1, T * D, self.g("pos_embed")), (self.e_pos, 1, D, self.g("cls_token")),
+            (self.e_mt, T, D, self.g("mask_token")), (self.e_pos[1:], L, D, self.g("patch_embed.proj.bias"))])
         ops.gemm(ops.EPI_WGRAD, self.dconv, self.patches, M=D, N=768, K=ML,
                  out0=self.g("patch_embed.proj.weight").view(D, 768), a_mn=True, b_mn=True)
         # ---- bi-mask: d gate (+ FLOPs / sparsity losses) -> d score, d alpha ----

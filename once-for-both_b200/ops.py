@@ -91,6 +91,17 @@ def reduce_partials(part, R, N, out, scale=1.0, div_by=None, accumulate=True):
           "ofb_reduce_partials")
 
 
+def reduce_partials_multi(jobs):
+    """jobs: list of (part, R, N, out[, scale, div_by, accumulate]) tuples or dicts finished in ONE launch."""
+    arr = (_lib.ReduceJob * len(jobs))()
+    for a, j in zip(arr, jobs):
+        if not isinstance(j, dict):
+            j = dict(zip(("part", "R", "N", "out", "scale", "div_by", "accumulate"), j))
+        a.part, a.out, a.div_by = ptr(j["part"]), ptr(j["out"]), ptr(j.get("div_by"))
+        a.R, a.N, a.scale, a.accumulate = j["R"], j["N"], j.get("scale", 1.0), int(j.get("accumulate", True))
+    check(lib().ofb_reduce_partials_multi(C.cast(arr, C.c_void_p), len(jobs), cur_stream()), "ofb_reduce_partials_multi")
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # token assembly / PMIM
 # ---------------------------------------------------------------------------------------------------------------------
