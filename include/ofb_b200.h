@@ -28,8 +28,11 @@ enum {
     OFB_EPI_STORE = 0,     /* out0 = rowscale*(acc+bias)*colscale + res
                               nn.Linear fwd / dgrad: layers.py:491 (qkv + gate 507-509), 515 (proj), 863 (fc2),
                               vision_transformer.py:744 (head); residual + DropPath vision_transformer.py:197,201 */
-    OFB_EPI_FC1 = 1,       /* out0 = u = acc+bias ; out1 = gelu(u*gate)            layers.py:845-861 */
-    OFB_EPI_FC2_DGRAD = 2, /* backward of layers.py:858-863: du, column partials of d gate and d bias */
+    OFB_EPI_FC1 = 1,       /* hidden activations TRANSPOSED [hidden, tokens]: rows (M) = hidden units = the fc1 weight,
+                              columns (N) = tokens: out0 = u^T = acc+bias[row] ; out1 = h^T = rowscale[col/rows_per_scale] *
+                              gelu(u^T*gate[row])                                   layers.py:845-861 */
+    OFB_EPI_FC2_DGRAD = 2, /* backward of layers.py:858-863 in the same transposed layout (A = fc2 weight, MN-major):
+                              out0 = du^T ; colpart0/1[2*n_tiles][M] = per-tile token sums of d gate[row], d bias[row] */
     OFB_EPI_WGRAD = 3,     /* out0(fp32) += scale * A^T B, split-K (weight gradients of every Linear / conv) */
     OFB_EPI_PATCH = 4,     /* layers.py:177-191 + vision_transformer.py:628-637 fused */
     OFB_EPI_DECODER = 5    /* vision_transformer.py:720-729 fused (1x1 conv + pixel-shuffle + masked L1) */

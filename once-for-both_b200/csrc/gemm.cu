@@ -34,16 +34,17 @@ struct GemmCfg {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int NOUT = (EPI == EPI_FC1) ? 2 : 1;
     static constexpr int STAGING_BYTES = TMA_OUT ? 2 * NOUT * PANEL_BYTES : 0;          // two slots
-    static constexpr int SCRATCH_BYTES = (EPI == EPI_FC2_DGRAD) ? 2 * 4 * BN * 4 : 0;   // column partials [4 quarters][BN] x2
+    static constexpr int AUX_BYTES = (TMA_OUT == 2) ? 2 * PANEL_BYTES : 0;              // two TMA-loaded residual / saved-activation panels
+    static constexpr int SCRATCH_BYTES = 0;
     static constexpr int VEC_BYTES = 2 * 2 * BN * 4;        // per-column epilogue vectors, double-buffered by tile parity
     static constexpr int BAR_BYTES = 256;
-    static constexpr int FIXED = STAGING_BYTES + SCRATCH_BYTES + VEC_BYTES + BAR_BYTES;
+    static constexpr int FIXED = STAGING_BYTES + AUX_BYTES + SCRATCH_BYTES + VEC_BYTES + BAR_BYTES;
     static constexpr int STAGES_RAW = (SMEM_LIMIT - FIXED) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED;
     static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
     static_assert(STAGES >= 3, "pipeline too shallow");
-    static_assert((2 * STAGES + 4) * 8 + 8 <= BAR_BYTES, "barrier block too small");
+    static_assert((2 * STAGES + 6) * 8 + 8 <= BAR_BYTES, "barrier block too small");
 };
 
 // 32 values per lane -> lane L ends with the sum over lanes of v[L] (31 shuffles).
@@ -145,13 +146,19 @@ __device__ __forceinline__ void stage_bf16x32(uint32_t panel, int row, int half,
     }
 }
 
+// TMA_OUT: 0 = direct global stores; 1 = bf16 output panels staged in smem and written by TMA; 2 = 1 + the residual (STORE) /
+// saved activation (FC2_DGRAD) tile is TMA-loaded into smem panels two panels ahead of its use.
 template <int BN, int A_MN, int B_MN, int EPI, int TMA_OUT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-            const __grid_constant__ CUtensorMap tma_o0, const __grid_constant__ CUtensorMap tma_o1, const GemmArgs g) {
+            const __grid_constant__ CUtensorMap tma_o0, const __grid_constant__ CUtensorMap tma_o1,
+            const __grid_constant__ CUtensorMap tma_aux, const GemmArgs g) {
     using Cfg = GemmCfg<BN, EPI, TMA_OUT>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr uint32_t IDESC = make_idesc_bf16(BM, BN, A_MN, B_MN);
+    // transposed-hidden epilogues: rows = hidden units (few m tiles, the weight operand), columns = tokens; walking the m
+    // tiles of one token tile back to back keeps that token tile in L2
+    constexpr bool M_FAST = (EPI == EPI_FC1 || EPI == EPI_FC2_DGRAD);
     constexpr int NCHUNK = BN / 32;          // 32-column chunks per tile; group g handles chunks c = g, g+2, ...
     constexpr int NPANEL = BN / 64;
 
@@ -159,15 +166,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
     uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;                       // 1024-aligned (stage sizes are multiples of 8 KB)
-    float* scratch0 = reinterpret_cast<float*>(staging + Cfg::STAGING_BYTES);
-    float* scratch1 = scratch0 + 4 * BN;
-    float* vecs = reinterpret_cast<float*>(staging + Cfg::STAGING_BYTES + Cfg::SCRATCH_BYTES);   // [2 parities][2][BN]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES + Cfg::SCRATCH_BYTES + Cfg::VEC_BYTES);
+    uint8_t* auxbuf = staging + Cfg::STAGING_BYTES;                            // [2 slots][PANEL_BYTES], 1024-aligned
+    float* vecs = reinterpret_cast<float*>(auxbuf + Cfg::AUX_BYTES + Cfg::SCRATCH_BYTES);   // [2 parities][2][BN]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(auxbuf + Cfg::AUX_BYTES + Cfg::SCRATCH_BYTES + Cfg::VEC_BYTES);
     uint64_t* full_bar = bars;                    // [STAGES]
     uint64_t* empty_bar = bars + STAGES;          // [STAGES]
     uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]
     uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    uint64_t* aux_full = bars + 2 * STAGES + 4;   // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -177,6 +184,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
         if (TMA_OUT) { tma_prefetch_desc(&tma_o0); if (Cfg::NOUT == 2) tma_prefetch_desc(&tma_o1); }
+        if (TMA_OUT == 2) { tma_prefetch_desc(&tma_aux); mbar_init(smem_u32(&aux_full[0]), 1); mbar_init(smem_u32(&aux_full[1]), 1); }
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(smem_u32(&full_bar[i]), 1);
             mbar_init(smem_u32(&empty_bar[i]), 1);
@@ -210,7 +218,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 const int split = t / (m_tiles * n_tiles);
                 const int mn = t % (m_tiles * n_tiles);
-                const int m_blk = mn / n_tiles, n_blk = mn % n_tiles;
+                const int m_blk = M_FAST ? mn % m_tiles : mn / n_tiles, n_blk = M_FAST ? mn / m_tiles : mn % n_tiles;
                 const int kb0 = split * kb_per_split;
                 const int kb1 = min(k_blocks, kb0 + kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
@@ -282,10 +290,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         const bool elected = (etid == 0);
         int it = 0;
         uint32_t panel_ctr = 0;
+        // TMA_OUT == 2: panel number P of this CTA (tile sequence P / NPT, panel P % NPT) is loaded into aux slot P & 1
+        constexpr uint32_t NPT = NCHUNK / 2;
+        auto issue_aux = [&](uint32_t P) {
+            const long t2 = long(blockIdx.x) + long(P / NPT) * gridDim.x;
+            if (t2 >= total_tiles) return;
+            const int mn2 = int(t2 % (long(m_tiles) * n_tiles));      // k_splits == 1 for these epilogues
+            const int m2 = M_FAST ? mn2 % m_tiles : mn2 / n_tiles, n2 = M_FAST ? mn2 / m_tiles : mn2 % n_tiles;
+            const uint32_t fb = smem_u32(&aux_full[P & 1u]);
+            mbar_arrive_expect_tx(fb, PANEL_BYTES);
+            tma_load_2d(smem_u32(auxbuf) + (P & 1u) * PANEL_BYTES, &tma_aux, fb, n2 * BN + int(P % NPT) * 64, m2 * BM);
+        };
+        if (TMA_OUT == 2 && elected) { issue_aux(0); issue_aux(1); }
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const int split = t / (m_tiles * n_tiles);
             const int mn = t % (m_tiles * n_tiles);
-            const int m_blk = mn / n_tiles, n_blk = mn % n_tiles;
+            const int m_blk = M_FAST ? mn % m_tiles : mn / n_tiles, n_blk = M_FAST ? mn / m_tiles : mn % n_tiles;
             const int kb0 = split * kb_per_split;
             const int kb1 = min(k_blocks, kb0 + kb_per_split);
             if (kb1 <= kb0) continue;
@@ -300,7 +320,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             // ---- per-column epilogue vectors of this tile -> smem (while the MMAs of the tile are still running) ----
             float* vb = vecs + acc * 2 * BN;     // bias-like vector
             float* vs = vb + BN;                 // scale-like vector
-            if (EPI == EPI_STORE || EPI == EPI_FC1 || EPI == EPI_FC2_DGRAD || EPI == EPI_PATCH || EPI == EPI_DECODER) {
+            if (EPI == EPI_STORE || EPI == EPI_PATCH || EPI == EPI_DECODER) {
                 for (int i = etid; i < BN; i += EPI_THREADS) {
                     const int col = n0 + i;
                     const bool ok = col < g.N;
@@ -312,28 +332,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 }
             }
             float rs = 1.f;
-            if (EPI == EPI_STORE || EPI == EPI_FC2_DGRAD || EPI == EPI_FC1) {
+            if (EPI == EPI_STORE) {
                 if (g.rowscale != nullptr && row_ok) rs = __ldg(g.rowscale + row / g.rows_per_scale);
+            }
+            // transposed-hidden epilogues: this thread's row is one hidden unit -> bias / gate are per-thread scalars
+            float bias_j = 0.f, gate_j = 0.f, acc_dg = 0.f, acc_db = 0.f;
+            if (EPI == EPI_FC1 || EPI == EPI_FC2_DGRAD) {
+                if (row_ok) {
+                    gate_j = __ldg(g.colscale + row);
+                    if (EPI == EPI_FC1) bias_j = __ldg(g.bias + row);
+                }
             }
             float gs = 1.f;   // global device scalar
             if (EPI == EPI_STORE || EPI == EPI_WGRAD) {
                 if (g.scale_ptr != nullptr) gs = __ldg(g.scale_ptr);
             }
             // ---- prefetch this thread's residual / saved-activation slices (latency hides behind the tfull wait) ----
-            Packed32 pre[(EPI == EPI_STORE || EPI == EPI_FC2_DGRAD) ? NCHUNK / 2 : 1];
-            if (EPI == EPI_STORE) {
+            Packed32 pre[(EPI == EPI_STORE && TMA_OUT == 0) ? NCHUNK / 2 : 1];
+            if (EPI == EPI_STORE && TMA_OUT == 0) {
                 if (g.res != nullptr) {
 #pragma unroll
                     for (int j = 0; j < NCHUNK / 2; ++j) {
                         const int col0 = n0 + (2 * j + grp) * 32;
                         pre[j] = load_packed32(g.res + size_t(row) * g.ldres + col0, row_ok, min(32, g.N - col0));
                     }
-                }
-            } else if (EPI == EPI_FC2_DGRAD) {
-#pragma unroll
-                for (int j = 0; j < NCHUNK / 2; ++j) {
-                    const int col0 = n0 + (2 * j + grp) * 32;
-                    pre[j] = load_packed32(g.aux + size_t(row) * g.ldaux + col0, row_ok, min(32, g.N - col0));
                 }
             }
             named_bar_sync(1, EPI_THREADS);       // epilogue vectors visible
@@ -359,16 +381,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 const float* cs = vs + c * 32;
                 const uint32_t slot = panel_ctr & 1u;
                 const uint32_t panel0 = smem_u32(staging) + slot * (Cfg::NOUT * PANEL_BYTES);
+                Packed32 ax;       // this row's 32 residual / saved-activation values of the chunk (TMA-loaded panel)
+                if (TMA_OUT == 2) {
+                    mbar_wait(smem_u32(&aux_full[slot]), (panel_ctr >> 1) & 1u);
+                    const uint32_t ab = smem_u32(auxbuf) + slot * PANEL_BYTES;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t ad = ab + sw128_offset(et, (c & 1) * 4 + i);
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(ax.p[i].x), "=r"(ax.p[i].y), "=r"(ax.p[i].z), "=r"(ax.p[i].w) : "r"(ad) : "memory");
+                    }
+                }
 
                 if (EPI == EPI_STORE) {
                     const float brs = g.bias_rowscaled ? rs : 1.f;
                     const float ars = (g.bias_rowscaled ? 1.f : rs) * gs;
                     float r[32];
-                    if (g.res != nullptr) unpack32(pre[j], r);
+                    const bool has_res = (TMA_OUT == 2) || (TMA_OUT == 0 && g.res != nullptr);
+                    if (TMA_OUT == 2) unpack32(ax, r);
+                    else if (has_res) unpack32(pre[j], r);
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         const float tt = fmaf(v[i], cs[i], brs * cb[i]);
-                        v[i] = (g.res != nullptr) ? fmaf(ars, tt, r[i]) : ars * tt;
+                        v[i] = has_res ? fmaf(ars, tt, r[i]) : ars * tt;
                     }
                     if (TMA_OUT) {
                         stage_bf16x32(panel0, et, c & 1, v);
@@ -376,33 +411,64 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         if (g.out_fp32) store_f32x32(reinterpret_cast<float*>(g.out0) + size_t(row) * g.ld0 + col0, v, nvalid);
                         else store_bf16x32(reinterpret_cast<__nv_bfloat16*>(g.out0) + size_t(row) * g.ld0 + col0, v, nvalid);
                     }
-                } else if (EPI == EPI_FC1) {
-                    float h[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        v[i] += cb[i];
-                        const float z = v[i] * cs[i];
-                        h[i] = rs * z * gelu_cdf(z);
+                } else if (EPI == EPI_FC1 || EPI == EPI_FC2_DGRAD) {
+                    // DropPath multiplier of each of the 32 tokens (columns) of this chunk: at most two samples per chunk
+                    float rsA = 1.f, rsB = 1.f;
+                    int nb = 32;
+                    if (g.rowscale != nullptr) {
+                        const int last = (g.N - 1) / g.rows_per_scale;
+                        const int b0 = min(col0 / g.rows_per_scale, last);
+                        nb = (b0 + 1) * g.rows_per_scale - col0;
+                        rsA = __ldg(g.rowscale + b0);
+                        rsB = __ldg(g.rowscale + min(b0 + 1, last));
                     }
-                    stage_bf16x32(panel0, et, c & 1, v);
-                    stage_bf16x32(panel0 + PANEL_BYTES, et, c & 1, h);
-                } else if (EPI == EPI_FC2_DGRAD) {
-                    float u[32];
-                    unpack32(pre[j], u);           // zero for rows / columns out of range
+                    if (EPI == EPI_FC1) {
+                        float h[32];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float gt = cs[i];
-                        float Phi, zphi;
-                        gelu_terms(u[i] * gt, Phi, zphi);
-                        const float tt = (row_ok ? v[i] * rs : 0.f) * (Phi + zphi);
-                        u[i] = tt * u[i];          // d gate contribution
-                        v[i] = tt * gt;            // du
+                        for (int i = 0; i < 32; ++i) {
+                            v[i] += bias_j;
+                            const float z = v[i] * gate_j;
+                            h[i] = z * gelu_cdf(z);
+                        }
+                        if (nb >= 32) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) h[i] *= rsA;
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) h[i] *= (i < nb ? rsA : rsB);
+                        }
+                        stage_bf16x32(panel0, et, c & 1, v);
+                        stage_bf16x32(panel0 + PANEL_BYTES, et, c & 1, h);
+                    } else {
+                        float u[32];
+                        unpack32(ax, u);               // saved pre-gate fc1 output; zero for rows / tokens out of range (TMA fill)
+                        if (nb >= 32) {
+                            // one DropPath multiplier for the whole chunk: fold it into the per-chunk constants
+                            const float rg = rsA * gate_j;
+                            float cdg = 0.f;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                float Phi, dgelu;
+                                gelu_terms(u[i] * gate_j, Phi, dgelu);
+                                const float w = v[i] * dgelu;              // dh/rs * gelu'(u g)
+                                cdg = fmaf(w, u[i], cdg);
+                                v[i] = w * rg;                             // du
+                                acc_db += v[i];                            // d bias[j]
+                            }
+                            acc_dg = fmaf(cdg, rsA, acc_dg);               // d gate[j]
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                float Phi, dgelu;
+                                gelu_terms(u[i] * gate_j, Phi, dgelu);
+                                const float tt = v[i] * (i < nb ? rsA : rsB) * dgelu;
+                                acc_dg = fmaf(tt, u[i], acc_dg);
+                                v[i] = tt * gate_j;
+                                acc_db += v[i];
+                            }
+                        }
+                        stage_bf16x32(panel0, et, c & 1, v);
                     }
-                    stage_bf16x32(panel0, et, c & 1, v);
-                    const float sdg = lane_transpose_sum(u);
-                    const float sdu = lane_transpose_sum(v);
-                    scratch0[q * BN + c * 32 + lane] = sdg;
-                    scratch1[q * BN + c * 32 + lane] = sdu;
                 } else if (EPI == EPI_WGRAD) {
                     if (row_ok && nvalid > 0) {
                         float* dst = reinterpret_cast<float*>(g.out0) + size_t(row) * g.ld0 + col0;
@@ -470,21 +536,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         if (Cfg::NOUT == 2) tma_store_2d(&tma_o1, panel0 + PANEL_BYTES, n0 + j * 64, m_blk * BM);
                         bulk_commit();
                     }
+                    // every thread has consumed aux slot `slot` (it was read before the barrier): refill it two panels ahead
+                    if (TMA_OUT == 2 && elected) { fence_proxy_async_smem(); issue_aux(panel_ctr + 2); }
                     ++panel_ctr;
                 }
             }
 
             if (EPI == EPI_FC2_DGRAD) {
-                named_bar_sync(3, EPI_THREADS);
-                for (int col = etid; col < BN; col += EPI_THREADS) {
-                    if (n0 + col < g.N) {
-                        const float a = scratch0[col] + scratch0[BN + col] + scratch0[2 * BN + col] + scratch0[3 * BN + col];
-                        const float b = scratch1[col] + scratch1[BN + col] + scratch1[2 * BN + col] + scratch1[3 * BN + col];
-                        g.colpart0[size_t(m_blk) * g.N + n0 + col] = a;
-                        g.colpart1[size_t(m_blk) * g.N + n0 + col] = b;
-                    }
+                // each thread owns one hidden unit: its token sums of this tile go out as one partial row per (n tile, group)
+                if (row_ok) {
+                    g.colpart0[size_t(n_blk * 2 + grp) * g.M + row] = acc_dg;
+                    g.colpart1[size_t(n_blk * 2 + grp) * g.M + row] = acc_db;
                 }
-                // the next tile's scratch writes happen after its named barrier 1, which every thread reaches after this loop
             }
             if (EPI == EPI_DECODER) {
                 const float s = warp_sum(loss_acc);
@@ -561,7 +624,7 @@ static int launch_gemm_inst(const void* A, int lda, const void* B, int ldb, cons
         if (e != cudaSuccess) return int(e);
         configured = true;
     }
-    CUtensorMap ta, tb, to0, to1;
+    CUtensorMap ta, tb, to0, to1, tx;
     {
         // K-major: tensor [rows, K] row-major -> dims {K, rows}, box {64, 128|BN}
         // MN-major: tensor [K, rows] row-major -> dims {rows, K}, box {64, 64}
@@ -577,7 +640,14 @@ static int launch_gemm_inst(const void* A, int lda, const void* B, int ldb, cons
         str[1] = uint64_t(ldb);
         r = make_tmap_bf16(&tb, B, 2, dims, str, box);
         if (r) return r;
-        to0 = ta; to1 = ta;
+        to0 = ta; to1 = ta; tx = ta;
+        if (TMA_OUT == 2) {
+            const void* xp = (EPI == EPI_STORE) ? static_cast<const void*>(g.res) : static_cast<const void*>(g.aux);
+            dims[0] = g.N; dims[1] = g.M; box[0] = 64; box[1] = BM;
+            str[1] = uint64_t(EPI == EPI_STORE ? g.ldres : g.ldaux);
+            r = make_tmap_bf16(&tx, xp, 2, dims, str, box);
+            if (r) return r;
+        }
         if (TMA_OUT) {
             // bf16 output [M, N] with row pitch ld: box = one swizzled [128 rows][64 cols] panel; the hardware clips
             // rows >= M and columns >= N
@@ -595,7 +665,7 @@ static int launch_gemm_inst(const void* A, int lda, const void* B, int ldb, cons
     const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + BN - 1) / BN;
     const int total = m_tiles * n_tiles * (g.k_splits > 0 ? g.k_splits : 1);
     const int grid = total < num_sms() ? total : num_sms();
-    kfn<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, to0, to1, g);
+    kfn<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, to0, to1, tx, g);
     return int(cudaGetLastError());
 }
 
@@ -639,7 +709,6 @@ int launch_gemm(int epi, int a_mn, int b_mn, int bn_hint, const void* A, int lda
     if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 0;
     int bn = bn_hint > 0 ? bn_hint : pick_bn(g.M, g.N, epi == EPI_WGRAD);
     if (epi == EPI_WGRAD) {
-        if (!(a_mn && b_mn)) return 1003;
         if (g.k_splits <= 0) {
             const int tiles = ((g.M + BM - 1) / BM) * ((g.N + bn - 1) / bn);
             int s = num_sms() / tiles;
@@ -648,31 +717,45 @@ int launch_gemm(int epi, int a_mn, int b_mn, int bn_hint, const void* A, int lda
             if (s > kb) s = kb;
             g.k_splits = s;
         }
-        return launch_gemm_bn<1, 1, EPI_WGRAD, 0>(bn, A, lda, B, ldb, g, stream);
+        // the reduction runs over tokens; operands are either token-major activations (MN-major here) or transposed
+        // hidden activations [hidden, tokens] (K-major here)
+        if (a_mn && b_mn) return launch_gemm_bn<1, 1, EPI_WGRAD, 0>(bn, A, lda, B, ldb, g, stream);
+        if (a_mn) return launch_gemm_bn<1, 0, EPI_WGRAD, 0>(bn, A, lda, B, ldb, g, stream);
+        if (b_mn) return launch_gemm_bn<0, 1, EPI_WGRAD, 0>(bn, A, lda, B, ldb, g, stream);
+        return 1003;
     }
-    if (a_mn) return 1003;
     g.k_splits = 1;
     const bool tma_out = !g.out_fp32 && tma_out_ok(g.out0, g.ld0);
-    if (b_mn) {   // data-gradient GEMMs read the nn.Linear weight [N_out, K_in] directly as an MN-major operand
-        switch (epi) {
-            case EPI_STORE:
-                return tma_out ? launch_gemm_bn<0, 1, EPI_STORE, 1>(bn, A, lda, B, ldb, g, stream)
-                               : launch_gemm_bn<0, 1, EPI_STORE, 0>(bn, A, lda, B, ldb, g, stream);
-            case EPI_FC2_DGRAD:
-                if (!tma_out) return 1005;
-                return launch_gemm_bn<0, 1, EPI_FC2_DGRAD, 1>(bn, A, lda, B, ldb, g, stream);
-            default: return 1003;
-        }
-    }
     switch (epi) {
-        case EPI_STORE:
-            return tma_out ? launch_gemm_bn<0, 0, EPI_STORE, 1>(bn, A, lda, B, ldb, g, stream)
-                           : launch_gemm_bn<0, 0, EPI_STORE, 0>(bn, A, lda, B, ldb, g, stream);
+        case EPI_STORE: {
+            // b_mn: data-gradient GEMMs read the nn.Linear weight [N_out, K_in] directly as an MN-major operand
+            // a_mn: the A operand is a transposed hidden activation [hidden, tokens]
+            // mode 2 (residual tile through TMA) needs a TMA-able residual; otherwise the direct path handles it
+            const int mode = !tma_out ? 0 : (g.res == nullptr ? 1 : (tma_out_ok(g.res, g.ldres) ? 2 : 0));
+#define OFB_STORE_CASE(AM, BMJ)                                                                              \
+            if (mode == 2) return launch_gemm_bn<AM, BMJ, EPI_STORE, 2>(bn, A, lda, B, ldb, g, stream);          \
+            if (mode == 1) return launch_gemm_bn<AM, BMJ, EPI_STORE, 1>(bn, A, lda, B, ldb, g, stream);          \
+            return launch_gemm_bn<AM, BMJ, EPI_STORE, 0>(bn, A, lda, B, ldb, g, stream);
+            if (a_mn && b_mn) { OFB_STORE_CASE(1, 1) }
+            if (a_mn) { OFB_STORE_CASE(1, 0) }
+            if (b_mn) { OFB_STORE_CASE(0, 1) }
+            OFB_STORE_CASE(0, 0)
+#undef OFB_STORE_CASE
+        }
         case EPI_FC1:
+            if (a_mn || b_mn) return 1003;
             if (!tma_out || !tma_out_ok(g.out1, g.ld1)) return 1005;
             return launch_gemm_bn<0, 0, EPI_FC1, 1>(bn, A, lda, B, ldb, g, stream);
-        case EPI_PATCH:     return launch_gemm_bn<0, 0, EPI_PATCH, 0>(bn, A, lda, B, ldb, g, stream);
-        case EPI_DECODER:   return launch_gemm_bn<0, 0, EPI_DECODER, 0>(bn, A, lda, B, ldb, g, stream);
+        case EPI_FC2_DGRAD:
+            if (!a_mn || b_mn) return 1003;
+            if (!tma_out || !tma_out_ok(g.aux, g.ldaux)) return 1005;
+            return launch_gemm_bn<1, 0, EPI_FC2_DGRAD, 2>(bn, A, lda, B, ldb, g, stream);
+        case EPI_PATCH:
+            if (a_mn || b_mn) return 1003;
+            return launch_gemm_bn<0, 0, EPI_PATCH, 0>(bn, A, lda, B, ldb, g, stream);
+        case EPI_DECODER:
+            if (a_mn || b_mn) return 1003;
+            return launch_gemm_bn<0, 0, EPI_DECODER, 0>(bn, A, lda, B, ldb, g, stream);
         default: return 1004;
     }
 }

@@ -8,8 +8,9 @@ namespace ofb {
 enum GemmEpilogue : int {
     EPI_STORE = 0,      // out0 = rowscale*(acc + bias)*colscale + res           (bf16 or fp32 out)
                         //   (bias_rowscaled: out0 = (acc + rowscale*bias)*colscale + res)
-    EPI_FC1 = 1,        // out0 = u = acc + bias ; out1 = rowscale * gelu(u * colscale)       (bi-masked fc1, layers.py:845-861)
-    EPI_FC2_DGRAD = 2,  // dh = rowscale*acc ; du = dh*gelu'(u*g)*g -> out0 ; column partials of dgate, dbias
+    EPI_FC1 = 1,        // TRANSPOSED hidden layout (rows = hidden units, columns = tokens):
+                        //   out0 = u^T = acc + bias[row] ; out1 = h^T = rowscale[col] * gelu(u^T * gate[row])   (layers.py:845-861)
+    EPI_FC2_DGRAD = 2,  // transposed: dh = rowscale[col]*acc ; du^T = dh*gelu'(u g)*g -> out0 ; per-row token sums of d gate, d bias
     EPI_WGRAD = 3,      // out0(fp32) += scale * acc   (split-K, red.global.add)
     EPI_PATCH = 4,      // patch-embed: gate, pos-embed, PMIM mask-token select, row remap (skip cls row)
     EPI_DECODER = 5,    // PMIM decoder: x_rec = acc + bias ; masked L1 vs normalised target ; sign*mask -> out0
@@ -29,8 +30,8 @@ struct GemmArgs {
     int rows_per_scale;
     const __nv_bfloat16* res; int ldres;   // residual or null
     const __nv_bfloat16* aux; int ldaux;   // EPI_FC2_DGRAD: saved pre-gate fc1 output u
-    float* colpart0;        // [m_tiles][N] column partial sums (dgate)  / EPI_DECODER: [tiles*8] loss partials (one per epilogue warp)
-    float* colpart1;        // [m_tiles][N] column partial sums (dbias)
+    float* colpart0;        // EPI_FC2_DGRAD: [2 * n_tiles][M] token-sum partials of d gate[row]  / EPI_DECODER: [tiles*8] loss partials (one per epilogue warp)
+    float* colpart1;        // EPI_FC2_DGRAD: [2 * n_tiles][M] token-sum partials of d bias[row]
     const float* scale_ptr; // EPI_WGRAD / EPI_STORE: optional device scalar multiplied into acc
     // EPI_PATCH / EPI_DECODER
     const float* pos;        // [tokens+1, N] fp32 positional embedding (row 0 = cls)

@@ -10,7 +10,8 @@ HBM layout
   * parameters, gradients, Adam m / v: four fp32 arenas with identical layout, tensors ordered by optimizer group
     [param no-decay | param decay | decoder no-decay | decoder decay | arch] (search.py:486-559) so one fused AdamW
     launch covers everything; a bf16 shadow arena (same offsets) feeds the GEMMs.
-  * activations: bf16, token-major [B*197, C]; per block the backward keeps x_in, LN stats, x1, qkv, lse, o, x2, x3, u, h.
+  * activations: bf16, token-major [B*197, C] except the MLP hidden activations u, h, du which are kept transposed
+    [hidden, B*197]; per block the backward keeps x_in, LN stats, x1, qkv, lse, o, x2, x3, u, h.
   * nn.Linear weights are used as stored ([out, in]) by forward (K-major B operand), data-gradient (MN-major B operand)
     and weight-gradient GEMMs (MN-major A/B operands) - no transposed copies exist.
 There is no CPU path: every op goes through the C ABI in libofb_b200.so.
@@ -223,6 +224,11 @@ class SearchStepEngine:
         dpr = torch.linspace(0, drop_path_rate, depth).repeat_interleave(2)
         self.drop_prob = dpr.to(self.dev)
         self.drop_scale = torch.ones(depth * 2, B, **f32)
+        # MLP hidden activations are kept TRANSPOSED, [hidden, tokens] with the token pitch padded to 16 bytes: the fc1 /
+        # fc2-dgrad epilogue threads then own one hidden unit each (gate, bias and their gradients are per-thread scalars)
+        self.ldT = (M + 7) // 8 * 8
+        self.mlp_bn = 256
+        self.mlp_parts = 2 * ((M + self.mlp_bn - 1) // self.mlp_bn)
         self.xs = [torch.zeros(M, D, **bf) for _ in range(depth + 1)]      # xs[l] = input of block l; xs[depth] = output
         self.blk = []
         for _ in range(depth):
@@ -230,7 +236,7 @@ class SearchStepEngine:
                 mean1=torch.empty(M, **f32), rstd1=torch.empty(M, **f32), x1=torch.empty(M, D, **bf),
                 qkv=torch.empty(M, 3 * D, **bf), lse=torch.empty(B, H, T, **f32), o=torch.empty(M, D, **bf),
                 x2=torch.empty(M, D, **bf), mean2=torch.empty(M, **f32), rstd2=torch.empty(M, **f32),
-                x3=torch.empty(M, D, **bf), u=torch.empty(M, hid, **bf), h=torch.empty(M, hid, **bf)))
+                x3=torch.empty(M, D, **bf), u=torch.empty(hid, self.ldT, **bf), h=torch.empty(hid, self.ldT, **bf)))
         self.meanf, self.rstdf = torch.empty(M, **f32), torch.empty(M, **f32)
         self.latent = torch.empty(M, D, **bf)
         self.logits = torch.empty(B, self.C, **f32)
@@ -242,17 +248,17 @@ class SearchStepEngine:
         self.scal = torch.zeros(8, **f32)
         # backward scratch
         self.gA, self.gB, self.gC = (torch.empty(M, D, **bf) for _ in range(3))
-        self.du = torch.empty(M, hid, **bf)
+        self.du = torch.empty(hid, self.ldT, **bf)
         self.dqkv = torch.empty(M, 3 * D, **bf)
         self.dconv = torch.empty(ML, D, **bf)
         self.ln_parts = ops.layernorm_bwd_parts(M)
         self.pg_, self.pb_, self.pd_ = (torch.empty(self.ln_parts, D, **f32) for _ in range(3))
         mt = (M + 127) // 128
-        self.cp0, self.cp1 = torch.empty(mt, hid, **f32), torch.empty(mt, hid, **f32)
+        self.cp0, self.cp1 = torch.empty(self.mlp_parts, hid, **f32), torch.empty(self.mlp_parts, hid, **f32)
         self.att_pg, self.att_pb = torch.empty(B, D, **f32), torch.empty(B, 3 * D, **f32)
         self.e_gx, self.e_pos, self.e_mt = (torch.empty(T, D, **f32) for _ in range(3))
         self.rand_u = torch.empty(B * self.L + depth * 2 * B, **f32)
-        self._graph = None
+        self._graphs = {}          # (images ptr, labels ptr, keep) -> (CUDAGraph, kernel launches per replay)
 
     # ------------------------------------------------------------------------------------------------------------
     def _param_shapes(self):
@@ -382,11 +388,12 @@ class SearchStepEngine:
                      res=a["x1"])
             ops.layernorm_fwd(a["x2"], self.p(pre + "norm2.weight"), self.p(pre + "norm2.bias"), a["x3"], a["mean2"],
                               a["rstd2"], self.eps_ln)
-            ops.gemm(ops.EPI_FC1, a["x3"], self.w(pre + "mlp.fc1.weight"), M=M, N=hid, K=D, out0=a["u"], out1=a["h"],
-                     bias=self.p(pre + "mlp.fc1.bias"), colscale=g_m, rowscale=dp2, rows_per_scale=T)
+            # fc1 computes the transposed hidden activations u^T, h^T = [hidden, tokens] (weight is the M operand)
+            ops.gemm(ops.EPI_FC1, self.w(pre + "mlp.fc1.weight"), a["x3"], M=hid, N=M, K=D, out0=a["u"], out1=a["h"],
+                     bias=self.p(pre + "mlp.fc1.bias"), colscale=g_m, rowscale=dp2, rows_per_scale=T, bn=self.mlp_bn)
             ops.gemm(ops.EPI_STORE, a["h"], self.w(pre + "mlp.fc2.weight"), M=M, N=D, K=hid, out0=self.xs[l + 1],
                      bias=self.p(pre + "mlp.fc2.bias"), rowscale=dp2, rows_per_scale=T, bias_rowscaled=True,
-                     res=a["x3"])
+                     res=a["x3"], a_mn=True)
         ops.layernorm_fwd(self.xs[self.depth], self.p("norm.weight"), self.p("norm.bias"), self.latent, self.meanf,
                           self.rstdf, self.eps_ln)
         # head on the cls rows (row stride T*D), label-smoothing CE
@@ -438,16 +445,17 @@ class SearchStepEngine:
             dp1, dp2 = self.drop_scale[2 * l], self.drop_scale[2 * l + 1]
             G4 = G
             # fc2: weight grad (h already carries DropPath), data grad fused with GELU' / gate / column partials
-            ops.gemm(ops.EPI_WGRAD, G4, a["h"], M=D, N=hid, K=M, out0=self.g(pre + "mlp.fc2.weight"), a_mn=True, b_mn=True)
-            ops.gemm(ops.EPI_FC2_DGRAD, G4, self.w(pre + "mlp.fc2.weight"), M=M, N=hid, K=D, out0=self.du, aux=a["u"],
-                     colscale=g_m, rowscale=dp2, rows_per_scale=T, colpart0=self.cp0, colpart1=self.cp1, b_mn=True)
+            ops.gemm(ops.EPI_WGRAD, G4, a["h"], M=D, N=hid, K=M, out0=self.g(pre + "mlp.fc2.weight"), a_mn=True)
+            ops.gemm(ops.EPI_FC2_DGRAD, self.w(pre + "mlp.fc2.weight"), G4, M=hid, N=M, K=D, out0=self.du, aux=a["u"],
+                     colscale=g_m, rowscale=dp2, rows_per_scale=T, colpart0=self.cp0, colpart1=self.cp1, a_mn=True,
+                     bn=self.mlp_bn)
             m_off = bm.modules[i_m]["gate_off"]
-            mlp_jobs = [dict(part=self.cp0, R=mt, N=hid, out=self.dgate[m_off:m_off + hid], accumulate=False),
-                        dict(part=self.cp1, R=mt, N=hid, out=self.g(pre + "mlp.fc1.bias"))]
-            ops.gemm(ops.EPI_WGRAD, self.du, a["x3"], M=hid, N=D, K=M, out0=self.g(pre + "mlp.fc1.weight"), a_mn=True,
-                     b_mn=True)
+            mlp_jobs = [dict(part=self.cp0, R=self.mlp_parts, N=hid, out=self.dgate[m_off:m_off + hid], accumulate=False),
+                        dict(part=self.cp1, R=self.mlp_parts, N=hid, out=self.g(pre + "mlp.fc1.bias"))]
+            ops.gemm(ops.EPI_WGRAD, self.du, a["x3"], M=hid, N=D, K=M, out0=self.g(pre + "mlp.fc1.weight"), b_mn=True)
             G3 = spare.pop()
-            ops.gemm(ops.EPI_STORE, self.du, self.w(pre + "mlp.fc1.weight"), M=M, N=D, K=hid, out0=G3, b_mn=True, res=G4)
+            ops.gemm(ops.EPI_STORE, self.du, self.w(pre + "mlp.fc1.weight"), M=M, N=D, K=hid, out0=G3, a_mn=True, b_mn=True,
+                     res=G4)
             spare.append(G4)
             # LayerNorm 2 (+ proj bias grad)
             G2 = spare.pop()
@@ -518,6 +526,47 @@ class SearchStepEngine:
         ops.adamw(self.params, self.grads, self.adam_m, self.adam_v, self.shadow, self.hyper, self._seg_end_c,
                   zero_grad=True)
         self.step_count += 1
+
+    def step_graphed(self, images, labels, lrs=None):
+        """One full search step replayed from a CUDA graph (forward, backward, AdamW; the whole step is ~270 launches of
+        ~10-200 us, so per-launch host work would otherwise bound it). The graph is captured on first use for this
+        (images buffer, labels buffer, PMIM keep count) and re-captured when the schedule changes the keep count; lr, AdamW
+        bias corrections and w_p are read from the device-side `hyper` vector, so they may change every step. Random draws
+        (PMIM noise, DropPath) come from torch's graph-safe generator. Multi-GPU: the all-reduce and the update stay
+        outside the graph (see step())."""
+        keep = int(self.L * self.keep_ratio)
+        key = (images.data_ptr(), labels.data_ptr(), keep)
+        self._fill_hyper(lrs)
+        self.hyper.copy_(self.hyper_host, non_blocking=True)
+        entry = self._graphs.get(key)
+        if entry is None:
+            # warm-up outside capture: first launches configure kernel attributes and load modules
+            cur = torch.cuda.current_stream(self.dev)
+            side = torch.cuda.Stream(device=self.dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                self.forward(images, labels)
+                self.backward()
+                self.grads.zero_()
+            cur.wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            n0 = ops.LAUNCHES
+            with torch.cuda.graph(graph):
+                self.forward(images, labels)
+                self.backward()
+                if self.world <= 1:
+                    ops.adamw(self.params, self.grads, self.adam_m, self.adam_v, self.shadow, self.hyper, self._seg_end_c,
+                              zero_grad=True)
+            entry = (graph, ops.LAUNCHES - n0)
+            self._graphs[key] = entry
+        entry[0].replay()
+        ops._count(entry[1])
+        if self.world > 1:
+            self.allreduce_grads()
+            ops.adamw(self.params, self.grads, self.adam_m, self.adam_v, self.shadow, self.hyper, self._seg_end_c,
+                      zero_grad=True)
+        self.step_count += 1
+        return self.scal
 
     def step(self, images, labels, noise=None, drop_u=None, update=True, lrs=None):
         """One full search step; returns the device tensor scal = [base, arch, decoder, total, w_dec, ...]."""

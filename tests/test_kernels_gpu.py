@@ -72,33 +72,51 @@ def test_gemm_strided_rows(cuda_dev):
 
 
 def test_gemm_fc1_and_fc2_dgrad(cuda_dev):
+    """bi-masked MLP (layers.py:845-863) with the hidden activations kept transposed [hidden, tokens]."""
     from ofb_b200 import ops
     torch.manual_seed(2)
-    M, D, Hd = 1576, 384, 1536
+    M, D, Hd = 1571, 384, 1536            # ragged token count: the token pitch is padded to 8
+    ldT = (M + 7) // 8 * 8
     x, W1 = rnd(M, D), rnd(Hd, D, s=0.05)
     b1, gate = torch.randn(Hd, device="cuda") * 0.1, torch.rand(Hd, device="cuda") + 0.3
     rs = (torch.rand((M + 196) // 197, device="cuda") > 0.3).float() / 0.7
     rows = torch.arange(M, device="cuda") // 197
-    u = torch.empty(M, Hd, device="cuda", dtype=torch.bfloat16)
-    h = torch.empty_like(u)
-    ops.gemm(ops.EPI_FC1, x, W1, M=M, N=Hd, K=D, out0=u, out1=h, bias=b1, colscale=gate, rowscale=rs, rows_per_scale=197)
+    u = torch.zeros(Hd, ldT, device="cuda", dtype=torch.bfloat16)
+    h = torch.zeros_like(u)
+    ops.gemm(ops.EPI_FC1, W1, x, M=Hd, N=M, K=D, out0=u, out1=h, bias=b1, colscale=gate, rowscale=rs, rows_per_scale=197, bn=256)
     ru = x.float() @ W1.float().t() + b1
-    assert rel(u, ru) < BF16_TOL
-    assert rel(h, rs[rows, None] * F.gelu(ru * gate)) < BF16_TOL
-    # backward of  y = gelu(u*g) @ W2^T  scaled by rs :  dh = rs * (dy @ W2)
+    assert rel(u[:, :M].t(), ru) < BF16_TOL
+    assert rel(h[:, :M].t(), rs[rows, None] * F.gelu(ru * gate)) < BF16_TOL
+    # (the pad columns M..ldT may be written: TMA clips stores at 16-byte granularity; every consumer bounds tokens by M)
+    # fc2 forward consumes h^T as an MN-major A operand
     W2 = rnd(D, Hd, s=0.05)
+    res = rnd(M, D)
+    y = torch.empty(M, D, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(ops.EPI_STORE, h, W2, M=M, N=D, K=Hd, out0=y, res=res, a_mn=True)
+    assert rel(y, h[:, :M].t().float() @ W2.float().t() + res.float()) < BF16_TOL
+    # backward of  y = rs * gelu(u*g) @ W2^T :  dh = rs * (dy @ W2)
     dy = rnd(M, D)
-    du = torch.empty_like(u)
-    mt = (M + 127) // 128
-    p0, p1 = torch.zeros(mt, Hd, device="cuda"), torch.zeros(mt, Hd, device="cuda")
-    ops.gemm(ops.EPI_FC2_DGRAD, dy, W2, M=M, N=Hd, K=D, out0=du, aux=u, colscale=gate, rowscale=rs, rows_per_scale=197,
-             colpart0=p0, colpart1=p1, b_mn=True)
-    uf = u.float().requires_grad_(True)
+    du = torch.zeros_like(u)
+    R = 2 * ((M + 255) // 256)
+    p0, p1 = torch.zeros(R, Hd, device="cuda"), torch.zeros(R, Hd, device="cuda")
+    ops.gemm(ops.EPI_FC2_DGRAD, W2, dy, M=Hd, N=M, K=D, out0=du, aux=u, colscale=gate, rowscale=rs, rows_per_scale=197,
+             colpart0=p0, colpart1=p1, a_mn=True, bn=256)
+    uf = u[:, :M].t().float().requires_grad_(True)
     gf = gate.clone().requires_grad_(True)
     F.gelu(uf * gf).backward(rs[rows, None] * (dy.float() @ W2.float()))
-    assert rel(du, uf.grad) < BF16_TOL
+    assert rel(du[:, :M].t(), uf.grad) < BF16_TOL
     assert rel(p0.sum(0), gf.grad) < 1e-3
-    assert rel(p1.sum(0), du.float().sum(0)) < 1e-2
+    assert rel(p1.sum(0), uf.grad.sum(0)) < 1e-3
+    # weight gradients / data gradient with the transposed operands
+    dW2 = torch.zeros(D, Hd, device="cuda")
+    ops.gemm(ops.EPI_WGRAD, dy, h, M=D, N=Hd, K=M, out0=dW2, a_mn=True)
+    assert rel(dW2, dy.float().t() @ h[:, :M].t().float()) < 1e-3
+    dW1 = torch.zeros(Hd, D, device="cuda")
+    ops.gemm(ops.EPI_WGRAD, du, x, M=Hd, N=D, K=M, out0=dW1, b_mn=True)
+    assert rel(dW1, du[:, :M].float() @ x.float()) < 1e-3
+    dx = torch.empty(M, D, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(ops.EPI_STORE, du, W1, M=M, N=D, K=Hd, out0=dx, a_mn=True, b_mn=True, res=res)
+    assert rel(dx, du[:, :M].t().float() @ W1.float() + res.float()) < BF16_TOL
 
 
 @pytest.mark.parametrize("R,NO,KI", [(128, 128, 128), (1576, 1536, 384), (1576, 1000, 384), (1576, 384, 768)])
