@@ -22,7 +22,7 @@ from typing import Dict, List, Optional
 
 import torch
 
-from . import ops
+from . import dp, ops
 from ._lib import BimaskModule
 
 T_PAD = 8   # arena tensors start at multiples of 8 elements (16 B in bf16, 32 B in fp32)
@@ -258,6 +258,7 @@ class SearchStepEngine:
         self.att_pg, self.att_pb = torch.empty(B, D, **f32), torch.empty(B, 3 * D, **f32)
         self.e_gx, self.e_pos, self.e_mt = (torch.empty(T, D, **f32) for _ in range(3))
         self.rand_u = torch.empty(B * self.L + depth * 2 * B, **f32)
+        self._dp_bounds = dp.bucket_bounds(self.n_arena)
         self._graphs = {}          # (images ptr, labels ptr, keep) -> (CUDAGraph, kernel launches per replay)
 
     # ------------------------------------------------------------------------------------------------------------
@@ -511,16 +512,8 @@ class SearchStepEngine:
 
     # ------------------------------------------------------------------------------------------------------------
     def allreduce_grads(self):
-        """Data-parallel mean of every gradient (DDP, search.py:619): one NCCL all-reduce per optimizer-group slab of the
-        flat gradient arena."""
-        if self.world <= 1:
-            return
-        lo = 0
-        for hi in self.seg_end:
-            if hi > lo:
-                torch.distributed.all_reduce(self.grads[lo:hi], group=self.pg)
-            lo = hi
-        self.grads.mul_(1.0 / self.world)
+        """Data-parallel mean of every gradient (DDP, search.py:619): a few large NCCL all-reduces over the flat arena."""
+        dp.allreduce_arena(self.grads, self.world, self.pg, self._dp_bounds)
 
     def optimizer_step(self):
         ops.adamw(self.params, self.grads, self.adam_m, self.adam_v, self.shadow, self.hyper, self._seg_end_c,
