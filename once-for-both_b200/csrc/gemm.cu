@@ -34,9 +34,13 @@ struct GemmCfg {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int NOUT = (EPI == EPI_FC1) ? 2 : 1;
     static constexpr int STAGING_BYTES = TMA_OUT ? 2 * NOUT * PANEL_BYTES : 0;          // two slots
-    static constexpr int AUX_BYTES = (TMA_OUT == 2) ? 2 * PANEL_BYTES : 0;              // two TMA-loaded residual / saved-activation panels
+    // TMA-loaded residual / saved-activation panels: the ring holds about one tile of panels so that the load of a panel is
+    // issued a whole tile time before its use (HBM latency is ~3 panel times)
+    static constexpr int AUX_SLOTS = (TMA_OUT != 2) ? 0 : (BN == 128 ? 3 : (BN == 192 ? 4 : ((BN == 256 && EPI == EPI_FC2_DGRAD) ? 3 : 2)));
+    static constexpr int AUX_BYTES = AUX_SLOTS * PANEL_BYTES;
     static constexpr int SCRATCH_BYTES = 0;
-    static constexpr int VEC_BYTES = 2 * 2 * BN * 4;        // per-column epilogue vectors, double-buffered by tile parity
+    // per-column epilogue vectors, double-buffered by tile parity (the transposed-hidden epilogues use per-thread scalars)
+    static constexpr int VEC_BYTES = (EPI == EPI_FC1 || EPI == EPI_FC2_DGRAD) ? 0 : 2 * 2 * BN * 4;
     static constexpr int BAR_BYTES = 256;
     static constexpr int FIXED = STAGING_BYTES + AUX_BYTES + SCRATCH_BYTES + VEC_BYTES + BAR_BYTES;
     static constexpr int STAGES_RAW = (SMEM_LIMIT - FIXED) / STAGE_BYTES;
@@ -44,7 +48,7 @@ struct GemmCfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED;
     static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
     static_assert(STAGES >= 3, "pipeline too shallow");
-    static_assert((2 * STAGES + 6) * 8 + 8 <= BAR_BYTES, "barrier block too small");
+    static_assert((2 * STAGES + 4 + 4) * 8 + 8 <= BAR_BYTES, "barrier block too small");
 };
 
 // 32 values per lane -> lane L ends with the sum over lanes of v[L] (31 shuffles).
@@ -146,6 +150,22 @@ __device__ __forceinline__ void stage_bf16x32(uint32_t panel, int row, int half,
     }
 }
 
+// same for 16 packed pairs
+__device__ __forceinline__ void stage_bf16x32_p(uint32_t panel, int row, int half, const float2 (&v)[16]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t a = panel + sw128_offset(row, half * 4 + i);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf16x2(v[4 * i].x, v[4 * i].y)),
+                     "r"(pack_bf16x2(v[4 * i + 1].x, v[4 * i + 1].y)), "r"(pack_bf16x2(v[4 * i + 2].x, v[4 * i + 2].y)),
+                     "r"(pack_bf16x2(v[4 * i + 3].x, v[4 * i + 3].y))
+                     : "memory");
+    }
+}
+__device__ __forceinline__ uint32_t packed_word(const Packed32& r, int i) {
+    const uint4& q = r.p[i >> 2];
+    return (i & 3) == 0 ? q.x : ((i & 3) == 1 ? q.y : ((i & 3) == 2 ? q.z : q.w));
+}
+
 // TMA_OUT: 0 = direct global stores; 1 = bf16 output panels staged in smem and written by TMA; 2 = 1 + the residual (STORE) /
 // saved activation (FC2_DGRAD) tile is TMA-loaded into smem panels two panels ahead of its use.
 template <int BN, int A_MN, int B_MN, int EPI, int TMA_OUT>
@@ -173,8 +193,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     uint64_t* empty_bar = bars + STAGES;          // [STAGES]
     uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]
     uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]
-    uint64_t* aux_full = bars + 2 * STAGES + 4;   // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
+    uint64_t* aux_full = bars + 2 * STAGES + 4;   // [AUX_SLOTS <= 4]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
+    constexpr uint32_t AUX_SLOTS = Cfg::AUX_SLOTS > 0 ? Cfg::AUX_SLOTS : 1;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -184,7 +205,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
         if (TMA_OUT) { tma_prefetch_desc(&tma_o0); if (Cfg::NOUT == 2) tma_prefetch_desc(&tma_o1); }
-        if (TMA_OUT == 2) { tma_prefetch_desc(&tma_aux); mbar_init(smem_u32(&aux_full[0]), 1); mbar_init(smem_u32(&aux_full[1]), 1); }
+        if (TMA_OUT == 2) {
+            tma_prefetch_desc(&tma_aux);
+            for (uint32_t i = 0; i < AUX_SLOTS; ++i) mbar_init(smem_u32(&aux_full[i]), 1);
+        }
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(smem_u32(&full_bar[i]), 1);
             mbar_init(smem_u32(&empty_bar[i]), 1);
@@ -290,18 +314,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         const bool elected = (etid == 0);
         int it = 0;
         uint32_t panel_ctr = 0;
-        // TMA_OUT == 2: panel number P of this CTA (tile sequence P / NPT, panel P % NPT) is loaded into aux slot P & 1
+        // TMA_OUT == 2: panel number P of this CTA (tile sequence P / NPT, panel P % NPT) is loaded into aux slot P % AUX_SLOTS
         constexpr uint32_t NPT = NCHUNK / 2;
         auto issue_aux = [&](uint32_t P) {
             const long t2 = long(blockIdx.x) + long(P / NPT) * gridDim.x;
             if (t2 >= total_tiles) return;
             const int mn2 = int(t2 % (long(m_tiles) * n_tiles));      // k_splits == 1 for these epilogues
             const int m2 = M_FAST ? mn2 % m_tiles : mn2 / n_tiles, n2 = M_FAST ? mn2 / m_tiles : mn2 % n_tiles;
-            const uint32_t fb = smem_u32(&aux_full[P & 1u]);
+            const uint32_t fb = smem_u32(&aux_full[P % AUX_SLOTS]);
             mbar_arrive_expect_tx(fb, PANEL_BYTES);
-            tma_load_2d(smem_u32(auxbuf) + (P & 1u) * PANEL_BYTES, &tma_aux, fb, n2 * BN + int(P % NPT) * 64, m2 * BM);
+            tma_load_2d(smem_u32(auxbuf) + (P % AUX_SLOTS) * PANEL_BYTES, &tma_aux, fb, n2 * BN + int(P % NPT) * 64, m2 * BM);
         };
-        if (TMA_OUT == 2 && elected) { issue_aux(0); issue_aux(1); }
+        if (TMA_OUT == 2 && elected) {
+            for (uint32_t i = 0; i < AUX_SLOTS; ++i) issue_aux(i);
+        }
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const int split = t / (m_tiles * n_tiles);
             const int mn = t % (m_tiles * n_tiles);
@@ -383,8 +409,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 const uint32_t panel0 = smem_u32(staging) + slot * (Cfg::NOUT * PANEL_BYTES);
                 Packed32 ax;       // this row's 32 residual / saved-activation values of the chunk (TMA-loaded panel)
                 if (TMA_OUT == 2) {
-                    mbar_wait(smem_u32(&aux_full[slot]), (panel_ctr >> 1) & 1u);
-                    const uint32_t ab = smem_u32(auxbuf) + slot * PANEL_BYTES;
+                    const uint32_t aslot = panel_ctr % AUX_SLOTS;
+                    mbar_wait(smem_u32(&aux_full[aslot]), (panel_ctr / AUX_SLOTS) & 1u);
+                    const uint32_t ab = smem_u32(auxbuf) + aslot * PANEL_BYTES;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const uint32_t ad = ab + sw128_offset(et, (c & 1) * 4 + i);
@@ -396,14 +423,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 if (EPI == EPI_STORE) {
                     const float brs = g.bias_rowscaled ? rs : 1.f;
                     const float ars = (g.bias_rowscaled ? 1.f : rs) * gs;
-                    float r[32];
                     const bool has_res = (TMA_OUT == 2) || (TMA_OUT == 0 && g.res != nullptr);
-                    if (TMA_OUT == 2) unpack32(ax, r);
-                    else if (has_res) unpack32(pre[j], r);
+                    const float2 brs2 = splat2(brs), ars2 = splat2(ars);
+                    const float2* cs2 = reinterpret_cast<const float2*>(cs);
+                    const float2* cb2 = reinterpret_cast<const float2*>(cb);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float tt = fmaf(v[i], cs[i], brs * cb[i]);
-                        v[i] = has_res ? fmaf(ars, tt, r[i]) : ars * tt;
+                    for (int i = 0; i < 16; ++i) {
+                        const float2 tt = fma2(make_float2(v[2 * i], v[2 * i + 1]), cs2[i], mul2(brs2, cb2[i]));
+                        float2 o;
+                        if (has_res) o = fma2(ars2, tt, unpack_bf16x2(packed_word(TMA_OUT == 2 ? ax : pre[j], i)));
+                        else o = mul2(ars2, tt);
+                        v[2 * i] = o.x; v[2 * i + 1] = o.y;
                     }
                     if (TMA_OUT) {
                         stage_bf16x32(panel0, et, c & 1, v);
@@ -423,51 +453,61 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         rsB = __ldg(g.rowscale + min(b0 + 1, last));
                     }
                     if (EPI == EPI_FC1) {
-                        float h[32];
+                        // packed fp32x2 math: the epilogue is fma-pipe bound (see ptx.cuh)
+                        float2 u2[16], h2[16];
+                        const float2 b2 = splat2(bias_j), g2 = splat2(gate_j);
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            v[i] += bias_j;
-                            const float z = v[i] * gate_j;
-                            h[i] = z * gelu_cdf(z);
+                        for (int i = 0; i < 16; ++i) {
+                            u2[i] = add2(make_float2(v[2 * i], v[2 * i + 1]), b2);
+                            const float2 z = mul2(u2[i], g2);
+                            h2[i] = mul2(z, gelu_cdf2(z));
                         }
                         if (nb >= 32) {
+                            const float2 r2 = splat2(rsA);
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) h[i] *= rsA;
+                            for (int i = 0; i < 16; ++i) h2[i] = mul2(h2[i], r2);
                         } else {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) h[i] *= (i < nb ? rsA : rsB);
+                            for (int i = 0; i < 16; ++i)
+                                h2[i] = mul2(h2[i], make_float2(2 * i < nb ? rsA : rsB, 2 * i + 1 < nb ? rsA : rsB));
                         }
-                        stage_bf16x32(panel0, et, c & 1, v);
-                        stage_bf16x32(panel0 + PANEL_BYTES, et, c & 1, h);
+                        stage_bf16x32_p(panel0, et, c & 1, u2);
+                        stage_bf16x32_p(panel0 + PANEL_BYTES, et, c & 1, h2);
                     } else {
-                        float u[32];
-                        unpack32(ax, u);               // saved pre-gate fc1 output; zero for rows / tokens out of range (TMA fill)
+                        // saved pre-gate fc1 output u (zero for rows / tokens out of range: TMA fill)
+                        float2 du2[16];
+                        float2 cdg2 = splat2(0.f), cdb2 = splat2(0.f);
+                        const float2 g2 = splat2(gate_j);
                         if (nb >= 32) {
                             // one DropPath multiplier for the whole chunk: fold it into the per-chunk constants
-                            const float rg = rsA * gate_j;
-                            float cdg = 0.f;
+                            const float2 rg2 = splat2(rsA * gate_j);
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                float Phi, dgelu;
-                                gelu_terms(u[i] * gate_j, Phi, dgelu);
-                                const float w = v[i] * dgelu;              // dh/rs * gelu'(u g)
-                                cdg = fmaf(w, u[i], cdg);
-                                v[i] = w * rg;                             // du
-                                acc_db += v[i];                            // d bias[j]
+                            for (int i = 0; i < 16; ++i) {
+                                const float2 u = unpack_bf16x2(packed_word(ax, i));
+                                float2 Phi, dgelu;
+                                gelu_terms2(mul2(u, g2), Phi, dgelu);
+                                const float2 w = mul2(make_float2(v[2 * i], v[2 * i + 1]), dgelu);     // dh/rs * gelu'(u g)
+                                cdg2 = fma2(w, u, cdg2);
+                                du2[i] = mul2(w, rg2);                                                // du
+                                cdb2 = add2(cdb2, du2[i]);                                            // d bias[j]
                             }
-                            acc_dg = fmaf(cdg, rsA, acc_dg);               // d gate[j]
+                            acc_dg = fmaf(cdg2.x + cdg2.y, rsA, acc_dg);                              // d gate[j]
                         } else {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                float Phi, dgelu;
-                                gelu_terms(u[i] * gate_j, Phi, dgelu);
-                                const float tt = v[i] * (i < nb ? rsA : rsB) * dgelu;
-                                acc_dg = fmaf(tt, u[i], acc_dg);
-                                v[i] = tt * gate_j;
-                                acc_db += v[i];
+                            for (int i = 0; i < 16; ++i) {
+                                const float2 u = unpack_bf16x2(packed_word(ax, i));
+                                float2 Phi, dgelu;
+                                gelu_terms2(mul2(u, g2), Phi, dgelu);
+                                const float2 rs2 = make_float2(2 * i < nb ? rsA : rsB, 2 * i + 1 < nb ? rsA : rsB);
+                                const float2 w = mul2(mul2(make_float2(v[2 * i], v[2 * i + 1]), rs2), dgelu);
+                                cdg2 = fma2(w, u, cdg2);
+                                du2[i] = mul2(w, g2);
+                                cdb2 = add2(cdb2, du2[i]);
                             }
+                            acc_dg += cdg2.x + cdg2.y;
                         }
-                        stage_bf16x32(panel0, et, c & 1, v);
+                        acc_db += cdb2.x + cdb2.y;
+                        stage_bf16x32_p(panel0, et, c & 1, du2);
                     }
                 } else if (EPI == EPI_WGRAD) {
                     if (row_ok && nvalid > 0) {
@@ -536,8 +576,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         if (Cfg::NOUT == 2) tma_store_2d(&tma_o1, panel0 + PANEL_BYTES, n0 + j * 64, m_blk * BM);
                         bulk_commit();
                     }
-                    // every thread has consumed aux slot `slot` (it was read before the barrier): refill it two panels ahead
-                    if (TMA_OUT == 2 && elected) { fence_proxy_async_smem(); issue_aux(panel_ctr + 2); }
+                    // every thread has consumed this panel's aux slot (it was read before the barrier): refill it AUX_SLOTS panels ahead
+                    if (TMA_OUT == 2 && elected) { fence_proxy_async_smem(); issue_aux(panel_ctr + AUX_SLOTS); }
                     ++panel_ctr;
                 }
             }
@@ -684,8 +724,10 @@ static int pick_bn(int M, int N, int splits_ok) {
             cost = double(tiles) * bn * (bn <= 64 ? 2.0 : (bn <= 128 ? 1.25 : 1.0));
             if (tiles > num_sms()) cost *= double((tiles + num_sms() - 1) / num_sms()) * num_sms() / tiles;
         } else {
+            // measured (tools/gemm_microbench.py): a 128-wide tile is shared-memory-bandwidth bound (A is re-read for every
+            // MMA and the TMA fill competes with it), 192 / 256 reach 1.25x / 1.35x its main-loop rate
             const long waves = (tiles + num_sms() - 1) / num_sms();
-            cost = double(waves) * bn * (bn <= 64 ? 1.5 : (bn <= 128 ? 1.10 : 1.0));
+            cost = double(waves) * bn * (bn <= 64 ? 1.9 : (bn <= 128 ? 1.30 : (bn <= 192 ? 1.05 : 1.0)));
         }
         if (cost < best_cost) { best_cost = cost; best = bn; }
     }

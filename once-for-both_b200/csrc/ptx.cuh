@@ -245,6 +245,46 @@ __device__ __forceinline__ float gelu_cdf(float z) {
     const float y = fast_rcp(p);                 // erfc(|z|/sqrt2) / 2  (p may overflow to inf -> rcp = 0)
     return z >= 0.f ? 1.0f - y : y;
 }
+// ---------------------------------------------------------------------------------------------
+// packed fp32x2 math (FFMA2 / FMUL2 / FADD2, sm_100+): a 3-register FFMA occupies the fma pipe for two cycles per warp, the
+// packed forms do two lanes' worth in the same slot, so ALU-issue-bound epilogues are written on float2
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 splat2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 abs2(float2 a) { return make_float2(fabsf(a.x), fabsf(a.y)); }
+__device__ __forceinline__ float2 copysign2(float2 mag, float2 sgn) { return make_float2(copysignf(mag.x, sgn.x), copysignf(mag.y, sgn.y)); }
+// Phi(z) for two values: same A&S 7.1.28 polynomial as gelu_cdf; Phi = 1/2 + copysign(1/2 - y, z) (absolute error of the
+// rewrite <= 2^-24)
+__device__ __forceinline__ float2 gelu_cdf2(float2 z) {
+    const float2 x = abs2(z);
+    float2 p = fma2(x, splat2(5.621299663962e-06f), splat2(5.105520900866e-05f));
+    p = fma2(x, p, splat2(3.968613701101e-05f));
+    p = fma2(x, p, splat2(3.422739238901e-03f));
+    p = fma2(x, p, splat2(2.207699845658e-02f));
+    p = fma2(x, p, splat2(5.207516303663e-02f));
+    p = fma2(x, p, splat2(1.044273782427e+00f));
+    p = mul2(p, p); p = mul2(p, p); p = mul2(p, p); p = mul2(p, p);
+    const float2 y = make_float2(fast_rcp(p.x), fast_rcp(p.y));
+    const float2 t = copysign2(fma2(y, splat2(-1.f), splat2(0.5f)), z);
+    return add2(t, splat2(0.5f));
+}
+// Phi(z) and gelu'(z) for two values (A&S 7.1.26, as gelu_terms)
+__device__ __forceinline__ void gelu_terms2(float2 z, float2& Phi, float2& dgelu) {
+    const float2 d = fma2(abs2(z), splat2(0.2316418883f), splat2(1.0f));
+    const float2 t = make_float2(fast_rcp(d.x), fast_rcp(d.y));
+    const float2 e = mul2(mul2(z, z), splat2(-0.7213475204f));
+    const float2 E = make_float2(fast_ex2(e.x), fast_ex2(e.y));          // exp(-z^2/2)
+    float2 p = fma2(t, splat2(0.5307027145f), splat2(-0.7265760135f));
+    p = fma2(t, p, splat2(0.7107068705f));
+    p = fma2(t, p, splat2(-0.1422483680f));
+    p = fma2(t, p, splat2(0.1274147960f));
+    const float2 y = mul2(mul2(p, t), E);                                // erfc(|z|/sqrt2) / 2
+    Phi = add2(copysign2(fma2(y, splat2(-1.f), splat2(0.5f)), z), splat2(0.5f));
+    dgelu = fma2(mul2(z, E), splat2(0.39894228040143267794f), Phi);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

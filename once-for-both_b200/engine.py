@@ -18,6 +18,7 @@ There is no CPU path: every op goes through the C ABI in libofb_b200.so.
 """
 import ctypes as C
 import math
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -227,7 +228,8 @@ class SearchStepEngine:
         # MLP hidden activations are kept TRANSPOSED, [hidden, tokens] with the token pitch padded to 16 bytes: the fc1 /
         # fc2-dgrad epilogue threads then own one hidden unit each (gate, bias and their gradients are per-thread scalars)
         self.ldT = (M + 7) // 8 * 8
-        self.mlp_bn = 256
+        self.mlp_bn = int(os.environ.get("OFB_MLP_BN", "256"))      # token tile of the transposed-hidden GEMMs
+        self.bn_nD = 0          # N tile of the N = embed_dim GEMMs (0 = the library's cost model); tools/step_breakdown.py A/Bs it
         self.mlp_parts = 2 * ((M + self.mlp_bn - 1) // self.mlp_bn)
         self.xs = [torch.zeros(M, D, **bf) for _ in range(depth + 1)]      # xs[l] = input of block l; xs[depth] = output
         self.blk = []
@@ -386,7 +388,7 @@ class SearchStepEngine:
             ops.attention_fwd(a["qkv"], a["o"], a["lse"], dp1, B, T, H, self.scale)
             ops.gemm(ops.EPI_STORE, a["o"], self.w(pre + "attn.proj.weight"), M=M, N=D, K=D, out0=a["x2"],
                      bias=self.p(pre + "attn.proj.bias"), rowscale=dp1, rows_per_scale=T, bias_rowscaled=True,
-                     res=a["x1"])
+                     res=a["x1"], bn=self.bn_nD)
             ops.layernorm_fwd(a["x2"], self.p(pre + "norm2.weight"), self.p(pre + "norm2.bias"), a["x3"], a["mean2"],
                               a["rstd2"], self.eps_ln)
             # fc1 computes the transposed hidden activations u^T, h^T = [hidden, tokens] (weight is the M operand)
@@ -394,7 +396,7 @@ class SearchStepEngine:
                      bias=self.p(pre + "mlp.fc1.bias"), colscale=g_m, rowscale=dp2, rows_per_scale=T, bn=self.mlp_bn)
             ops.gemm(ops.EPI_STORE, a["h"], self.w(pre + "mlp.fc2.weight"), M=M, N=D, K=hid, out0=self.xs[l + 1],
                      bias=self.p(pre + "mlp.fc2.bias"), rowscale=dp2, rows_per_scale=T, bias_rowscaled=True,
-                     res=a["x3"], a_mn=True)
+                     res=a["x3"], a_mn=True, bn=self.bn_nD)
         ops.layernorm_fwd(self.xs[self.depth], self.p("norm.weight"), self.p("norm.bias"), self.latent, self.meanf,
                           self.rstdf, self.eps_ln)
         # head on the cls rows (row stride T*D), label-smoothing CE
@@ -456,7 +458,7 @@ class SearchStepEngine:
             ops.gemm(ops.EPI_WGRAD, self.du, a["x3"], M=hid, N=D, K=M, out0=self.g(pre + "mlp.fc1.weight"), b_mn=True)
             G3 = spare.pop()
             ops.gemm(ops.EPI_STORE, self.du, self.w(pre + "mlp.fc1.weight"), M=M, N=D, K=hid, out0=G3, a_mn=True, b_mn=True,
-                     res=G4)
+                     res=G4, bn=self.bn_nD)
             spare.append(G4)
             # LayerNorm 2 (+ proj bias grad)
             G2 = spare.pop()
@@ -471,7 +473,7 @@ class SearchStepEngine:
             ops.gemm(ops.EPI_WGRAD, G2, a["o"], M=D, N=D, K=M, out0=self.g(pre + "attn.proj.weight"), a_mn=True, b_mn=True)
             dO = spare.pop()
             ops.gemm(ops.EPI_STORE, G2, self.w(pre + "attn.proj.weight"), M=M, N=D, K=D, out0=dO, b_mn=True, rowscale=dp1,
-                     rows_per_scale=T)
+                     rows_per_scale=T, bn=self.bn_nD)
             # attention
             ops.attention_bwd(a["qkv"], a["o"], dO, a["lse"], g_a, dp1, self.dqkv, self.att_pg, self.att_pb, B, T, H,
                               self.scale)
@@ -483,7 +485,7 @@ class SearchStepEngine:
                      b_mn=True)
             G1 = spare.pop()
             ops.gemm(ops.EPI_STORE, self.dqkv, self.w(pre + "attn.qkv.weight"), M=M, N=D, K=3 * D, out0=G1, b_mn=True,
-                     res=G2)
+                     res=G2, bn=self.bn_nD)
             spare.append(G2)
             # LayerNorm 1 (+ previous block's fc2 bias grad)
             G0 = spare.pop()

@@ -17,6 +17,36 @@ LAUNCHES = 0
 GEMM_TIMING = None
 
 
+# optional per-launch timing of EVERY library call (tools/step_breakdown.py): set to a list -> each launch appends
+# (entry point, tag, start_event, end_event); the tag carries the GEMM shape / epilogue
+OP_TIMING = None
+_TAG = ""
+_raw_lib = lib
+
+
+class _TimedLib:
+    def __init__(self, inner):
+        self._inner = inner
+
+    def __getattr__(self, name):
+        fn = getattr(self._inner, name)
+        if not name.startswith("ofb_") or name in ("ofb_version", "ofb_layernorm_bwd_parts"):
+            return fn
+
+        def run(*args):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*args)
+            e1.record()
+            OP_TIMING.append((name, _TAG, e0, e1))
+            return r
+        return run
+
+
+def lib():  # noqa: F811  (shadows the import on purpose: same object unless OP_TIMING is armed)
+    return _TimedLib(_raw_lib()) if OP_TIMING is not None else _raw_lib()
+
+
 def _count(n=1):
     global LAUNCHES
     LAUNCHES += n
@@ -55,6 +85,8 @@ def gemm(epi, A, B, *, M, N, K, out0=None, ld0=0, out1=None, ld1=0, out_fp32=Fal
     g.tokens = tokens
     lda = lda if lda is not None else A.stride(0)
     ldb = ldb if ldb is not None else B.stride(0)
+    global _TAG
+    _TAG = f"epi{epi} M{M} N{N} K{K} a{int(a_mn)}b{int(b_mn)}"
     if GEMM_TIMING is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -63,6 +95,7 @@ def gemm(epi, A, B, *, M, N, K, out0=None, ld0=0, out1=None, ld1=0, out_fp32=Fal
     if GEMM_TIMING is not None:
         e1.record()
         GEMM_TIMING.append((e0, e1, 2.0 * M * N * K, epi))
+    _TAG = ""
 
 
 # ---------------------------------------------------------------------------------------------------------------------
