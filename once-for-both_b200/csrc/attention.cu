@@ -302,40 +302,35 @@ __device__ __forceinline__ float bfly16(float (&v)[16]) {
     return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
-// epilogue of one 16-column slice of dQ / dK / dV for one token row: multiply by the gate (d pre-gate), store, and add
-// the row's contributions to the gate / bias column sums (shared-memory accumulators). x0/x1 = the row's 16 gated
-// q/k/v values (prefetched by the caller so the global-load latency overlaps the MMAs).
-__device__ __forceinline__ void dqkv_slice_epilogue(float (&v)[16], bool ok, const uint4& x0, const uint4& x1, __nv_bfloat16* dy,
-                                                    const float (&gate16)[16], float* cs_gate, float* cs_bias) {
-    float gy[16];
-    if (ok) {
-        float2 f;
-        f = unpack_bf16x2(x0.x); gy[0] = f.x * v[0]; gy[1] = f.y * v[1];
-        f = unpack_bf16x2(x0.y); gy[2] = f.x * v[2]; gy[3] = f.y * v[3];
-        f = unpack_bf16x2(x0.z); gy[4] = f.x * v[4]; gy[5] = f.y * v[5];
-        f = unpack_bf16x2(x0.w); gy[6] = f.x * v[6]; gy[7] = f.y * v[7];
-        f = unpack_bf16x2(x1.x); gy[8] = f.x * v[8]; gy[9] = f.y * v[9];
-        f = unpack_bf16x2(x1.y); gy[10] = f.x * v[10]; gy[11] = f.y * v[11];
-        f = unpack_bf16x2(x1.z); gy[12] = f.x * v[12]; gy[13] = f.y * v[13];
-        f = unpack_bf16x2(x1.w); gy[14] = f.x * v[14]; gy[15] = f.y * v[15];
+// epilogue of one 16-column slice of dQ / dK / dV for one token row: multiply by the gate (d pre-gate) and store; the row's
+// contributions to the gate / bias column sums are accumulated in REGISTERS (packed fp32x2) and reduced across rows once
+// per item and quantity (reduce_cols16), not once per slice. x0/x1 = the row's 16 gated q/k/v values (prefetched by the
+// caller so the global-load latency overlaps the MMAs).
+__device__ __forceinline__ void dqkv_slice_acc(const float (&v)[16], bool ok, const uint4& x0, const uint4& x1, __nv_bfloat16* dy,
+                                               const float2 (&g2)[8], float2 (&ag)[8], float2 (&ab)[8]) {
+    if (!ok) return;
+    const uint32_t xw[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    uint32_t ow[8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] *= gate16[j];
-        uint4 p0, p1;
-        p0.x = pack_bf16x2(v[0], v[1]); p0.y = pack_bf16x2(v[2], v[3]); p0.z = pack_bf16x2(v[4], v[5]); p0.w = pack_bf16x2(v[6], v[7]);
-        p1.x = pack_bf16x2(v[8], v[9]); p1.y = pack_bf16x2(v[10], v[11]); p1.z = pack_bf16x2(v[12], v[13]); p1.w = pack_bf16x2(v[14], v[15]);
-        reinterpret_cast<uint4*>(dy)[0] = p0;
-        reinterpret_cast<uint4*>(dy)[1] = p1;
-    } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) { gy[j] = 0.f; v[j] = 0.f; }
+    for (int j = 0; j < 8; ++j) {
+        const float2 vv = make_float2(v[2 * j], v[2 * j + 1]);
+        ag[j] = fma2(unpack_bf16x2(xw[j]), vv, ag[j]);
+        const float2 o = mul2(vv, g2[j]);
+        ab[j] = add2(ab[j], o);
+        ow[j] = pack_bf16x2(o.x, o.y);
     }
-    const float sg = bfly16(gy);
-    const float sb = bfly16(v);
+    reinterpret_cast<uint4*>(dy)[0] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    reinterpret_cast<uint4*>(dy)[1] = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+}
+// column sums over the 32 rows of this warp of 16 per-thread accumulators -> shared-memory accumulators (one atomic per column
+// and warp); the accumulators are cleared
+__device__ __forceinline__ void reduce_cols16(float2 (&acc)[8], float* cs) {
+    float t[16];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { t[2 * j] = acc[j].x; t[2 * j + 1] = acc[j].y; acc[j] = make_float2(0.f, 0.f); }
+    const float sum = bfly16(t);
     const uint32_t lane = lane_id();
-    if ((lane & 1u) == 0) {
-        atomicAdd(cs_gate + (lane >> 1), sg);
-        atomicAdd(cs_bias + (lane >> 1), sb);
-    }
+    if ((lane & 1u) == 0) atomicAdd(cs + (lane >> 1), sum);
 }
 __device__ __forceinline__ float dot8(const uint4& x, const uint4& y) {
     float2 f, g;
@@ -479,9 +474,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             float* cs_bias = cs + pi * 256 + 64 + cg * 16;
             const float dps = a.drop_scale != nullptr ? __ldg(a.drop_scale + b) : 1.f;
             const float inv_dps = dps != 0.f ? 1.f / dps : 0.f;
-            float g16[16];
+            float2 g2[8], ag[8], ab[8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) g16[j] = __ldg(a.gate + h * HD + cg * 16 + j);
+            for (int j = 0; j < 8; ++j) {
+                g2[j] = __ldg(reinterpret_cast<const float2*>(a.gate + h * HD + cg * 16) + j);
+                ag[j] = make_float2(0.f, 0.f); ab[j] = make_float2(0.f, 0.f);
+            }
             for (int i = 0; i < 2; ++i) {
                 const int t = i * QT + r;
                 const bool t_ok = t < a.T;
@@ -505,8 +503,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 named_bar_sync(2 + q, 128);
                 const float delta = (ld_shared_f32(sXD + r * 4) + ld_shared_f32(sXD + (128 + r) * 4)) +
                                     (ld_shared_f32(sXD + (256 + r) * 4) + ld_shared_f32(sXD + (384 + r) * 4));
-                const float lse2 = lse * 1.4426950408889634f;
-                const float dsc = delta * a.scale;
+                const float2 sl22 = splat2(sl2), nlse2 = splat2(-lse * 1.4426950408889634f);
+                const float2 sc2 = splat2(a.scale), ndsc2 = splat2(-delta * a.scale);
                 // ---- P = exp(S*scale - LSE) over this warp's kv columns ----
                 mbar_wait(bar(S_FULL), i);
                 tc_fence_after();
@@ -517,12 +515,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     if (nj == 32) tmem_ld32(tA + lane_base + col, v);
                     else tmem_ld16(tA + lane_base + col, v);
                     tmem_ld_wait();
-                    if (col + nj <= a.T) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = fast_ex2(fmaf(v[j], sl2, -lse2));
-                    } else {
+                    for (int j = 0; j < 16; ++j) {
+                        const float2 e = fma2(make_float2(v[2 * j], v[2 * j + 1]), sl22, nlse2);
+                        v[2 * j] = fast_ex2(e.x); v[2 * j + 1] = fast_ex2(e.y);
+                    }
+                    if (col + nj > a.T) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = (col + j < a.T) ? fast_ex2(fmaf(v[j], sl2, -lse2)) : 0.f;
+                        for (int j = 0; j < 32; ++j) v[j] = (col + j < a.T) ? v[j] : 0.f;
                     }
 #pragma unroll
                     for (int q4 = 0; q4 < 4; ++q4) {
@@ -552,13 +552,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     for (int q4 = 0; q4 < 4; ++q4) {
                         if (q4 * 8 < nj) {
                             const uint4 pp = ld_shared_v4(pbuf_addr(sP, r, (col >> 3) + q4));
-                            float2 p0 = unpack_bf16x2(pp.x), p1 = unpack_bf16x2(pp.y), p2 = unpack_bf16x2(pp.z), p3 = unpack_bf16x2(pp.w);
                             const float* w = v + q4 * 8;
+                            const float2 d0 = mul2(unpack_bf16x2(pp.x), fma2(make_float2(w[0], w[1]), sc2, ndsc2));
+                            const float2 d1 = mul2(unpack_bf16x2(pp.y), fma2(make_float2(w[2], w[3]), sc2, ndsc2));
+                            const float2 d2 = mul2(unpack_bf16x2(pp.z), fma2(make_float2(w[4], w[5]), sc2, ndsc2));
+                            const float2 d3 = mul2(unpack_bf16x2(pp.w), fma2(make_float2(w[6], w[7]), sc2, ndsc2));
                             uint4 pk;
-                            pk.x = pack_bf16x2(p0.x * fmaf(w[0], a.scale, -dsc), p0.y * fmaf(w[1], a.scale, -dsc));
-                            pk.y = pack_bf16x2(p1.x * fmaf(w[2], a.scale, -dsc), p1.y * fmaf(w[3], a.scale, -dsc));
-                            pk.z = pack_bf16x2(p2.x * fmaf(w[4], a.scale, -dsc), p2.y * fmaf(w[5], a.scale, -dsc));
-                            pk.w = pack_bf16x2(p3.x * fmaf(w[6], a.scale, -dsc), p3.y * fmaf(w[7], a.scale, -dsc));
+                            pk.x = pack_bf16x2(d0.x, d0.y); pk.y = pack_bf16x2(d1.x, d1.y);
+                            pk.z = pack_bf16x2(d2.x, d2.y); pk.w = pack_bf16x2(d3.x, d3.y);
                             st_shared_v4(pbuf_addr(sDS, r, (col >> 3) + q4), pk);
                         }
                     }
@@ -576,8 +577,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar(A_EMPTY));
-                dqkv_slice_epilogue(w16, t_ok, y0, y1, a.dqkv + qoff, g16, cs_gate, cs_bias);
+                dqkv_slice_acc(w16, t_ok, y0, y1, a.dqkv + qoff, g2, ag, ab);
             }
+            reduce_cols16(ab, cs_bias);                      // d bias of q
             // ---- dK / dV epilogue (kv rows: tile m covers kv = m*128 + r); the gated k / v slices are prefetched one ahead ----
             auto slice_off = [&](int idx) {
                 const int which = 1 + (idx >> 1), kv = (idx & 1) * QT + r;
@@ -604,8 +606,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar(ACC_EMPTY));
                 }
-                dqkv_slice_epilogue(w16, kv_ok, x0, x1, a.dqkv + slice_off(idx), g16, cs_gate, cs_bias + which * 64);
+                dqkv_slice_acc(w16, kv_ok, x0, x1, a.dqkv + slice_off(idx), g2, ag, ab);
+                if (m == 1) reduce_cols16(ab, cs_bias + which * 64);     // d bias of k, then of v
             }
+            reduce_cols16(ag, cs_gate);                      // d gate: q, k and v contributions together
             // ---- per-item column sums -> global partials; the accumulator of this parity is re-zeroed for item it+2 ----
             named_bar_sync(1, BWD_CT);
             {

@@ -50,13 +50,29 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 #endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > OFB_MBAR_TIMEOUT_CYCLES) {
-            printf("ofb: mbarrier timeout blk=%d thr=%d bar=%u parity=%u\n", blockIdx.x, threadIdx.x, bar, parity);
-            __trap();
+    const long long t0 = clock64();
+    do {
+#pragma unroll 1
+        for (int i = 0; i < 32; ++i)
+            if (mbar_try_wait(bar, parity)) return;
+    } while (clock64() - t0 <= OFB_MBAR_TIMEOUT_CYCLES);
+    printf("ofb: mbarrier timeout blk=%d thr=%d bar=%u parity=%u\n", blockIdx.x, threadIdx.x, bar, parity);
+    __trap();
+}
+// same, for waits that are far off the critical path (producer waiting for a free stage): sleeps between polls so that the
+// spinning warp does not take issue slots from the epilogue warps of its scheduler
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    do {
+#pragma unroll 1
+        for (int i = 0; i < 32; ++i) {
+            __nanosleep(40);
+            if (mbar_try_wait(bar, parity)) return;
         }
-    }
+    } while (clock64() - t0 <= OFB_MBAR_TIMEOUT_CYCLES);
+    printf("ofb: mbarrier timeout blk=%d thr=%d bar=%u parity=%u\n", blockIdx.x, threadIdx.x, bar, parity);
+    __trap();
 }
 
 // generic-proxy smem writes -> visible to the async proxy (TMA / UMMA reads)
