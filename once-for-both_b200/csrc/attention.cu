@@ -276,15 +276,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward: persistent, warp-specialised; one CTA per SM loops over (image, head) items, two q tiles per item.
-//   warps 0-15 : compute.  warp w: TMEM lane quarter w&3, column group w>>2
-//                (kv columns [0,64) [64,112) [112,160) [160,208) of S / dP; head-dim columns 16 cg .. 16 cg + 15 of dQ / dK / dV)
-//   warp 16    : TMA producer        warp 17 : MMA issuer (+ TMEM allocation)
-// TMEM columns: [0,208) S then dP then (first 64) dQ ; [256,384) dK (2 kv tiles x 64) ; [384,512) dV (2 kv tiles x 64)
+// backward: persistent, warp-specialised; one CTA per SM loops over (image, head) items. An item is cut into 128 x 128
+// sub-tiles (q tile i, kv half j), j outer:
+//     S_ij = Q_i K_j^T -> P_ij = exp(S*scale - LSE)          dP_ij = dO_i V_j^T -> dS_ij = scale * P (dP - delta)
+//     dV_j += P_ij^T dO_i      dK_j += dS_ij^T Q_i      dQ_i += dS_ij K_j
+// so that S / dP need only 128 TMEM columns and TWO sub-tiles can be in flight: the S MMA of sub-tile t+1 is issued into the
+// other TMEM region while the compute warps are still busy with sub-tile t (the one-tile-at-a-time version was bound by the
+// MMA -> mbarrier -> compute round trips, not by instruction issue: profiles/r01). dS overwrites P in place (dV is issued
+// before dP, so the dP commit also covers the MMA that reads P), which frees the shared memory to keep Q and dO of both q
+// tiles resident for the whole item.
+//   warps 0-15: compute.  warp w: TMEM lane quarter w&3 (q rows), column group w>>2 (32 kv columns of S / dP; 16 head-dim
+//               columns of dQ / dK / dV). Every phase is a chain of long-latency steps (tcgen05.ld, MUFU, shared memory),
+//               so the phases are spread over many warps rather than over long per-thread loops.
+//   warp 16   : TMA producer        warp 17 : MMA issuer (+ TMEM allocation)
+// TMEM columns: R0 [0,128) R1 [128,256) S then dP of even / odd sub-tiles ; dQ_0 [256,320) dQ_1 [320,384) ; dK_j [384,448) ;
+//               dV_j [448,512)
 // ---------------------------------------------------------------------------------------------
 static constexpr int BWD_CW = 16;
+static constexpr int BWD_NCG = BWD_CW / 4;                  // column groups
+static constexpr int BWD_PC = 128 / BWD_NCG;              // kv columns of a sub-tile per warp (32)
+static constexpr int BWD_EC = HD / BWD_NCG;               // head-dim columns per warp in the epilogues (16)
 static constexpr int BWD_THREADS = (BWD_CW + 2) * 32;     // 576
 static constexpr int BWD_CT = BWD_CW * 32;                // compute threads
+static constexpr int PB_B = 2 * TILE_B;                   // 32 KB: one P / dS buffer = 2 atoms of [128 q rows][64 kv columns]
 
 // 16 values per lane -> lanes with even index end with the sum over all 32 lanes of column (lane >> 1) & 15
 __device__ __forceinline__ float bfly16(float (&v)[16]) {
@@ -303,86 +317,82 @@ __device__ __forceinline__ float bfly16(float (&v)[16]) {
 }
 
 // epilogue of one 16-column slice of dQ / dK / dV for one token row: multiply by the gate (d pre-gate) and store; the row's
-// contributions to the gate / bias column sums are accumulated in REGISTERS (packed fp32x2) and reduced across rows once
-// per item and quantity (reduce_cols16), not once per slice. x0/x1 = the row's 16 gated q/k/v values (prefetched by the
-// caller so the global-load latency overlaps the MMAs).
-__device__ __forceinline__ void dqkv_slice_acc(const float (&v)[16], bool ok, const uint4& x0, const uint4& x1, __nv_bfloat16* dy,
-                                               const float2 (&g2)[8], float2 (&ag)[8], float2 (&ab)[8]) {
-    if (!ok) return;
-    const uint32_t xw[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-    uint32_t ow[8];
+// gate products are accumulated in registers (ag, reduced once per item), the bias column sums are reduced across the 32
+// rows of the warp right away and added to the shared-memory accumulators. x0/x1 = the row's 16 gated q/k/v values.
+__device__ __forceinline__ void dqkv_slice16(float (&v)[16], bool ok, const uint4& x0, const uint4& x1, __nv_bfloat16* dy,
+                                             const float* gate16, float2 (&ag)[8], float* cs_bias) {
+    if (ok) {
+        const uint32_t xw[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+        uint32_t ow[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const float2 vv = make_float2(v[2 * j], v[2 * j + 1]);
-        ag[j] = fma2(unpack_bf16x2(xw[j]), vv, ag[j]);
-        const float2 o = mul2(vv, g2[j]);
-        ab[j] = add2(ab[j], o);
-        ow[j] = pack_bf16x2(o.x, o.y);
+        for (int j = 0; j < 8; ++j) {
+            const float2 vv = make_float2(v[2 * j], v[2 * j + 1]);
+            ag[j] = fma2(unpack_bf16x2(xw[j]), vv, ag[j]);
+            const float2 o = mul2(vv, __ldg(reinterpret_cast<const float2*>(gate16) + j));
+            v[2 * j] = o.x; v[2 * j + 1] = o.y;
+            ow[j] = pack_bf16x2(o.x, o.y);
+        }
+        reinterpret_cast<uint4*>(dy)[0] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        reinterpret_cast<uint4*>(dy)[1] = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.f;
     }
-    reinterpret_cast<uint4*>(dy)[0] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-    reinterpret_cast<uint4*>(dy)[1] = make_uint4(ow[4], ow[5], ow[6], ow[7]);
-}
-// column sums over the 32 rows of this warp of 16 per-thread accumulators -> shared-memory accumulators (one atomic per column
-// and warp); the accumulators are cleared
-__device__ __forceinline__ void reduce_cols16(float2 (&acc)[8], float* cs) {
-    float t[16];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { t[2 * j] = acc[j].x; t[2 * j + 1] = acc[j].y; acc[j] = make_float2(0.f, 0.f); }
-    const float sum = bfly16(t);
+    const float sb = bfly16(v);
     const uint32_t lane = lane_id();
-    if ((lane & 1u) == 0) atomicAdd(cs + (lane >> 1), sum);
+    if ((lane & 1u) == 0) atomicAdd(cs_bias + (lane >> 1), sb);
 }
 __device__ __forceinline__ float dot8(const uint4& x, const uint4& y) {
-    float2 f, g;
-    float d = 0.f;
-    f = unpack_bf16x2(x.x); g = unpack_bf16x2(y.x); d = fmaf(f.x, g.x, fmaf(f.y, g.y, d));
-    f = unpack_bf16x2(x.y); g = unpack_bf16x2(y.y); d = fmaf(f.x, g.x, fmaf(f.y, g.y, d));
-    f = unpack_bf16x2(x.z); g = unpack_bf16x2(y.z); d = fmaf(f.x, g.x, fmaf(f.y, g.y, d));
-    f = unpack_bf16x2(x.w); g = unpack_bf16x2(y.w); d = fmaf(f.x, g.x, fmaf(f.y, g.y, d));
-    return d;
+    float2 d = mul2(unpack_bf16x2(x.x), unpack_bf16x2(y.x));
+    d = fma2(unpack_bf16x2(x.y), unpack_bf16x2(y.y), d);
+    d = fma2(unpack_bf16x2(x.z), unpack_bf16x2(y.z), d);
+    d = fma2(unpack_bf16x2(x.w), unpack_bf16x2(y.w), d);
+    return d.x + d.y;
 }
 
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                 const __grid_constant__ CUtensorMap tm_do, const AttnArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const uint32_t sQ = smem_u32(smem);
-    const uint32_t sDO = sQ + TILE_B;
-    const uint32_t sK = sDO + TILE_B;
+    const uint32_t sQ = smem_u32(smem);                   // 2 q tiles
+    const uint32_t sDO = sQ + 2 * TILE_B;                 // 2 q tiles
+    const uint32_t sK = sDO + 2 * TILE_B;
     const uint32_t sV = sK + KV_B;
-    const uint32_t sP = sV + KV_B;
-    const uint32_t sDS = sP + PBUF_B;
-    uint8_t* tail = smem + 2 * TILE_B + 2 * KV_B + 2 * PBUF_B;
+    const uint32_t sP = sV + KV_B;                        // 2 buffers (even / odd sub-tiles), P then dS in place
+    uint8_t* tail = smem + 4 * TILE_B + 2 * KV_B + 2 * PB_B;
     float* cs = reinterpret_cast<float*>(tail);                 // [2 parities][256]: gate[64] | bias q,k,v [3][64]
-    const uint32_t sXD = smem_u32(tail + 2048);                 // [4 column groups][128 rows] delta partials
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 4096);
-    enum { KV_FULL = 0, KV_EMPTY, QDO_FULL, QDO_EMPTY, S_FULL, P_FULL, DP_FULL, DS_FULL, DQ_FULL, A_EMPTY, ACC_FULL, ACC_EMPTY, NBAR };
+    const uint32_t sXD = smem_u32(tail + 2048);                 // [2 q tiles][4 column groups][128 rows] delta partials
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 2048 + 4096);
+    enum { QK_FULL = 0, DOV_FULL, ITEM_EMPTY, S_FULL, P_FULL = S_FULL + 2, DP_FULL = P_FULL + 2, DS_FULL = DP_FULL + 2,
+           PB_FREE = DS_FULL + 2, ACC_FULL = PB_FREE + 2, ACC_EMPTY, DQ_FULL, DQ_EMPTY, NBAR };
     auto bar = [&](int k) { return smem_u32(&bars[k]); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[NBAR]);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_items = a.B * a.H;
     const int D = a.H * HD;
+    const int kvp = (a.T + 15) & ~15;                     // kv columns, padded to the MMA granularity
+    const int nh = a.T > QT ? 2 : 1;                      // q tiles = kv halves
+    const int nt = nh * nh;                               // sub-tiles per item
+    const int n_kv1 = kvp - QT;                           // kv columns of half 1 (if any)
 
     if (threadIdx.x == 0) {
         if ((sQ & 1023u) != 0) { printf("ofb: dynamic smem base not 1024-aligned\n"); __trap(); }
-        mbar_init(bar(KV_FULL), 1); mbar_init(bar(KV_EMPTY), 1); mbar_init(bar(QDO_FULL), 1); mbar_init(bar(QDO_EMPTY), 1);
-        mbar_init(bar(S_FULL), 1); mbar_init(bar(P_FULL), BWD_CW); mbar_init(bar(DP_FULL), 1); mbar_init(bar(DS_FULL), BWD_CW);
-        mbar_init(bar(DQ_FULL), 1); mbar_init(bar(A_EMPTY), BWD_CW); mbar_init(bar(ACC_FULL), 1); mbar_init(bar(ACC_EMPTY), BWD_CW);
+        mbar_init(bar(QK_FULL), 1); mbar_init(bar(DOV_FULL), 1); mbar_init(bar(ITEM_EMPTY), 1);
+        for (int s2 = 0; s2 < 2; ++s2) {
+            mbar_init(bar(S_FULL + s2), 1); mbar_init(bar(P_FULL + s2), BWD_CW); mbar_init(bar(DP_FULL + s2), 1);
+            mbar_init(bar(DS_FULL + s2), BWD_CW); mbar_init(bar(PB_FREE + s2), 1);
+        }
+        mbar_init(bar(ACC_FULL), 1); mbar_init(bar(ACC_EMPTY), BWD_CW); mbar_init(bar(DQ_FULL), 1); mbar_init(bar(DQ_EMPTY), BWD_CW);
         mbar_fence_init();
     }
     if (warp == BWD_CW + 1) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
-    // kv columns >= 208 of the P / dS buffers are never written; they only feed accumulator rows that are never read, but
-    // keep them finite
-    for (int i = threadIdx.x; i < 2 * PBUF_B / 16; i += BWD_THREADS) st_shared_v4(sP + i * 16, make_uint4(0, 0, 0, 0));
     for (int i = threadIdx.x; i < 512; i += BWD_THREADS) cs[i] = 0.f;
-    fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tA = tmem, tDK = tmem + 256, tDV = tmem + 384;
-    constexpr uint32_t IDESC_S = make_idesc_bf16(128, KVP, 0, 0);     // S, dP : K-major x K-major
+    const uint32_t tDQ = tmem + 256, tDK = tmem + 384, tDV = tmem + 448;
     constexpr uint32_t IDESC_DQ = make_idesc_bf16(128, HD, 0, 1);     // dQ     : dS K-major, K MN-major
     constexpr uint32_t IDESC_KV = make_idesc_bf16(128, HD, 1, 1);     // dK, dV : MN-major x MN-major
 
@@ -393,67 +403,104 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             int it = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
                 const int b = item / a.H, h = item % a.H;
-                mbar_wait(bar(KV_EMPTY), (it & 1) ^ 1);
-                mbar_arrive_expect_tx(bar(KV_FULL), 2 * KV_B);
-                tma_load_5d(sK, &tm_kv, bar(KV_FULL), 0, 0, h, 1, b);
-                tma_load_5d(sV, &tm_kv, bar(KV_FULL), 0, 0, h, 2, b);
-                for (int i = 0; i < 2; ++i) {
-                    mbar_wait(bar(QDO_EMPTY), i ^ 1);            // tile counter 2*it + i -> parity i
-                    mbar_arrive_expect_tx(bar(QDO_FULL), 2 * TILE_B);
-                    tma_load_5d(sQ, &tm_q, bar(QDO_FULL), 0, i * QT, h, 0, b);
-                    tma_load_4d(sDO, &tm_do, bar(QDO_FULL), h * HD, i * QT, b, 0);
+                mbar_wait(bar(ITEM_EMPTY), (it & 1) ^ 1);        // every MMA of the previous item has retired
+                mbar_arrive_expect_tx(bar(QK_FULL), nh * TILE_B + KV_B);
+                tma_load_5d(sQ, &tm_q, bar(QK_FULL), 0, 0, h, 0, b);
+                tma_load_5d(sK, &tm_kv, bar(QK_FULL), 0, 0, h, 1, b);
+                if (nh == 2) tma_load_5d(sQ + TILE_B, &tm_q, bar(QK_FULL), 0, QT, h, 0, b);
+                mbar_arrive_expect_tx(bar(DOV_FULL), nh * TILE_B + KV_B);
+                tma_load_4d(sDO, &tm_do, bar(DOV_FULL), h * HD, 0, b, 0);
+                tma_load_5d(sV, &tm_kv, bar(DOV_FULL), 0, 0, h, 2, b);
+                if (nh == 2) tma_load_4d(sDO + TILE_B, &tm_do, bar(DOV_FULL), h * HD, QT, b, 0);
+                // pull the next item's tiles into L2 while this one is being computed
+                const int nxt = item + gridDim.x;
+                if (nxt < n_items) {
+                    const int b2 = nxt / a.H, h2 = nxt % a.H;
+                    tma_prefetch_5d(&tm_kv, 0, 0, h2, 1, b2);
+                    tma_prefetch_5d(&tm_kv, 0, 0, h2, 2, b2);
+                    for (int i = 0; i < nh; ++i) {
+                        tma_prefetch_5d(&tm_q, 0, i * QT, h2, 0, b2);
+                        tma_prefetch_4d(&tm_do, h2 * HD, i * QT, b2, 0);
+                    }
                 }
             }
         }
     } else if (warp == BWD_CW + 1) {
         // ===================== MMA issuer =====================
+        // Sub-tiles are processed in pairs (t0, t0+1) = the two q tiles of one kv half; the compute warps run
+        //   P(t0) P(t0+1) dS(t0) dS(t0+1)
+        // so that every MMA -> mbarrier -> compute round trip of one sub-tile is covered by compute work on the other one.
         if (lane == 0) {
+            uint32_t use0 = 0, use1 = 0;       // completed uses of the per-slot barriers (slot = sub-tile parity)
+            uint32_t n_acc = 0;                // kv halves started (ACC_EMPTY waits)
+            const uint32_t n_kv0 = uint32_t(min(kvp, QT));
+            auto issue_s = [&](int t) {
+                const int j = (nh == 2) ? (t >> 1) : 0, i = (nh == 2) ? (t & 1) : 0;
+                const uint32_t idesc = make_idesc_bf16(128, j == 0 ? n_kv0 : uint32_t(n_kv1), 0, 0);
+                const uint32_t qa = sQ + i * TILE_B, kb = sK + j * (QT * 128);
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k)
+                    umma_bf16(tmem + (t & 1) * 128, make_smem_desc_sw128(qa + k * 32, 0, 1024),
+                              make_smem_desc_sw128(kb + k * 32, 0, 1024), idesc, k > 0);
+                umma_commit(bar(S_FULL + (t & 1)));
+            };
             int it = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
                 const uint32_t pi = it & 1;
-                mbar_wait(bar(KV_FULL), pi);
-                for (int i = 0; i < 2; ++i) {
-                    mbar_wait(bar(QDO_FULL), i);
-                    mbar_wait(bar(A_EMPTY), i ^ 1);              // dQ of the previous tile drained from region A
-                    tc_fence_after();
-                    // S = Q K^T
-#pragma unroll
-                    for (int k = 0; k < HD / 16; ++k)
-                        umma_bf16(tA, make_smem_desc_sw128(sQ + k * 32, 0, 1024), make_smem_desc_sw128(sK + k * 32, 0, 1024), IDESC_S, k > 0);
-                    umma_commit(bar(S_FULL));
-                    mbar_wait(bar(P_FULL), i);
-                    tc_fence_after();
-                    // dP = dO V^T  (region A again: S fully consumed once P_FULL completes)
-#pragma unroll
-                    for (int k = 0; k < HD / 16; ++k)
-                        umma_bf16(tA, make_smem_desc_sw128(sDO + k * 32, 0, 1024), make_smem_desc_sw128(sV + k * 32, 0, 1024), IDESC_S, k > 0);
-                    umma_commit(bar(DP_FULL));
-                    if (i == 0) { mbar_wait(bar(ACC_EMPTY), pi ^ 1); tc_fence_after(); }   // previous item's dK / dV read out
-                    // dV[kv tile m] += P^T dO      (M = kv, K = q rows of this tile)
-#pragma unroll
-                    for (int m = 0; m < 2; ++m)
+                mbar_wait(bar(QK_FULL), pi);
+                tc_fence_after();
+                issue_s(0);
+                if (nt > 1) issue_s(1);
+#pragma unroll 1
+                for (int t0 = 0; t0 < nt; t0 += 2) {
+                    const int np = min(2, nt - t0);
+                    const int j = (nh == 2) ? (t0 >> 1) : 0;
+                    const uint32_t nj = (j == 0) ? n_kv0 : uint32_t(n_kv1);
+                    const uint32_t vb = sV + j * (QT * 128), kb = sK + j * (QT * 128);
+                    // ---- dV_j (+)= P^T dO_i, then dP = dO_i V_j^T, as soon as P of the sub-tile is in shared memory ----
+#pragma unroll 1
+                    for (int i = 0; i < np; ++i) {
+                        const uint32_t par = (i == 0 ? use0 : use1) & 1u;
+                        const uint32_t pbuf = sP + i * PB_B, doa = sDO + i * TILE_B;
+                        mbar_wait(bar(P_FULL + i), par);
+                        if (t0 == 0 && i == 0) mbar_wait(bar(DOV_FULL), pi);
+                        if (i == 0) { mbar_wait(bar(ACC_EMPTY), (n_acc & 1u) ^ 1u); ++n_acc; }   // previous dK / dV read out
+                        tc_fence_after();
 #pragma unroll
                         for (int k = 0; k < QT / 16; ++k)
-                            umma_bf16(tDV + m * HD, make_smem_desc_sw128(sP + (2 * m) * TILE_B + k * 2048, TILE_B, 1024),
-                                      make_smem_desc_sw128(sDO + k * 2048, 0, 1024), IDESC_KV, (i > 0 || k > 0) ? 1u : 0u);
-                    mbar_wait(bar(DS_FULL), i);
-                    tc_fence_after();
-                    // dQ = dS K   (K = kv)
+                            umma_bf16(tDV, make_smem_desc_sw128(pbuf + k * 2048, TILE_B, 1024),
+                                      make_smem_desc_sw128(doa + k * 2048, 0, 1024), IDESC_KV, (i > 0 || k > 0) ? 1u : 0u);
+                        const uint32_t idesc = make_idesc_bf16(128, nj, 0, 0);
 #pragma unroll
-                    for (int k = 0; k < KVP / 16; ++k)
-                        umma_bf16(tA, make_smem_desc_sw128(sDS + (k >> 2) * TILE_B + (k & 3) * 32, 0, 1024),
-                                  make_smem_desc_sw128(sK + k * 2048, 0, 1024), IDESC_DQ, k > 0);
-                    umma_commit(bar(DQ_FULL));
-                    // dK[kv tile m] += dS^T Q
-#pragma unroll
-                    for (int m = 0; m < 2; ++m)
+                        for (int k = 0; k < HD / 16; ++k)
+                            umma_bf16(tmem + i * 128, make_smem_desc_sw128(doa + k * 32, 0, 1024),
+                                      make_smem_desc_sw128(vb + k * 32, 0, 1024), idesc, k > 0);
+                        umma_commit(bar(DP_FULL + i));
+                    }
+                    // ---- once dS of a sub-tile is in place: S of the sub-tile two ahead (its TMEM region is free now), then
+                    //      dQ_i (+)= dS K_j and dK_j (+)= dS^T Q_i ----
+#pragma unroll 1
+                    for (int i = 0; i < np; ++i) {
+                        const uint32_t par = (i == 0 ? use0 : use1) & 1u;
+                        if (i == 0) ++use0; else ++use1;
+                        const uint32_t pbuf = sP + i * PB_B, qa = sQ + i * TILE_B;
+                        mbar_wait(bar(DS_FULL + i), par);
+                        if (t0 == 0 && i == 0) mbar_wait(bar(DQ_EMPTY), pi ^ 1u);       // previous item's dQ read out
+                        tc_fence_after();
+                        if (t0 + 2 + i < nt) issue_s(t0 + 2 + i);
+                        for (uint32_t k = 0; k < nj / 16; ++k)
+                            umma_bf16(tDQ + i * HD, make_smem_desc_sw128(pbuf + (k >> 2) * TILE_B + (k & 3) * 32, 0, 1024),
+                                      make_smem_desc_sw128(kb + k * 2048, 0, 1024), IDESC_DQ, (j > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
                         for (int k = 0; k < QT / 16; ++k)
-                            umma_bf16(tDK + m * HD, make_smem_desc_sw128(sDS + (2 * m) * TILE_B + k * 2048, TILE_B, 1024),
-                                      make_smem_desc_sw128(sQ + k * 2048, 0, 1024), IDESC_KV, (i > 0 || k > 0) ? 1u : 0u);
-                    umma_commit(bar(QDO_EMPTY));                 // every MMA reading Q_i / dO_i has been issued before this commit
-                    if (i == 1) { umma_commit(bar(KV_EMPTY)); umma_commit(bar(ACC_FULL)); }
+                            umma_bf16(tDK, make_smem_desc_sw128(pbuf + k * 2048, TILE_B, 1024),
+                                      make_smem_desc_sw128(qa + k * 2048, 0, 1024), IDESC_KV, (i > 0 || k > 0) ? 1u : 0u);
+                        umma_commit(bar(PB_FREE + i));
+                    }
+                    umma_commit(bar(ACC_FULL));
                 }
+                umma_commit(bar(DQ_FULL));
+                umma_commit(bar(ITEM_EMPTY));
             }
         }
     } else {
@@ -461,155 +508,194 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const int q = warp & 3, cg = warp >> 2;
         const int r = q * 32 + lane;
         const uint32_t lane_base = uint32_t(q * 32) << 16;
-        const int cbase = cg == 0 ? 0 : 16 + 48 * cg;           // 0, 64, 112, 160
-        const int n1 = cg == 0 ? 32 : 16;                        // second piece width
-        const uint32_t xd_mine = sXD + (cg * 128 + r) * 4;       // delta partial of this warp's 16 head-dim columns
         const float sl2 = a.scale * 1.4426950408889634f;
+        const float2 sl22 = splat2(sl2), sc2 = splat2(a.scale);
         float v[32];
+        uint32_t use0 = 0, use1 = 0;
+        uint32_t n_acc = 0;
         int it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const int b = item / a.H, h = item % a.H;
             const uint32_t pi = it & 1;
-            float* cs_gate = cs + pi * 256 + cg * 16;
-            float* cs_bias = cs + pi * 256 + 64 + cg * 16;
+            float* cs_gate = cs + pi * 256 + cg * BWD_EC;
+            float* cs_bias = cs + pi * 256 + 64 + cg * BWD_EC;
             const float dps = a.drop_scale != nullptr ? __ldg(a.drop_scale + b) : 1.f;
             const float inv_dps = dps != 0.f ? 1.f / dps : 0.f;
-            float2 g2[8], ag[8], ab[8];
+            const float* gate16 = a.gate + h * HD + cg * BWD_EC;
+            float2 ag[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                g2[j] = __ldg(reinterpret_cast<const float2*>(a.gate + h * HD + cg * 16) + j);
-                ag[j] = make_float2(0.f, 0.f); ab[j] = make_float2(0.f, 0.f);
-            }
-            for (int i = 0; i < 2; ++i) {
-                const int t = i * QT + r;
-                const bool t_ok = t < a.T;
-                // ---- early global loads (consumed after the S / dQ MMAs): LSE, this warp's 16-column slices of O and q ----
-                float lse = INFINITY;                            // rows >= T: exp2(-inf) = 0 everywhere
-                uint4 o0 = make_uint4(0, 0, 0, 0), o1 = o0, y0 = o0, y1 = o0;
-                const size_t qoff = ((size_t(b) * a.T + (t_ok ? t : 0)) * 3 + 0) * D + h * HD + cg * 16;
-                if (t_ok) {
-                    lse = __ldg(a.lse + (size_t(b) * a.H + h) * a.T + t);
-                    const uint4* po = reinterpret_cast<const uint4*>(a.o_in + (size_t(b) * a.T + t) * D + h * HD + cg * 16);
-                    o0 = __ldg(po); o1 = __ldg(po + 1);
-                    const uint4* py = reinterpret_cast<const uint4*>(a.qkv + qoff);
-                    y0 = __ldg(py); y1 = __ldg(py + 1);
+            for (int j = 0; j < 8; ++j) ag[j] = make_float2(0.f, 0.f);
+            // ---- per-row statistics of both q tiles: LSE and delta = rowsum(dO * O) / droppath ----
+            float nlse2_0 = -INFINITY, nlse2_1 = -INFINITY, ndsc_0 = 0.f, ndsc_1 = 0.f;   // rows >= T: exp2(-inf) = 0 everywhere
+            {
+                uint4 ov[2][2];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int t = i * QT + r;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) ov[i][c] = make_uint4(0, 0, 0, 0);
+                    if (i < nh && t < a.T) {
+                        const float l2 = -__ldg(a.lse + (size_t(b) * a.H + h) * a.T + t) * 1.4426950408889634f;
+                        if (i == 0) nlse2_0 = l2; else nlse2_1 = l2;
+                        const uint4* po = reinterpret_cast<const uint4*>(a.o_in + (size_t(b) * a.T + t) * D + h * HD + cg * BWD_EC);
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) ov[i][c] = __ldg(po + c);
+                    }
                 }
-                // ---- delta = rowsum(dO * O) / droppath: dO slice from the TMA-loaded tile, partials exchanged through smem ----
-                mbar_wait(bar(QDO_FULL), i);
+                mbar_wait(bar(DOV_FULL), pi);
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    if (i < nh) {
+                        float d = 0.f;
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) d += dot8(ov[i][c], ld_shared_v4(sDO + i * TILE_B + sw128_offset(r, cg * 2 + c)));
+                        st_shared_f32(sXD + ((i * 4 + cg) * 128 + r) * 4, d * inv_dps);
+                    }
+                }
+                named_bar_sync(2 + q, 128);                      // the four warps (column groups) of this row quarter
+                ndsc_0 = -((ld_shared_f32(sXD + r * 4) + ld_shared_f32(sXD + (128 + r) * 4)) +
+                           (ld_shared_f32(sXD + (256 + r) * 4) + ld_shared_f32(sXD + (384 + r) * 4))) * a.scale;
+                if (nh == 2) ndsc_1 = -((ld_shared_f32(sXD + (512 + r) * 4) + ld_shared_f32(sXD + (640 + r) * 4)) +
+                                        (ld_shared_f32(sXD + (768 + r) * 4) + ld_shared_f32(sXD + (896 + r) * 4))) * a.scale;
+            }
+            // ---- P = exp(S*scale - LSE) of sub-tile (q tile i, kv half j) over this warp's 32 kv columns ----
+            auto phase_p = [&](int i, int j) {
+                const uint32_t par = (i == 0 ? use0 : use1) & 1u;
+                const uint32_t tR = tmem + i * 128 + lane_base;
+                const uint32_t pbuf = sP + i * PB_B;
+                const float2 nl2 = splat2(i == 0 ? nlse2_0 : nlse2_1);
+                mbar_wait(bar(S_FULL + i), par);
+                mbar_wait(bar(PB_FREE + i), par ^ 1u);            // the MMAs that read this buffer one pair ago have retired
+                tc_fence_after();
                 {
-                    const uint4 d0 = ld_shared_v4(sDO + sw128_offset(r, cg * 2)), d1 = ld_shared_v4(sDO + sw128_offset(r, cg * 2 + 1));
-                    st_shared_f32(xd_mine, (dot8(o0, d0) + dot8(o1, d1)) * inv_dps);
-                }
-                named_bar_sync(2 + q, 128);
-                const float delta = (ld_shared_f32(sXD + r * 4) + ld_shared_f32(sXD + (128 + r) * 4)) +
-                                    (ld_shared_f32(sXD + (256 + r) * 4) + ld_shared_f32(sXD + (384 + r) * 4));
-                const float2 sl22 = splat2(sl2), nlse2 = splat2(-lse * 1.4426950408889634f);
-                const float2 sc2 = splat2(a.scale), ndsc2 = splat2(-delta * a.scale);
-                // ---- P = exp(S*scale - LSE) over this warp's kv columns ----
-                mbar_wait(bar(S_FULL), i);
-                tc_fence_after();
-#pragma unroll
-                for (int pc = 0; pc < 2; ++pc) {
-                    const int col = cbase + pc * 32;
-                    const int nj = pc == 0 ? 32 : n1;
-                    if (nj == 32) tmem_ld32(tA + lane_base + col, v);
-                    else tmem_ld16(tA + lane_base + col, v);
+                    const int col = cg * BWD_PC;                  // column inside the sub-tile
+                    const int kv0 = j * QT + col;                 // kv index of the chunk
+                    tmem_ld32(tR + col, v);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float2 e = fma2(make_float2(v[2 * j], v[2 * j + 1]), sl22, nlse2);
-                        v[2 * j] = fast_ex2(e.x); v[2 * j + 1] = fast_ex2(e.y);
+                    for (int k = 0; k < 16; ++k) {
+                        const float2 e = fma2(make_float2(v[2 * k], v[2 * k + 1]), sl22, nl2);
+                        v[2 * k] = fast_ex2(e.x); v[2 * k + 1] = fast_ex2(e.y);
                     }
-                    if (col + nj > a.T) {
+                    if (kv0 + 32 > a.T) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = (col + j < a.T) ? v[j] : 0.f;
+                        for (int k = 0; k < 32; ++k) v[k] = (kv0 + k < a.T) ? v[k] : 0.f;
                     }
 #pragma unroll
                     for (int q4 = 0; q4 < 4; ++q4) {
-                        if (q4 * 8 < nj) {
-                            uint4 pk;
-                            pk.x = pack_bf16x2(v[q4 * 8 + 0], v[q4 * 8 + 1]); pk.y = pack_bf16x2(v[q4 * 8 + 2], v[q4 * 8 + 3]);
-                            pk.z = pack_bf16x2(v[q4 * 8 + 4], v[q4 * 8 + 5]); pk.w = pack_bf16x2(v[q4 * 8 + 6], v[q4 * 8 + 7]);
-                            st_shared_v4(pbuf_addr(sP, r, (col >> 3) + q4), pk);
-                        }
+                        uint4 pk;
+                        pk.x = pack_bf16x2(v[q4 * 8 + 0], v[q4 * 8 + 1]); pk.y = pack_bf16x2(v[q4 * 8 + 2], v[q4 * 8 + 3]);
+                        pk.z = pack_bf16x2(v[q4 * 8 + 4], v[q4 * 8 + 5]); pk.w = pack_bf16x2(v[q4 * 8 + 6], v[q4 * 8 + 7]);
+                        st_shared_v4(pbuf_addr(pbuf, r, (col >> 3) + q4), pk);
                     }
                 }
                 fence_proxy_async_smem();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar(P_FULL));
-                // ---- dS = scale * P * (dP - delta) ----
-                mbar_wait(bar(DP_FULL), i);
-                tc_fence_after();
-#pragma unroll
-                for (int pc = 0; pc < 2; ++pc) {
-                    const int col = cbase + pc * 32;
-                    const int nj = pc == 0 ? 32 : n1;
-                    if (nj == 32) tmem_ld32(tA + lane_base + col, v);
-                    else tmem_ld16(tA + lane_base + col, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) {
-                        if (q4 * 8 < nj) {
-                            const uint4 pp = ld_shared_v4(pbuf_addr(sP, r, (col >> 3) + q4));
-                            const float* w = v + q4 * 8;
-                            const float2 d0 = mul2(unpack_bf16x2(pp.x), fma2(make_float2(w[0], w[1]), sc2, ndsc2));
-                            const float2 d1 = mul2(unpack_bf16x2(pp.y), fma2(make_float2(w[2], w[3]), sc2, ndsc2));
-                            const float2 d2 = mul2(unpack_bf16x2(pp.z), fma2(make_float2(w[4], w[5]), sc2, ndsc2));
-                            const float2 d3 = mul2(unpack_bf16x2(pp.w), fma2(make_float2(w[6], w[7]), sc2, ndsc2));
-                            uint4 pk;
-                            pk.x = pack_bf16x2(d0.x, d0.y); pk.y = pack_bf16x2(d1.x, d1.y);
-                            pk.z = pack_bf16x2(d2.x, d2.y); pk.w = pack_bf16x2(d3.x, d3.y);
-                            st_shared_v4(pbuf_addr(sDS, r, (col >> 3) + q4), pk);
-                        }
-                    }
-                }
-                fence_proxy_async_smem();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar(DS_FULL));
-                // ---- dQ epilogue: head-dim columns [16 cg, 16 cg + 16) ----
-                mbar_wait(bar(DQ_FULL), i);
-                tc_fence_after();
-                float w16[16];
-                tmem_ld16(tA + lane_base + cg * 16, w16);
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar(A_EMPTY));
-                dqkv_slice_acc(w16, t_ok, y0, y1, a.dqkv + qoff, g2, ag, ab);
-            }
-            reduce_cols16(ab, cs_bias);                      // d bias of q
-            // ---- dK / dV epilogue (kv rows: tile m covers kv = m*128 + r); the gated k / v slices are prefetched one ahead ----
-            auto slice_off = [&](int idx) {
-                const int which = 1 + (idx >> 1), kv = (idx & 1) * QT + r;
-                return ((size_t(b) * a.T + (kv < a.T ? kv : 0)) * 3 + which) * D + h * HD + cg * 16;
+                if (lane == 0) mbar_arrive(bar(P_FULL + i));
             };
-            uint4 n0 = __ldg(reinterpret_cast<const uint4*>(a.qkv + slice_off(0))),
-                  n1v = __ldg(reinterpret_cast<const uint4*>(a.qkv + slice_off(0)) + 1);
-            mbar_wait(bar(ACC_FULL), pi);
-            tc_fence_after();
+            // ---- dS = scale * P * (dP - delta), in place over P ----
+            auto phase_ds = [&](int i, int j) {
+                const uint32_t par = (i == 0 ? use0 : use1) & 1u;
+                if (i == 0) ++use0; else ++use1;
+                const uint32_t tR = tmem + i * 128 + lane_base;
+                const uint32_t pbuf = sP + i * PB_B;
+                const float2 nd2 = splat2(i == 0 ? ndsc_0 : ndsc_1);
+                mbar_wait(bar(DP_FULL + i), par);
+                tc_fence_after();
+                {
+                    const int col = cg * BWD_PC;
+                    const int kv0 = j * QT + col;
+                    tmem_ld32(tR + col, v);
+                    tmem_ld_wait();
+                    const bool ragged = kv0 + 32 > a.T;           // dP columns past T were never written by the MMA
 #pragma unroll
-            for (int idx = 0; idx < 4; ++idx) {
-                const int which = 1 + (idx >> 1), m = idx & 1;
-                const bool kv_ok = m * QT + r < a.T;
-                const uint4 x0 = n0, x1 = n1v;
-                if (idx < 3) {
-                    n0 = __ldg(reinterpret_cast<const uint4*>(a.qkv + slice_off(idx + 1)));
-                    n1v = __ldg(reinterpret_cast<const uint4*>(a.qkv + slice_off(idx + 1)) + 1);
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        const uint32_t ad = pbuf_addr(pbuf, r, (col >> 3) + q4);
+                        const uint4 pp = ld_shared_v4(ad);
+                        const float* w = v + q4 * 8;
+                        float2 d0 = mul2(unpack_bf16x2(pp.x), fma2(make_float2(w[0], w[1]), sc2, nd2));
+                        float2 d1 = mul2(unpack_bf16x2(pp.y), fma2(make_float2(w[2], w[3]), sc2, nd2));
+                        float2 d2 = mul2(unpack_bf16x2(pp.z), fma2(make_float2(w[4], w[5]), sc2, nd2));
+                        float2 d3 = mul2(unpack_bf16x2(pp.w), fma2(make_float2(w[6], w[7]), sc2, nd2));
+                        if (ragged) {
+                            const int k0 = kv0 + q4 * 8;
+                            d0.x = k0 + 0 < a.T ? d0.x : 0.f; d0.y = k0 + 1 < a.T ? d0.y : 0.f;
+                            d1.x = k0 + 2 < a.T ? d1.x : 0.f; d1.y = k0 + 3 < a.T ? d1.y : 0.f;
+                            d2.x = k0 + 4 < a.T ? d2.x : 0.f; d2.y = k0 + 5 < a.T ? d2.y : 0.f;
+                            d3.x = k0 + 6 < a.T ? d3.x : 0.f; d3.y = k0 + 7 < a.T ? d3.y : 0.f;
+                        }
+                        uint4 pk;
+                        pk.x = pack_bf16x2(d0.x, d0.y); pk.y = pack_bf16x2(d1.x, d1.y);
+                        pk.z = pack_bf16x2(d2.x, d2.y); pk.w = pack_bf16x2(d3.x, d3.y);
+                        st_shared_v4(ad, pk);
+                    }
                 }
-                float w16[16];
-                tmem_ld16((which == 1 ? tDK : tDV) + lane_base + m * HD + cg * 16, w16);
+                fence_proxy_async_smem();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(DS_FULL + i));
+            };
+            // ---- dK_j / dV_j epilogue of a finished kv half (kv row = j*128 + r, head-dim columns [32 cg, 32 cg + 32)) ----
+            auto epi_kv = [&](int j) {
+                const int kv = j * QT + r;
+                const bool kv_ok = kv < a.T;
+                const size_t off = ((size_t(b) * a.T + (kv_ok ? kv : 0)) * 3 + 1) * D + h * HD + cg * BWD_EC;
+                const uint4 k0 = __ldg(reinterpret_cast<const uint4*>(a.qkv + off)), k1 = __ldg(reinterpret_cast<const uint4*>(a.qkv + off) + 1);
+                const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(a.qkv + off + D)), v1 = __ldg(reinterpret_cast<const uint4*>(a.qkv + off + D) + 1);
+                mbar_wait(bar(ACC_FULL), n_acc & 1u);
+                ++n_acc;
+                tc_fence_after();
+                float w1[16], w2[16];
+                tmem_ld16(tDK + lane_base + cg * BWD_EC, w1);
+                tmem_ld16(tDV + lane_base + cg * BWD_EC, w2);
                 tmem_ld_wait();
-                if (idx == 3) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar(ACC_EMPTY));
-                }
-                dqkv_slice_acc(w16, kv_ok, x0, x1, a.dqkv + slice_off(idx), g2, ag, ab);
-                if (m == 1) reduce_cols16(ab, cs_bias + which * 64);     // d bias of k, then of v
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(ACC_EMPTY));
+                dqkv_slice16(w1, kv_ok, k0, k1, a.dqkv + off, gate16, ag, cs_bias + 64);
+                dqkv_slice16(w2, kv_ok, v0, v1, a.dqkv + off + D, gate16, ag, cs_bias + 128);
+            };
+            if (nt == 1) {
+                phase_p(0, 0);
+                phase_ds(0, 0);
+            } else {
+                phase_p(0, 0); phase_p(1, 0);
+                phase_ds(0, 0); phase_ds(1, 0);
+                phase_p(0, 1);
+                epi_kv(0);                                       // its TMEM reads release dK / dV for the second kv half
+                phase_p(1, 1);
+                phase_ds(0, 1); phase_ds(1, 1);
             }
-            reduce_cols16(ag, cs_gate);                      // d gate: q, k and v contributions together
+            epi_kv(nh - 1);
+            // ---- dQ epilogue of both q tiles ----
+            {
+                mbar_wait(bar(DQ_FULL), pi);
+                tc_fence_after();
+#pragma unroll 1
+                for (int i = 0; i < nh; ++i) {
+                    const int t = i * QT + r;
+                    const size_t qoff = ((size_t(b) * a.T + (t < a.T ? t : 0)) * 3 + 0) * D + h * HD + cg * BWD_EC;
+                    const uint4 x0 = __ldg(reinterpret_cast<const uint4*>(a.qkv + qoff)), x1 = __ldg(reinterpret_cast<const uint4*>(a.qkv + qoff) + 1);
+                    float w1[16];
+                    tmem_ld16(tDQ + i * HD + lane_base + cg * BWD_EC, w1);
+                    tmem_ld_wait();
+                    if (i == nh - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar(DQ_EMPTY));
+                    }
+                    dqkv_slice16(w1, t < a.T, x0, x1, a.dqkv + qoff, gate16, ag, cs_bias);
+                }
+            }
+            // d gate: q, k and v contributions of all rows of this warp
+            {
+                float tsum[16];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { tsum[2 * j] = ag[j].x; tsum[2 * j + 1] = ag[j].y; }
+                const float sg = bfly16(tsum);
+                if ((lane & 1) == 0) atomicAdd(cs_gate + (lane >> 1), sg);
+            }
             // ---- per-item column sums -> global partials; the accumulator of this parity is re-zeroed for item it+2 ----
             named_bar_sync(1, BWD_CT);
             {
@@ -633,7 +719,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 // host
 // ---------------------------------------------------------------------------------------------
 static constexpr int FWD_SMEM = 2 * TILE_B + 2 * KV_B + 2 * PBUF_B + 4096 + 256;
-static constexpr int BWD_SMEM = 2 * TILE_B + 2 * KV_B + 2 * PBUF_B + 4096 + 256;
+static constexpr int BWD_SMEM = 4 * TILE_B + 2 * KV_B + 2 * PB_B + 2048 + 4096 + 256;
 
 static int make_qkv_maps(const void* qkv, int B, int T, int H, CUtensorMap* tq, CUtensorMap* tkv) {
     const uint64_t D = uint64_t(H) * HD;
