@@ -16,6 +16,7 @@
 #include "ptx.cuh"
 #include "gemm.cuh"
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace ofb {
 
@@ -27,10 +28,13 @@ static constexpr int GEMM_THREADS = 64 + EPI_THREADS;     // warp0 TMA, warp1 MM
 static constexpr int SMEM_LIMIT = 232448;                 // 227 KB
 static constexpr int PANEL_BYTES = BM * 128;              // one [128 rows][64 bf16] SWIZZLE_128B output panel
 
-template <int BN, int EPI, int TMA_OUT>
+// CG = CTAs per tile: 1, or 2 for a CTA pair (cta_group::2) that shares one 256-row UMMA: each CTA stages its own 128 rows of A
+// but only HALF of the B tile, which cuts the L2 -> shared-memory operand traffic per MAC from (128 + BN) / (128 BN) to
+// (128 + BN / 2) / (128 BN). The 1-CTA kernel is bound by exactly that feed (profiles/r01_experiments.md).
+template <int BN, int EPI, int TMA_OUT, int CG = 1>
 struct GemmCfg {
     static constexpr int A_BYTES = BM * BK * 2;
-    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2 / CG;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int NOUT = (EPI == EPI_FC1) ? 2 : 1;
     static constexpr int STAGING_BYTES = TMA_OUT ? 2 * NOUT * PANEL_BYTES : 0;          // two slots
@@ -168,14 +172,18 @@ __device__ __forceinline__ uint32_t packed_word(const Packed32& r, int i) {
 
 // TMA_OUT: 0 = direct global stores; 1 = bf16 output panels staged in smem and written by TMA; 2 = 1 + the residual (STORE) /
 // saved activation (FC2_DGRAD) tile is TMA-loaded into smem panels two panels ahead of its use.
-template <int BN, int A_MN, int B_MN, int EPI, int TMA_OUT>
+template <int BN, int A_MN, int B_MN, int EPI, int TMA_OUT, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_o0, const __grid_constant__ CUtensorMap tma_o1,
             const __grid_constant__ CUtensorMap tma_aux, const GemmArgs g) {
-    using Cfg = GemmCfg<BN, EPI, TMA_OUT>;
+    using Cfg = GemmCfg<BN, EPI, TMA_OUT, CG>;
     constexpr int STAGES = Cfg::STAGES;
-    constexpr uint32_t IDESC = make_idesc_bf16(BM, BN, A_MN, B_MN);
+    constexpr uint32_t IDESC = make_idesc_bf16(BM * CG, BN, A_MN, B_MN);
+    // CTA pair: rank in the cluster (0 = leader, issues the MMAs), pair index / pair count replace the CTA index / grid size
+    const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const int cta_first = (CG == 2) ? int(blockIdx.x >> 1) : int(blockIdx.x);
+    const int cta_stride = (CG == 2) ? int(gridDim.x >> 1) : int(gridDim.x);
     // transposed-hidden epilogues: rows = hidden units (few m tiles, the weight operand), columns = tokens; walking the m
     // tiles of one token tile back to back keeps that token tile in L2
     constexpr bool M_FAST = (EPI == EPI_FC1 || EPI == EPI_FC2_DGRAD);
@@ -215,65 +223,93 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&tfull_bar[i]), 1);
-            mbar_init(smem_u32(&tempty_bar[i]), EPI_WARPS);
+            mbar_init(smem_u32(&tempty_bar[i]), EPI_WARPS * CG);      // pair: the epilogue warps of both CTAs release the leader's MMA
         }
         mbar_fence_init();
     }
     if (warp == 1) {
-        tmem_alloc(smem_u32(tmem_slot), Cfg::TMEM_COLS);
-        tmem_relinquish();
+        if (CG == 2) { tmem_alloc_cg2(smem_u32(tmem_slot), Cfg::TMEM_COLS); tmem_relinquish_cg2(); }
+        else { tmem_alloc(smem_u32(tmem_slot), Cfg::TMEM_COLS); tmem_relinquish(); }
     }
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();          // the peer's barriers are initialised before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int m_tiles = (g.M + BM - 1) / BM;
+    const int m_tiles = (g.M + BM - 1) / BM;              // 128-row tiles (epilogue granularity)
+    const int mt = (CG == 2) ? (m_tiles + 1) / 2 : m_tiles;   // scheduled row tiles (128 CG rows each)
     const int n_tiles = (g.N + BN - 1) / BN;
     const int k_blocks = (g.K + BK - 1) / BK;
     const int splits = g.k_splits > 0 ? g.k_splits : 1;
     const int kb_per_split = (k_blocks + splits - 1) / splits;
-    const int total_tiles = m_tiles * n_tiles * splits;
+    const int total_tiles = mt * n_tiles * splits;
+    // scheduled tile index -> (split, 128-row tile of THIS CTA, column tile)
+    auto decode = [&](int t, int& split, int& m_blk, int& n_blk) {
+        split = t / (mt * n_tiles);
+        const int mn = t % (mt * n_tiles);
+        const int pm = M_FAST ? mn % mt : mn / n_tiles;
+        n_blk = M_FAST ? mn / mt : mn % n_tiles;
+        m_blk = (CG == 2) ? pm * 2 + int(rank) : pm;
+    };
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int split = t / (m_tiles * n_tiles);
-                const int mn = t % (m_tiles * n_tiles);
-                const int m_blk = M_FAST ? mn % m_tiles : mn / n_tiles, n_blk = M_FAST ? mn / m_tiles : mn % n_tiles;
+            for (int t = cta_first; t < total_tiles; t += cta_stride) {
+                int split, m_blk, n_blk;
+                decode(t, split, m_blk, n_blk);
                 const int kb0 = split * kb_per_split;
                 const int kb1 = min(k_blocks, kb0 + kb_per_split);
+                const int nrow0 = n_blk * BN + int(rank) * (BN / CG);     // pair: this CTA stages its half of the B tile
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-                    const uint32_t fb = smem_u32(&full_bar[stage]);
-                    mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
                     const uint32_t sa = smem_u32(smem_a + stage * Cfg::A_BYTES);
                     const uint32_t sb = smem_u32(smem_b + stage * Cfg::B_BYTES);
-                    if (A_MN) {
+                    if (CG == 2) {
+                        // both CTAs' copies complete on the LEADER's full barrier, which expects the bytes of the pair
+                        const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
+                        if (rank == 0) mbar_arrive_expect_tx(smem_u32(&full_bar[stage]), 2 * Cfg::STAGE_BYTES);
+                        if (A_MN) {
 #pragma unroll
-                        for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BK * 128), &tma_a, fb, m_blk * BM + j * 64, kb * BK);
-                    } else {
-                        tma_load_2d(sa, &tma_a, fb, kb * BK, m_blk * BM);
-                    }
-                    if (B_MN) {
+                            for (int j = 0; j < BM / 64; ++j) tma_load_2d_cg2(sa + j * (BK * 128), &tma_a, fb, m_blk * BM + j * 64, kb * BK);
+                        } else {
+                            tma_load_2d_cg2(sa, &tma_a, fb, kb * BK, m_blk * BM);
+                        }
+                        if (B_MN) {
 #pragma unroll
-                        for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * (BK * 128), &tma_b, fb, n_blk * BN + j * 64, kb * BK);
+                            for (int j = 0; j < BN / CG / 64; ++j) tma_load_2d_cg2(sb + j * (BK * 128), &tma_b, fb, nrow0 + j * 64, kb * BK);
+                        } else {
+                            tma_load_2d_cg2(sb, &tma_b, fb, kb * BK, nrow0);
+                        }
                     } else {
-                        tma_load_2d(sb, &tma_b, fb, kb * BK, n_blk * BN);
+                        const uint32_t fb = smem_u32(&full_bar[stage]);
+                        mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
+                        if (A_MN) {
+#pragma unroll
+                            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BK * 128), &tma_a, fb, m_blk * BM + j * 64, kb * BK);
+                        } else {
+                            tma_load_2d(sa, &tma_a, fb, kb * BK, m_blk * BM);
+                        }
+                        if (B_MN) {
+#pragma unroll
+                            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * (BK * 128), &tma_b, fb, n_blk * BN + j * 64, kb * BK);
+                        } else {
+                            tma_load_2d(sb, &tma_b, fb, kb * BK, n_blk * BN);
+                        }
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (pair: the leader CTA only) =====================
+        if (lane == 0 && rank == 0) {
             int stage = 0; uint32_t phase = 0;
             int it = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int split = t / (m_tiles * n_tiles);
+            for (int t = cta_first; t < total_tiles; t += cta_stride) {
+                const int split = t / (mt * n_tiles);
                 const int kb0 = split * kb_per_split;
                 const int kb1 = min(k_blocks, kb0 + kb_per_split);
                 if (kb1 <= kb0) continue;
@@ -296,10 +332,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                                                  : make_smem_desc_sw128(sa + k * 32, 0, 1024);
                         const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * 2048, BK * 128, 1024)
                                                  : make_smem_desc_sw128(sb + k * 32, 0, 1024);
-                        umma_bf16(d_tmem, da, db, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+                        if (CG == 2) umma_bf16_cg2(d_tmem, da, db, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+                        else umma_bf16(d_tmem, da, db, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
                     }
-                    umma_commit(smem_u32(&empty_bar[stage]));
-                    if (kb == kb1 - 1) umma_commit(smem_u32(&tfull_bar[acc]));
+                    if (CG == 2) {
+                        umma_commit_cg2(smem_u32(&empty_bar[stage]));          // frees the stage in both CTAs
+                        if (kb == kb1 - 1) umma_commit_cg2(smem_u32(&tfull_bar[acc]));
+                    } else {
+                        umma_commit(smem_u32(&empty_bar[stage]));
+                        if (kb == kb1 - 1) umma_commit(smem_u32(&tfull_bar[acc]));
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -317,10 +359,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         // TMA_OUT == 2: panel number P of this CTA (tile sequence P / NPT, panel P % NPT) is loaded into aux slot P % AUX_SLOTS
         constexpr uint32_t NPT = NCHUNK / 2;
         auto issue_aux = [&](uint32_t P) {
-            const long t2 = long(blockIdx.x) + long(P / NPT) * gridDim.x;
+            const long t2 = long(cta_first) + long(P / NPT) * cta_stride;
             if (t2 >= total_tiles) return;
-            const int mn2 = int(t2 % (long(m_tiles) * n_tiles));      // k_splits == 1 for these epilogues
-            const int m2 = M_FAST ? mn2 % m_tiles : mn2 / n_tiles, n2 = M_FAST ? mn2 / m_tiles : mn2 % n_tiles;
+            int s2, m2, n2;                                           // k_splits == 1 for these epilogues
+            decode(int(t2), s2, m2, n2);
             const uint32_t fb = smem_u32(&aux_full[P % AUX_SLOTS]);
             mbar_arrive_expect_tx(fb, PANEL_BYTES);
             tma_load_2d(smem_u32(auxbuf) + (P % AUX_SLOTS) * PANEL_BYTES, &tma_aux, fb, n2 * BN + int(P % NPT) * 64, m2 * BM);
@@ -328,10 +370,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         if (TMA_OUT == 2 && elected) {
             for (uint32_t i = 0; i < AUX_SLOTS; ++i) issue_aux(i);
         }
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            const int split = t / (m_tiles * n_tiles);
-            const int mn = t % (m_tiles * n_tiles);
-            const int m_blk = M_FAST ? mn % m_tiles : mn / n_tiles, n_blk = M_FAST ? mn / m_tiles : mn % n_tiles;
+        // pair: the accumulator stage is handed back to the leader's MMA warp (remote arrive from the peer CTA)
+        const uint32_t tempty_remote0 = (CG == 2) ? mapa_shared(smem_u32(&tempty_bar[0]), 0) : 0u;
+        for (int t = cta_first; t < total_tiles; t += cta_stride) {
+            int split, m_blk, n_blk;
+            decode(t, split, m_blk, n_blk);
+            const int mn = m_blk * n_tiles + n_blk;       // tile id for per-tile partial outputs
             const int kb0 = split * kb_per_split;
             const int kb1 = min(k_blocks, kb0 + kb_per_split);
             if (kb1 <= kb0) continue;
@@ -399,7 +443,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     // this warp's last TMEM read of the tile: hand the accumulator stage back to the MMA warp early
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+                    if (lane == 0) {
+                        if (CG == 2) mbar_arrive_cluster(tempty_remote0 + acc * 8);
+                        else mbar_arrive(smem_u32(&tempty_bar[acc]));
+                    }
                 }
                 const int col0 = n0 + c * 32;
                 const int nvalid = min(32, g.N - col0);
@@ -591,7 +638,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             }
             if (EPI == EPI_DECODER) {
                 const float s = warp_sum(loss_acc);
-                if (lane == 0) g.colpart0[size_t(mn) * EPI_WARPS + ew] = s;
+                if (lane == 0 && m_blk < m_tiles) g.colpart0[size_t(mn) * EPI_WARPS + ew] = s;
             }
         }
         if (TMA_OUT && elected) bulk_wait<0>();    // all output panels fully written before the CTA retires
@@ -599,10 +646,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();          // neither CTA may retire while the pair's MMAs / remote arrivals can still touch it
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        if (CG == 2) tmem_dealloc_cg2(tmem_base, Cfg::TMEM_COLS);
+        else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
 }
 
@@ -654,11 +703,11 @@ int num_sms() {
     return g_num_sms;
 }
 
-template <int BN, int A_MN, int B_MN, int EPI, int TMA_OUT>
+template <int BN, int A_MN, int B_MN, int EPI, int TMA_OUT, int CG>
 static int launch_gemm_inst(const void* A, int lda, const void* B, int ldb, const GemmArgs& g, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN, EPI, TMA_OUT>;
+    using Cfg = GemmCfg<BN, EPI, TMA_OUT, CG>;
     static bool configured = false;
-    auto kfn = gemm_kernel<BN, A_MN, B_MN, EPI, TMA_OUT>;
+    auto kfn = gemm_kernel<BN, A_MN, B_MN, EPI, TMA_OUT, CG>;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return int(e);
@@ -666,7 +715,7 @@ static int launch_gemm_inst(const void* A, int lda, const void* B, int ldb, cons
     }
     CUtensorMap ta, tb, to0, to1, tx;
     {
-        // K-major: tensor [rows, K] row-major -> dims {K, rows}, box {64, 128|BN}
+        // K-major: tensor [rows, K] row-major -> dims {K, rows}, box {64, 128|BN/CG}
         // MN-major: tensor [K, rows] row-major -> dims {rows, K}, box {64, 64}
         uint64_t dims[2], str[2];
         uint32_t box[2];
@@ -676,7 +725,7 @@ static int launch_gemm_inst(const void* A, int lda, const void* B, int ldb, cons
         int r = make_tmap_bf16(&ta, A, 2, dims, str, box);
         if (r) return r;
         if (B_MN) { dims[0] = g.N; dims[1] = g.K; box[0] = 64; box[1] = BK; }
-        else      { dims[0] = g.K; dims[1] = g.N; box[0] = BK; box[1] = BN; }
+        else      { dims[0] = g.K; dims[1] = g.N; box[0] = BK; box[1] = BN / CG; }
         str[1] = uint64_t(ldb);
         r = make_tmap_bf16(&tb, B, 2, dims, str, box);
         if (r) return r;
@@ -703,10 +752,21 @@ static int launch_gemm_inst(const void* A, int lda, const void* B, int ldb, cons
         }
     }
     const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + BN - 1) / BN;
-    const int total = m_tiles * n_tiles * (g.k_splits > 0 ? g.k_splits : 1);
-    const int grid = total < num_sms() ? total : num_sms();
-    kfn<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, to0, to1, tx, g);
-    return int(cudaGetLastError());
+    const int mt = (m_tiles + CG - 1) / CG;
+    const int total = mt * n_tiles * (g.k_splits > 0 ? g.k_splits : 1);
+    const int slots = num_sms() / CG;
+    const int grid = (total < slots ? total : slots) * CG;
+    if (CG == 1) {
+        kfn<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, to0, to1, tx, g);
+        return int(cudaGetLastError());
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return int(cudaLaunchKernelEx(&cfg, kfn, ta, tb, to0, to1, tx, g));
 }
 
 // pick the N tile: fewest (waves x tile width) with a penalty for narrow tiles (shared-memory bandwidth per MMA)
@@ -734,13 +794,38 @@ static int pick_bn(int M, int N, int splits_ok) {
     return best;
 }
 
+// CTA pairs (cta_group::2) per epilogue: bit e of the mask allows them for epilogue e. Default: the main-loop-bound epilogues
+// (plain / residual stores, patch embed, decoder). The transposed-hidden epilogues (FC1, FC2_DGRAD) are bound by their
+// epilogue arithmetic and lose a little when two CTAs have to hand their accumulators back together (measured in situ:
+// +11 % / +9 %), and the split-K weight gradients gain nothing. OFB_GEMM_PAIR_MASK overrides (0 = never).
+static int pair_mask() {
+    static int mask = -1;
+    if (mask < 0) {
+        const char* e = getenv("OFB_GEMM_PAIR_MASK");
+        mask = e ? atoi(e) : ((1 << EPI_STORE) | (1 << EPI_PATCH) | (1 << EPI_DECODER));
+    }
+    return mask;
+}
+static bool pair_ok(int epi, int M, int bn, bool b_mn) {
+    // a pair needs at least two 128-row tiles, a B half that is a whole number of 64-wide MN atoms, and a tile width >= 128
+    return ((pair_mask() >> epi) & 1) && M > BM && bn >= 128 && (!b_mn || bn % 128 == 0);
+}
+
 template <int A_MN, int B_MN, int EPI, int TMA_OUT>
 static int launch_gemm_bn(int bn, const void* A, int lda, const void* B, int ldb, const GemmArgs& g, cudaStream_t s) {
+    const bool pair = pair_ok(EPI, g.M, bn, B_MN != 0);
+    if (pair) {
+        switch (bn) {
+            case 256: return launch_gemm_inst<256, A_MN, B_MN, EPI, TMA_OUT, 2>(A, lda, B, ldb, g, s);
+            case 192: if constexpr (!B_MN) return launch_gemm_inst<192, A_MN, B_MN, EPI, TMA_OUT, 2>(A, lda, B, ldb, g, s); else break;
+            default:  return launch_gemm_inst<128, A_MN, B_MN, EPI, TMA_OUT, 2>(A, lda, B, ldb, g, s);
+        }
+    }
     switch (bn) {
-        case 256: return launch_gemm_inst<256, A_MN, B_MN, EPI, TMA_OUT>(A, lda, B, ldb, g, s);
-        case 192: return launch_gemm_inst<192, A_MN, B_MN, EPI, TMA_OUT>(A, lda, B, ldb, g, s);
-        case 128: return launch_gemm_inst<128, A_MN, B_MN, EPI, TMA_OUT>(A, lda, B, ldb, g, s);
-        default:  return launch_gemm_inst<64, A_MN, B_MN, EPI, TMA_OUT>(A, lda, B, ldb, g, s);
+        case 256: return launch_gemm_inst<256, A_MN, B_MN, EPI, TMA_OUT, 1>(A, lda, B, ldb, g, s);
+        case 192: return launch_gemm_inst<192, A_MN, B_MN, EPI, TMA_OUT, 1>(A, lda, B, ldb, g, s);
+        case 128: return launch_gemm_inst<128, A_MN, B_MN, EPI, TMA_OUT, 1>(A, lda, B, ldb, g, s);
+        default:  return launch_gemm_inst<64, A_MN, B_MN, EPI, TMA_OUT, 1>(A, lda, B, ldb, g, s);
     }
 }
 
@@ -750,10 +835,17 @@ int launch_gemm(int epi, int a_mn, int b_mn, int bn_hint, const void* A, int lda
                 cudaStream_t stream) {
     if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 0;
     int bn = bn_hint > 0 ? bn_hint : pick_bn(g.M, g.N, epi == EPI_WGRAD);
+    // data-gradient GEMMs read the weight as an MN-major B operand, whose half per CTA of a pair must be whole 64-wide atoms:
+    // with a long reduction a 256-wide pair tile beats the 192-wide single-CTA tile even at 25 % column padding (measured in
+    // situ at N = 384: K = 1536 94 -> 79 us, K = 1152 75 -> 65 us; K = 384 is epilogue-bound and stays on 192)
+    if (bn_hint <= 0 && epi == EPI_STORE && b_mn && g.K >= 768 && g.N > 128 && pair_ok(EPI_STORE, g.M, 256, true)) bn = 256;
     if (epi == EPI_WGRAD) {
         if (g.k_splits <= 0) {
-            const int tiles = ((g.M + BM - 1) / BM) * ((g.N + bn - 1) / bn);
-            int s = num_sms() / tiles;
+            // same predicate as launch_gemm_bn: a CTA pair covers 256 rows and there are num_sms / 2 pairs
+            const bool pair = pair_ok(EPI_WGRAD, g.M, bn, b_mn != 0);
+            const int m_tiles = (g.M + BM - 1) / BM;
+            const int tiles = (pair ? (m_tiles + 1) / 2 : m_tiles) * ((g.N + bn - 1) / bn);
+            int s = (pair ? num_sms() / 2 : num_sms()) / tiles;
             const int kb = (g.K + BK - 1) / BK;
             if (s < 1) s = 1;
             if (s > kb) s = kb;
