@@ -43,6 +43,15 @@ def parse():
     return ap.parse_args()
 
 
+def gemm_traffic():
+    """Measured DRAM traffic of the GEMM family per launch (ncu --set full capture of this workload, profiles/): only valid
+    for the configuration it was captured on (DeiT-small, batch 256)."""
+    path = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    if os.path.exists(path):
+        return json.load(open(path))
+    return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -262,6 +271,7 @@ def main():
 
     if rank == 0:
         pk = peaks()
+        tr = gemm_traffic()
         achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
         line = {
             "metric": "images/sec DeiT-S bi-mask search step (fwd+bwd+update, PMIM on)",
@@ -269,7 +279,7 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"DeiT-{args.model} bi-mask search + PMIM step, depth {args.depth}, batch {B}/GPU, 224px "
-                                   f"(BASELINE.json configs[1])", "global_batch": eff, "parallelism": f"dp{world}",
+                                   + ("(BASELINE.json configs[1])" if args.model == "small" else "(BASELINE.json parity / extra configuration)"), "global_batch": eff, "parallelism": f"dp{world}",
                        "l2": "activations per step (>7 GB) exceed the 126 MB L2; no explicit flush",
                        "launch": "host launches" if args.no_graph else "CUDA graph replay (one graph per input buffer)",
                        "step_gflop_per_image": STEP_GFLOP.get(args.model)},
@@ -277,7 +287,12 @@ def main():
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": "ofb::gemm_kernel (tcgen05, all epilogues)", "achieved": achieved,
-                         "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": None,
+                         "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
+                         "traffic": (tr["dram_bytes_per_launch"] if tr and args.model == "small" and B == 256 and args.depth == 12
+                                     else None),
+                         "traffic_note": "DRAM bytes per GEMM launch (mean over the 152 launches of a step), ncu --set full, "
+                                         "profiles/r01_gemm_traffic.json; algorithmic FLOPs per launch = "
+                                         f"{gemm_flops / max(len(gemm_t), 1):.4g}",
                          "peak_source": pk["src"], "launches_per_step": len(gemm_t) / max(n_roof, 1),
                          "share_of_step": (gemm_ms / n_roof) / (ms / args.steps) if ms > 0 else None,
                          "timed_over": f"{n_roof} host-launched steps, one CUDA-event pair per GEMM launch",

@@ -570,34 +570,64 @@ __global__ void cls_rows_kernel(const float* __restrict__ cls, const float* __re
 //   part_mt[t,:]   = sum_b g0*gate*mask                    (d mask_token, rows t >= 1)
 // grid = (T, ceil(D/128)); thread = one column, loops over the batch.
 // =============================================================================================
-__global__ void embed_bwd_kernel(const __nv_bfloat16* __restrict__ g0, const __nv_bfloat16* __restrict__ x0,
+// one block per token position t: thread (vc, gq) owns 8 columns and the images b = gq, gq + G, ...; 16-byte loads, several rows
+// in flight per thread, then a shared-memory reduction over the G image groups
+__global__ void __launch_bounds__(512) embed_bwd_kernel(const __nv_bfloat16* __restrict__ g0, const __nv_bfloat16* __restrict__ x0,
                                  const float* __restrict__ gate, const float* __restrict__ mask, __nv_bfloat16* __restrict__ dconv,
                                  float* __restrict__ part_gx, float* __restrict__ part_pos, float* __restrict__ part_mt, int B, int T,
-                                 int D) {
+                                 int D, int G) {
+    extern __shared__ float eb_red[];                  // [G][D]
     const int t = blockIdx.x;
-    const int col = blockIdx.y * blockDim.x + threadIdx.x;
-    if (col >= D) return;
-    const float g = gate[col];
+    const int VC = D >> 3;
+    const int vc = threadIdx.x % VC, gq = threadIdx.x / VC;
     const int L = T - 1;
-    float agx = 0.f, apos = 0.f, amt = 0.f;
-    for (int b = 0; b < B; ++b) {
-        const size_t off = (size_t(b) * T + t) * D + col;
-        const float gr = __bfloat162float(g0[off]);
-        const float xv = __bfloat162float(x0[off]);
-        agx += gr * xv;
-        if (t == 0) {
-            apos += gr * g;
-        } else {
-            const float mk = mask[size_t(b) * L + t - 1];
-            const float dc = gr * g * (1.f - mk);
-            apos += dc;
-            amt += gr * g * mk;
-            dconv[(size_t(b) * L + t - 1) * D + col] = __float2bfloat16(dc);
+    float agx[8], apos[8], amt[8], gt[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { agx[j] = apos[j] = amt[j] = 0.f; gt[j] = 0.f; }
+    if (gq < G) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gt[j] = __ldg(gate + vc * 8 + j);
+#pragma unroll 4
+        for (int b = gq; b < B; b += G) {
+            const size_t off = (size_t(b) * T + t) * D + vc * 8;
+            float gr[8], xv[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(g0 + off)), gr);
+            unpack8(__ldg(reinterpret_cast<const uint4*>(x0 + off)), xv);
+            if (t == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { agx[j] = fmaf(gr[j], xv[j], agx[j]); apos[j] = fmaf(gr[j], gt[j], apos[j]); }
+            } else {
+                const float mk = __ldg(mask + size_t(b) * L + t - 1);
+                float dc[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    agx[j] = fmaf(gr[j], xv[j], agx[j]);
+                    const float gg = gr[j] * gt[j];
+                    dc[j] = gg * (1.f - mk);
+                    apos[j] += dc[j];
+                    amt[j] = fmaf(gg, mk, amt[j]);
+                }
+                *reinterpret_cast<uint4*>(dconv + (size_t(b) * L + t - 1) * D + vc * 8) = pack8(dc);
+            }
         }
     }
-    part_gx[size_t(t) * D + col] = agx;
-    part_pos[size_t(t) * D + col] = apos;
-    part_mt[size_t(t) * D + col] = amt;
+    // three reductions over the image groups through the same buffer
+    float* outs[3] = {part_gx, part_pos, part_mt};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float* src = k == 0 ? agx : (k == 1 ? apos : amt);
+        __syncthreads();
+        if (gq < G) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) eb_red[gq * D + vc * 8 + j] = src[j];
+        }
+        __syncthreads();
+        for (int col = threadIdx.x; col < D; col += blockDim.x) {
+            float a = 0.f;
+            for (int q2 = 0; q2 < G; ++q2) a += eb_red[q2 * D + col];
+            outs[k][size_t(t) * D + col] = a;
+        }
+    }
 }
 
 // =============================================================================================
@@ -965,9 +995,15 @@ int launch_cls_rows(const float* cls, const float* pos, const float* gate, void*
 
 int launch_embed_bwd(const void* g0, const void* x0, const float* gate, const float* mask, void* dconv, float* part_gx, float* part_pos,
                      float* part_mt, int B, int T, int D, cudaStream_t s) {
-    dim3 grid(T, (D + 127) / 128);
-    embed_bwd_kernel<<<grid, 128, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(g0), reinterpret_cast<const __nv_bfloat16*>(x0), gate, mask,
-                                          reinterpret_cast<__nv_bfloat16*>(dconv), part_gx, part_pos, part_mt, B, T, D);
+    if (D % 8 != 0 || D > 4096) return 1011;
+    const int VC = D / 8;
+    int G = 512 / VC;
+    if (G > 16) G = 16;
+    if (G > B) G = B;
+    if (G < 1) return 1011;
+    const int threads = ((VC * G + 31) / 32) * 32;
+    embed_bwd_kernel<<<T, threads, size_t(G) * D * sizeof(float), s>>>(reinterpret_cast<const __nv_bfloat16*>(g0),
+        reinterpret_cast<const __nv_bfloat16*>(x0), gate, mask, reinterpret_cast<__nv_bfloat16*>(dconv), part_gx, part_pos, part_mt, B, T, D, G);
     return err();
 }
 

@@ -577,13 +577,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     if (row_ok && nvalid > 0) {
                         const int b = row / g.tokens, l = row % g.tokens;
                         const float mk = __ldg(g.rowmask + row);
-                        const float* pos = g.pos + size_t(1 + l) * g.N + col0;
+                        float add[32];        // positional embedding of a kept patch, or the mask token of a removed one
+                        if (mk != 0.f) {
+                            load_f32x32(g.mask_token + col0, add, nvalid);
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            if (i < nvalid) {
-                                const float val = v[i] + cb[i] + __ldg(pos + i);
-                                v[i] = (mk != 0.f ? __ldg(g.mask_token + col0 + i) : val) * cs[i];
-                            }
+                            for (int i = 0; i < 32; ++i) v[i] = add[i] * cs[i];
+                        } else {
+                            load_f32x32(g.pos + size_t(1 + l) * g.N + col0, add, nvalid);
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = (v[i] + cb[i] + add[i]) * cs[i];
                         }
                         const size_t orow = size_t(b) * (g.tokens + 1) + 1 + l;
                         store_bf16x32(reinterpret_cast<__nv_bfloat16*>(g.out0) + orow * g.ld0 + col0, v, nvalid);

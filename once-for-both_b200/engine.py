@@ -138,6 +138,27 @@ class BimaskTable:
         m = self.modules[i]
         return self.gate[m["gate_off"]:m["gate_off"] + m["heads"] * m["dim"]]
 
+    def pruned_index_sets(self):
+        """Kept-unit index sets of every searchable module for every candidate of its search space, i.e. what the reference's
+        compress() would physically keep when it slices to that candidate: channels = argsort(score, descending)[:width]
+        (per head for attention: layers.py:614-620, 666-670; MLP 932-933, 967-968; embed 268-269, 308-309), heads =
+        argsort(sigmoid(score).sum(-1), descending)[:n]. Read from the device-side ranks of the last forward (ties broken by
+        the lower index). Returns {prefix: {"channels": {width: [sorted indices per head]}, "heads": {n: sorted indices}}}."""
+        rank = self.rank.cpu()
+        wl = self._widths
+        out = {}
+        for m in self.modules:
+            H, dim = m["heads"], m["dim"]
+            r = rank[m["gate_off"]:m["gate_off"] + H * dim].view(H, dim)
+            hr, cr = r[:, 0] // dim, r % dim
+            widths = wl[m["width_off"]:m["width_off"] + m["n_j"]]
+            counts = wl[m["width_off"] + m["n_j"]:m["width_off"] + m["n_j"] + (m["n_i"] if m["kind"] == 2 else 0)]
+            out[m["prefix"]] = {
+                "channels": {int(w): [torch.nonzero(cr[h] < w).flatten().tolist() for h in range(H)] for w in widths},
+                "heads": {int(n): torch.nonzero(hr < n).flatten().tolist() for n in counts},
+            }
+        return out
+
     def forward(self, params, w_p_dev):
         n = len(self.modules)
         ops.bimask_fwd(self.mods_dev, n, self.max_n, params, self.switches_dev, self.widths_dev, w_p_dev, self.gate,
@@ -262,6 +283,7 @@ class SearchStepEngine:
         self.rand_u = torch.empty(B * self.L + depth * 2 * B, **f32)
         self._dp_bounds = dp.bucket_bounds(self.n_arena)
         self._graphs = {}          # (images ptr, labels ptr, keep) -> (CUDAGraph, kernel launches per replay)
+        self._side = None          # side stream of the gate construction (see forward)
 
     # ------------------------------------------------------------------------------------------------------------
     def _param_shapes(self):
@@ -333,6 +355,10 @@ class SearchStepEngine:
             self.p(k).copy_(t)
         self.sync_shadow()
 
+    def pruned_index_sets(self):
+        """Per-layer kept-unit index sets after thresholding (see BimaskTable.pruned_index_sets); valid after a forward."""
+        return self.bimask.pruned_index_sets()
+
     def sync_shadow(self):
         ops.cast_bf16(self.params, self.shadow)
 
@@ -360,7 +386,15 @@ class SearchStepEngine:
         B, D, H, T, L, M, ML, hid = self.B, self.D, self.H, self.T, self.L, self.M, self.ML, self.hid
         bm = self.bimask
         w_p_dev = self.hyper[40:41]
-        bm.forward(self.params, w_p_dev)
+        # the gate construction (two small latency-bound kernels) runs on a side stream next to the image-side preparation
+        # (PMIM mask, patchify, target normalisation); it joins before the patch-embed GEMM, the first consumer of a gate.
+        # Under CUDA-graph capture this becomes a parallel branch of the graph.
+        cur = torch.cuda.current_stream(self.dev)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.dev)
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            bm.forward(self.params, w_p_dev)
         # random draws stay in PyTorch (RNG parity with the reference's torch.rand), masks are built by our kernels
         if noise is None:
             noise = torch.rand(B, L, device=self.dev)
@@ -371,6 +405,7 @@ class SearchStepEngine:
         ops.droppath_scale(drop_u, self.drop_prob, self.drop_scale)
         ops.patchify(images, self.patches, self.P)
         ops.norm_targets(images, self.mask, self.tgt)
+        cur.wait_stream(self._side)
         g_e = bm.gate_of(0)
         x0 = self.xs[0]
         ops.gemm(ops.EPI_PATCH, self.patches, self.w("patch_embed.proj.weight"), M=ML, N=D, K=768, out0=x0,

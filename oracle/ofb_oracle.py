@@ -141,6 +141,18 @@ def gate_attn(alpha, switch, score, heads: List[int], widths: List[int], w_p: fl
     return gate, wr, table.sum()
 
 
+def keep_index_sets(score: torch.Tensor, widths: List[int], heads: List[int] = ()):
+    """Unit index sets the reference's compress() keeps when it slices a module to a candidate of its search space:
+    channels: `torch.argsort(score, descending=True)[:width]` per head (layers.py:614-620, 666-670 attention; 932-933,
+    967-968 MLP; 268-269, 308-309 embed); heads: `torch.argsort(sigmoid(score).sum(-1), descending=True)[:n]`.
+    score [H, d] (H = 1 for MLP / embed). Returned sorted, like the engine's pruned_index_sets()."""
+    score = score.reshape(-1, score.shape[-1])
+    order = torch.argsort(score, dim=-1, descending=True, stable=True)
+    horder = torch.argsort(torch.sigmoid(score).sum(-1), descending=True, stable=True)
+    return {"channels": {int(w): [sorted(order[h, :w].tolist()) for h in range(score.shape[0])] for w in widths},
+            "heads": {int(n): sorted(horder[:n].tolist()) for n in heads}}
+
+
 # --------------------------------------------------------------------------------------------------------------------
 # PMIM helpers
 # --------------------------------------------------------------------------------------------------------------------

@@ -392,6 +392,17 @@ def test_bimask_fwd_bwd_vs_oracle(cuda_dev, D, H, depth, dead):
     wp_dev = torch.tensor([w_p], device="cuda")
     tab.forward(params, wp_dev)
     torch.cuda.synchronize()
+    # ---- pruned-unit index sets after thresholding: must match the reference's argsort rule EXACTLY ----
+    from ofb_oracle import keep_index_sets
+    got_sets = tab.pruned_index_sets()
+    for mod in tab.modules:
+        pre = mod["prefix"]
+        sc = P[pre + ".score"]
+        if mod["kind"] == 2:
+            ref_sets = keep_index_sets(sc, head_channel_widths(cfg.head_dim), head_counts(cfg.num_heads))
+        else:
+            ref_sets = keep_index_sets(sc, embed_widths(D) if mod["kind"] == 0 else hidden_widths(cfg.hidden))
+        assert got_sets[pre] == ref_sets, pre
     # ---- oracle ----
     leaves = {k: P[k].clone().requires_grad_(True) for k in names}
     gates, wsums, terms = {}, {}, {"attn": 0., "mlp": 0., "embed": 0.}
