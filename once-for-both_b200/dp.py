@@ -50,3 +50,77 @@ def allreduce_arena(grads: torch.Tensor, world: int, group=None, bounds=None, as
                 w.wait()
         grads.mul_(1.0 / world)
     return works if async_op else []
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# exchange overlapped with backward (north_star "bucketed gradient all-reduce ... overlapped with backward"; the reference
+# gets the same from DDP's reducer hooks, search.py:619)
+# ---------------------------------------------------------------------------------------------------------------------
+def overlap_plan(n_elems: int, block_ranges: List[Tuple[int, int]], blocks_per_bucket: int = 2, tail_blocks: int = 2):
+    """Bucket schedule of the flat gradient arena for a backward pass that finishes block depth-1 first and block 0 last.
+
+    block_ranges[l] = [lo, hi) of the contiguous run holding the large (decay-group) weight gradients of block l; the runs
+    ascend with l and are adjacent. Returns (early, tail):
+      early  [(ready_after_block, lo, hi), ...] in launch order: the bucket may start as soon as the backward of block
+             `ready_after_block` has been enqueued (all blocks >= it are complete);
+      tail   [(lo, hi), ...] everything else - the small no-decay group, embedding / head / decoder tensors, the first
+             `tail_blocks` blocks and the architecture parameters, whose gradients only complete at the very end.
+    early + tail cover [0, n_elems) exactly once."""
+    depth = len(block_ranges)
+    early = []
+    hi_blk = depth
+    while hi_blk > tail_blocks:
+        lo_blk = max(tail_blocks, hi_blk - blocks_per_bucket)
+        early.append((lo_blk, block_ranges[lo_blk][0], block_ranges[hi_blk - 1][1]))
+        hi_blk = lo_blk
+    if not early:
+        return [], [(0, n_elems)]
+    first_lo = early[-1][1]
+    last_hi = early[0][2]
+    tail = [(lo, hi) for lo, hi in ((0, first_lo), (last_hi, n_elems)) if hi > lo]
+    return early, tail
+
+
+class OverlappedReducer:
+    """Launches the bucket all-reduces of `overlap_plan` asynchronously while backward is still producing the remaining
+    gradients, and joins them in `finish()`. Backend-agnostic: NCCL averages in the collective, gloo (CPU tests) sums and
+    scales after the wait. One instance per engine; `begin()` at the start of every backward."""
+
+    def __init__(self, grads: torch.Tensor, world: int, group, early, tail):
+        self.grads, self.world, self.group = grads, world, group
+        self.early, self.tail = list(early), list(tail)
+        self.avg = world > 1 and dist.get_backend(group) == "nccl"
+        self._works, self._launched = [], 0
+
+    def begin(self):
+        self._works, self._launched = [], 0
+
+    def _launch(self, lo, hi):
+        chunk = self.grads[lo:hi]
+        op = dist.ReduceOp.AVG if self.avg else dist.ReduceOp.SUM
+        self._works.append((dist.all_reduce(chunk, op=op, group=self.group, async_op=True), lo, hi))
+
+    def on_block_done(self, l: int):
+        """Backward of block l has been enqueued: launch every bucket that became complete."""
+        if self.world <= 1:
+            return
+        while self._launched < len(self.early) and self.early[self._launched][0] >= l:
+            _, lo, hi = self.early[self._launched]
+            self._launch(lo, hi)
+            self._launched += 1
+
+    def finish(self):
+        """All gradients are complete: launch what is left, wait for everything (stream-ordered on CUDA)."""
+        if self.world <= 1:
+            return
+        while self._launched < len(self.early):
+            _, lo, hi = self.early[self._launched]
+            self._launch(lo, hi)
+            self._launched += 1
+        for lo, hi in self.tail:
+            self._launch(lo, hi)
+        for w, lo, hi in self._works:
+            w.wait()
+            if not self.avg:
+                self.grads[lo:hi].mul_(1.0 / self.world)
+        self._works = []

@@ -282,6 +282,19 @@ class SearchStepEngine:
         self.e_gx, self.e_pos, self.e_mt = (torch.empty(T, D, **f32) for _ in range(3))
         self.rand_u = torch.empty(B * self.L + depth * 2 * B, **f32)
         self._dp_bounds = dp.bucket_bounds(self.n_arena)
+        # exchange overlapped with backward: buckets of whole blocks' weight gradients (contiguous in the decay group) are
+        # all-reduced as soon as backward has passed them; OFB_DP_OVERLAP=0 keeps the single exchange after backward
+        self.dp_overlap = self.world > 1 and os.environ.get("OFB_DP_OVERLAP", "1") != "0"
+        blk_rng = []
+        for l in range(depth):
+            lo = self.offsets[f"blocks.{l}.attn.qkv.weight"]
+            k = f"blocks.{l}.mlp.fc2.weight"
+            hi = self.offsets[k] + (math.prod(shapes[k]) + T_PAD - 1) // T_PAD * T_PAD
+            assert not blk_rng or blk_rng[-1][1] == lo, "block weight runs must be adjacent in the arena"
+            blk_rng.append((lo, hi))
+        early, tail = dp.overlap_plan(self.n_arena, blk_rng, int(os.environ.get("OFB_DP_BLOCKS_PER_BUCKET", "2")),
+                                      int(os.environ.get("OFB_DP_TAIL_BLOCKS", "2")))
+        self._reducer = dp.OverlappedReducer(self.grads, self.world, self.pg, early, tail)
         self._graphs = {}          # (images ptr, labels ptr, keep) -> (CUDAGraph, kernel launches per replay)
         self._side = None          # side stream of the gate construction (see forward)
 
@@ -447,9 +460,14 @@ class SearchStepEngine:
         return self.scal
 
     # ------------------------------------------------------------------------------------------------------------
-    def backward(self):
+    def backward(self, exchange=False):
+        """Backward of the step. exchange=True: the data-parallel bucket all-reduces are launched from inside (each bucket
+        as soon as backward has passed its blocks) and joined at the end, so the gradients are averaged on return."""
         B, D, H, T, L, M, ML, hid = self.B, self.D, self.H, self.T, self.L, self.M, self.ML, self.hid
         bm = self.bimask
+        red = self._reducer if (exchange and self.world > 1) else None
+        if red is not None:
+            red.begin()
         gs = 1.0 / self.accum_iter
         dec_scale = self.scal[5:6]
         R = self.ln_parts
@@ -534,6 +552,8 @@ class SearchStepEngine:
                 ln1_jobs.append((self.pd_, R, D, self.g(f"blocks.{l - 1}.mlp.fc2.bias")))
             ops.reduce_partials_multi(attn_jobs + ln1_jobs)
             G = G0
+            if red is not None:
+                red.on_block_done(l)
 
         # ---- embed stage ----
         g_e = bm.gate_of(0)
@@ -546,6 +566,8 @@ class SearchStepEngine:
                  out0=self.g("patch_embed.proj.weight").view(D, 768), a_mn=True, b_mn=True)
         # ---- bi-mask: d gate (+ FLOPs / sparsity losses) -> d score, d alpha ----
         bm.backward(self.params, self.hyper[40:41], self.dgate, gs, self.grads)
+        if red is not None:
+            red.finish()
 
     # ------------------------------------------------------------------------------------------------------------
     def allreduce_grads(self):
@@ -576,22 +598,22 @@ class SearchStepEngine:
             side.wait_stream(cur)
             with torch.cuda.stream(side):
                 self.forward(images, labels)
-                self.backward()
+                self.backward(exchange=self.dp_overlap)      # also brings up the NCCL communicator before capture
                 self.grads.zero_()
             cur.wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             n0 = ops.LAUNCHES
             with torch.cuda.graph(graph):
                 self.forward(images, labels)
-                self.backward()
-                if self.world <= 1:
+                self.backward(exchange=self.dp_overlap)      # overlapped exchange: the NCCL launches are graph nodes
+                if self.world <= 1 or self.dp_overlap:
                     ops.adamw(self.params, self.grads, self.adam_m, self.adam_v, self.shadow, self.hyper, self._seg_end_c,
                               zero_grad=True)
             entry = (graph, ops.LAUNCHES - n0)
             self._graphs[key] = entry
         entry[0].replay()
         ops._count(entry[1])
-        if self.world > 1:
+        if self.world > 1 and not self.dp_overlap:
             self.allreduce_grads()
             ops.adamw(self.params, self.grads, self.adam_m, self.adam_v, self.shadow, self.hyper, self._seg_end_c,
                       zero_grad=True)
@@ -603,8 +625,9 @@ class SearchStepEngine:
         self._fill_hyper(lrs)
         self.hyper.copy_(self.hyper_host, non_blocking=True)
         self.forward(images, labels, noise, drop_u)
-        self.backward()
+        self.backward(exchange=update and self.dp_overlap)
         if update:
-            self.allreduce_grads()
+            if not self.dp_overlap:
+                self.allreduce_grads()
             self.optimizer_step()
         return self.scal
