@@ -146,6 +146,18 @@ def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    # stray writes to fd 1 (NCCL prints its version banner there) must not end up next to the JSON line: everything but
+    # the result goes to stderr
+    out_fd = os.dup(1)
+    os.dup2(2, 1)
+    trace = os.environ.get("OFB_BENCH_TRACE")
+    if trace:          # debugging aid: stage markers on stderr and a Python stack dump if a stage hangs
+        import faulthandler
+        faulthandler.dump_traceback_later(int(trace), repeat=False, exit=False)
+
+    def mark(what):
+        if trace:
+            print(f"[bench rank {os.environ.get('RANK', '0')}] {what}", file=sys.stderr, flush=True)
 
     import torch
     import torch.distributed as dist
@@ -186,9 +198,14 @@ def main():
     step = eng.step if args.no_graph else eng.step_graphed
 
     # ---------------- device-resident measurement ----------------
+    mark("engine built")
     for i in range(args.warmup):
         step(dev_img[i % n_host], dev_lab[i % n_host])
+        if trace:
+            torch.cuda.synchronize()
+            mark(f"warmup step {i} done")
     sync_all()
+    mark("warmup done")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -202,6 +219,7 @@ def main():
     e1.record()
     sync_all()
     ms = e0.elapsed_time(e1)
+    mark("timed region done")
     launches = ops.LAUNCHES - launches0
     gemm_t = ops.GEMM_TIMING
     ops.GEMM_TIMING = None
@@ -227,6 +245,7 @@ def main():
     gemm_flops = sum(f for _, _, f, _ in gemm_t)
     scal = eng.scal.cpu().tolist()
 
+    mark("roofline pass done")
     # ---------------- end to end: host buffers -> step -> loss on host ----------------
     copy_stream = torch.cuda.Stream(device=dev)
     stage_img = [torch.empty_like(dev_img[0]) for _ in range(2)]
@@ -259,6 +278,7 @@ def main():
 
     e2e_loop(max(2, min(args.warmup, 3)))
     sync_all()
+    mark("e2e warmup done")
     e0.record()
     e2e_loop(args.steps)
     e1.record()
@@ -304,9 +324,17 @@ def main():
             line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
                                     "sample": f"{args.cpu_sample_batch} images / step of the same DeiT-{args.model} search "
                                               f"step (oracle port, fp32, {cores} threads, {dt:.1f} s/step)"}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(out_fd, (json.dumps(line) + "\n").encode())
+    mark("result written")
     if world > 1:
+        # graphs that captured NCCL launches must be gone before the communicator is torn down (destroy_process_group
+        # otherwise blocks); the timer guarantees the process ends even if the teardown stalls
+        eng.release_graphs()
+        torch.cuda.synchronize()
+        threading.Timer(30.0, os._exit, (0,)).start()
         dist.destroy_process_group()
+        os._exit(0)
 
 
 if __name__ == "__main__":

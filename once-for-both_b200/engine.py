@@ -620,6 +620,11 @@ class SearchStepEngine:
         self.step_count += 1
         return self.scal
 
+    def release_graphs(self):
+        """Drop every captured step graph (required before the process group is destroyed when the graphs hold NCCL
+        launches, and after a prune event changes shapes)."""
+        self._graphs.clear()
+
     def step(self, images, labels, noise=None, drop_u=None, update=True, lrs=None):
         """One full search step; returns the device tensor scal = [base, arch, decoder, total, w_dec, ...]."""
         self._fill_hyper(lrs)
