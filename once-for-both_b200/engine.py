@@ -282,9 +282,12 @@ class SearchStepEngine:
         self.e_gx, self.e_pos, self.e_mt = (torch.empty(T, D, **f32) for _ in range(3))
         self.rand_u = torch.empty(B * self.L + depth * 2 * B, **f32)
         self._dp_bounds = dp.bucket_bounds(self.n_arena)
-        # exchange overlapped with backward: buckets of whole blocks' weight gradients (contiguous in the decay group) are
-        # all-reduced as soon as backward has passed them; OFB_DP_OVERLAP=0 keeps the single exchange after backward
-        self.dp_overlap = self.world > 1 and os.environ.get("OFB_DP_OVERLAP", "1") != "0"
+        # exchange overlapped with backward (OFB_DP_OVERLAP=1): buckets of whole blocks' weight gradients (contiguous in the
+        # decay group) are all-reduced as soon as backward has passed them. Default is the single exchange after backward:
+        # measured on 2 x B200 (profiles/r01c_dp_overlap_ab.txt) the overlapped form is 0.1-0.2 ms/step SLOWER - every
+        # compute kernel is persistent with one CTA per SM and 200+ KB of shared memory, so the NCCL CTAs cannot co-reside
+        # and instead delay the CTAs of the next compute kernel on the SMs they hold - while the whole exchange costs 0.2 ms
+        self.dp_overlap = self.world > 1 and os.environ.get("OFB_DP_OVERLAP", "0") == "1"
         blk_rng = []
         for l in range(depth):
             lo = self.offsets[f"blocks.{l}.attn.qkv.weight"]
