@@ -70,6 +70,11 @@ int ofb_gemm_bf16(int epilogue, int a_mn, int b_mn, int bn_hint, const void* A, 
  * D % 8 == 0, D <= 1024. */
 int ofb_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
                       int M, int D, float eps, void* stream);
+/* Physically pruned embeddings (finetune of a searched subnet, models/vision_transformer.py:157-160 Block; pruned widths are
+ * multiples of 12): the row holds D_valid real channels followed by D - D_valid (< 8) zero channels; statistics
+ * run over D_valid. */
+int ofb_layernorm_fwd_ex(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                         int M, int D, int D_valid, float eps, void* stream);
 /* number of partial rows ofb_layernorm_bwd writes (size the part_* buffers as [ofb_layernorm_bwd_parts(M), D]) */
 int ofb_layernorm_bwd_parts(int M);
 /* backward + fused column partials: part_dgamma/part_dbeta always; part_dbias (may be NULL) = sum_rows
@@ -78,6 +83,12 @@ int ofb_layernorm_bwd_parts(int M);
 int ofb_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
                       void* dx, float* part_dgamma, float* part_dbeta, float* part_dbias, const float* rowscale,
                       int rows_per_scale, int M, int D, void* stream);
+/* same with D_valid (padding columns of dx are zero) and dres (may be NULL): the gradient of the residual branch that
+ * bypasses this LayerNorm in a pre-norm Block (vision_transformer.py:157-160), added to dx before it is stored and
+ * column-summed into part_dbias. */
+int ofb_layernorm_bwd_ex(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                         const void* dres, void* dx, float* part_dgamma, float* part_dbeta, float* part_dbias,
+                         const float* rowscale, int rows_per_scale, int M, int D, int D_valid, void* stream);
 /* out[col] (+)= scale * sum_r part[r,col] / (div_by ? div_by[col] : 1) */
 int ofb_reduce_partials(const float* part, int R, int N, float* out, float scale, const float* div_by, int accumulate,
                         void* stream);
@@ -110,13 +121,21 @@ int ofb_norm_targets(const float* images, const float* mask, float* target, int 
  * scal[0..6] = {base, arch, decoder, total, w_dec, decoder_grad_scale, n_masked} */
 int ofb_ls_cross_entropy(const float* logits, const int64_t* labels, float* loss_rows, void* dlogits_bf16, int B, int C,
                          float smoothing, float grad_scale, void* stream);
+/* timm SoftTargetCrossEntropy fwd+bwd on Mixup targets (finetune.py:388-389, search.py:655): target fp32 [B, C] */
+int ofb_soft_target_cross_entropy(const float* logits, const float* target, float* loss_rows, void* dlogits_bf16, int B,
+                                  int C, float grad_scale, void* stream);
+/* evaluate() metrics (engine.py:222-257): out_rows[b] = {cross entropy, top-1 hit, top-5 hit} */
+int ofb_eval_metrics(const float* logits, const int64_t* labels, float* out_rows, int B, int C, void* stream);
 int ofb_loss_finalize(const float* loss_rows, int B, const float* dec_part, int n_dec_part, const float* mask,
                       int n_mask, const float* arch_loss, float grad_scale, float* scal, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * fused multi-segment AdamW (optim.py:56-120; groups search.py:486-559). hyper[seg*8 + {0..6}] =
  * {lr, weight_decay, beta1, beta2, eps, 1-beta1^t, 1-beta2^t}; seg_end[] exclusive ends (multiples of 4).
- * Writes the bf16 shadow copy used by the GEMMs and optionally zeroes the gradient. */
+ * Writes the bf16 shadow copy used by the GEMMs and optionally zeroes the gradient. Up to OFB_ADAMW_MAX_SEGMENTS
+ * segments: the finetune optimizer (torch.optim.AdamW over lr_decay.param_groups_lrd, finetune.py:378-383) has
+ * 2 x (depth + 2) of them; same update rule. */
+#define OFB_ADAMW_MAX_SEGMENTS 64
 int ofb_adamw(float* p, float* g, float* m, float* v, void* shadow_bf16, const float* hyper, int nseg,
               const int64_t* seg_end, int64_t n, int zero_grad, void* stream);
 int ofb_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);

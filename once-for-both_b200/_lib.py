@@ -57,7 +57,9 @@ SIGNATURES = {
     "ofb_num_sms": [],
     "ofb_gemm_bf16": [_I, _I, _I, _I, _P, _I, _P, _I, _P, _P],
     "ofb_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _F, _P],
+    "ofb_layernorm_fwd_ex": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
     "ofb_layernorm_bwd_parts": [_I],
+    "ofb_layernorm_bwd_ex": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "ofb_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "ofb_reduce_partials": [_P, _I, _I, _P, _F, _P, _I, _P],
     "ofb_reduce_partials_multi": [_P, _I, _P],
@@ -68,6 +70,8 @@ SIGNATURES = {
     "ofb_embed_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "ofb_norm_targets": [_P, _P, _P, _I, _I, _P],
     "ofb_ls_cross_entropy": [_P, _P, _P, _P, _I, _I, _F, _F, _P],
+    "ofb_soft_target_cross_entropy": [_P, _P, _P, _P, _I, _I, _F, _P],
+    "ofb_eval_metrics": [_P, _P, _P, _I, _I, _P],
     "ofb_loss_finalize": [_P, _I, _P, _I, _P, _I, _P, _F, _P, _P],
     "ofb_adamw": [_P, _P, _P, _P, _P, _P, _I, _P, _L, _I, _P],
     "ofb_cast_bf16": [_P, _P, _L, _P],

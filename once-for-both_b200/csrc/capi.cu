@@ -7,10 +7,12 @@ namespace ofb {
 int launch_gemm(int epi, int a_mn, int b_mn, int bn_hint, const void* A, int lda, const void* B, int ldb, GemmArgs g,
                 cudaStream_t stream);
 int num_sms();
-int launch_ln_fwd(const void*, const float*, const float*, void*, float*, float*, int, int, float, cudaStream_t);
+int launch_ln_fwd(const void*, const float*, const float*, void*, float*, float*, int, int, float, int, cudaStream_t);
 int ln_bwd_grid(int M);
 int launch_ln_bwd(const void*, const void*, const float*, const float*, const float*, void*, float*, float*, float*, const float*, int,
-                  int, int, cudaStream_t);
+                  int, int, int, const void*, cudaStream_t);
+int launch_soft_ce(const float*, const float*, float*, void*, int, int, float, cudaStream_t);
+int launch_eval_metrics(const float*, const int64_t*, float*, int, int, cudaStream_t);
 int launch_reduce_partials(const float*, int, int, float*, float, const float*, int, cudaStream_t);
 int launch_reduce_partials_multi(const void*, int, cudaStream_t);
 int launch_patchify(const float*, void*, int, int, int, cudaStream_t);
@@ -39,7 +41,7 @@ int launch_attn_bwd(const void*, const void*, const void*, const float*, const f
 
 extern "C" {
 
-int ofb_version(void) { return 1; }
+int ofb_version(void) { return 2; }
 int ofb_num_sms(void) { return ofb::num_sms(); }
 
 int ofb_gemm_bf16(int epilogue, int a_mn, int b_mn, int bn_hint, const void* A, int lda, const void* B, int ldb,
@@ -61,13 +63,24 @@ int ofb_gemm_bf16(int epilogue, int a_mn, int b_mn, int bn_hint, const void* A, 
 
 int ofb_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M, int D, float eps,
                       void* stream) {
-    return ofb::launch_ln_fwd(x, gamma, beta, y, mean, rstd, M, D, eps, ST(stream));
+    return ofb::launch_ln_fwd(x, gamma, beta, y, mean, rstd, M, D, eps, D, ST(stream));
+}
+int ofb_layernorm_fwd_ex(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M, int D,
+                         int D_valid, float eps, void* stream) {
+    return ofb::launch_ln_fwd(x, gamma, beta, y, mean, rstd, M, D, eps, D_valid, ST(stream));
 }
 int ofb_layernorm_bwd_parts(int M) { return ofb::ln_bwd_grid(M); }
 int ofb_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
                       float* part_dgamma, float* part_dbeta, float* part_dbias, const float* rowscale, int rows_per_scale, int M, int D,
                       void* stream) {
-    return ofb::launch_ln_bwd(dy, x, mean, rstd, gamma, dx, part_dgamma, part_dbeta, part_dbias, rowscale, rows_per_scale, M, D, ST(stream));
+    return ofb::launch_ln_bwd(dy, x, mean, rstd, gamma, dx, part_dgamma, part_dbeta, part_dbias, rowscale, rows_per_scale, M, D, D,
+                              nullptr, ST(stream));
+}
+int ofb_layernorm_bwd_ex(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, const void* dres,
+                         void* dx, float* part_dgamma, float* part_dbeta, float* part_dbias, const float* rowscale,
+                         int rows_per_scale, int M, int D, int D_valid, void* stream) {
+    return ofb::launch_ln_bwd(dy, x, mean, rstd, gamma, dx, part_dgamma, part_dbeta, part_dbias, rowscale, rows_per_scale, M, D,
+                              D_valid, dres, ST(stream));
 }
 int ofb_reduce_partials(const float* part, int R, int N, float* out, float scale, const float* div_by, int accumulate, void* stream) {
     return ofb::launch_reduce_partials(part, R, N, out, scale, div_by, accumulate, ST(stream));
@@ -100,14 +113,21 @@ int ofb_ls_cross_entropy(const float* logits, const int64_t* labels, float* loss
                          float grad_scale, void* stream) {
     return ofb::launch_ce(logits, labels, loss_rows, dlogits, B, C, smoothing, grad_scale, ST(stream));
 }
+int ofb_soft_target_cross_entropy(const float* logits, const float* target, float* loss_rows, void* dlogits, int B, int C,
+                                  float grad_scale, void* stream) {
+    return ofb::launch_soft_ce(logits, target, loss_rows, dlogits, B, C, grad_scale, ST(stream));
+}
+int ofb_eval_metrics(const float* logits, const int64_t* labels, float* out_rows, int B, int C, void* stream) {
+    return ofb::launch_eval_metrics(logits, labels, out_rows, B, C, ST(stream));
+}
 int ofb_loss_finalize(const float* loss_rows, int B, const float* dec_part, int n_dec_part, const float* mask, int n_mask,
                       const float* arch_loss, float grad_scale, float* scal, void* stream) {
     return ofb::launch_loss_finalize(loss_rows, B, dec_part, n_dec_part, mask, n_mask, arch_loss, grad_scale, scal, ST(stream));
 }
 int ofb_adamw(float* p, float* g, float* m, float* v, void* shadow, const float* hyper, int nseg, const int64_t* seg_end, int64_t n,
               int zero_grad, void* stream) {
-    long long ends[8];
-    if (nseg < 1 || nseg > 8) return 1013;
+    long long ends[OFB_ADAMW_MAX_SEGMENTS];
+    if (nseg < 1 || nseg > OFB_ADAMW_MAX_SEGMENTS) return 1013;
     for (int i = 0; i < nseg; ++i) ends[i] = seg_end[i];
     return ofb::launch_adamw(p, g, m, v, shadow, hyper, nseg, ends, n, zero_grad, ST(stream));
 }

@@ -36,7 +36,10 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 template <int LN_MAXC>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
-                                                     float* __restrict__ mean, float* __restrict__ rstd, int M, int D, float eps) {
+                                                     float* __restrict__ mean, float* __restrict__ rstd, int M, int D, float eps,
+                                                     int Dv) {
+    // Dv <= D: number of real channels; columns [Dv, D) are zero padding of a physically pruned embedding (they hold zeros,
+    // carry gamma = beta = 0 and must not enter the statistics: the reference normalises over Dv channels)
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     const int nchunk = D >> 3;
@@ -53,17 +56,17 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const __nv_bfloat16* __rest
                 for (int j = 0; j < 8; ++j) s += v[i][j];
             }
         }
-        const float mu = warp_sum(s) / D;
+        const float mu = warp_sum(s) / Dv;
         float q = 0.f;
 #pragma unroll
         for (int i = 0; i < LN_MAXC; ++i) {
             const int c = lane + 32 * i;
             if (c < nchunk) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mu; q += d * d; }
+                for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mu; q += (c * 8 + j < Dv) ? d * d : 0.f; }
             }
         }
-        const float rs = rsqrtf(warp_sum(q) / D + eps);
+        const float rs = rsqrtf(warp_sum(q) / Dv + eps);
         uint4* yr = reinterpret_cast<uint4*>(y + size_t(row) * D);
 #pragma unroll
         for (int i = 0; i < LN_MAXC; ++i) {
@@ -107,7 +110,10 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
                                                      const float* __restrict__ gamma, __nv_bfloat16* __restrict__ dx,
                                                      float* __restrict__ part_dgamma, float* __restrict__ part_dbeta,
                                                      float* __restrict__ part_dbias, const float* __restrict__ rowscale,
-                                                     int rows_per_scale, int M, int D) {
+                                                     int rows_per_scale, int M, int D, int Dv,
+                                                     const __nv_bfloat16* __restrict__ dres) {
+    // Dv: real channels (see ln_fwd_kernel); dres (optional): gradient arriving over the residual connection that bypasses
+    // this LayerNorm (pre-norm blocks, vision_transformer.py:157-160), added to dx before it is stored / column-summed
     extern __shared__ __align__(128) uint8_t ln_smem_raw[];
     // layout: ring [8 warps][LN_STAGES][2][D bf16] | barriers [8][LN_STAGES]; the ring is reused as float [3][8][D] at the end
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -198,17 +204,23 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
                 }
             }
         }
-        s1 = warp_sum(s1) / D;
-        s2 = warp_sum(s2) / D;
+        s1 = warp_sum(s1) / Dv;
+        s2 = warp_sum(s2) / Dv;
         uint4* dxr = reinterpret_cast<uint4*>(dx + size_t(row) * D);
 #pragma unroll
         for (int i = 0; i < LN_MAXC; ++i) {
             const int c = lane + 32 * i;
             if (c < nchunk) {
-                float o[8];
+                float o[8], rr[8];
+                if (dres != nullptr) {
+                    unpack8(__ldg(reinterpret_cast<const uint4*>(dres + size_t(row) * D) + c), rr);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) rr[j] = 0.f;
+                }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    o[j] = rs * (dyv[i][j] * gam[i][j] - s1 - xh[i][j] * s2);
+                    o[j] = (c * 8 + j < Dv ? rs * (dyv[i][j] * gam[i][j] - s1 - xh[i][j] * s2) : 0.f) + rr[j];
                     ad[i][j] += rsc * o[j];
                 }
                 dxr[c] = pack8(o);
@@ -723,6 +735,81 @@ __global__ void __launch_bounds__(128) ce_kernel(const float* __restrict__ logit
 }
 
 // =============================================================================================
+// soft-target cross entropy fwd + bwd (timm SoftTargetCrossEntropy after Mixup: finetune.py:388-389, search.py:655)
+//   loss_rows[b] = sum_c -t[b,c] * logp[b,c];   dlogits = (softmax * sum_c t - t) * gscale / B   (bf16)
+// =============================================================================================
+__global__ void __launch_bounds__(128) soft_ce_kernel(const float* __restrict__ logits, const float* __restrict__ target,
+                                                      float* __restrict__ loss_rows, __nv_bfloat16* __restrict__ dlogits, int C,
+                                                      float gscale_over_B) {
+    const int b = blockIdx.x;
+    const float* lr = logits + size_t(b) * C;
+    const float* tr = target + size_t(b) * C;
+    __shared__ float red[4];
+    auto block_sum = [&](float v) {
+        v = warp_sum(v);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+        __syncthreads();
+        return red[0] + red[1] + red[2] + red[3];
+    };
+    float mx = -INFINITY;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) mx = fmaxf(mx, lr[c]);
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    float se = 0.f, st = 0.f, stl = 0.f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) { se += expf(lr[c] - mx); st += tr[c]; stl += tr[c] * lr[c]; }
+    se = block_sum(se);
+    st = block_sum(st);
+    stl = block_sum(stl);
+    const float lse = mx + logf(se);
+    if (threadIdx.x == 0) loss_rows[b] = st * lse - stl;
+    for (int c = threadIdx.x; c < C; c += blockDim.x)
+        dlogits[size_t(b) * C + c] = __float2bfloat16((expf(lr[c] - lse) * st - tr[c]) * gscale_over_B);
+}
+
+// =============================================================================================
+// evaluation metrics (engine.evaluate, engine.py:222-257): plain cross entropy and top-1 / top-5 hits per row.
+//   out_rows[b] = {nll, hit@1, hit@5}; the label is in the top k iff fewer than k logits are larger (ties: lower index wins,
+//   torch.topk order)
+// =============================================================================================
+__global__ void __launch_bounds__(128) eval_metrics_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels,
+                                                           float* __restrict__ out_rows, int C) {
+    const int b = blockIdx.x;
+    const float* lr = logits + size_t(b) * C;
+    __shared__ float red[4];
+    const int y = int(labels[b]);
+    const float ly = lr[y];
+    float mx = -INFINITY;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) mx = fmaxf(mx, lr[c]);
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    __syncthreads();
+    float se = 0.f, ahead = 0.f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        se += expf(lr[c] - mx);
+        ahead += (lr[c] > ly || (lr[c] == ly && c < y)) ? 1.f : 0.f;
+    }
+    se = warp_sum(se);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = se;
+    __syncthreads();
+    se = red[0] + red[1] + red[2] + red[3];
+    __syncthreads();
+    ahead = warp_sum(ahead);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ahead;
+    __syncthreads();
+    ahead = red[0] + red[1] + red[2] + red[3];
+    if (threadIdx.x == 0) {
+        out_rows[3 * b + 0] = mx + logf(se) - ly;
+        out_rows[3 * b + 1] = ahead < 1.f ? 1.f : 0.f;
+        out_rows[3 * b + 2] = ahead < 5.f ? 1.f : 0.f;
+    }
+}
+
+// =============================================================================================
 // loss finalisation (engine.py:134-144): one CTA.
 //   scal[0]=base CE  [1]=arch  [2]=decoder  [3]=total  [4]=w_dec=(base/dec)  [5]=decoder grad scale  [6]=#masked patches
 // =============================================================================================
@@ -757,9 +844,10 @@ __global__ void __launch_bounds__(256) loss_finalize_kernel(const float* __restr
 // hyper[seg] = {lr, weight_decay, beta1, beta2, eps, bias_corr1, bias_corr2, unused}; seg_end[] are exclusive
 // prefix ends (elements, multiples of 4) of the contiguous optimizer groups of the flat parameter arena.
 // =============================================================================================
+static constexpr int ADAM_MAX_SEGS = 64;      // search: 5 groups; finetune: 2 x (depth + 2) layer-decay groups (lr_decay.py)
 struct AdamSegs {
     int nseg;
-    long long end[8];
+    long long end[ADAM_MAX_SEGS];
 };
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                                                     float* __restrict__ v, __nv_bfloat16* __restrict__ shadow,
@@ -850,13 +938,13 @@ int launch_colsum_bf16(const void* x, int ld, int R, int N, float* out, float sc
 
 template <int MAXC>
 static int ln_fwd_inst(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M, int D, float eps,
-                       cudaStream_t s) {
+                       int Dv, cudaStream_t s) {
     const int wpb = 8;
     int grid = (M + wpb - 1) / wpb;
     const int cap = num_sms() * 8;
     if (grid > cap) grid = cap;
     ln_fwd_kernel<MAXC><<<grid, wpb * 32, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta,
-                                                  reinterpret_cast<__nv_bfloat16*>(y), mean, rstd, M, D, eps);
+                                                  reinterpret_cast<__nv_bfloat16*>(y), mean, rstd, M, D, eps, Dv);
     return err();
 }
 template <int W>
@@ -872,18 +960,20 @@ static int ln_fwd3_inst(const void* x, const float* gamma, const float* beta, vo
 }
 static bool ln_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 int launch_ln_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M, int D, float eps,
-                  cudaStream_t s) {
+                  int Dv, cudaStream_t s) {
     if (D % 8 != 0 || D > 1024) return 1010;
-    if (ln_aligned16(x) && ln_aligned16(y) && ln_aligned16(gamma) && ln_aligned16(beta)) {
+    if (Dv <= 0) Dv = D;
+    if (Dv > D || Dv <= D - 8) return 1010;      // padding is at most the ragged tail of the last 8-channel chunk
+    if (Dv == D && ln_aligned16(x) && ln_aligned16(y) && ln_aligned16(gamma) && ln_aligned16(beta)) {
         if (D == 192) return ln_fwd3_inst<1>(x, gamma, beta, y, mean, rstd, M, eps, s);
         if (D == 384) return ln_fwd3_inst<2>(x, gamma, beta, y, mean, rstd, M, eps, s);
         if (D == 768) return ln_fwd3_inst<4>(x, gamma, beta, y, mean, rstd, M, eps, s);
     }
     switch ((D + 255) / 256) {
-        case 1: return ln_fwd_inst<1>(x, gamma, beta, y, mean, rstd, M, D, eps, s);
-        case 2: return ln_fwd_inst<2>(x, gamma, beta, y, mean, rstd, M, D, eps, s);
-        case 3: return ln_fwd_inst<3>(x, gamma, beta, y, mean, rstd, M, D, eps, s);
-        default: return ln_fwd_inst<4>(x, gamma, beta, y, mean, rstd, M, D, eps, s);
+        case 1: return ln_fwd_inst<1>(x, gamma, beta, y, mean, rstd, M, D, eps, Dv, s);
+        case 2: return ln_fwd_inst<2>(x, gamma, beta, y, mean, rstd, M, D, eps, Dv, s);
+        case 3: return ln_fwd_inst<3>(x, gamma, beta, y, mean, rstd, M, D, eps, Dv, s);
+        default: return ln_fwd_inst<4>(x, gamma, beta, y, mean, rstd, M, D, eps, Dv, s);
     }
 }
 
@@ -897,7 +987,7 @@ int ln_bwd_grid(int M) {
 template <int MAXC>
 static int ln_bwd_inst(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
                        float* part_dgamma, float* part_dbeta, float* part_dbias, const float* rowscale, int rows_per_scale, int M, int D,
-                       cudaStream_t s) {
+                       int Dv, const void* dres, cudaStream_t s) {
     const int wpb = 8;
     const int grid = ln_bwd_grid(M);
     const size_t ring = size_t(wpb) * LN_STAGES * 2 * D * 2, red = size_t(3) * wpb * D * sizeof(float);
@@ -912,7 +1002,8 @@ static int ln_bwd_inst(const void* dy, const void* x, const float* mean, const f
     }
     ln_bwd_kernel<MAXC><<<grid, wpb * 32, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x),
                                                      mean, rstd, gamma, reinterpret_cast<__nv_bfloat16*>(dx), part_dgamma, part_dbeta,
-                                                     part_dbias, rowscale, rows_per_scale > 0 ? rows_per_scale : 1, M, D);
+                                                     part_dbias, rowscale, rows_per_scale > 0 ? rows_per_scale : 1, M, D, Dv,
+                                                     reinterpret_cast<const __nv_bfloat16*>(dres));
     return err();
 }
 template <int W>
@@ -934,18 +1025,22 @@ static int ln_bwd3_inst(const void* dy, const void* x, const float* mean, const 
     return err();
 }
 int launch_ln_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx, float* part_dgamma,
-                  float* part_dbeta, float* part_dbias, const float* rowscale, int rows_per_scale, int M, int D, cudaStream_t s) {
+                  float* part_dbeta, float* part_dbias, const float* rowscale, int rows_per_scale, int M, int D, int Dv, const void* dres,
+                  cudaStream_t s) {
     if (D % 8 != 0 || D > 1024) return 1010;
-    if (ln_aligned16(dy) && ln_aligned16(x) && ln_aligned16(dx) && ln_aligned16(gamma)) {
+    if (Dv <= 0) Dv = D;
+    if (Dv > D || Dv <= D - 8) return 1010;
+    if (dres != nullptr && !ln_aligned16(dres)) return 1010;
+    if (Dv == D && dres == nullptr && ln_aligned16(dy) && ln_aligned16(x) && ln_aligned16(dx) && ln_aligned16(gamma)) {
         if (D == 192) return ln_bwd3_inst<1>(dy, x, mean, rstd, gamma, dx, part_dgamma, part_dbeta, part_dbias, rowscale, rows_per_scale, M, s);
         if (D == 384) return ln_bwd3_inst<2>(dy, x, mean, rstd, gamma, dx, part_dgamma, part_dbeta, part_dbias, rowscale, rows_per_scale, M, s);
         if (D == 768) return ln_bwd3_inst<4>(dy, x, mean, rstd, gamma, dx, part_dgamma, part_dbeta, part_dbias, rowscale, rows_per_scale, M, s);
     }
     switch ((D + 255) / 256) {
-        case 1: return ln_bwd_inst<1>(dy, x, mean, rstd, gamma, dx, part_dgamma, part_dbeta, part_dbias, rowscale, rows_per_scale, M, D, s);
-        case 2: return ln_bwd_inst<2>(dy, x, mean, rstd, gamma, dx, part_dgamma, part_dbeta, part_dbias, rowscale, rows_per_scale, M, D, s);
-        case 3: return ln_bwd_inst<3>(dy, x, mean, rstd, gamma, dx, part_dgamma, part_dbeta, part_dbias, rowscale, rows_per_scale, M, D, s);
-        default: return ln_bwd_inst<4>(dy, x, mean, rstd, gamma, dx, part_dgamma, part_dbeta, part_dbias, rowscale, rows_per_scale, M, D, s);
+        case 1: return ln_bwd_inst<1>(dy, x, mean, rstd, gamma, dx, part_dgamma, part_dbeta, part_dbias, rowscale, rows_per_scale, M, D, Dv, dres, s);
+        case 2: return ln_bwd_inst<2>(dy, x, mean, rstd, gamma, dx, part_dgamma, part_dbeta, part_dbias, rowscale, rows_per_scale, M, D, Dv, dres, s);
+        case 3: return ln_bwd_inst<3>(dy, x, mean, rstd, gamma, dx, part_dgamma, part_dbeta, part_dbias, rowscale, rows_per_scale, M, D, Dv, dres, s);
+        default: return ln_bwd_inst<4>(dy, x, mean, rstd, gamma, dx, part_dgamma, part_dbeta, part_dbias, rowscale, rows_per_scale, M, D, Dv, dres, s);
     }
 }
 
@@ -1021,6 +1116,15 @@ int launch_ce(const float* logits, const int64_t* labels, float* loss_rows, void
     return err();
 }
 
+int launch_soft_ce(const float* logits, const float* target, float* loss_rows, void* dlogits, int B, int C, float gscale, cudaStream_t s) {
+    soft_ce_kernel<<<B, 128, 0, s>>>(logits, target, loss_rows, reinterpret_cast<__nv_bfloat16*>(dlogits), C, gscale / B);
+    return err();
+}
+int launch_eval_metrics(const float* logits, const int64_t* labels, float* out_rows, int B, int C, cudaStream_t s) {
+    eval_metrics_kernel<<<B, 128, 0, s>>>(logits, labels, out_rows, C);
+    return err();
+}
+
 int launch_loss_finalize(const float* loss_rows, int B, const float* dec_part, int n_dec_part, const float* mask, int n_mask,
                          const float* arch_loss, float grad_scale, float* scal, cudaStream_t s) {
     loss_finalize_kernel<<<1, 256, 0, s>>>(loss_rows, B, dec_part, n_dec_part, mask, n_mask, arch_loss, grad_scale, scal);
@@ -1029,7 +1133,7 @@ int launch_loss_finalize(const float* loss_rows, int B, const float* dec_part, i
 
 int launch_adamw(float* p, float* g, float* m, float* v, void* shadow, const float* hyper, int nseg, const long long* seg_end,
                  long long n, int zero_grad, cudaStream_t s) {
-    if (nseg < 1 || nseg > 8 || n % 4 != 0) return 1013;
+    if (nseg < 1 || nseg > ADAM_MAX_SEGS || n % 4 != 0) return 1013;
     AdamSegs segs;
     segs.nseg = nseg;
     for (int i = 0; i < nseg; ++i) {

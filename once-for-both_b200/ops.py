@@ -101,10 +101,15 @@ def gemm(epi, A, B, *, M, N, K, out0=None, ld0=0, out1=None, ld1=0, out_fp32=Fal
 # ---------------------------------------------------------------------------------------------------------------------
 # LayerNorm
 # ---------------------------------------------------------------------------------------------------------------------
-def layernorm_fwd(x, gamma, beta, y, mean, rstd, eps):
+def layernorm_fwd(x, gamma, beta, y, mean, rstd, eps, d_valid=None):
+    """d_valid: real channels of a zero-padded pruned embedding (None = all D)."""
     M, D = x.shape
-    check(lib().ofb_layernorm_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(rstd), M, D, eps, cur_stream()),
-          "ofb_layernorm_fwd")
+    if d_valid is None or d_valid == D:
+        check(lib().ofb_layernorm_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(rstd), M, D, eps, cur_stream()),
+              "ofb_layernorm_fwd")
+    else:
+        check(lib().ofb_layernorm_fwd_ex(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(rstd), M, D, d_valid, eps,
+                                         cur_stream()), "ofb_layernorm_fwd_ex")
 
 
 def layernorm_bwd_parts(M):
@@ -112,11 +117,17 @@ def layernorm_bwd_parts(M):
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, dx, part_dgamma, part_dbeta, part_dbias=None, rowscale=None,
-                  rows_per_scale=1):
+                  rows_per_scale=1, dres=None, d_valid=None):
+    """dres: residual-branch gradient added to dx (pre-norm blocks); d_valid as in layernorm_fwd."""
     M, D = x.shape
-    check(lib().ofb_layernorm_bwd(ptr(dy), ptr(x), ptr(mean), ptr(rstd), ptr(gamma), ptr(dx), ptr(part_dgamma),
-                                  ptr(part_dbeta), ptr(part_dbias), ptr(rowscale), rows_per_scale, M, D, cur_stream()),
-          "ofb_layernorm_bwd")
+    if dres is None and (d_valid is None or d_valid == D):
+        check(lib().ofb_layernorm_bwd(ptr(dy), ptr(x), ptr(mean), ptr(rstd), ptr(gamma), ptr(dx), ptr(part_dgamma),
+                                      ptr(part_dbeta), ptr(part_dbias), ptr(rowscale), rows_per_scale, M, D, cur_stream()),
+              "ofb_layernorm_bwd")
+    else:
+        check(lib().ofb_layernorm_bwd_ex(ptr(dy), ptr(x), ptr(mean), ptr(rstd), ptr(gamma), ptr(dres), ptr(dx),
+                                         ptr(part_dgamma), ptr(part_dbeta), ptr(part_dbias), ptr(rowscale), rows_per_scale, M,
+                                         D, d_valid or D, cur_stream()), "ofb_layernorm_bwd_ex")
 
 
 def reduce_partials(part, R, N, out, scale=1.0, div_by=None, accumulate=True):
@@ -174,6 +185,17 @@ def ls_cross_entropy(logits, labels, loss_rows, dlogits, smoothing, grad_scale):
     B, Cn = logits.shape
     check(lib().ofb_ls_cross_entropy(ptr(logits), ptr(labels), ptr(loss_rows), ptr(dlogits), B, Cn, smoothing,
                                      grad_scale, cur_stream()), "ofb_ls_cross_entropy")
+
+
+def soft_target_cross_entropy(logits, target, loss_rows, dlogits, grad_scale):
+    B, Cn = logits.shape
+    check(lib().ofb_soft_target_cross_entropy(ptr(logits), ptr(target), ptr(loss_rows), ptr(dlogits), B, Cn, grad_scale,
+                                              cur_stream()), "ofb_soft_target_cross_entropy")
+
+
+def eval_metrics(logits, labels, out_rows):
+    B, Cn = logits.shape
+    check(lib().ofb_eval_metrics(ptr(logits), ptr(labels), ptr(out_rows), B, Cn, cur_stream()), "ofb_eval_metrics")
 
 
 def loss_finalize(loss_rows, dec_part, mask, arch_loss, grad_scale, scal):

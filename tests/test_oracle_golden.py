@@ -11,7 +11,8 @@ from fixtures import make_inputs, make_params, summarize
 from ofb_oracle import (ModelCfg, adamw_step, default_switches, group_hparams, norm_targets, param_group, pmim_mask,
                         train_step)
 
-GOLD = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz")))
+GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz"))
+              if not os.path.basename(p).startswith("ft_"))       # ft_*: finetune-step fixtures (test_ft_*.py)
 
 
 def _rel(a, b):

@@ -10,7 +10,8 @@ import torch
 from step_compare import BF16_TOL, DEC_TOL, LOSS_TOL, compare_step_with_oracle
 
 pytestmark = pytest.mark.gpu
-GOLD = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz")))
+GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz"))
+              if not os.path.basename(p).startswith("ft_"))       # ft_*: finetune-step fixtures (test_ft_*.py)
 
 
 @pytest.mark.parametrize("D,H,depth,B,ef,dpr", [(192, 3, 2, 2, 0.0, 0.1), (192, 3, 12, 4, 10.0, 0.1),
