@@ -24,6 +24,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 MODELS = {"tiny": (192, 3), "small": (384, 6), "base": (768, 12)}
+METRIC = {"search": "images/sec DeiT-S bi-mask search step (fwd+bwd+update, PMIM on)",
+          "finetune": "images/sec finetune step of a physically pruned DeiT-S subnet (fwd+bwd+update)"}
 # algorithmic GFLOP / image of one search step: tiny 7.64, small 27.82, base 105.85
 STEP_GFLOP = {"tiny": 7.64, "small": 27.82, "base": 105.85}
 
@@ -40,6 +42,9 @@ def parse():
     ap.add_argument("--cpu-sample-batch", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying CUDA graphs")
+    ap.add_argument("--workload", default="search", choices=["search", "finetune"],
+                    help="search: the bi-mask search step (BASELINE.json metric, default); finetune: the training step of a "
+                         "physically pruned DeiT-S subnet (BASELINE.json configs[4], extra configuration)")
     return ap.parse_args()
 
 
@@ -100,6 +105,35 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+# BASELINE.json configs[4]: a searched OFB-DeiT-C-like subnet (README.md:23: 1.7 GFLOPs). The release checkpoints are not
+# shipped, so the per-layer dims are synthesised (fixed): pruned embedding 288, per-block heads / head dims / hidden widths
+# drawn from the DeiT-S search space (heads 2-6, head dims 16-64 step 8, hidden 384-1536 step 192).
+FT_SUBNET = dict(embed_dim=288,
+                 heads=[6, 4, 4, 6, 4, 4, 6, 4, 4, 4, 4, 6],
+                 head_dims=[48, 56, 40, 48, 64, 40, 48, 56, 40, 48, 32, 64],
+                 hiddens=[768, 576, 576, 768, 576, 576, 768, 576, 384, 576, 768, 960])
+
+
+def cpu_ft_oracle_rate(sample_batch, steps=1, warmup=1):
+    """images/s of the CPU finetune oracle (reference step restated, fp32, all host threads) on a bounded sample."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    from ft_oracle import SubnetCfg, ft_train_step, make_ft_inputs, make_ft_params
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = SubnetCfg(**FT_SUBNET)
+    P = make_ft_params(cfg, seed=0)
+    images, labels, _, _ = make_ft_inputs(cfg, sample_batch, seed=1)
+    state = {}
+    for i in range(warmup):
+        ft_train_step(P, state, images, labels, cfg, lr=1e-3, step=i + 1)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        ft_train_step(P, state, images, labels, cfg, lr=1e-3, step=warmup + i + 1)
+    dt = (time.perf_counter() - t0) / steps
+    return sample_batch / dt, cores, dt
+
+
 def cpu_oracle_rate(model, depth, sample_batch, steps=1, warmup=1):
     """images/s of the CPU oracle port (reference step restated, fp32, all host threads) on a bounded sample."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -127,14 +161,19 @@ def run_reference(args):
     if rank != 0:
         return
     D, H = MODELS[args.model]
-    rate, cores, dt = cpu_oracle_rate(args.model, args.depth, args.cpu_sample_batch, steps=max(1, min(args.steps, 3)),
-                                      warmup=max(1, min(args.warmup, 1)))
-    sample = f"{args.cpu_sample_batch} images / step of the same DeiT-{args.model} search step, fp32, {cores} threads"
+    if args.workload == "finetune":
+        rate, cores, dt = cpu_ft_oracle_rate(args.cpu_sample_batch, steps=max(1, min(args.steps, 3)), warmup=1)
+    else:
+        rate, cores, dt = cpu_oracle_rate(args.model, args.depth, args.cpu_sample_batch, steps=max(1, min(args.steps, 3)),
+                                          warmup=max(1, min(args.warmup, 1)))
+    sample = f"{args.cpu_sample_batch} images / step of the same DeiT-{args.model} {args.workload} step, fp32, {cores} threads"
     line = {
-        "impl": "reference", "metric": "images/sec DeiT-S bi-mask search step (fwd+bwd+update, PMIM on)", "value": rate,
+        "impl": "reference", "metric": METRIC[args.workload], "value": rate,
         "unit": "images/s", "n_gpus": args.gpus, "steps": max(1, min(args.steps, 3)), "warmup": 1, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"DeiT-{args.model} bi-mask search + PMIM step, depth {args.depth}, 224px, CPU sample"},
+        "config": {"workload": (f"DeiT-{args.model} bi-mask search + PMIM step, depth {args.depth}, 224px, CPU sample"
+                                if args.workload == "search" else
+                                "finetune step of a pruned DeiT-S subnet (BASELINE.json configs[4]), 224px, CPU sample")},
         "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -178,9 +217,21 @@ def main():
     B = args.batch
     eff = B * world
     lr = 2.5e-4 * eff / 256                     # search.py:509-518
-    eng = SearchStepEngine(D, H, args.depth, B, drop_path_rate=0.1, lr=lr, device=dev, process_group=pg)
-    eng.init_params(seed=0)                     # same initial weights on every rank (DDP broadcast equivalent)
-    eng.set_schedule(0.0)
+    if args.workload == "finetune":
+        from ofb_b200.finetune_engine import FinetuneStepEngine
+        eng = FinetuneStepEngine(batch=B, lr=lr, device=dev, process_group=pg, **FT_SUBNET)
+        eng.init_params(seed=0)
+        step_gflop = eng.step_flops_per_image() / 1e9
+        workload = (f"finetune step of a pruned DeiT-S subnet (embed {FT_SUBNET['embed_dim']}, per-block heads / head dims / "
+                    f"hidden widths fixed in bench.py FT_SUBNET), depth 12, batch {B}/GPU, 224px (BASELINE.json configs[4], "
+                    "extra configuration)")
+    else:
+        eng = SearchStepEngine(D, H, args.depth, B, drop_path_rate=0.1, lr=lr, device=dev, process_group=pg)
+        eng.init_params(seed=0)                     # same initial weights on every rank (DDP broadcast equivalent)
+        eng.set_schedule(0.0)
+        step_gflop = STEP_GFLOP.get(args.model)
+        workload = (f"DeiT-{args.model} bi-mask search + PMIM step, depth {args.depth}, batch {B}/GPU, 224px "
+                    + ("(BASELINE.json configs[1])" if args.model == "small" else "(BASELINE.json parity / extra configuration)"))
 
     g = torch.Generator(device="cpu").manual_seed(1 + rank)
     n_host = 2
@@ -294,35 +345,37 @@ def main():
         tr = gemm_traffic()
         achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
         line = {
-            "metric": "images/sec DeiT-S bi-mask search step (fwd+bwd+update, PMIM on)",
+            "metric": METRIC[args.workload],
             "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"DeiT-{args.model} bi-mask search + PMIM step, depth {args.depth}, batch {B}/GPU, 224px "
-                                   + ("(BASELINE.json configs[1])" if args.model == "small" else "(BASELINE.json parity / extra configuration)"), "global_batch": eff, "parallelism": f"dp{world}",
+            "config": {"workload": workload, "global_batch": eff, "parallelism": f"dp{world}",
                        "l2": "activations per step (>7 GB) exceed the 126 MB L2; no explicit flush",
                        "launch": "host launches" if args.no_graph else "CUDA graph replay (one graph per input buffer)",
-                       "step_gflop_per_image": STEP_GFLOP.get(args.model)},
+                       "step_gflop_per_image": step_gflop},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": "ofb::gemm_kernel (tcgen05, all epilogues)", "achieved": achieved,
                          "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
-                         "traffic": (tr["dram_bytes_per_launch"] if tr and args.model == "small" and B == 256 and args.depth == 12
-                                     else None),
+                         "traffic": (tr["dram_bytes_per_launch"] if tr and args.workload == "search" and args.model == "small"
+                                     and B == 256 and args.depth == 12 else None),
                          "traffic_note": "DRAM bytes per GEMM launch (mean over the 152 launches of a step), ncu --set full, "
                                          "profiles/r01_gemm_traffic.json; algorithmic FLOPs per launch = "
                                          f"{gemm_flops / max(len(gemm_t), 1):.4g}",
                          "peak_source": pk["src"], "launches_per_step": len(gemm_t) / max(n_roof, 1),
                          "share_of_step": (gemm_ms / n_roof) / (ms / args.steps) if ms > 0 else None,
                          "timed_over": f"{n_roof} host-launched steps, one CUDA-event pair per GEMM launch",
-                         "step_tflops": STEP_GFLOP.get(args.model, 0) * value / 1e3 / world},
+                         "step_tflops": (step_gflop or 0) * value / 1e3 / world},
             "losses": {"base": scal[0], "arch": scal[1], "decoder": scal[2], "total": scal[3]},
         }
         if world == 1 and not args.no_cpu_baseline:
-            rate, cores, dt = cpu_oracle_rate(args.model, args.depth, args.cpu_sample_batch)
+            if args.workload == "finetune":
+                rate, cores, dt = cpu_ft_oracle_rate(args.cpu_sample_batch)
+            else:
+                rate, cores, dt = cpu_oracle_rate(args.model, args.depth, args.cpu_sample_batch)
             line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
-                                    "sample": f"{args.cpu_sample_batch} images / step of the same DeiT-{args.model} search "
+                                    "sample": f"{args.cpu_sample_batch} images / step of the same DeiT-{args.model} {args.workload} "
                                               f"step (oracle port, fp32, {cores} threads, {dt:.1f} s/step)"}
         sys.stdout.flush()
         os.write(out_fd, (json.dumps(line) + "\n").encode())

@@ -231,6 +231,30 @@ class FinetuneStepEngine:
             self.p(k).copy_(self._pad(k, named[k].to(self.dev, torch.float32)))
         ops.cast_bf16(self.params, self.shadow)
 
+    def init_params(self, seed=0):
+        """Reference-style initialisation of the pruned shapes (trunc-normal .02 weights and tokens, zero biases, unit LayerNorm
+        weights: vision_transformer.py:300-312); benchmarks only - a real run loads the searched weights."""
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        named = {}
+        for k, shp in self.ref_shapes.items():
+            if k.endswith("norm1.weight") or k.endswith("norm2.weight") or k == "norm.weight":
+                named[k] = torch.ones(shp)
+            elif len(shp) == 1:
+                named[k] = torch.zeros(shp)
+            else:
+                named[k] = (torch.randn(shp, generator=g) * .02).clamp_(-.04, .04)
+        self.load_params(named)
+
+    def step_flops_per_image(self) -> float:
+        """Algorithmic FLOPs (2 x MAC) of one training step per image on the LOGICAL pruned shapes (SURVEY 8d formula:
+        3 x forward minus the patch-embed data gradient)."""
+        N, L, D = self.T, self.L, self.Dv
+        f = 2.0 * L * 768 * D + 2.0 * D * self.C
+        for H, d, hid in zip(self.heads, self.head_dims, self.hiddens):
+            A = H * d
+            f += 2.0 * N * D * 3 * A + 2.0 * N * A * D + 4.0 * N * D * hid + 4.0 * H * N * N * d
+        return 3.0 * f - 2.0 * L * 768 * D
+
     def named_parameters(self):
         return {k: self._unpad(k, self.p(k)) for k in self.offsets}
 
