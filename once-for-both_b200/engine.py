@@ -269,6 +269,8 @@ class SearchStepEngine:
         self.dec_bn = 256
         self.dec_part = torch.zeros(((M + 127) // 128) * (768 // self.dec_bn) * 8, **f32)   # one partial per epilogue warp
         self.scal = torch.zeros(8, **f32)
+        self.zero_mask = torch.zeros(B, self.L, **f32)           # eval mode: no PMIM masking
+        self.eval_rows, self.eval_out = torch.zeros(B, 3, **f32), torch.zeros(3, **f32)
         # backward scratch
         self.gA, self.gB, self.gC = (torch.empty(M, D, **bf) for _ in range(3))
         self.du = torch.empty(hid, self.ldT, **bf)
@@ -397,8 +399,11 @@ class SearchStepEngine:
         h[40] = self.w_p
 
     # ------------------------------------------------------------------------------------------------------------
-    def forward(self, images, labels, noise=None, drop_u=None):
-        """Forward + losses. images fp32 [B,3,224,224] (device), labels int64 [B]."""
+    def forward(self, images, labels, noise=None, drop_u=None, train=True):
+        """Forward + losses. images fp32 [B,3,224,224] (device), labels int64 [B].
+        train=False is the reference's eval mode while the search is running (engine.evaluate, engine.py:222-257 ->
+        MIMVisionTransformer.forward with self.training False): same gates, no PMIM masking (vt:631-638), DropPath identity,
+        no decoder branch (vt:719), and instead of the training losses the per-image {cross entropy, top-1, top-5} rows."""
         B, D, H, T, L, M, ML, hid = self.B, self.D, self.H, self.T, self.L, self.M, self.ML, self.hid
         bm = self.bimask
         w_p_dev = self.hyper[40:41]
@@ -412,26 +417,29 @@ class SearchStepEngine:
         with torch.cuda.stream(self._side):
             bm.forward(self.params, w_p_dev)
         # random draws stay in PyTorch (RNG parity with the reference's torch.rand), masks are built by our kernels
-        if noise is None:
-            noise = torch.rand(B, L, device=self.dev)
-        if drop_u is None:
-            drop_u = torch.rand(self.depth * 2, B, device=self.dev)
-        keep = int(L * self.keep_ratio)
-        ops.pmim_mask(noise, self.mask, keep)
-        ops.droppath_scale(drop_u, self.drop_prob, self.drop_scale)
+        if train:
+            if noise is None:
+                noise = torch.rand(B, L, device=self.dev)
+            if drop_u is None:
+                drop_u = torch.rand(self.depth * 2, B, device=self.dev)
+            keep = int(L * self.keep_ratio)
+            ops.pmim_mask(noise, self.mask, keep)
+            ops.droppath_scale(drop_u, self.drop_prob, self.drop_scale)
+        rowmask = self.mask if train else self.zero_mask
         ops.patchify(images, self.patches, self.P)
-        ops.norm_targets(images, self.mask, self.tgt)
+        if train:
+            ops.norm_targets(images, self.mask, self.tgt)
         cur.wait_stream(self._side)
         g_e = bm.gate_of(0)
         x0 = self.xs[0]
         ops.gemm(ops.EPI_PATCH, self.patches, self.w("patch_embed.proj.weight"), M=ML, N=D, K=768, out0=x0,
                  bias=self.p("patch_embed.proj.bias"), colscale=g_e, pos=self.p("pos_embed"),
-                 mask_token=self.p("mask_token"), rowmask=self.mask, tokens=L)
+                 mask_token=self.p("mask_token"), rowmask=rowmask, tokens=L)
         ops.cls_rows(self.p("cls_token"), self.p("pos_embed"), g_e, x0, B, T, D)
         for l in range(self.depth):
             pre, a = f"blocks.{l}.", self.blk[l]
             g_a, g_m = bm.gate_of(1 + 2 * l), bm.gate_of(2 + 2 * l)
-            dp1, dp2 = self.drop_scale[2 * l], self.drop_scale[2 * l + 1]
+            dp1, dp2 = (self.drop_scale[2 * l], self.drop_scale[2 * l + 1]) if train else (None, None)
             ops.layernorm_fwd(self.xs[l], self.p(pre + "norm1.weight"), self.p(pre + "norm1.bias"), a["x1"], a["mean1"],
                               a["rstd1"], self.eps_ln)
             ops.gemm(ops.EPI_STORE, a["x1"], self.w(pre + "attn.qkv.weight"), M=M, N=3 * D, K=D, out0=a["qkv"],
@@ -453,6 +461,10 @@ class SearchStepEngine:
         # head on the cls rows (row stride T*D), label-smoothing CE
         ops.gemm(ops.EPI_STORE, self.latent, self.w("head.weight"), M=B, N=self.C, K=D, out0=self.logits, out_fp32=True,
                  bias=self.p("head.bias"), lda=T * D)
+        if not train:
+            ops.eval_metrics(self.logits, labels, self.eval_rows)
+            ops.reduce_partials(self.eval_rows, B, 3, self.eval_out, scale=1.0 / B, accumulate=False)
+            return self.eval_out
         gs = 1.0 / self.accum_iter
         ops.ls_cross_entropy(self.logits, labels, self.loss_rows, self.dlogits, self.smoothing, gs)
         # PMIM decoder + masked L1 against the locally normalised pixels
@@ -622,6 +634,13 @@ class SearchStepEngine:
                       zero_grad=True)
         self.step_count += 1
         return self.scal
+
+    def evaluate(self, images, labels):
+        """One evaluate() batch (engine.py:222-257) in the reference's eval mode of an unfinished search: returns the device
+        tensor [mean cross entropy, top-1 fraction, top-5 fraction] of this batch; logits stay in self.logits."""
+        self.hyper_host[40] = self.w_p
+        self.hyper.copy_(self.hyper_host, non_blocking=True)
+        return self.forward(images, labels, train=False)
 
     def release_graphs(self):
         """Drop every captured step graph (required before the process group is destroyed when the graphs hold NCCL

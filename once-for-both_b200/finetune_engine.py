@@ -121,6 +121,7 @@ class FinetuneStepEngine:
         self.loss_rows = torch.empty(B, **f32)
         self.dlogits = torch.empty(B, self.C, **bf)
         self.scal = torch.zeros(8, **f32)
+        self.eval_rows, self.eval_out = torch.zeros(B, 3, **f32), torch.zeros(3, **f32)
         # backward scratch
         Amax, hmax = max(heads) * HD, max(hiddens)
         self.gA, self.gB, self.gC = (torch.zeros(M, Dp, **bf) for _ in range(3))
@@ -281,10 +282,11 @@ class FinetuneStepEngine:
             h[i * 8:i * 8 + 7] = torch.tensor([lr * sc, self.wd if dec else 0.0, 0.9, 0.999, 1e-8, 1 - 0.9 ** t, 1 - 0.999 ** t])
 
     # ------------------------------------------------------------------------------------------------------------
-    def forward(self, images, labels=None, target=None, drop_u=None):
-        """logits + loss. labels int64 [B] (label smoothing) or target fp32 [B, C] (Mixup soft targets)."""
+    def forward(self, images, labels=None, target=None, drop_u=None, train=True):
+        """logits + loss. labels int64 [B] (label smoothing) or target fp32 [B, C] (Mixup soft targets).
+        train=False: evaluate() (engine.py:222-257) - DropPath off, per-image {cross entropy, top-1, top-5} instead of the loss."""
         B, T, L, M, ML, Dp, Dv = self.B, self.T, self.L, self.M, self.ML, self.Dp, self.Dv
-        use_dp = self.training_mode and self.drop_path_rate > 0
+        use_dp = train and self.training_mode and self.drop_path_rate > 0
         if use_dp:
             if drop_u is None:
                 drop_u = torch.rand(self.depth * 2, B, device=self.dev)
@@ -320,6 +322,10 @@ class FinetuneStepEngine:
                           self.rstdf, self.eps_ln, d_valid=Dv)
         ops.gemm(ops.EPI_STORE, self.latent, self.w("head.weight"), M=B, N=self.C, K=Dp, out0=self.logits, out_fp32=True,
                  bias=self.p("head.bias"), lda=T * Dp)
+        if not train:
+            ops.eval_metrics(self.logits, labels, self.eval_rows)
+            ops.reduce_partials(self.eval_rows, B, 3, self.eval_out, scale=1.0 / B, accumulate=False)
+            return self.eval_out
         gs = 1.0 / self.accum_iter
         if target is not None:
             ops.soft_target_cross_entropy(self.logits, target, self.loss_rows, self.dlogits, gs)
@@ -452,6 +458,10 @@ class FinetuneStepEngine:
                       zero_grad=True)
         self.step_count += 1
         return self.scal
+
+    def evaluate(self, images, labels):
+        """One evaluate() batch (engine.py:222-257): device tensor [mean cross entropy, top-1 fraction, top-5 fraction]."""
+        return self.forward(images, labels, train=False)
 
     def release_graphs(self):
         self._graphs.clear()
