@@ -32,7 +32,7 @@ enum {
                               columns (N) = tokens: out0 = u^T = acc+bias[row] ; out1 = h^T = rowscale[col/rows_per_scale] *
                               gelu(u^T*gate[row])                                   layers.py:845-861 */
     OFB_EPI_FC2_DGRAD = 2, /* backward of layers.py:858-863 in the same transposed layout (A = fc2 weight, MN-major):
-                              out0 = du^T ; colpart0/1[2*n_tiles][M] = per-tile token sums of d gate[row], d bias[row] */
+                              out0 = du^T ; colpart0/1[ofb_gemm_mlp_partial_rows()][M] = per-tile token sums of d gate[row], d bias[row] */
     OFB_EPI_WGRAD = 3,     /* out0(fp32) += scale * A^T B, split-K (weight gradients of every Linear / conv) */
     OFB_EPI_PATCH = 4,     /* layers.py:177-191 + vision_transformer.py:628-637 fused */
     OFB_EPI_DECODER = 5    /* vision_transformer.py:720-729 fused (1x1 conv + pixel-shuffle + masked L1) */
@@ -64,6 +64,10 @@ typedef struct ofb_gemm_args {
  * bn_hint: 0 = auto, else 64/128/192/256. */
 int ofb_gemm_bf16(int epilogue, int a_mn, int b_mn, int bn_hint, const void* A, int lda, const void* B, int ldb,
                   const ofb_gemm_args* args, void* stream);
+/* rows R of the colpart0 / colpart1 buffers ([R][M] floats) the OFB_EPI_FC2_DGRAD epilogue writes for n_tokens columns at
+ * column tile bn (64/128/192/256, must be passed as bn_hint): one row per (column tile, epilogue column group); returns -1
+ * for an invalid bn. (Value, not an error code.) */
+int ofb_gemm_mlp_partial_rows(int n_tokens, int bn);
 
 /* ------------------------------------------------------------------------------------------------------------
  * LayerNorm (reference LayerNorm.forward, models/layers.py:96-98, eps 1e-6) — bf16 in/out, fp32 statistics.

@@ -56,6 +56,7 @@ SIGNATURES = {
     "ofb_version": [],
     "ofb_num_sms": [],
     "ofb_gemm_bf16": [_I, _I, _I, _I, _P, _I, _P, _I, _P, _P],
+    "ofb_gemm_mlp_partial_rows": [_I, _I],
     "ofb_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _F, _P],
     "ofb_layernorm_fwd_ex": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
     "ofb_layernorm_bwd_parts": [_I],

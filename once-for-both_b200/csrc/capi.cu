@@ -7,6 +7,7 @@ namespace ofb {
 int launch_gemm(int epi, int a_mn, int b_mn, int bn_hint, const void* A, int lda, const void* B, int ldb, GemmArgs g,
                 cudaStream_t stream);
 int num_sms();
+int mlp_partial_rows(int N, int bn);
 int launch_ln_fwd(const void*, const float*, const float*, void*, float*, float*, int, int, float, int, cudaStream_t);
 int ln_bwd_grid(int M);
 int launch_ln_bwd(const void*, const void*, const float*, const float*, const float*, void*, float*, float*, float*, const float*, int,
@@ -43,6 +44,7 @@ extern "C" {
 
 int ofb_version(void) { return 2; }
 int ofb_num_sms(void) { return ofb::num_sms(); }
+int ofb_gemm_mlp_partial_rows(int n_tokens, int bn) { return ofb::mlp_partial_rows(n_tokens, bn); }
 
 int ofb_gemm_bf16(int epilogue, int a_mn, int b_mn, int bn_hint, const void* A, int lda, const void* B, int ldb,
                   const ofb_gemm_args* a, void* stream) {

@@ -37,10 +37,18 @@ struct GemmCfg {
     static constexpr int B_BYTES = BN * BK * 2 / CG;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int NOUT = (EPI == EPI_FC1) ? 2 : 1;
-    static constexpr int STAGING_BYTES = TMA_OUT ? 2 * NOUT * PANEL_BYTES : 0;          // two slots
+    // Epilogue warps. The transposed-hidden epilogues (GELU / GELU' on every element) are bound by their own arithmetic, and
+    // that arithmetic is latency-bound at two warps per scheduler: measured (tools/micro/epi_alu_bench.cu) 35.5 -> 47.5
+    // element-pair-warps / us / scheduler going from 8 to 16 warps per SM. They therefore run 16 epilogue warps = 4 column
+    // groups = 2 independent panel pipelines (groups {0,1} -> even 64-column panels, groups {2,3} -> odd panels).
+    static constexpr int EW = ((EPI == EPI_FC1 || EPI == EPI_FC2_DGRAD) && BN % 128 == 0) ? 2 * EPI_WARPS : EPI_WARPS;
+    static constexpr int NG = EW / 4;                 // column groups (one warp per TMEM lane quarter each)
+    static constexpr int NPIPE = NG / 2;              // panel pipelines of two groups (256 threads) each
+    static constexpr int THREADS = 64 + EW * 32;
+    static constexpr int STAGING_BYTES = TMA_OUT ? 2 * NOUT * PANEL_BYTES : 0;          // two slots (NPIPE == 2: one per pipeline)
     // TMA-loaded residual / saved-activation panels: the ring holds about one tile of panels so that the load of a panel is
-    // issued a whole tile time before its use (HBM latency is ~3 panel times)
-    static constexpr int AUX_SLOTS = (TMA_OUT != 2) ? 0 : (BN == 128 ? 3 : (BN == 192 ? 4 : ((BN == 256 && EPI == EPI_FC2_DGRAD) ? 3 : 2)));
+    // issued a whole tile time before its use (HBM latency is ~3 panel times). Two pipelines: two slots each.
+    static constexpr int AUX_SLOTS = (TMA_OUT != 2) ? 0 : (NPIPE == 2 ? 4 : (BN == 128 ? 3 : (BN == 192 ? 4 : ((BN == 256 && EPI == EPI_FC2_DGRAD) ? 3 : 2))));
     static constexpr int AUX_BYTES = AUX_SLOTS * PANEL_BYTES;
     static constexpr int SCRATCH_BYTES = 0;
     // per-column epilogue vectors, double-buffered by tile parity (the transposed-hidden epilogues use per-thread scalars)
@@ -51,7 +59,8 @@ struct GemmCfg {
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED;
     static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
-    static_assert(STAGES >= 3, "pipeline too shallow");
+    // the 16-warp epilogues take ~4x the main loop of a tile: two operand stages keep the (double-buffered) accumulators ahead
+    static_assert(STAGES >= (NPIPE == 2 ? 2 : 3), "pipeline too shallow");
     static_assert((2 * STAGES + 4 + 4) * 8 + 8 <= BAR_BYTES, "barrier block too small");
 };
 
@@ -165,6 +174,18 @@ __device__ __forceinline__ void stage_bf16x32_p(uint32_t panel, int row, int hal
                      : "memory");
     }
 }
+// NP packed pairs (2 NP bf16 = NP / 4 16-byte chunks) of one row, starting at 16-byte chunk `chunk16` of the row's 128-byte line
+template <int NP>
+__device__ __forceinline__ void stage_bf16_pairs(uint32_t panel, int row, int chunk16, const float2 (&v)[NP]) {
+#pragma unroll
+    for (int i = 0; i < NP / 4; ++i) {
+        const uint32_t a = panel + sw128_offset(row, chunk16 + i);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf16x2(v[4 * i].x, v[4 * i].y)),
+                     "r"(pack_bf16x2(v[4 * i + 1].x, v[4 * i + 1].y)), "r"(pack_bf16x2(v[4 * i + 2].x, v[4 * i + 2].y)),
+                     "r"(pack_bf16x2(v[4 * i + 3].x, v[4 * i + 3].y))
+                     : "memory");
+    }
+}
 __device__ __forceinline__ uint32_t packed_word(const Packed32& r, int i) {
     const uint4& q = r.p[i >> 2];
     return (i & 3) == 0 ? q.x : ((i & 3) == 1 ? q.y : ((i & 3) == 2 ? q.z : q.w));
@@ -173,7 +194,7 @@ __device__ __forceinline__ uint32_t packed_word(const Packed32& r, int i) {
 // TMA_OUT: 0 = direct global stores; 1 = bf16 output panels staged in smem and written by TMA; 2 = 1 + the residual (STORE) /
 // saved activation (FC2_DGRAD) tile is TMA-loaded into smem panels two panels ahead of its use.
 template <int BN, int A_MN, int B_MN, int EPI, int TMA_OUT, int CG>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__((GemmCfg<BN, EPI, TMA_OUT, CG>::THREADS), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_o0, const __grid_constant__ CUtensorMap tma_o1,
             const __grid_constant__ CUtensorMap tma_aux, const GemmArgs g) {
@@ -187,8 +208,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     // transposed-hidden epilogues: rows = hidden units (few m tiles, the weight operand), columns = tokens; walking the m
     // tiles of one token tile back to back keeps that token tile in L2
     constexpr bool M_FAST = (EPI == EPI_FC1 || EPI == EPI_FC2_DGRAD);
-    constexpr int NCHUNK = BN / 32;          // 32-column chunks per tile; group g handles chunks c = g, g+2, ...
+    constexpr int NCHUNK = BN / 32;          // 32-column chunks per tile; group g handles chunks c = g, g + NG, ...
     constexpr int NPANEL = BN / 64;
+    constexpr int EW = Cfg::EW, NG = Cfg::NG, NPIPE = Cfg::NPIPE;
+    constexpr int EPI_THREADS = EW * 32;     // (shadows the 8-warp constant of the file scope)
+    static_assert(NCHUNK % NG == 0, "column chunks must divide evenly over the groups");
 
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* smem_a = smem;
@@ -223,7 +247,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&tfull_bar[i]), 1);
-            mbar_init(smem_u32(&tempty_bar[i]), EPI_WARPS * CG);      // pair: the epilogue warps of both CTAs release the leader's MMA
+            mbar_init(smem_u32(&tempty_bar[i]), EW * CG);             // pair: the epilogue warps of both CTAs release the leader's MMA
         }
         mbar_fence_init();
     }
@@ -348,16 +372,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         }
     } else {
         // ===================== epilogue warps =====================
-        const int ew = warp - 2;           // 0..7
+        const int ew = warp - 2;           // 0..EW-1
         const int q = warp & 3;            // TMEM lane quarter this warp may access
-        const int grp = ew >> 2;           // column-chunk parity handled by this warp
+        const int grp = ew >> 2;           // column group: chunks c = grp, grp + NG, ...
+        const int pp = (NPIPE == 2) ? (grp >> 1) : 0;      // panel pipeline of this warp
         const int et = q * 32 + lane;      // row inside the tile
-        const int etid = ew * 32 + lane;   // 0..255
-        const bool elected = (etid == 0);
+        const int etid = ew * 32 + lane;   // 0..EPI_THREADS-1
+        const bool elected = (etid == pp * 256);           // one thread per pipeline issues its TMA stores / aux loads
         int it = 0;
-        uint32_t panel_ctr = 0;
-        // TMA_OUT == 2: panel number P of this CTA (tile sequence P / NPT, panel P % NPT) is loaded into aux slot P % AUX_SLOTS
+        uint32_t panel_ctr = 0;            // panels this pipeline has processed
+        // TMA_OUT == 2: panel number P of this CTA (tile sequence P / NPT, panel P % NPT) is loaded into aux slot P % AUX_SLOTS;
+        // with two pipelines P alternates between them (NPT is even), so each owns the slots of its own parity
         constexpr uint32_t NPT = NCHUNK / 2;
+        constexpr uint32_t PPT = NPT / NPIPE;              // panels per tile per pipeline
+        static_assert(NPIPE == 1 || (NPT % 2 == 0 && Cfg::AUX_SLOTS % 2 == 0), "two pipelines need an even panel count");
         auto issue_aux = [&](uint32_t P) {
             const long t2 = long(cta_first) + long(P / NPT) * cta_stride;
             if (t2 >= total_tiles) return;
@@ -368,8 +396,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             tma_load_2d(smem_u32(auxbuf) + (P % AUX_SLOTS) * PANEL_BYTES, &tma_aux, fb, n2 * BN + int(P % NPT) * 64, m2 * BM);
         };
         if (TMA_OUT == 2 && elected) {
-            for (uint32_t i = 0; i < AUX_SLOTS; ++i) issue_aux(i);
+            for (uint32_t i = 0; i < AUX_SLOTS; ++i)
+                if (int(i % NPIPE) == pp) issue_aux(i);
         }
+        // two pipelines share the two staging slots (one each): the slot's previous TMA store must have been read out before
+        // the pipeline stages its next panel
+        auto pre_stage = [&]() {
+            if (NPIPE == 2) {
+                if (elected) bulk_wait_read<0>();
+                named_bar_sync(4 + pp, 256);
+            }
+        };
         // pair: the accumulator stage is handed back to the leader's MMA warp (remote arrive from the peer CTA)
         const uint32_t tempty_remote0 = (CG == 2) ? mapa_shared(smem_u32(&tempty_bar[0]), 0) : 0u;
         for (int t = cta_first; t < total_tiles; t += cta_stride) {
@@ -425,28 +462,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 if (g.scale_ptr != nullptr) gs = __ldg(g.scale_ptr);
             }
             // ---- prefetch this thread's residual / saved-activation slices (latency hides behind the tfull wait) ----
-            Packed32 pre[(EPI == EPI_STORE && TMA_OUT == 0) ? NCHUNK / 2 : 1];
+            Packed32 pre[(EPI == EPI_STORE && TMA_OUT == 0) ? NCHUNK / NG : 1];
             if (EPI == EPI_STORE && TMA_OUT == 0) {
                 if (g.res != nullptr) {
 #pragma unroll
-                    for (int j = 0; j < NCHUNK / 2; ++j) {
-                        const int col0 = n0 + (2 * j + grp) * 32;
+                    for (int j = 0; j < NCHUNK / NG; ++j) {
+                        const int col0 = n0 + (NG * j + grp) * 32;
                         pre[j] = load_packed32(g.res + size_t(row) * g.ldres + col0, row_ok, min(32, g.N - col0));
                     }
                 }
             }
-            named_bar_sync(1, EPI_THREADS);       // epilogue vectors visible
+            if (Cfg::VEC_BYTES > 0) named_bar_sync(1, EPI_THREADS);       // epilogue vectors visible
             mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
             tc_fence_after();
 
             float loss_acc = 0.f;
 #pragma unroll
-            for (int j = 0; j < NCHUNK / 2; ++j) {
-                const int c = 2 * j + grp;
+            for (int j = 0; j < NCHUNK / NG; ++j) {
+                const int c = NG * j + grp;
+                const int pj = c >> 1;            // 64-column panel of this chunk inside the tile
                 float v[32];
                 tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + c * 32), v);
                 tmem_ld_wait();
-                if (j == NCHUNK / 2 - 1) {
+                if (j == NCHUNK / NG - 1) {
                     // this warp's last TMEM read of the tile: hand the accumulator stage back to the MMA warp early
                     tc_fence_before();
                     __syncwarp();
@@ -459,12 +497,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 const int nvalid = min(32, g.N - col0);
                 const float* cb = vb + c * 32;
                 const float* cs = vs + c * 32;
-                const uint32_t slot = panel_ctr & 1u;
+                const uint32_t slot = (NPIPE == 2) ? uint32_t(pp) : (panel_ctr & 1u);
                 const uint32_t panel0 = smem_u32(staging) + slot * (Cfg::NOUT * PANEL_BYTES);
+                // global panel number of this CTA (see issue_aux)
+                const uint32_t P = (panel_ctr / PPT) * NPT + (panel_ctr % PPT) * NPIPE + uint32_t(pp);
                 Packed32 ax;       // this row's 32 residual / saved-activation values of the chunk (TMA-loaded panel)
                 if (TMA_OUT == 2) {
-                    const uint32_t aslot = panel_ctr % AUX_SLOTS;
-                    mbar_wait(smem_u32(&aux_full[aslot]), (panel_ctr / AUX_SLOTS) & 1u);
+                    const uint32_t aslot = P % AUX_SLOTS;
+                    mbar_wait(smem_u32(&aux_full[aslot]), (P / AUX_SLOTS) & 1u);
                     const uint32_t ab = smem_u32(auxbuf) + aslot * PANEL_BYTES;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -510,62 +550,78 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         rsA = __ldg(g.rowscale + b0);
                         rsB = __ldg(g.rowscale + min(b0 + 1, tile_last));
                     }
+                    // The 16-warp variant works on 16 columns at a time (112 registers per thread), the 8-warp variant on all 32
+                    constexpr int HALVES = (EW == 16) ? 2 : 1;
+                    constexpr int HP = 16 / HALVES;                 // packed pairs per half
                     if (EPI == EPI_FC1) {
                         // packed fp32x2 math: the epilogue is fma-pipe bound (see ptx.cuh)
-                        float2 u2[16], h2[16];
                         const float2 b2 = splat2(bias_j), g2 = splat2(gate_j);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            u2[i] = add2(make_float2(v[2 * i], v[2 * i + 1]), b2);
-                            const float2 z = mul2(u2[i], g2);
-                            h2[i] = mul2(z, gelu_cdf2(z));
-                        }
-                        if (nb >= 32) {
-                            const float2 r2 = splat2(rsA);
+                        for (int hh = 0; hh < HALVES; ++hh) {
+                            float2 u2[HP], h2[HP];
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) h2[i] = mul2(h2[i], r2);
-                        } else {
+                            for (int i = 0; i < HP; ++i) {
+                                const int e = 2 * (hh * HP + i);    // column of the pair inside the chunk
+                                u2[i] = add2(make_float2(v[e], v[e + 1]), b2);
+                                const float2 z = mul2(u2[i], g2);
+                                h2[i] = mul2(z, gelu_cdf2(z));
+                            }
+                            if (nb >= 32) {
+                                const float2 r2 = splat2(rsA);
 #pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                h2[i] = mul2(h2[i], make_float2(2 * i < nb ? rsA : rsB, 2 * i + 1 < nb ? rsA : rsB));
+                                for (int i = 0; i < HP; ++i) h2[i] = mul2(h2[i], r2);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < HP; ++i) {
+                                    const int e = 2 * (hh * HP + i);
+                                    h2[i] = mul2(h2[i], make_float2(e < nb ? rsA : rsB, e + 1 < nb ? rsA : rsB));
+                                }
+                            }
+                            if (hh == 0) pre_stage();
+                            stage_bf16_pairs<HP>(panel0, et, (c & 1) * 4 + hh * (HP / 4), u2);
+                            stage_bf16_pairs<HP>(panel0 + PANEL_BYTES, et, (c & 1) * 4 + hh * (HP / 4), h2);
                         }
-                        stage_bf16x32_p(panel0, et, c & 1, u2);
-                        stage_bf16x32_p(panel0 + PANEL_BYTES, et, c & 1, h2);
                     } else {
                         // saved pre-gate fc1 output u (zero for rows / tokens out of range: TMA fill)
-                        float2 du2[16];
-                        float2 cdg2 = splat2(0.f), cdb2 = splat2(0.f);
                         const float2 g2 = splat2(gate_j);
-                        if (nb >= 32) {
-                            // one DropPath multiplier for the whole chunk: fold it into the per-chunk constants
-                            const float2 rg2 = splat2(rsA * gate_j);
+                        float2 cdg2 = splat2(0.f), cdb2 = splat2(0.f);
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                const float2 u = unpack_bf16x2(packed_word(ax, i));
-                                float2 Phi, dgelu;
-                                gelu_terms2(mul2(u, g2), Phi, dgelu);
-                                const float2 w = mul2(make_float2(v[2 * i], v[2 * i + 1]), dgelu);     // dh/rs * gelu'(u g)
-                                cdg2 = fma2(w, u, cdg2);
-                                du2[i] = mul2(w, rg2);                                                // du
-                                cdb2 = add2(cdb2, du2[i]);                                            // d bias[j]
-                            }
-                            acc_dg = fmaf(cdg2.x + cdg2.y, rsA, acc_dg);                              // d gate[j]
-                        } else {
+                        for (int hh = 0; hh < HALVES; ++hh) {
+                            float2 du2[HP];
+                            if (nb >= 32) {
+                                // one DropPath multiplier for the whole chunk: fold it into the per-chunk constants
+                                const float2 rg2 = splat2(rsA * gate_j);
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                const float2 u = unpack_bf16x2(packed_word(ax, i));
-                                float2 Phi, dgelu;
-                                gelu_terms2(mul2(u, g2), Phi, dgelu);
-                                const float2 rs2 = make_float2(2 * i < nb ? rsA : rsB, 2 * i + 1 < nb ? rsA : rsB);
-                                const float2 w = mul2(mul2(make_float2(v[2 * i], v[2 * i + 1]), rs2), dgelu);
-                                cdg2 = fma2(w, u, cdg2);
-                                du2[i] = mul2(w, g2);
-                                cdb2 = add2(cdb2, du2[i]);
+                                for (int i = 0; i < HP; ++i) {
+                                    const int pi = hh * HP + i;
+                                    const float2 u = unpack_bf16x2(packed_word(ax, pi));
+                                    float2 Phi, dgelu;
+                                    gelu_terms2(mul2(u, g2), Phi, dgelu);
+                                    const float2 w = mul2(make_float2(v[2 * pi], v[2 * pi + 1]), dgelu);    // dh/rs * gelu'(u g)
+                                    cdg2 = fma2(w, u, cdg2);
+                                    du2[i] = mul2(w, rg2);                                                // du
+                                    cdb2 = add2(cdb2, du2[i]);                                            // d bias[j]
+                                }
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < HP; ++i) {
+                                    const int pi = hh * HP + i;
+                                    const float2 u = unpack_bf16x2(packed_word(ax, pi));
+                                    float2 Phi, dgelu;
+                                    gelu_terms2(mul2(u, g2), Phi, dgelu);
+                                    const float2 rs2 = make_float2(2 * pi < nb ? rsA : rsB, 2 * pi + 1 < nb ? rsA : rsB);
+                                    const float2 w = mul2(mul2(make_float2(v[2 * pi], v[2 * pi + 1]), rs2), dgelu);
+                                    cdg2 = fma2(w, u, cdg2);
+                                    du2[i] = mul2(w, g2);
+                                    cdb2 = add2(cdb2, du2[i]);
+                                }
                             }
-                            acc_dg += cdg2.x + cdg2.y;
+                            if (hh == 0) pre_stage();
+                            stage_bf16_pairs<HP>(panel0, et, (c & 1) * 4 + hh * (HP / 4), du2);
                         }
+                        if (nb >= 32) acc_dg = fmaf(cdg2.x + cdg2.y, rsA, acc_dg);                        // d gate[j]
+                        else acc_dg += cdg2.x + cdg2.y;
                         acc_db += cdb2.x + cdb2.y;
-                        stage_bf16x32_p(panel0, et, c & 1, du2);
                     }
                 } else if (EPI == EPI_WGRAD) {
                     if (row_ok && nvalid > 0) {
@@ -627,17 +683,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 }
 
                 if (TMA_OUT) {
-                    // panel j of this tile (chunks 2j, 2j+1) is complete once both groups have staged their chunk
+                    // panel pj of this tile (chunks 2 pj, 2 pj + 1) is complete once both groups of the pipeline have staged
+                    // their chunk
                     fence_proxy_async_smem();
-                    if (elected) bulk_wait_read<0>();          // the other slot's previous store has been read out
-                    named_bar_sync(2, EPI_THREADS);
-                    if (elected && n0 + j * 64 < g.N) {
-                        tma_store_2d(&tma_o0, panel0, n0 + j * 64, m_blk * BM);
-                        if (Cfg::NOUT == 2) tma_store_2d(&tma_o1, panel0 + PANEL_BYTES, n0 + j * 64, m_blk * BM);
+                    if (NPIPE == 1 && elected) bulk_wait_read<0>();          // the other slot's previous store has been read out
+                    named_bar_sync(2 + pp, 256);
+                    if (elected && n0 + pj * 64 < g.N) {
+                        tma_store_2d(&tma_o0, panel0, n0 + pj * 64, m_blk * BM);
+                        if (Cfg::NOUT == 2) tma_store_2d(&tma_o1, panel0 + PANEL_BYTES, n0 + pj * 64, m_blk * BM);
                         bulk_commit();
                     }
                     // every thread has consumed this panel's aux slot (it was read before the barrier): refill it AUX_SLOTS panels ahead
-                    if (TMA_OUT == 2 && elected) { fence_proxy_async_smem(); issue_aux(panel_ctr + AUX_SLOTS); }
+                    if (TMA_OUT == 2 && elected) { fence_proxy_async_smem(); issue_aux(P + AUX_SLOTS); }
                     ++panel_ctr;
                 }
             }
@@ -645,8 +702,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             if (EPI == EPI_FC2_DGRAD) {
                 // each thread owns one hidden unit: its token sums of this tile go out as one partial row per (n tile, group)
                 if (row_ok) {
-                    g.colpart0[size_t(n_blk * 2 + grp) * g.M + row] = acc_dg;
-                    g.colpart1[size_t(n_blk * 2 + grp) * g.M + row] = acc_db;
+                    g.colpart0[size_t(n_blk * NG + grp) * g.M + row] = acc_dg;
+                    g.colpart1[size_t(n_blk * NG + grp) * g.M + row] = acc_db;
                 }
             }
             if (EPI == EPI_DECODER) {
@@ -770,11 +827,11 @@ static int launch_gemm_inst(const void* A, int lda, const void* B, int ldb, cons
     const int slots = num_sms() / CG;
     const int grid = (total < slots ? total : slots) * CG;
     if (CG == 1) {
-        kfn<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, to0, to1, tx, g);
+        kfn<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, to0, to1, tx, g);
         return int(cudaGetLastError());
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = stream;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(Cfg::THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -840,6 +897,14 @@ static int launch_gemm_bn(int bn, const void* A, int lda, const void* B, int ldb
         case 128: return launch_gemm_inst<128, A_MN, B_MN, EPI, TMA_OUT, 1>(A, lda, B, ldb, g, s);
         default:  return launch_gemm_inst<64, A_MN, B_MN, EPI, TMA_OUT, 1>(A, lda, B, ldb, g, s);
     }
+}
+
+// rows of the [rows][M] token-sum partial buffers the FC2_DGRAD epilogue writes for N tokens at column tile bn: one per
+// (column tile, epilogue column group)
+int mlp_partial_rows(int N, int bn) {
+    if (bn != 64 && bn != 128 && bn != 192 && bn != 256) return -1;
+    const int ng = (bn % 128 == 0) ? 4 : 2;
+    return ng * ((N + bn - 1) / bn);
 }
 
 static bool tma_out_ok(const void* p, int ld) { return p != nullptr && (reinterpret_cast<uintptr_t>(p) & 15u) == 0 && ld % 8 == 0; }

@@ -251,7 +251,7 @@ class SearchStepEngine:
         self.ldT = (M + 7) // 8 * 8
         self.mlp_bn = int(os.environ.get("OFB_MLP_BN", "256"))      # token tile of the transposed-hidden GEMMs
         self.bn_nD = 0          # N tile of the N = embed_dim GEMMs (0 = the library's cost model); tools/step_breakdown.py A/Bs it
-        self.mlp_parts = 2 * ((M + self.mlp_bn - 1) // self.mlp_bn)
+        self.mlp_parts = ops.gemm_mlp_partial_rows(M, self.mlp_bn)
         self.xs = [torch.zeros(M, D, **bf) for _ in range(depth + 1)]      # xs[l] = input of block l; xs[depth] = output
         self.blk = []
         for _ in range(depth):

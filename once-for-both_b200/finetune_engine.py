@@ -99,7 +99,7 @@ class FinetuneStepEngine:
         M, ML, Dp, B, T = self.M, self.ML, self.Dp, batch, self.T
         self.ldT = (M + 7) // 8 * 8
         self.mlp_bn = int(os.environ.get("OFB_MLP_BN", "256"))
-        self.mlp_parts = 2 * ((M + self.mlp_bn - 1) // self.mlp_bn)
+        self.mlp_parts = ops.gemm_mlp_partial_rows(M, self.mlp_bn)
         self.patches = torch.empty(ML, 3 * patch * patch, **bf)
         self.zero_mask = torch.zeros(B, self.L, **f32)          # no PMIM in finetuning: every patch is kept
         self.ones = torch.ones(max(Dp, max(hiddens), max(heads) * HD), **f32)     # identity gate of the shared epilogues

@@ -30,7 +30,7 @@ class _TimedLib:
 
     def __getattr__(self, name):
         fn = getattr(self._inner, name)
-        if not name.startswith("ofb_") or name in ("ofb_version", "ofb_layernorm_bwd_parts"):
+        if not name.startswith("ofb_") or name in ("ofb_version", "ofb_layernorm_bwd_parts", "ofb_gemm_mlp_partial_rows"):
             return fn
 
         def run(*args):
@@ -110,6 +110,14 @@ def layernorm_fwd(x, gamma, beta, y, mean, rstd, eps, d_valid=None):
     else:
         check(lib().ofb_layernorm_fwd_ex(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(rstd), M, D, d_valid, eps,
                                          cur_stream()), "ofb_layernorm_fwd_ex")
+
+
+def gemm_mlp_partial_rows(n_tokens, bn):
+    """Rows of the colpart buffers of the EPI_FC2_DGRAD epilogue (depends on how many epilogue column groups the kernel runs)."""
+    r = _raw_lib().ofb_gemm_mlp_partial_rows(n_tokens, bn)
+    if r <= 0:
+        raise _lib.OfbError(f"ofb_gemm_mlp_partial_rows: invalid column tile {bn}")
+    return r
 
 
 def layernorm_bwd_parts(M):

@@ -97,7 +97,7 @@ def test_gemm_fc1_and_fc2_dgrad(cuda_dev):
     # backward of  y = rs * gelu(u*g) @ W2^T :  dh = rs * (dy @ W2)
     dy = rnd(M, D)
     du = torch.zeros_like(u)
-    R = 2 * ((M + 255) // 256)
+    R = ops.gemm_mlp_partial_rows(M, 256)
     p0, p1 = torch.zeros(R, Hd, device="cuda"), torch.zeros(R, Hd, device="cuda")
     ops.gemm(ops.EPI_FC2_DGRAD, W2, dy, M=Hd, N=M, K=D, out0=du, aux=u, colscale=gate, rowscale=rs, rows_per_scale=197,
              colpart0=p0, colpart1=p1, a_mn=True, bn=256)
