@@ -212,7 +212,18 @@ class SearchStepEngine:
             seg_end.append(off)
         self.n_arena = off
         self.seg_end = seg_end
-        self._seg_end_c = (C.c_int64 * len(GROUPS))(*seg_end)
+        # AdamW segments: the four weight / decoder groups, then ONE SEGMENT PER ALPHA TENSOR - a prune event restarts the
+        # optimizer state of the alphas it touches, step counter included (optim.AdamW.update(..., initialize=True),
+        # optim.py:152-159), so every alpha carries its own bias-correction step
+        self.alpha_names = [k for k in order if param_group(k, shapes[k]) == "arch"]
+        self.segments = [(gname, None) for gname in GROUPS[:4]] + [("arch", k) for k in self.alpha_names]
+        ends = list(seg_end[:4])
+        for k in self.alpha_names:
+            ends.append(self.offsets[k] + (math.prod(shapes[k]) + T_PAD - 1) // T_PAD * T_PAD)
+        assert ends[-1] == off and len(ends) <= 64
+        self._seg_end_c = (C.c_int64 * len(ends))(*ends)
+        self.alpha_restart = {k: 0 for k in self.alpha_names}     # optimizer step at which the alpha's state was (re)started
+        self._wp_idx = len(self.segments) * 8
         f32 = dict(dtype=torch.float32, device=self.dev)
         bf = dict(dtype=torch.bfloat16, device=self.dev)
         self.params = torch.zeros(off, **f32)
@@ -221,9 +232,9 @@ class SearchStepEngine:
         self.adam_v = torch.zeros(off, **f32)
         self.shadow = torch.zeros(off, **bf)
         self.alpha_patch = torch.ones(1, 1, **f32)          # frozen when --patch_search is off
-        self.hyper_host = torch.zeros(len(GROUPS) * 8 + 8, dtype=torch.float32).pin_memory() \
-            if self.dev.type == "cuda" else torch.zeros(len(GROUPS) * 8 + 8)
-        self.hyper = torch.zeros(len(GROUPS) * 8 + 8, **f32)   # [..., w_p] at index 40
+        nh = self._wp_idx + 8
+        self.hyper_host = torch.zeros(nh, dtype=torch.float32).pin_memory() if self.dev.type == "cuda" else torch.zeros(nh)
+        self.hyper = torch.zeros(nh, **f32)                    # [segments x 8 ..., w_p]
 
         # ---- bi-mask ----
         if switches is None:
@@ -388,15 +399,15 @@ class SearchStepEngine:
         self.keep_ratio = self.max_ratio - (self.max_ratio - self.min_ratio) * e / self.warmup_epochs
 
     def _fill_hyper(self, lrs=None):
-        t = self.step_count + 1
         lrs = lrs or {}
         h = self.hyper_host
-        for i, gname in enumerate(GROUPS):
+        for i, (gname, alpha_name) in enumerate(self.segments):
+            t = self.step_count + 1 - (self.alpha_restart[alpha_name] if alpha_name else 0)
             b1, b2 = (0.5, 0.999) if gname == "arch" else (0.9, 0.999)
             lr = lrs.get(gname, self.lr)
             wd = 0.0 if gname.endswith("_nd") else self.wd
             h[i * 8:i * 8 + 7] = torch.tensor([lr, wd, b1, b2, 1e-8, 1 - b1 ** t, 1 - b2 ** t])
-        h[40] = self.w_p
+        h[self._wp_idx] = self.w_p
 
     # ------------------------------------------------------------------------------------------------------------
     def forward(self, images, labels, noise=None, drop_u=None, train=True):
@@ -406,7 +417,7 @@ class SearchStepEngine:
         no decoder branch (vt:719), and instead of the training losses the per-image {cross entropy, top-1, top-5} rows."""
         B, D, H, T, L, M, ML, hid = self.B, self.D, self.H, self.T, self.L, self.M, self.ML, self.hid
         bm = self.bimask
-        w_p_dev = self.hyper[40:41]
+        w_p_dev = self.hyper[self._wp_idx:self._wp_idx + 1]
         # the gate construction (two small latency-bound kernels) runs on a side stream next to the image-side preparation
         # (PMIM mask, patchify, target normalisation); it joins before the patch-embed GEMM, the first consumer of a gate.
         # Under CUDA-graph capture this becomes a parallel branch of the graph.
@@ -580,7 +591,7 @@ class SearchStepEngine:
         ops.gemm(ops.EPI_WGRAD, self.dconv, self.patches, M=D, N=768, K=ML,
                  out0=self.g("patch_embed.proj.weight").view(D, 768), a_mn=True, b_mn=True)
         # ---- bi-mask: d gate (+ FLOPs / sparsity losses) -> d score, d alpha ----
-        bm.backward(self.params, self.hyper[40:41], self.dgate, gs, self.grads)
+        bm.backward(self.params, self.hyper[self._wp_idx:self._wp_idx + 1], self.dgate, gs, self.grads)
         if red is not None:
             red.finish()
 
@@ -638,9 +649,67 @@ class SearchStepEngine:
     def evaluate(self, images, labels):
         """One evaluate() batch (engine.py:222-257) in the reference's eval mode of an unfinished search: returns the device
         tensor [mean cross entropy, top-1 fraction, top-5 fraction] of this batch; logits stay in self.logits."""
-        self.hyper_host[40] = self.w_p
+        self.hyper_host[self._wp_idx] = self.w_p
         self.hyper.copy_(self.hyper_host, non_blocking=True)
         return self.forward(images, labels, train=False)
+
+    # ------------------------------------------------------------------------------------------------------------
+    # prune event (vision_transformer.py:785-950; see prune.py)
+    def plan_prune(self, thresh=0.2):
+        """Decisions and kept-unit index sets of compress(thresh) for every searchable module, from the alphas (averaged over
+        the ranks, layers.py:9-14), the switch cells and the ranks the bi-mask kernel built in the last forward."""
+        from . import prune
+        bm = self.bimask
+        rank = bm.rank.cpu()
+        plans = {}
+        for m in bm.modules:
+            pre, H, dim = m["prefix"], m["heads"], m["dim"]
+            alpha = self.p(pre + ".alpha").detach().clone()
+            if self.world > 1:
+                torch.distributed.all_reduce(alpha, group=self.pg)
+                alpha /= self.world
+            r = rank[m["gate_off"]:m["gate_off"] + H * dim].view(H, dim)
+            widths = bm._widths[m["width_off"]:m["width_off"] + m["n_j"]]
+            counts = bm._widths[m["width_off"] + m["n_j"]:m["width_off"] + m["n_j"] + (m["n_i"] if m["kind"] == 2 else 0)]
+            sw = self.switches[pre].reshape(m["n_i"], m["n_j"])
+            plans[pre] = prune.plan_module(pre, m["kind"], alpha.reshape(m["n_i"], m["n_j"]), sw, list(widths), list(counts),
+                                           r[:, 0] // dim, r % dim, thresh)
+        return plans
+
+    def gather_pruned(self, plans):
+        """Every parameter in the shape compress() would leave it in (device tensors, reference names / shapes)."""
+        from . import prune
+        dims = {m["prefix"]: dict(heads=m["heads"], dim=m["dim"]) for m in self.bimask.modules}
+        return prune.gather_pruned(plans, {k: self.p(k) for k in self.offsets}, dims, self.w_p)
+
+    def apply_prune(self, plans):
+        """Apply a prune event in place. Events that only switch cells off (no physical slicing) are supported: new switch
+        cells, alpha <- where(alive, mean alpha, 0), Adam state of those alphas restarted (optim.py:152-159), step graphs
+        dropped. Truncating / finalising events need the search step on pruned shapes, which is not built yet."""
+        if any(pl.truncated for pl in plans.values()):
+            raise NotImplementedError("this prune event slices tensors; post-prune search shapes are not built yet "
+                                      "(gather_pruned() returns the pruned tensors)")
+        changed = False
+        for pre, pl in plans.items():
+            if not pl.executed:
+                continue
+            changed = True
+            self.switches[pre] = pl.switch.clone()
+            name = pre + ".alpha"
+            self.p(name).copy_(pl.alpha.to(self.dev).reshape(self.shapes[name]))
+            self._view(self.adam_m, name).zero_()
+            self._view(self.adam_v, name).zero_()
+            self.alpha_restart[name] = self.step_count
+        if changed:
+            bm = self.bimask
+            sw_bytes = []
+            for m in bm.modules:
+                sw_bytes.extend(int(x) for x in self.switches[m["prefix"]].reshape(-1).tolist())
+            bm._sw_bytes = sw_bytes
+            bm.switches_dev.copy_(torch.tensor(sw_bytes, dtype=torch.uint8))
+            self.sync_shadow()
+            self.release_graphs()
+        return changed
 
     def release_graphs(self):
         """Drop every captured step graph (required before the process group is destroyed when the graphs hold NCCL
