@@ -156,3 +156,38 @@ def gather_pruned(plans: Dict[str, ModulePlan], named: Dict[str, torch.Tensor], 
     if pe is not None:
         out["patch_embed.alpha"] = pe.alpha.to(dev)
     return out
+
+
+def fuse_params(named: Dict[str, torch.Tensor], prefixes: List[str]) -> Dict[str, torch.Tensor]:
+    """MIMVisionTransformer.fuse (vision_transformer.py:747-757) + the module fuse() methods (layers.py:202-206, 539-543,
+    867-871) on a fully finalised model: the frozen gates (the finalised `score` tensors) are folded into the weights that
+    produce the gated activations, which leaves a plain pre-norm ViT on pruned shapes - the model `finetune.intersect` copies
+    and `FinetuneStepEngine` trains / evaluates. Returns the tensors under the plain VisionTransformer's names (scores, alphas,
+    mask token and decoder dropped)."""
+    out = {k: v for k, v in named.items()}
+    se = named["patch_embed.score"].reshape(-1)
+    for k in ("cls_token", "pos_embed"):
+        out[k] = named[k] * se
+    out["patch_embed.proj.weight"] = named["patch_embed.proj.weight"] * se.view(-1, 1, 1, 1)
+    out["patch_embed.proj.bias"] = named["patch_embed.proj.bias"] * se
+    for p in prefixes:
+        if p == "patch_embed":
+            continue
+        s = named[p + ".score"].reshape(-1)
+        if p.endswith(".attn"):
+            s3 = s.repeat(3)
+            out[p + ".qkv.weight"] = named[p + ".qkv.weight"] * s3.unsqueeze(-1)
+            out[p + ".qkv.bias"] = named[p + ".qkv.bias"] * s3
+        else:
+            out[p + ".fc1.weight"] = named[p + ".fc1.weight"] * s.unsqueeze(-1)
+            out[p + ".fc1.bias"] = named[p + ".fc1.bias"] * s
+    return {k: v for k, v in out.items()
+            if not (k.endswith(".score") or k.endswith(".alpha") or k == "mask_token" or k.startswith("decoder."))}
+
+
+def subnet_dims(plans: Dict[str, ModulePlan], depth: int):
+    """(embed_dim, heads[], head_dims[], hiddens[]) of a fully finalised model, the constructor arguments of
+    FinetuneStepEngine."""
+    assert all(pl.finalised for pl in plans.values()), "every searchable module must be finalised"
+    return (plans["patch_embed"].width, [plans[f"blocks.{l}.attn"].head_num for l in range(depth)],
+            [plans[f"blocks.{l}.attn"].width for l in range(depth)], [plans[f"blocks.{l}.mlp"].width for l in range(depth)])
