@@ -260,8 +260,9 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    ln_t = []
     if args.no_graph:
-        ops.GEMM_TIMING = []
+        ops.GEMM_TIMING, ops.LN_TIMING = [], []
     launches0 = ops.LAUNCHES
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -273,7 +274,9 @@ def main():
     mark("timed region done")
     launches = ops.LAUNCHES - launches0
     gemm_t = ops.GEMM_TIMING
-    ops.GEMM_TIMING = None
+    if args.no_graph:
+        ln_t = ops.LN_TIMING
+    ops.GEMM_TIMING = ops.LN_TIMING = None
     clocks = sampler.stop() if rank == 0 else None
     n_roof = args.steps
     if gemm_t is None:
@@ -281,12 +284,12 @@ def main():
         # host-launched steps of the same workload with CUDA events on the launching stream (the stream stays saturated:
         # ~270 launches of ~60 us per step, so an event pair brackets exactly one kernel)
         n_roof = min(3, args.steps)
-        ops.GEMM_TIMING = []
+        ops.GEMM_TIMING, ops.LN_TIMING = [], []
         for i in range(n_roof):
             eng.step(dev_img[i % n_host], dev_lab[i % n_host])
         sync_all()
-        gemm_t = ops.GEMM_TIMING
-        ops.GEMM_TIMING = None
+        gemm_t, ln_t = ops.GEMM_TIMING, ops.LN_TIMING
+        ops.GEMM_TIMING = ops.LN_TIMING = None
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -294,6 +297,8 @@ def main():
     value = eff * args.steps / (ms / 1e3)
     gemm_ms = sum(a.elapsed_time(b) for a, b, _, _ in gemm_t)
     gemm_flops = sum(f for _, _, f, _ in gemm_t)
+    ln_ms = sum(a.elapsed_time(b) for a, b, _ in ln_t)
+    ln_bytes = sum(nb for _, _, nb in ln_t)
     scal = eng.scal.cpu().tolist()
 
     mark("roofline pass done")
@@ -367,6 +372,13 @@ def main():
                          "share_of_step": (gemm_ms / n_roof) / (ms / args.steps) if ms > 0 else None,
                          "timed_over": f"{n_roof} host-launched steps, one CUDA-event pair per GEMM launch",
                          "step_tflops": (step_gflop or 0) * value / 1e3 / world},
+            # the HBM-bound kernel family of the step: LayerNorm forward / backward, algorithmic bytes (bf16 rows
+            # read + written) over CUDA-event durations of the same host-launched steps, against the measured copy bandwidth
+            "roofline_hbm": {"bound": "hbm", "kernel": "ofb::ln_fwd*/ln_bwd* (LayerNorm forward + backward)",
+                             "achieved": (ln_bytes / (ln_ms / 1e3) / 1e9) if ln_ms > 0 else None, "peak": pk["hbm"],
+                             "unit": "GB/s", "frac": (ln_bytes / (ln_ms / 1e3) / 1e9 / pk["hbm"]) if ln_ms > 0 else None,
+                             "launches_per_step": len(ln_t) / max(n_roof, 1),
+                             "share_of_step": (ln_ms / n_roof) / (ms / args.steps) if ms > 0 else None, "traffic": None},
             "losses": {"base": scal[0], "arch": scal[1], "decoder": scal[2], "total": scal[3]},
         }
         if world == 1 and not args.no_cpu_baseline:

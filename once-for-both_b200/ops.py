@@ -15,6 +15,18 @@ EPI_STORE, EPI_FC1, EPI_FC2_DGRAD, EPI_WGRAD, EPI_PATCH, EPI_DECODER = range(6)
 LAUNCHES = 0
 # optional per-launch GEMM timing: set to a list -> gemm() appends (start_event, end_event, flops)
 GEMM_TIMING = None
+# optional per-launch LayerNorm timing (the HBM-bound kernel family): list of (start_event, end_event, algorithmic bytes)
+LN_TIMING = None
+
+
+def _ln_timed(call, nbytes):
+    if LN_TIMING is None:
+        return call()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    call()
+    e1.record()
+    LN_TIMING.append((e0, e1, nbytes))
 
 
 # optional per-launch timing of EVERY library call (tools/step_breakdown.py): set to a list -> each launch appends
@@ -104,12 +116,15 @@ def gemm(epi, A, B, *, M, N, K, out0=None, ld0=0, out1=None, ld1=0, out_fp32=Fal
 def layernorm_fwd(x, gamma, beta, y, mean, rstd, eps, d_valid=None):
     """d_valid: real channels of a zero-padded pruned embedding (None = all D)."""
     M, D = x.shape
-    if d_valid is None or d_valid == D:
-        check(lib().ofb_layernorm_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(rstd), M, D, eps, cur_stream()),
-              "ofb_layernorm_fwd")
-    else:
-        check(lib().ofb_layernorm_fwd_ex(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(rstd), M, D, d_valid, eps,
-                                         cur_stream()), "ofb_layernorm_fwd_ex")
+
+    def call():
+        if d_valid is None or d_valid == D:
+            check(lib().ofb_layernorm_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(rstd), M, D, eps, cur_stream()),
+                  "ofb_layernorm_fwd")
+        else:
+            check(lib().ofb_layernorm_fwd_ex(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(rstd), M, D, d_valid, eps,
+                                             cur_stream()), "ofb_layernorm_fwd_ex")
+    _ln_timed(call, 2.0 * M * D * 2)              # algorithmic bytes: read x, write y (bf16); SURVEY 8d
 
 
 def gemm_mlp_partial_rows(n_tokens, bn):
@@ -128,14 +143,17 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dx, part_dgamma, part_dbeta, part_db
                   rows_per_scale=1, dres=None, d_valid=None):
     """dres: residual-branch gradient added to dx (pre-norm blocks); d_valid as in layernorm_fwd."""
     M, D = x.shape
-    if dres is None and (d_valid is None or d_valid == D):
-        check(lib().ofb_layernorm_bwd(ptr(dy), ptr(x), ptr(mean), ptr(rstd), ptr(gamma), ptr(dx), ptr(part_dgamma),
-                                      ptr(part_dbeta), ptr(part_dbias), ptr(rowscale), rows_per_scale, M, D, cur_stream()),
-              "ofb_layernorm_bwd")
-    else:
-        check(lib().ofb_layernorm_bwd_ex(ptr(dy), ptr(x), ptr(mean), ptr(rstd), ptr(gamma), ptr(dres), ptr(dx),
-                                         ptr(part_dgamma), ptr(part_dbeta), ptr(part_dbias), ptr(rowscale), rows_per_scale, M,
-                                         D, d_valid or D, cur_stream()), "ofb_layernorm_bwd_ex")
+
+    def call():
+        if dres is None and (d_valid is None or d_valid == D):
+            check(lib().ofb_layernorm_bwd(ptr(dy), ptr(x), ptr(mean), ptr(rstd), ptr(gamma), ptr(dx), ptr(part_dgamma),
+                                          ptr(part_dbeta), ptr(part_dbias), ptr(rowscale), rows_per_scale, M, D, cur_stream()),
+                  "ofb_layernorm_bwd")
+        else:
+            check(lib().ofb_layernorm_bwd_ex(ptr(dy), ptr(x), ptr(mean), ptr(rstd), ptr(gamma), ptr(dres), ptr(dx),
+                                             ptr(part_dgamma), ptr(part_dbeta), ptr(part_dbias), ptr(rowscale), rows_per_scale,
+                                             M, D, d_valid or D, cur_stream()), "ofb_layernorm_bwd_ex")
+    _ln_timed(call, (3.0 + (1.0 if dres is not None else 0.0)) * M * D * 2)      # read dy, x (, dres), write dx
 
 
 def reduce_partials(part, R, N, out, scale=1.0, div_by=None, accumulate=True):
