@@ -313,6 +313,7 @@ class SearchStepEngine:
         self._reducer = dp.OverlappedReducer(self.grads, self.world, self.pg, early, tail)
         self._graphs = {}          # (images ptr, labels ptr, keep) -> (CUDAGraph, kernel launches per replay)
         self._side = None          # side stream of the gate construction (see forward)
+        self._side2 = None         # side stream of the PMIM target normalisation
 
     # ------------------------------------------------------------------------------------------------------------
     def _param_shapes(self):
@@ -437,9 +438,19 @@ class SearchStepEngine:
             ops.pmim_mask(noise, self.mask, keep)
             ops.droppath_scale(drop_u, self.drop_prob, self.drop_scale)
         rowmask = self.mask if train else self.zero_mask
-        ops.patchify(images, self.patches, self.P)
         if train:
-            ops.norm_targets(images, self.mask, self.tgt)
+            # the PMIM targets (local normalisation of the masked patches) are only consumed by the decoder GEMM at the very
+            # end of forward: a second branch, filling the tails of the block kernels instead of sitting on the critical path
+            if self._side2 is None:
+                self._side2 = torch.cuda.Stream(device=self.dev)
+            side_targets = os.environ.get("OFB_SIDE_TARGETS", "1") == "1"
+            if side_targets:
+                self._side2.wait_stream(cur)
+                with torch.cuda.stream(self._side2):
+                    ops.norm_targets(images, self.mask, self.tgt)
+            else:
+                ops.norm_targets(images, self.mask, self.tgt)
+        ops.patchify(images, self.patches, self.P)
         cur.wait_stream(self._side)
         g_e = bm.gate_of(0)
         x0 = self.xs[0]
@@ -479,6 +490,8 @@ class SearchStepEngine:
         gs = 1.0 / self.accum_iter
         ops.ls_cross_entropy(self.logits, labels, self.loss_rows, self.dlogits, self.smoothing, gs)
         # PMIM decoder + masked L1 against the locally normalised pixels
+        if side_targets:
+            cur.wait_stream(self._side2)
         ops.gemm(ops.EPI_DECODER, self.latent, self.w("decoder.0.weight"), M=M, N=768, K=D, out0=self.sgn,
                  bias=self.p("decoder.0.bias"), rowmask=self.mask, target=self.tgt, tokens=L, colpart0=self.dec_part,
                  bn=self.dec_bn)
