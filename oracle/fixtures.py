@@ -90,3 +90,32 @@ def summarize(t: torch.Tensor) -> torch.Tensor:
     n = f.numel()
     idx = (torch.arange(SUMMARY_SAMPLES, dtype=torch.float64) * (n - 1) / max(SUMMARY_SAMPLES - 1, 1)).long()
     return torch.cat([torch.stack([f.sum(), f.abs().sum(), f.pow(2).sum().sqrt()]), f[idx]])
+
+
+def search_modules(cfg: ModelCfg):
+    """(prefix, kind, heads, dim, widths, head_counts) of every searchable module in model order (kind 0 embed, 1 mlp, 2 attn)."""
+    mods = [("patch_embed", 0, 1, cfg.embed_dim, embed_widths(cfg.embed_dim), [])]
+    for l in range(cfg.depth):
+        mods.append((f"blocks.{l}.attn", 2, cfg.num_heads, cfg.head_dim, head_channel_widths(cfg.head_dim),
+                     head_counts(cfg.num_heads)))
+        mods.append((f"blocks.{l}.mlp", 1, 1, cfg.hidden, hidden_widths(cfg.hidden), []))
+    return mods
+
+
+def pruned_shape_from_plans(cfg: ModelCfg, plans):
+    """PrunedShape (oracle) of the model a set of prune plans (ofb_b200.prune.ModulePlan, duck-typed) leaves behind."""
+    from ofb_oracle import PrunedShape
+    spaces, heads, dims, hids = {}, [], [], []
+    embed = cfg.embed_dim
+    for prefix, kind, H, dim, widths, counts in search_modules(cfg):
+        pl = plans[prefix]
+        n_i, n_j = pl.switch.shape
+        spaces[prefix] = (list(widths[:n_j]), list(counts[:n_i]))
+        if kind == 0:
+            embed = pl.width if pl.truncated else dim
+        elif kind == 2:
+            heads.append(pl.head_num if pl.truncated else H)
+            dims.append(pl.width if pl.truncated else dim)
+        else:
+            hids.append(pl.width if pl.truncated else dim)
+    return PrunedShape(embed=embed, heads=heads, head_dims=dims, hiddens=hids, spaces=spaces)

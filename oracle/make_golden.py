@@ -39,7 +39,9 @@ def kill_cells(switches, seed=7):
     return switches
 
 
-def run_reference(cfg, P0, inp, switches, drop_path_rate, lr, epoch_frac):
+def run_reference(cfg, P0, inp, switches, drop_path_rate, lr, epoch_frac, after_load=None):
+    """after_load(model): optional hook run once the parameters and switch cells are in place and before the optimizers are
+    built (make_golden_pruned_step.py uses it to run compress())."""
     ref_shim.install()
     import optim as ref_optim
     from losses import DistillationLoss, OFBSearchLOSS
@@ -55,6 +57,8 @@ def run_reference(cfg, P0, inp, switches, drop_path_rate, lr, epoch_frac):
         mods[f"blocks.{l}.mlp"] = blk.mlp
     for k, m in mods.items():
         m.switch_cell = switches[k].clone()
+    if after_load is not None:
+        after_load(model)
     model.train()
     ddp = ref_shim.FakeDDP(model)
 

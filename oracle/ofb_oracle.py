@@ -76,6 +76,17 @@ class ModelCfg:
         return (self.img // self.patch) ** 2
 
 
+@dataclass
+class PrunedShape:
+    """Shapes and remaining search space of a model that compress() has physically truncated (vision_transformer.py:785-950)
+    while every module is still being searched. widths / head_counts are the surviving prefixes of the search-space lists."""
+    embed: int                                   # D'
+    heads: List[int]                             # H'_l
+    head_dims: List[int]                         # d'_l
+    hiddens: List[int]                           # h'_l
+    spaces: Dict[str, tuple]                     # prefix -> (widths, head_counts)
+
+
 def w_p_schedule(epoch_frac: float, warmup_epochs: int = 20, hi: float = 0.99, lo: float = 0.1) -> float:
     """layers.py:484-486 update_w."""
     e = min(epoch_frac, warmup_epochs)
@@ -237,28 +248,34 @@ def _sparsity_term(alpha, switch, score, coef):
     return loss
 
 
-def forward_step(P: Dict[str, torch.Tensor], inp: StepInputs, cfg: ModelCfg, switches=None) -> StepOutputs:
+def forward_step(P: Dict[str, torch.Tensor], inp: StepInputs, cfg: ModelCfg, switches=None, shape: Optional[PrunedShape] = None) -> StepOutputs:
     """MIMVisionTransformer.forward (vision_transformer.py:614-669, 717-745) in search/training mode with embed,
     attention and MLP search active, followed by OFBSearchLOSS (losses.py:80-106) and the decoder-loss weighting of
-    engine.search_one_epoch (engine.py:131-144)."""
+    engine.search_one_epoch (engine.py:131-144).
+    shape: the model after truncating prune events (tensors physically sliced, every module still searched). The attention
+    scale and the ORIGINAL-FLOPs side of the FLOPs loss keep the unpruned dims (layers.py:418, 747-753); the
+    searched side uses the pruned LayerNorm width and head counts (vt:206-213 active_dim, layers.py:749 active_H)."""
     sw = switches or default_switches(cfg)
     D, H, d, hid, L = cfg.embed_dim, cfg.num_heads, cfg.head_dim, cfg.hidden, cfg.num_patches
+    Dc = shape.embed if shape is not None else D                      # current (pruned) embedding width
+    sp = (lambda k, default: shape.spaces[k] if shape is not None else default)
     B = inp.images.shape[0]
     w_p = inp.w_p
     gates = {}
 
     # ---- patch embed + embed gate (layers.py:173-191) ----
-    g_e, wr_e, wsum_e = gate_1d(P["patch_embed.alpha"], sw["patch_embed"], P["patch_embed.score"], embed_widths(D), w_p)
+    g_e, wr_e, wsum_e = gate_1d(P["patch_embed.alpha"], sw["patch_embed"], P["patch_embed.score"],
+                                sp("patch_embed", (embed_widths(D), []))[0], w_p)
     gates["patch_embed"] = g_e
     patches = inp.images.reshape(B, 3, 14, 16, 14, 16).permute(0, 2, 4, 1, 3, 5).reshape(B, L, 768)
-    x = patches @ P["patch_embed.proj.weight"].reshape(D, 768).t() + P["patch_embed.proj.bias"]
+    x = patches @ P["patch_embed.proj.weight"].reshape(Dc, 768).t() + P["patch_embed.proj.bias"]
     x = x * g_e
     # pos embed, PMIM masking, mask token, cls (vision_transformer.py:628-651); masked patches lose their pos-embed
     x = x + P["pos_embed"][0, 1:] * g_e
     keep = int(L * inp.keep_ratio)
     mask = pmim_mask(inp.noise, keep) if keep != L else None
     if mask is not None:
-        x = x * (1 - mask).unsqueeze(-1) + mask.unsqueeze(-1) * (P["mask_token"].reshape(1, 1, D) * g_e)
+        x = x * (1 - mask).unsqueeze(-1) + mask.unsqueeze(-1) * (P["mask_token"].reshape(1, 1, Dc) * g_e)
     cls = ((P["cls_token"] + P["pos_embed"][:, :1]) * g_e).expand(B, -1, -1)
     x = torch.cat([cls, x], dim=1)
     N = L + 1
@@ -269,18 +286,20 @@ def forward_step(P: Dict[str, torch.Tensor], inp: StepInputs, cfg: ModelCfg, swi
     for l in range(cfg.depth):
         pre = f"blocks.{l}."
         x = _ln(x, P[pre + "norm1.weight"], P[pre + "norm1.bias"], cfg.eps)
-        g_a, _, ws_a = gate_attn(P[pre + "attn.alpha"], sw[pre + "attn"], P[pre + "attn.score"], head_counts(H),
-                                 head_channel_widths(d), w_p)
+        Hl, dl = (shape.heads[l], shape.head_dims[l]) if shape is not None else (H, d)
+        wj_a, ni_a = sp(pre + "attn", (head_channel_widths(d), head_counts(H)))
+        g_a, _, ws_a = gate_attn(P[pre + "attn.alpha"], sw[pre + "attn"], P[pre + "attn.score"], ni_a, wj_a, w_p)
         gates[pre + "attn"] = g_a
         qkv = x @ P[pre + "attn.qkv.weight"].t() + P[pre + "attn.qkv.bias"]
-        qkv = qkv.reshape(B, N, 3, H, d) * g_a                      # q,k,v all gated (layers.py:507-509)
+        qkv = qkv.reshape(B, N, 3, Hl, dl) * g_a                    # q,k,v all gated (layers.py:507-509)
         q, k, v = qkv.permute(2, 0, 3, 1, 4)
         att = torch.softmax((q @ k.transpose(-2, -1)) * scale, dim=-1)
-        o = (att @ v).transpose(1, 2).reshape(B, N, D)
+        o = (att @ v).transpose(1, 2).reshape(B, N, Hl * dl)
         o = o @ P[pre + "attn.proj.weight"].t() + P[pre + "attn.proj.bias"]
         x = x + inp.drop_scale[l, 0].reshape(B, 1, 1) * o
         x = _ln(x, P[pre + "norm2.weight"], P[pre + "norm2.bias"], cfg.eps)
-        g_m, _, ws_m = gate_1d(P[pre + "mlp.alpha"], sw[pre + "mlp"], P[pre + "mlp.score"], hidden_widths(hid), w_p)
+        g_m, _, ws_m = gate_1d(P[pre + "mlp.alpha"], sw[pre + "mlp"], P[pre + "mlp.score"],
+                               sp(pre + "mlp", (hidden_widths(hid), []))[0], w_p)
         gates[pre + "mlp"] = g_m
         hdn = F.gelu((x @ P[pre + "mlp.fc1.weight"].t() + P[pre + "mlp.fc1.bias"]) * g_m)
         y = hdn @ P[pre + "mlp.fc2.weight"].t() + P[pre + "mlp.fc2.bias"]
@@ -295,7 +314,7 @@ def forward_step(P: Dict[str, torch.Tensor], inp: StepInputs, cfg: ModelCfg, swi
 
     # ---- PMIM decoder branch (vision_transformer.py:720-729) ----
     if mask is not None:
-        rec = latent[:, 1:] @ P["decoder.0.weight"].reshape(768, D).t() + P["decoder.0.bias"]   # [B,L,768]
+        rec = latent[:, 1:] @ P["decoder.0.weight"].reshape(768, Dc).t() + P["decoder.0.bias"]   # [B,L,768]
         tgt = patchify_pixel_shuffle(norm_targets(inp.images, 47))
         l1 = (tgt - rec).abs() * mask.unsqueeze(-1)
         loss_dec = l1.sum() / (mask.sum() * 256 + 1e-5) / 3
@@ -322,10 +341,11 @@ def forward_step(P: Dict[str, torch.Tensor], inp: StepInputs, cfg: ModelCfg, swi
     f_s = L * ae * 768.
     for l in range(cfg.depth):
         sd, sm = attn_wsum[l], mlp_wsum[l]
+        Ha = shape.heads[l] if shape is not None else H               # active_H (layers.py:749)
         f_ori += 2 * D * n
-        f_s = f_s + 2 * D * n
+        f_s = f_s + 2 * Dc * n                                        # active_dim = norm1.normalized_shape[0] (vt:210)
         f_ori += n * (D * 3 * D) + 3 * n * D + H * n * d * n + H * n * n + 5 * H * n * n + H * n * n * d + n * D * D + n * D
-        f_s = f_s + n * (ae * 3 * sd) + 3 * n * sd + n * n * sd + H * n * n + 5 * H * n * n + n * n * sd \
+        f_s = f_s + n * (ae * 3 * sd) + 3 * n * sd + n * n * sd + Ha * n * n + 5 * Ha * n * n + n * n * sd \
             + n * (sd * ae) + n * ae
         f_ori += (2 * D * hid + D + hid) * n
         f_s = f_s + (ae * sm * 2 + ae + sm) * n
@@ -377,11 +397,11 @@ def adamw_step(p, g, m, v, step, lr, betas, eps, weight_decay):
 
 
 def train_step(P: Dict[str, torch.Tensor], state: Dict[str, Dict[str, torch.Tensor]], inp: StepInputs, cfg: ModelCfg,
-               lr: float, step: int, switches=None, frozen=("alpha_patch",)):
+               lr: float, step: int, switches=None, frozen=("alpha_patch",), shape: Optional[PrunedShape] = None):
     """One full search step: forward, losses, backward, three AdamW updates (engine.py:131-184).
     P entries are leaf tensors; returns (outputs, grads)."""
     leaves = {k: v.detach().clone().requires_grad_(True) for k, v in P.items() if k not in frozen}
-    out = forward_step(leaves, inp, cfg, switches)
+    out = forward_step(leaves, inp, cfg, switches, shape)
     out.loss_total.backward()
     grads = {k: (v.grad if v.grad is not None else None) for k, v in leaves.items()}
     with torch.no_grad():
