@@ -153,6 +153,9 @@ typedef struct ofb_bimask_module {
     int32_t kind;        /* 0 embed, 1 mlp, 2 attention */
     int32_t dim, heads, n_i, n_j;
     int32_t switch_off, width_off, gate_off;
+    int32_t stride;      /* distance between heads in the score tensor and in gate / rank / dgate (>= dim; 64 for an attention
+                            module whose head dim has been pruned below 64: heads stay 64 wide physically) */
+    int32_t pad_;
     int64_t alpha_off, score_off;     /* offsets (floats) into the parameter / gradient arenas */
     float coef, loss_w;
 } ofb_bimask_module;
@@ -160,10 +163,12 @@ typedef struct ofb_bimask_module {
 int ofb_bimask_fwd(const ofb_bimask_module* mods_dev, int nmod, int max_n, const float* params, const uint8_t* switches,
                    const int32_t* widths, const float* w_p_dev, float* gate, int32_t* rank, float* aprob, float* wsum,
                    float* sp_loss, void* stream);
-/* arch[0..6] = {loss_arch, l_attn, l_mlp, l_embed, l_flops, searched GFLOPs, original GFLOPs}; dwsum[nmod] */
+/* arch[0..6] = {loss_arch, l_attn, l_mlp, l_embed, l_flops, searched GFLOPs, original GFLOPs}; dwsum[nmod].
+ * D, H, d, hidden: ORIGINAL dims (total-FLOPs side, layers.py:747-753); D_active: current LayerNorm width after truncating
+ * prune events (vision_transformer.py:210; 0 = D); active head counts are read from the attention module records. */
 int ofb_arch_finalize(const ofb_bimask_module* mods_dev, int nmod, const float* wsum, const float* sp_loss, int depth,
-                      int D, int H, int d, int hidden, int L, int C, float target_flops, float w_flops, float* arch,
-                      float* dwsum, void* stream);
+                      int D, int H, int d, int hidden, int D_active, int L, int C, float target_flops, float w_flops,
+                      float* arch, float* dwsum, void* stream);
 int ofb_bimask_bwd(const ofb_bimask_module* mods_dev, int nmod, int max_n, const float* params, const uint8_t* switches,
                    const int32_t* widths, const float* w_p_dev, const float* dgate, const int32_t* rank,
                    const float* aprob, const float* dwsum, float grad_scale, float* grads, void* stream);

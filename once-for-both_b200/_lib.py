@@ -39,6 +39,7 @@ class BimaskModule(C.Structure):
     _fields_ = [
         ("kind", C.c_int32), ("dim", C.c_int32), ("heads", C.c_int32), ("n_i", C.c_int32), ("n_j", C.c_int32),
         ("switch_off", C.c_int32), ("width_off", C.c_int32), ("gate_off", C.c_int32),
+        ("stride", C.c_int32), ("pad_", C.c_int32),
         ("alpha_off", C.c_int64), ("score_off", C.c_int64),
         ("coef", C.c_float), ("loss_w", C.c_float),
     ]
@@ -78,7 +79,7 @@ SIGNATURES = {
     "ofb_cast_bf16": [_P, _P, _L, _P],
     "ofb_colsum_bf16": [_P, _I, _I, _I, _P, _F, _P, _P],
     "ofb_bimask_fwd": [_P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
-    "ofb_arch_finalize": [_P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P, _P, _P],
+    "ofb_arch_finalize": [_P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P, _P, _P],
     "ofb_bimask_bwd": [_P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _F, _P, _P],
     "ofb_attention_fwd": [_P, _P, _P, _P, _I, _I, _I, _F, _P],
     "ofb_attention_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P],

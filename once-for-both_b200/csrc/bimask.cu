@@ -19,7 +19,9 @@ struct BimaskModule {
     int n_i, n_j;         // alpha shape
     int switch_off;       // into uint8 switch array (n_i*n_j entries, row-major)
     int width_off;        // into int widths array: n_j channel widths, then n_i head counts (attention)
-    int gate_off;         // into gate / rank / dgate buffers (heads*dim entries)
+    int gate_off;         // into gate / rank / dgate buffers (heads*stride entries)
+    int stride;           // distance between heads in the score tensor and the gate / rank / dgate buffers (>= dim): a pruned
+                          // attention module keeps its heads 64 wide physically (zero-padded layout, finetune_engine.py)
     long long alpha_off;  // into the fp32 parameter arena
     long long score_off;
     float coef;           // score-norm coefficient: 4e-4 attention, 1e-4 otherwise (base_model.py:72-75)
@@ -27,7 +29,8 @@ struct BimaskModule {
 };
 
 struct ArchDims {
-    int depth, D, H, d, hidden, L, C;
+    int depth, D, H, d, hidden, L, C;   // ORIGINAL dims: the reference keeps them for the total-FLOPs side (layers.py:747-753)
+    int D_active;                       // current LayerNorm width (vt:210 active_dim); active heads come from the module records
     float target_flops, w_flops;
 };
 
@@ -93,7 +96,7 @@ __global__ void __launch_bounds__(BM_THREADS) bimask_fwd_kernel(const BimaskModu
     }
     float ssum = 0.f;
     for (int i = tid; i < n; i += BM_THREADS) {
-        const float s = score[i];
+        const float s = score[(i / md.dim) * md.stride + (i % md.dim)];
         sc[i] = s;
         const float sg = 1.f / (1.f + expf(-s));
         sig[i] = sg;
@@ -136,8 +139,8 @@ __global__ void __launch_bounds__(BM_THREADS) bimask_fwd_kernel(const BimaskModu
                 if (wj[jj] > r) t += a[ii * md.n_j + jj];
         }
         tsum += t;
-        gate[md.gate_off + i] = w_p * sig[i] + (1.f - w_p) * t;
-        rank[md.gate_off + i] = hr * md.dim + r;
+        gate[md.gate_off + h * md.stride + c] = w_p * sig[i] + (1.f - w_p) * t;
+        rank[md.gate_off + h * md.stride + c] = hr * md.dim + r;
     }
     tsum = block_sum(tsum, red);
     if (tid == 0) wsum[blockIdx.x] = tsum;   // == weighted_mask.sum()
@@ -150,17 +153,18 @@ __global__ void __launch_bounds__(BM_THREADS) bimask_fwd_kernel(const BimaskModu
 __global__ void arch_finalize_kernel(const BimaskModule* __restrict__ mods, int nmod, const float* __restrict__ wsum,
                                      const float* __restrict__ sp_loss, ArchDims ad, float* __restrict__ arch, float* __restrict__ dwsum) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const double n = ad.L, D = ad.D, H = ad.H, d = ad.d, hid = ad.hidden, C = ad.C;
+    const double n = ad.L, D = ad.D, H = ad.H, d = ad.d, hid = ad.hidden, C = ad.C, Da = ad.D_active;
     const double ae = wsum[0];
     double f_ori = ad.L * D * 768.0, f_s = ad.L * ae * 768.0;
     double dae = ad.L * 768.0;
     double l_attn = 0, l_mlp = 0, l_embed = sp_loss[0];
     for (int l = 0; l < ad.depth; ++l) {
         const double sd = wsum[1 + 2 * l], sm = wsum[2 + 2 * l];
+        const double Ha = mods[1 + 2 * l].heads;        // active_H (layers.py:749)
         f_ori += 2 * D * n;
-        f_s += 2 * D * n;
+        f_s += 2 * Da * n;
         f_ori += n * (D * 3 * D) + 3 * n * D + H * n * d * n + H * n * n + 5 * H * n * n + H * n * n * d + n * D * D + n * D;
-        f_s += n * (ae * 3 * sd) + 3 * n * sd + n * n * sd + H * n * n + 5 * H * n * n + n * n * sd + n * (sd * ae) + n * ae;
+        f_s += n * (ae * 3 * sd) + 3 * n * sd + n * n * sd + Ha * n * n + 5 * Ha * n * n + n * n * sd + n * (sd * ae) + n * ae;
         f_ori += (2 * D * hid + D + hid) * n;
         f_s += (ae * sm * 2 + ae + sm) * n;
         dae += n * 4 * sd + n + (2 * sm + 1) * n;
@@ -215,12 +219,13 @@ __global__ void __launch_bounds__(BM_THREADS) bimask_bwd_kernel(const BimaskModu
     const float dws = dwsum[blockIdx.x] * grad_scale;
 
     for (int i = tid; i < n; i += BM_THREADS) {
-        const float dg = dgate[md.gate_off + i];
-        const float s = score[i];
+        const int ph = (i / md.dim) * md.stride + (i % md.dim);       // physical position (head stride)
+        const float dg = dgate[md.gate_off + ph];
+        const float s = score[ph];
         const float sg = 1.f / (1.f + expf(-s));
         const float dsig = dg * w_p + (alive > 1 ? md.loss_w * md.coef * grad_scale : 0.f);
-        grads[md.score_off + i] += dsig * sg * (1.f - sg);
-        dtable[rank[md.gate_off + i]] = dg * (1.f - w_p) + dws;
+        grads[md.score_off + ph] += dsig * sg * (1.f - sg);
+        dtable[rank[md.gate_off + ph]] = dg * (1.f - w_p) + dws;
     }
     __syncthreads();
     if (alive <= 1) return;   // alpha frozen (finish_search): no alpha gradient
@@ -271,8 +276,8 @@ int launch_bimask_fwd(const void* mods, int nmod, int max_n, const float* params
 }
 
 int launch_arch_finalize(const void* mods, int nmod, const float* wsum, const float* sp_loss, int depth, int D, int H, int d, int hidden,
-                         int L, int C, float target_flops, float w_flops, float* arch, float* dwsum, cudaStream_t s) {
-    ArchDims ad{depth, D, H, d, hidden, L, C, target_flops, w_flops};
+                         int D_active, int L, int C, float target_flops, float w_flops, float* arch, float* dwsum, cudaStream_t s) {
+    ArchDims ad{depth, D, H, d, hidden, L, C, D_active > 0 ? D_active : D, target_flops, w_flops};
     arch_finalize_kernel<<<1, 32, 0, s>>>(reinterpret_cast<const BimaskModule*>(mods), nmod, wsum, sp_loss, ad, arch, dwsum);
     return int(cudaGetLastError());
 }

@@ -29,7 +29,7 @@ int launch_cast_bf16(const float*, void*, long long, cudaStream_t);
 int launch_colsum_bf16(const void*, int, int, int, float*, float, const float*, cudaStream_t);
 int launch_bimask_fwd(const void*, int, int, const float*, const uint8_t*, const int*, const float*, float*, int*, float*, float*, float*,
                       cudaStream_t);
-int launch_arch_finalize(const void*, int, const float*, const float*, int, int, int, int, int, int, int, float, float, float*, float*,
+int launch_arch_finalize(const void*, int, const float*, const float*, int, int, int, int, int, int, int, int, float, float, float*, float*,
                          cudaStream_t);
 int launch_bimask_bwd(const void*, int, int, const float*, const uint8_t*, const int*, const float*, const float*, const int*,
                       const float*, const float*, float, float*, cudaStream_t);
@@ -42,7 +42,7 @@ int launch_attn_bwd(const void*, const void*, const void*, const float*, const f
 
 extern "C" {
 
-int ofb_version(void) { return 2; }
+int ofb_version(void) { return 3; }
 int ofb_num_sms(void) { return ofb::num_sms(); }
 int ofb_gemm_mlp_partial_rows(int n_tokens, int bn) { return ofb::mlp_partial_rows(n_tokens, bn); }
 
@@ -144,9 +144,11 @@ int ofb_bimask_fwd(const ofb_bimask_module* mods, int nmod, int max_n, const flo
     return ofb::launch_bimask_fwd(mods, nmod, max_n, params, switches, widths, w_p, gate, rank, aprob, wsum, sp_loss, ST(stream));
 }
 int ofb_arch_finalize(const ofb_bimask_module* mods, int nmod, const float* wsum, const float* sp_loss, int depth, int D, int H, int d,
-                      int hidden, int L, int C, float target_flops, float w_flops, float* arch, float* dwsum, void* stream) {
-    return ofb::launch_arch_finalize(mods, nmod, wsum, sp_loss, depth, D, H, d, hidden, L, C, target_flops, w_flops, arch, dwsum,
-                                     ST(stream));
+                      int hidden, int D_active, int L, int C, float target_flops, float w_flops, float* arch, float* dwsum,
+                      void* stream) {
+    static_assert(sizeof(ofb_bimask_module) == 64, "ofb_bimask_module layout");
+    return ofb::launch_arch_finalize(mods, nmod, wsum, sp_loss, depth, D, H, d, hidden, D_active, L, C, target_flops, w_flops, arch,
+                                     dwsum, ST(stream));
 }
 int ofb_bimask_bwd(const ofb_bimask_module* mods, int nmod, int max_n, const float* params, const uint8_t* switches,
                    const int32_t* widths, const float* w_p, const float* dgate, const int32_t* rank, const float* aprob,

@@ -566,7 +566,7 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, int R, in
         float t = 0.f;
         for (int i = 0; i < ny; ++i) t += sm[i][threadIdx.x];
         t *= scale;
-        if (inv_colscale != nullptr) t /= inv_colscale[col];
+        if (inv_colscale != nullptr) { const float dv = inv_colscale[col]; t = dv != 0.f ? t / dv : 0.f; }   // zero gate = padding channel
         out[col] = accumulate ? out[col] + t : t;
     }
 }
@@ -590,7 +590,7 @@ __global__ void reduce_partials_multi_kernel(const ReduceJobs jobs) {
         float t = 0.f;
         for (int i = 0; i < ny; ++i) t += sm[i][threadIdx.x];
         t *= jb.scale;
-        if (jb.div_by != nullptr) t /= jb.div_by[col];
+        if (jb.div_by != nullptr) { const float dv = jb.div_by[col]; t = dv != 0.f ? t / dv : 0.f; }       // zero gate = padding channel
         jb.out[col] = jb.accumulate ? jb.out[col] + t : t;
     }
 }

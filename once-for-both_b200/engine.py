@@ -80,32 +80,44 @@ def flops_polynomial(D, H, d, hid, L, Cn, depth, ae, sd_list, sm_list):
 
 class BimaskTable:
     """Device-side description of every searchable module (order: patch_embed, then attn / mlp per block) plus the
-    buffers of the fused bimask_prepare kernels."""
+    buffers of the fused bimask_prepare kernels.
+
+    D, H, hidden are the ORIGINAL dims (they stay in the total-FLOPs side of the FLOPs loss). After truncating prune events
+    `pruned` carries the current shapes - embed (real width), embed_phys (padded to 8), heads / head_dims / hiddens per block -
+    and `spaces[prefix] = (widths, head_counts)` the surviving prefixes of the search-space lists. A pruned attention module
+    keeps its heads HD_PHYS = 64 wide physically: score, gate, rank and d gate use that head stride, padding entries stay 0."""
 
     def __init__(self, D, H, depth, hidden, switches: Dict[str, torch.Tensor], *, w_attn=0.5, w_mlp=0.5, w_embed=0.5,
-                 w_flops=5.0, target_flops=1.0, num_classes=1000, num_patches=196):
+                 w_flops=5.0, target_flops=1.0, num_classes=1000, num_patches=196, pruned=None, spaces=None):
         self.D, self.H, self.depth, self.hidden = D, H, depth, hidden
         self.d = D // H
         self.L, self.C = num_patches, num_classes
         self.target_flops, self.w_flops = target_flops, w_flops
         self.modules: List[dict] = []
         sw_bytes, widths, gate_off = [], [], 0
+        pr = pruned or dict(embed=D, embed_phys=D, heads=[H] * depth, head_dims=[self.d] * depth, hiddens=[hidden] * depth)
+        self.D_active = pr["embed"]
 
-        def add(prefix, kind, dim, heads, wj, ni, coef, loss_w):
+        def space(prefix, wj, ni):
+            return (list(spaces[prefix][0]), list(spaces[prefix][1])) if spaces is not None else (wj, ni)
+
+        def add(prefix, kind, dim, heads, stride, slot, wj, ni, coef, loss_w):
             nonlocal gate_off
+            wj, ni = space(prefix, wj, ni)
             sw = switches[prefix].to(torch.bool).reshape(len(ni) if kind == 2 else 1, len(wj))
-            self.modules.append(dict(prefix=prefix, kind=kind, dim=dim, heads=heads, n_i=sw.shape[0], n_j=sw.shape[1],
-                                     switch_off=len(sw_bytes), width_off=len(widths), gate_off=gate_off, coef=coef,
-                                     loss_w=loss_w))
+            self.modules.append(dict(prefix=prefix, kind=kind, dim=dim, heads=heads, stride=stride, slot=slot, n_i=sw.shape[0],
+                                     n_j=sw.shape[1], switch_off=len(sw_bytes), width_off=len(widths), gate_off=gate_off,
+                                     coef=coef, loss_w=loss_w))
             sw_bytes.extend(int(x) for x in sw.reshape(-1).tolist())
             widths.extend(wj)
             widths.extend(ni)
-            gate_off += heads * dim
+            gate_off += slot
 
-        add("patch_embed", 0, D, 1, embed_widths(D), [], 1e-4, w_embed)
+        add("patch_embed", 0, pr["embed"], 1, pr["embed_phys"], pr["embed_phys"], embed_widths(D), [], 1e-4, w_embed)
         for l in range(depth):
-            add(f"blocks.{l}.attn", 2, self.d, H, head_channel_widths(self.d), head_counts(H), 4e-4, w_attn)
-            add(f"blocks.{l}.mlp", 1, hidden, 1, hidden_widths(hidden), [], 1e-4, w_mlp)
+            Hl, dl, hl = pr["heads"][l], pr["head_dims"][l], pr["hiddens"][l]
+            add(f"blocks.{l}.attn", 2, dl, Hl, self.d, Hl * self.d, head_channel_widths(self.d), head_counts(H), 4e-4, w_attn)
+            add(f"blocks.{l}.mlp", 1, hl, 1, hl, hl, hidden_widths(hidden), [], 1e-4, w_mlp)
         self.total_gate = gate_off
         self._sw_bytes, self._widths = sw_bytes, widths
         self.max_n = max(m["heads"] * m["dim"] for m in self.modules)
@@ -117,7 +129,7 @@ class BimaskTable:
         for i, m in enumerate(self.modules):
             a = arr[i]
             a.kind, a.dim, a.heads, a.n_i, a.n_j = m["kind"], m["dim"], m["heads"], m["n_i"], m["n_j"]
-            a.switch_off, a.width_off, a.gate_off = m["switch_off"], m["width_off"], m["gate_off"]
+            a.switch_off, a.width_off, a.gate_off, a.stride = m["switch_off"], m["width_off"], m["gate_off"], m["stride"]
             a.alpha_off, a.score_off = offsets[m["prefix"] + ".alpha"], offsets[m["prefix"] + ".score"]
             a.coef, a.loss_w = m["coef"], m["loss_w"]
         raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
@@ -135,8 +147,15 @@ class BimaskTable:
         return self
 
     def gate_of(self, i):
+        """Physical gate slot of module i (zero at padding entries): what the GEMM / attention epilogues consume."""
         m = self.modules[i]
-        return self.gate[m["gate_off"]:m["gate_off"] + m["heads"] * m["dim"]]
+        return self.gate[m["gate_off"]:m["gate_off"] + m["slot"]]
+
+    def logical(self, i, buf):
+        """[heads, dim] view of module i's real entries in a gate-shaped buffer (gate, rank, d gate)."""
+        m = self.modules[i]
+        return buf[m["gate_off"]:m["gate_off"] + m["heads"] * m["stride"]].view(m["heads"], m["stride"])[:, :m["dim"]] \
+            if m["kind"] == 2 else buf[m["gate_off"]:m["gate_off"] + m["dim"]].view(1, m["dim"])
 
     def pruned_index_sets(self):
         """Kept-unit index sets of every searchable module for every candidate of its search space, i.e. what the reference's
@@ -147,9 +166,9 @@ class BimaskTable:
         rank = self.rank.cpu()
         wl = self._widths
         out = {}
-        for m in self.modules:
+        for i, m in enumerate(self.modules):
             H, dim = m["heads"], m["dim"]
-            r = rank[m["gate_off"]:m["gate_off"] + H * dim].view(H, dim)
+            r = self.logical(i, rank)
             hr, cr = r[:, 0] // dim, r % dim
             widths = wl[m["width_off"]:m["width_off"] + m["n_j"]]
             counts = wl[m["width_off"] + m["n_j"]:m["width_off"] + m["n_j"] + (m["n_i"] if m["kind"] == 2 else 0)]
@@ -164,7 +183,7 @@ class BimaskTable:
         ops.bimask_fwd(self.mods_dev, n, self.max_n, params, self.switches_dev, self.widths_dev, w_p_dev, self.gate,
                        self.rank, self.aprob, self.wsum, self.sp_loss)
         ops.arch_finalize(self.mods_dev, n, self.wsum, self.sp_loss, self.depth, self.D, self.H, self.d, self.hidden,
-                          self.L, self.C, self.target_flops, self.w_flops, self.arch, self.dwsum)
+                          self.L, self.C, self.target_flops, self.w_flops, self.arch, self.dwsum, d_active=self.D_active)
 
     def backward(self, params, w_p_dev, dgate, grad_scale, grads):
         ops.bimask_bwd(self.mods_dev, len(self.modules), self.max_n, params, self.switches_dev, self.widths_dev, w_p_dev,
@@ -175,11 +194,22 @@ class SearchStepEngine:
     def __init__(self, embed_dim=384, num_heads=6, depth=12, batch=256, *, mlp_ratio=4, num_classes=1000, img=224,
                  patch=16, drop_path_rate=0.1, lr=1e-3, weight_decay=1e-3, eps_ln=1e-6, smoothing=0.1, w_attn=0.5,
                  w_mlp=0.5, w_embed=0.5, w_flops=5.0, target_flops=1.0, accum_iter=1, warmup_epochs=20, max_ratio=0.95,
-                 min_ratio=0.75, device="cuda", switches=None, process_group=None):
+                 min_ratio=0.75, device="cuda", switches=None, process_group=None, pruned=None):
+        """pruned: shapes of a model that truncating prune events have physically sliced while it is still being searched
+        (see from_pruned): dict(embed=D', heads=[H'_l], head_dims=[d'_l], hiddens=[h'_l], spaces={prefix: (widths, head_counts)}).
+        embed_dim / num_heads / mlp_ratio stay the ORIGINAL dims (attention scale, total-FLOPs side of the FLOPs loss). The pruned
+        tensors live in the zero-padded layout of finetune_engine.py: embedding axis padded to a multiple of 8, heads 64 wide."""
         assert embed_dim % num_heads == 0 and embed_dim // num_heads == 64, "attention kernel is built for head_dim 64"
-        self.D, self.H, self.depth, self.B = embed_dim, num_heads, depth, batch
+        self.D0, self.H, self.depth, self.B = embed_dim, num_heads, depth, batch
         self.d = 64
         self.hid = embed_dim * mlp_ratio
+        self.Dv = pruned["embed"] if pruned else embed_dim                   # real embedding width
+        self.D = (self.Dv + 7) // 8 * 8                                      # physical (padded) embedding width
+        self.heads = list(pruned["heads"]) if pruned else [num_heads] * depth
+        self.hdims = list(pruned["head_dims"]) if pruned else [64] * depth
+        self.hids = list(pruned["hiddens"]) if pruned else [self.hid] * depth
+        self.spaces = pruned.get("spaces") if pruned else None
+        assert all(0 < x <= 64 and x % 8 == 0 for x in self.hdims) and all(x % 8 == 0 for x in self.hids)
         self.C, self.img, self.P = num_classes, img, patch
         self.L = (img // patch) ** 2
         self.T = self.L + 1
@@ -196,7 +226,8 @@ class SearchStepEngine:
         self.drop_path_rate = drop_path_rate
 
         # ---- parameter arenas ----
-        shapes = self._param_shapes()
+        self.ref_shapes = self._param_shapes()                       # reference (logical) shapes
+        shapes = {k: self._padded_shape(k, v) for k, v in self.ref_shapes.items()}      # physical shapes (== logical when unpruned)
         order = sorted(shapes, key=lambda k: GROUPS.index(param_group(k, shapes[k])))   # stable: keeps model order
         self.offsets, self.shapes, off = {}, shapes, 0
         seg_end, cur = [], GROUPS[0]
@@ -238,15 +269,19 @@ class SearchStepEngine:
 
         # ---- bi-mask ----
         if switches is None:
-            switches = {"patch_embed": torch.ones(1, len(embed_widths(self.D)), dtype=torch.bool)}
+            assert pruned is None, "a pruned engine needs the surviving switch cells"
+            switches = {"patch_embed": torch.ones(1, len(embed_widths(self.D0)), dtype=torch.bool)}
             for l in range(depth):
                 switches[f"blocks.{l}.attn"] = torch.ones(len(head_counts(self.H)), len(head_channel_widths(self.d)),
                                                           dtype=torch.bool)
                 switches[f"blocks.{l}.mlp"] = torch.ones(1, len(hidden_widths(self.hid)), dtype=torch.bool)
         self.switches = switches
-        self.bimask = BimaskTable(self.D, self.H, depth, self.hid, switches, w_attn=w_attn, w_mlp=w_mlp, w_embed=w_embed,
-                                  w_flops=w_flops, target_flops=target_flops, num_classes=num_classes,
-                                  num_patches=self.L).bind(self.offsets, self.dev)
+        self._loss_w = dict(w_attn=w_attn, w_mlp=w_mlp, w_embed=w_embed, w_flops=w_flops, target_flops=target_flops)
+        self.bimask = BimaskTable(self.D0, self.H, depth, self.hid, switches, w_attn=w_attn, w_mlp=w_mlp, w_embed=w_embed,
+                                  w_flops=w_flops, target_flops=target_flops, num_classes=num_classes, num_patches=self.L,
+                                  pruned=dict(embed=self.Dv, embed_phys=self.D, heads=self.heads, head_dims=self.hdims,
+                                              hiddens=self.hids),
+                                  spaces=self.spaces).bind(self.offsets, self.dev)
         self.dgate = torch.zeros(self.bimask.total_gate, **f32)
 
         # ---- activations ----
@@ -265,12 +300,14 @@ class SearchStepEngine:
         self.mlp_parts = ops.gemm_mlp_partial_rows(M, self.mlp_bn)
         self.xs = [torch.zeros(M, D, **bf) for _ in range(depth + 1)]      # xs[l] = input of block l; xs[depth] = output
         self.blk = []
-        for _ in range(depth):
+        for l in range(depth):
+            A, hl = self.heads[l] * 64, self.hids[l]
             self.blk.append(dict(
                 mean1=torch.empty(M, **f32), rstd1=torch.empty(M, **f32), x1=torch.empty(M, D, **bf),
-                qkv=torch.empty(M, 3 * D, **bf), lse=torch.empty(B, H, T, **f32), o=torch.empty(M, D, **bf),
+                qkv=torch.empty(M, 3 * A, **bf), lse=torch.empty(B, self.heads[l], T, **f32), o=torch.empty(M, A, **bf),
                 x2=torch.empty(M, D, **bf), mean2=torch.empty(M, **f32), rstd2=torch.empty(M, **f32),
-                x3=torch.empty(M, D, **bf), u=torch.empty(hid, self.ldT, **bf), h=torch.empty(hid, self.ldT, **bf)))
+                x3=torch.empty(M, D, **bf), u=torch.empty(hl, self.ldT, **bf), h=torch.empty(hl, self.ldT, **bf)))
+        Amax, hid = max(self.heads) * 64, max(self.hids)
         self.meanf, self.rstdf = torch.empty(M, **f32), torch.empty(M, **f32)
         self.latent = torch.empty(M, D, **bf)
         self.logits = torch.empty(B, self.C, **f32)
@@ -285,13 +322,14 @@ class SearchStepEngine:
         # backward scratch
         self.gA, self.gB, self.gC = (torch.empty(M, D, **bf) for _ in range(3))
         self.du = torch.empty(hid, self.ldT, **bf)
-        self.dqkv = torch.empty(M, 3 * D, **bf)
+        self.dqkv = torch.empty(M, 3 * Amax, **bf)
+        self.dObuf = torch.empty(M, Amax, **bf)
         self.dconv = torch.empty(ML, D, **bf)
         self.ln_parts = ops.layernorm_bwd_parts(M)
         self.pg_, self.pb_, self.pd_ = (torch.empty(self.ln_parts, D, **f32) for _ in range(3))
         mt = (M + 127) // 128
         self.cp0, self.cp1 = torch.empty(self.mlp_parts, hid, **f32), torch.empty(self.mlp_parts, hid, **f32)
-        self.att_pg, self.att_pb = torch.empty(B, D, **f32), torch.empty(B, 3 * D, **f32)
+        self.att_pg, self.att_pb = torch.empty(B, Amax, **f32), torch.empty(B, 3 * Amax, **f32)
         self.e_gx, self.e_pos, self.e_mt = (torch.empty(T, D, **f32) for _ in range(3))
         self.rand_u = torch.empty(B * self.L + depth * 2 * B, **f32)
         self._dp_bounds = dp.bucket_bounds(self.n_arena)
@@ -316,26 +354,94 @@ class SearchStepEngine:
         self._side2 = None         # side stream of the PMIM target normalisation
 
     # ------------------------------------------------------------------------------------------------------------
+    def _space(self, prefix, widths, counts):
+        return (self.spaces[prefix][0], self.spaces[prefix][1]) if self.spaces is not None else (widths, counts)
+
     def _param_shapes(self):
-        D, hid, L, Cn, H, d = self.D, self.hid, self.L, self.C, self.H, self.d
+        """Reference state_dict names / shapes of the (possibly truncated) search model, in named_parameters() order."""
+        D, L, Cn, H0, d0 = self.Dv, self.L, self.C, self.H, self.d
         s = {"cls_token": (1, 1, D), "pos_embed": (1, L + 1, D), "mask_token": (1, 1, D),
-             "patch_embed.alpha": (1, len(embed_widths(D))), "patch_embed.score": (1, D),
+             "patch_embed.alpha": (1, len(self._space("patch_embed", embed_widths(self.D0), [])[0])), "patch_embed.score": (1, D),
              "patch_embed.proj.weight": (D, 3, self.P, self.P), "patch_embed.proj.bias": (D,)}
         for l in range(self.depth):
             p = f"blocks.{l}."
+            H, d, hid = self.heads[l], self.hdims[l], self.hids[l]
+            wj, ni = self._space(p + "attn", head_channel_widths(d0), head_counts(H0))
             s[p + "norm1.weight"] = (D,); s[p + "norm1.bias"] = (D,)
-            s[p + "attn.alpha"] = (len(head_counts(H)), len(head_channel_widths(d)))
+            s[p + "attn.alpha"] = (len(ni), len(wj))
             s[p + "attn.score"] = (H, d)
-            s[p + "attn.qkv.weight"] = (3 * D, D); s[p + "attn.qkv.bias"] = (3 * D,)
-            s[p + "attn.proj.weight"] = (D, D); s[p + "attn.proj.bias"] = (D,)
+            s[p + "attn.qkv.weight"] = (3 * H * d, D); s[p + "attn.qkv.bias"] = (3 * H * d,)
+            s[p + "attn.proj.weight"] = (D, H * d); s[p + "attn.proj.bias"] = (D,)
             s[p + "norm2.weight"] = (D,); s[p + "norm2.bias"] = (D,)
-            s[p + "mlp.alpha"] = (1, len(hidden_widths(hid))); s[p + "mlp.score"] = (1, hid)
+            s[p + "mlp.alpha"] = (1, len(self._space(p + "mlp", hidden_widths(self.hid), [])[0])); s[p + "mlp.score"] = (1, hid)
             s[p + "mlp.fc1.weight"] = (hid, D); s[p + "mlp.fc1.bias"] = (hid,)
             s[p + "mlp.fc2.weight"] = (D, hid); s[p + "mlp.fc2.bias"] = (D,)
         s["norm.weight"] = (D,); s["norm.bias"] = (D,)
         s["head.weight"] = (Cn, D); s["head.bias"] = (Cn,)
         s["decoder.0.weight"] = (768, D, 1, 1); s["decoder.0.bias"] = (768,)
         return s
+
+    def _blk(self, name):
+        return int(name.split(".")[1])
+
+    def _padded_shape(self, name, shp):
+        """Physical (arena) shape of a tensor: embedding axis padded to self.D, attention heads 64 wide."""
+        Dv, Dp = self.Dv, self.D
+        if name.endswith(".alpha") or name.endswith("mlp.score") or name.endswith("mlp.fc1.bias") or name in ("head.bias",
+                                                                                                           "decoder.0.bias"):
+            return tuple(shp)
+        if name.endswith("attn.score"):
+            return (shp[0], 64)
+        if name.endswith("attn.qkv.weight"):
+            return (3 * self.heads[self._blk(name)] * 64, Dp)
+        if name.endswith("attn.qkv.bias"):
+            return (3 * self.heads[self._blk(name)] * 64,)
+        if name.endswith("attn.proj.weight"):
+            return (Dp, self.heads[self._blk(name)] * 64)
+        return tuple(Dp if (x == Dv and i == self._embed_axis(name, len(shp))) else x for i, x in enumerate(shp))
+
+    @staticmethod
+    def _embed_axis(name, rank):
+        """Axis of the embedding dimension in a tensor that is padded along it only."""
+        if name in ("cls_token", "pos_embed", "mask_token", "patch_embed.score", "head.weight") or name.endswith("mlp.fc1.weight"):
+            return rank - 1
+        if name == "decoder.0.weight":
+            return 1
+        return 0          # vectors over the embedding axis, patch_embed.proj.weight, fc2.weight
+
+    def _pad(self, name, t):
+        """reference-shaped tensor -> zero-padded physical layout."""
+        phys = self.shapes[name]
+        if tuple(t.shape) == tuple(phys):
+            return t
+        out = torch.zeros(phys, dtype=t.dtype, device=t.device)
+        if name.endswith("attn.qkv.weight") or name.endswith("attn.qkv.bias") or name.endswith("attn.proj.weight"):
+            l = self._blk(name)
+            H, d, Dv, Dp = self.heads[l], self.hdims[l], self.Dv, self.D
+            if name.endswith("qkv.weight"):
+                out.view(3, H, 64, Dp)[:, :, :d, :Dv] = t.reshape(3, H, d, Dv)
+            elif name.endswith("qkv.bias"):
+                out.view(3, H, 64)[:, :, :d] = t.reshape(3, H, d)
+            else:
+                out.view(Dp, H, 64)[:Dv, :, :d] = t.reshape(Dv, H, d)
+            return out
+        out[tuple(slice(0, x) for x in t.shape)] = t
+        return out
+
+    def _unpad(self, name, t):
+        """physical layout -> reference-shaped tensor."""
+        ref = self.ref_shapes[name]
+        if tuple(t.shape) == tuple(ref):
+            return t
+        if name.endswith("attn.qkv.weight") or name.endswith("attn.qkv.bias") or name.endswith("attn.proj.weight"):
+            l = self._blk(name)
+            H, d, Dv, Dp = self.heads[l], self.hdims[l], self.Dv, self.D
+            if name.endswith("qkv.weight"):
+                return t.view(3, H, 64, Dp)[:, :, :d, :Dv].reshape(ref)
+            if name.endswith("qkv.bias"):
+                return t.view(3, H, 64)[:, :, :d].reshape(ref)
+            return t.view(Dp, H, 64)[:Dv, :, :d].reshape(ref)
+        return t[tuple(slice(0, x) for x in ref)]
 
     def _view(self, arena, name):
         o, shp = self.offsets[name], self.shapes[name]
@@ -353,21 +459,31 @@ class SearchStepEngine:
         return v.reshape(v.shape[0], -1)
 
     def named_parameters(self):
-        return {k: self.p(k) for k in self.offsets}
+        """Parameters in reference shapes (views of the arena when the model is unpruned)."""
+        return {k: self._unpad(k, self.p(k)) for k in self.offsets}
 
     def named_grads(self):
-        return {k: self.g(k) for k in self.offsets}
+        return {k: self._unpad(k, self.g(k)) for k in self.offsets}
 
     def load_params(self, named: Dict[str, torch.Tensor]):
         for k in self.offsets:
-            self.p(k).copy_(named[k].to(self.dev))
+            self.p(k).copy_(self._pad(k, named[k].to(self.dev, torch.float32).reshape(self.ref_shapes[k])))
         self.sync_shadow()
+
+    def padding_is_clean(self) -> bool:
+        """Every padding entry of the parameter and gradient arenas is exactly zero (invariant of the pruned layout)."""
+        for k in self.offsets:
+            for arena in (self.params, self.grads):
+                full = self._view(arena, k)
+                if not torch.equal(full, self._pad(k, self._unpad(k, full).clone())):
+                    return False
+        return True
 
     def init_params(self, seed=0):
         """Reference-style initialisation (trunc-normal .02 weights, zero biases, alpha~U(0,1), score~trunc-normal .2:
         vision_transformer.py:497-519, layers.py:147-155, 455-467, 817-824)."""
         g = torch.Generator(device="cpu").manual_seed(seed)
-        for k, shp in self.shapes.items():
+        for k, shp in self.ref_shapes.items():
             t = torch.zeros(shp)
             if k.endswith("alpha"):
                 t = torch.rand(shp, generator=g)
@@ -378,11 +494,11 @@ class SearchStepEngine:
             elif k.endswith(".bias"):
                 t = torch.zeros(shp)
             elif k == "patch_embed.proj.weight":
-                bound = math.sqrt(6.0 / (768 + self.D))
+                bound = math.sqrt(6.0 / (768 + self.Dv))
                 t = (torch.rand(shp, generator=g) * 2 - 1) * bound
             else:
                 t = (torch.randn(shp, generator=g) * .02).clamp_(-2, 2)
-            self.p(k).copy_(t)
+            self.p(k).copy_(self._pad(k, t))
         self.sync_shadow()
 
     def pruned_index_sets(self):
@@ -458,20 +574,22 @@ class SearchStepEngine:
                  bias=self.p("patch_embed.proj.bias"), colscale=g_e, pos=self.p("pos_embed"),
                  mask_token=self.p("mask_token"), rowmask=rowmask, tokens=L)
         ops.cls_rows(self.p("cls_token"), self.p("pos_embed"), g_e, x0, B, T, D)
+        Dv = self.Dv
         for l in range(self.depth):
             pre, a = f"blocks.{l}.", self.blk[l]
+            H, A, hid = self.heads[l], self.heads[l] * 64, self.hids[l]     # this block's heads, physical qkv width, hidden width
             g_a, g_m = bm.gate_of(1 + 2 * l), bm.gate_of(2 + 2 * l)
             dp1, dp2 = (self.drop_scale[2 * l], self.drop_scale[2 * l + 1]) if train else (None, None)
             ops.layernorm_fwd(self.xs[l], self.p(pre + "norm1.weight"), self.p(pre + "norm1.bias"), a["x1"], a["mean1"],
-                              a["rstd1"], self.eps_ln)
-            ops.gemm(ops.EPI_STORE, a["x1"], self.w(pre + "attn.qkv.weight"), M=M, N=3 * D, K=D, out0=a["qkv"],
-                     bias=self.p(pre + "attn.qkv.bias"), colscale=g_a, colscale_period=D)
+                              a["rstd1"], self.eps_ln, d_valid=Dv)
+            ops.gemm(ops.EPI_STORE, a["x1"], self.w(pre + "attn.qkv.weight"), M=M, N=3 * A, K=D, out0=a["qkv"],
+                     bias=self.p(pre + "attn.qkv.bias"), colscale=g_a, colscale_period=A)
             ops.attention_fwd(a["qkv"], a["o"], a["lse"], dp1, B, T, H, self.scale)
-            ops.gemm(ops.EPI_STORE, a["o"], self.w(pre + "attn.proj.weight"), M=M, N=D, K=D, out0=a["x2"],
+            ops.gemm(ops.EPI_STORE, a["o"], self.w(pre + "attn.proj.weight"), M=M, N=D, K=A, out0=a["x2"],
                      bias=self.p(pre + "attn.proj.bias"), rowscale=dp1, rows_per_scale=T, bias_rowscaled=True,
                      res=a["x1"], bn=self.bn_nD)
             ops.layernorm_fwd(a["x2"], self.p(pre + "norm2.weight"), self.p(pre + "norm2.bias"), a["x3"], a["mean2"],
-                              a["rstd2"], self.eps_ln)
+                              a["rstd2"], self.eps_ln, d_valid=Dv)
             # fc1 computes the transposed hidden activations u^T, h^T = [hidden, tokens] (weight is the M operand)
             ops.gemm(ops.EPI_FC1, self.w(pre + "mlp.fc1.weight"), a["x3"], M=hid, N=M, K=D, out0=a["u"], out1=a["h"],
                      bias=self.p(pre + "mlp.fc1.bias"), colscale=g_m, rowscale=dp2, rows_per_scale=T, bn=self.mlp_bn)
@@ -479,7 +597,7 @@ class SearchStepEngine:
                      bias=self.p(pre + "mlp.fc2.bias"), rowscale=dp2, rows_per_scale=T, bias_rowscaled=True,
                      res=a["x3"], a_mn=True, bn=self.bn_nD)
         ops.layernorm_fwd(self.xs[self.depth], self.p("norm.weight"), self.p("norm.bias"), self.latent, self.meanf,
-                          self.rstdf, self.eps_ln)
+                          self.rstdf, self.eps_ln, d_valid=Dv)
         # head on the cls rows (row stride T*D), label-smoothing CE
         ops.gemm(ops.EPI_STORE, self.latent, self.w("head.weight"), M=B, N=self.C, K=D, out0=self.logits, out_fp32=True,
                  bias=self.p("head.bias"), lda=T * D)
@@ -527,56 +645,59 @@ class SearchStepEngine:
         # ---- final LayerNorm ----
         last_dp2 = self.drop_scale[2 * self.depth - 1]
         G = self.gB
+        Dv = self.Dv
         ops.layernorm_bwd(dlat, self.xs[self.depth], self.meanf, self.rstdf, self.p("norm.weight"), G, self.pg_,
-                          self.pb_, self.pd_, last_dp2, T)
+                          self.pb_, self.pd_, last_dp2, T, d_valid=Dv)
         ops.reduce_partials_multi([(self.pg_, R, D, self.g("norm.weight")), (self.pb_, R, D, self.g("norm.bias")),
                                    (self.pd_, R, D, self.g(f"blocks.{self.depth - 1}.mlp.fc2.bias"))])
         spare = [self.gA, self.gC]
 
         for l in reversed(range(self.depth)):
             pre, a = f"blocks.{l}.", self.blk[l]
+            H, A, hid = self.heads[l], self.heads[l] * 64, self.hids[l]
+            du = self.du[:hid]
+            dqkv = self.dqkv.view(-1)[:M * 3 * A].view(M, 3 * A)
+            dO = self.dObuf.view(-1)[:M * A].view(M, A)
             i_a, i_m = 1 + 2 * l, 2 + 2 * l
             g_a, g_m = bm.gate_of(i_a), bm.gate_of(i_m)
             dp1, dp2 = self.drop_scale[2 * l], self.drop_scale[2 * l + 1]
             G4 = G
             # fc2: weight grad (h already carries DropPath), data grad fused with GELU' / gate / column partials
             ops.gemm(ops.EPI_WGRAD, G4, a["h"], M=D, N=hid, K=M, out0=self.g(pre + "mlp.fc2.weight"), a_mn=True)
-            ops.gemm(ops.EPI_FC2_DGRAD, self.w(pre + "mlp.fc2.weight"), G4, M=hid, N=M, K=D, out0=self.du, aux=a["u"],
+            ops.gemm(ops.EPI_FC2_DGRAD, self.w(pre + "mlp.fc2.weight"), G4, M=hid, N=M, K=D, out0=du, aux=a["u"],
                      colscale=g_m, rowscale=dp2, rows_per_scale=T, colpart0=self.cp0, colpart1=self.cp1, a_mn=True,
                      bn=self.mlp_bn)
             m_off = bm.modules[i_m]["gate_off"]
             mlp_jobs = [dict(part=self.cp0, R=self.mlp_parts, N=hid, out=self.dgate[m_off:m_off + hid], accumulate=False),
                         dict(part=self.cp1, R=self.mlp_parts, N=hid, out=self.g(pre + "mlp.fc1.bias"))]
-            ops.gemm(ops.EPI_WGRAD, self.du, a["x3"], M=hid, N=D, K=M, out0=self.g(pre + "mlp.fc1.weight"), b_mn=True)
+            ops.gemm(ops.EPI_WGRAD, du, a["x3"], M=hid, N=D, K=M, out0=self.g(pre + "mlp.fc1.weight"), b_mn=True)
             G3 = spare.pop()
-            ops.gemm(ops.EPI_STORE, self.du, self.w(pre + "mlp.fc1.weight"), M=M, N=D, K=hid, out0=G3, a_mn=True, b_mn=True,
+            ops.gemm(ops.EPI_STORE, du, self.w(pre + "mlp.fc1.weight"), M=M, N=D, K=hid, out0=G3, a_mn=True, b_mn=True,
                      res=G4, bn=self.bn_nD)
             spare.append(G4)
             # LayerNorm 2 (+ proj bias grad)
             G2 = spare.pop()
             ops.layernorm_bwd(G3, a["x2"], a["mean2"], a["rstd2"], self.p(pre + "norm2.weight"), G2, self.pg_, self.pb_,
-                              self.pd_, dp1, T)
+                              self.pd_, dp1, T, d_valid=Dv)
             spare.append(G3)
             # one launch finishes the column partials of the fc2 data-gradient GEMM and of this LayerNorm
             ops.reduce_partials_multi(mlp_jobs + [(self.pg_, R, D, self.g(pre + "norm2.weight")),
                                                   (self.pb_, R, D, self.g(pre + "norm2.bias")),
                                                   (self.pd_, R, D, self.g(pre + "attn.proj.bias"))])
             # proj
-            ops.gemm(ops.EPI_WGRAD, G2, a["o"], M=D, N=D, K=M, out0=self.g(pre + "attn.proj.weight"), a_mn=True, b_mn=True)
-            dO = spare.pop()
-            ops.gemm(ops.EPI_STORE, G2, self.w(pre + "attn.proj.weight"), M=M, N=D, K=D, out0=dO, b_mn=True, rowscale=dp1,
-                     rows_per_scale=T, bn=self.bn_nD)
+            ops.gemm(ops.EPI_WGRAD, G2, a["o"], M=D, N=A, K=M, out0=self.g(pre + "attn.proj.weight"), a_mn=True, b_mn=True)
+            ops.gemm(ops.EPI_STORE, G2, self.w(pre + "attn.proj.weight"), M=M, N=A, K=D, out0=dO, b_mn=True, rowscale=dp1,
+                     rows_per_scale=T, bn=self.bn_nD if A == D else 0)
             # attention
-            ops.attention_bwd(a["qkv"], a["o"], dO, a["lse"], g_a, dp1, self.dqkv, self.att_pg, self.att_pb, B, T, H,
+            ops.attention_bwd(a["qkv"], a["o"], dO, a["lse"], g_a, dp1, dqkv, self.att_pg, self.att_pb, B, T, H,
                               self.scale)
-            spare.append(dO)
             a_off = bm.modules[i_a]["gate_off"]
-            attn_jobs = [dict(part=self.att_pg, R=B, N=D, out=self.dgate[a_off:a_off + D], div_by=g_a, accumulate=False),
-                         dict(part=self.att_pb, R=B, N=3 * D, out=self.g(pre + "attn.qkv.bias"))]
-            ops.gemm(ops.EPI_WGRAD, self.dqkv, a["x1"], M=3 * D, N=D, K=M, out0=self.g(pre + "attn.qkv.weight"), a_mn=True,
+            attn_jobs = [dict(part=self.att_pg, R=B, N=A, out=self.dgate[a_off:a_off + A], div_by=g_a, accumulate=False),
+                         dict(part=self.att_pb, R=B, N=3 * A, out=self.g(pre + "attn.qkv.bias"))]
+            ops.gemm(ops.EPI_WGRAD, dqkv, a["x1"], M=3 * A, N=D, K=M, out0=self.g(pre + "attn.qkv.weight"), a_mn=True,
                      b_mn=True)
             G1 = spare.pop()
-            ops.gemm(ops.EPI_STORE, self.dqkv, self.w(pre + "attn.qkv.weight"), M=M, N=D, K=3 * D, out0=G1, b_mn=True,
+            ops.gemm(ops.EPI_STORE, dqkv, self.w(pre + "attn.qkv.weight"), M=M, N=D, K=3 * A, out0=G1, b_mn=True,
                      res=G2, bn=self.bn_nD)
             spare.append(G2)
             # LayerNorm 1 (+ previous block's fc2 bias grad)
@@ -584,7 +705,7 @@ class SearchStepEngine:
             has_prev = l > 0
             ops.layernorm_bwd(G1, self.xs[l], a["mean1"], a["rstd1"], self.p(pre + "norm1.weight"), G0, self.pg_,
                               self.pb_, self.pd_ if has_prev else None,
-                              self.drop_scale[2 * l - 1] if has_prev else None, T)
+                              self.drop_scale[2 * l - 1] if has_prev else None, T, d_valid=Dv)
             spare.append(G1)
             ln1_jobs = [(self.pg_, R, D, self.g(pre + "norm1.weight")), (self.pb_, R, D, self.g(pre + "norm1.bias"))]
             if has_prev:
@@ -675,13 +796,13 @@ class SearchStepEngine:
         bm = self.bimask
         rank = bm.rank.cpu()
         plans = {}
-        for m in bm.modules:
+        for i, m in enumerate(bm.modules):
             pre, H, dim = m["prefix"], m["heads"], m["dim"]
             alpha = self.p(pre + ".alpha").detach().clone()
             if self.world > 1:
                 torch.distributed.all_reduce(alpha, group=self.pg)
                 alpha /= self.world
-            r = rank[m["gate_off"]:m["gate_off"] + H * dim].view(H, dim)
+            r = bm.logical(i, rank)
             widths = bm._widths[m["width_off"]:m["width_off"] + m["n_j"]]
             counts = bm._widths[m["width_off"] + m["n_j"]:m["width_off"] + m["n_j"] + (m["n_i"] if m["kind"] == 2 else 0)]
             sw = self.switches[pre].reshape(m["n_i"], m["n_j"])
@@ -693,7 +814,54 @@ class SearchStepEngine:
         """Every parameter in the shape compress() would leave it in (device tensors, reference names / shapes)."""
         from . import prune
         dims = {m["prefix"]: dict(heads=m["heads"], dim=m["dim"]) for m in self.bimask.modules}
-        return prune.gather_pruned(plans, {k: self.p(k) for k in self.offsets}, dims, self.w_p)
+        return prune.gather_pruned(plans, self.named_parameters(), dims, self.w_p)
+
+    def pruned_config(self, plans):
+        """Constructor argument `pruned` (and the surviving switch cells) of the engine a set of plans leaves behind."""
+        bm = self.bimask
+        spaces, heads, hdims, hids, switches = {}, [], [], [], {}
+        embed = self.Dv
+        for m in bm.modules:
+            pl = plans[m["prefix"]]
+            n_i, n_j = pl.switch.shape
+            wl = bm._widths[m["width_off"]:m["width_off"] + m["n_j"] + (m["n_i"] if m["kind"] == 2 else 0)]
+            spaces[m["prefix"]] = (list(wl[:n_j]), list(wl[m["n_j"]:m["n_j"] + n_i]) if m["kind"] == 2 else [])
+            switches[m["prefix"]] = pl.switch.clone()
+            if m["kind"] == 0:
+                embed = pl.width if pl.truncated else m["dim"]
+            elif m["kind"] == 2:
+                heads.append(pl.head_num if pl.truncated else m["heads"])
+                hdims.append(pl.width if pl.truncated else m["dim"])
+            else:
+                hids.append(pl.width if pl.truncated else m["dim"])
+        return dict(embed=embed, heads=heads, head_dims=hdims, hiddens=hids, spaces=spaces), switches
+
+    def rebuild_pruned(self, plans):
+        """The search engine after a TRUNCATING prune event (compress(), vision_transformer.py:785-950): a new engine on the
+        sliced shapes with the gathered parameters and the sliced Adam state (optim.AdamW.update, optim.py:122-182: moments
+        follow the same index gathers; the alphas of modules that executed a prune restart from zero with their own step
+        counter). Finalising events (a module left with one cell) are not supported yet."""
+        from . import prune
+        if any(pl.finalised for pl in plans.values()):
+            raise NotImplementedError("finalised modules (frozen gates) are not supported by the search engine yet")
+        pruned, switches = self.pruned_config(plans)
+        eng = SearchStepEngine(self.D0, self.H, self.depth, self.B, mlp_ratio=self.hid // self.D0, num_classes=self.C,
+                               img=self.img, patch=self.P, drop_path_rate=self.drop_path_rate, lr=self.lr, weight_decay=self.wd,
+                               eps_ln=self.eps_ln, smoothing=self.smoothing, accum_iter=self.accum_iter,
+                               warmup_epochs=self.warmup_epochs, max_ratio=self.max_ratio, min_ratio=self.min_ratio,
+                               device=self.dev, switches=switches, process_group=self.pg, pruned=pruned, **self._loss_w)
+        dims = {m["prefix"]: dict(heads=m["heads"], dim=m["dim"]) for m in self.bimask.modules}
+        eng.load_params(prune.gather_pruned(plans, self.named_parameters(), dims, self.w_p))
+        for arena_old, arena_new in ((self.adam_m, eng.adam_m), (self.adam_v, eng.adam_v)):
+            state = prune.gather_pruned(plans, {k: self._unpad(k, self._view(arena_old, k)) for k in self.offsets}, dims,
+                                        self.w_p, state=True)
+            for k in eng.offsets:
+                eng._view(arena_new, k).copy_(eng._pad(k, state[k].to(self.dev, torch.float32).reshape(eng.ref_shapes[k])))
+        eng.step_count = self.step_count
+        eng.w_p, eng.keep_ratio = self.w_p, self.keep_ratio
+        for pre, pl in plans.items():
+            eng.alpha_restart[pre + ".alpha"] = self.step_count if pl.executed else self.alpha_restart[pre + ".alpha"]
+        return eng
 
     def apply_prune(self, plans):
         """Apply a prune event in place. Events that only switch cells off (no physical slicing) are supported: new switch

@@ -254,8 +254,9 @@ def bimask_fwd(mods_dev, nmod, max_n, params, switches, widths, w_p_dev, gate, r
                                ptr(gate), ptr(rank), ptr(aprob), ptr(wsum), ptr(sp_loss), cur_stream()), "ofb_bimask_fwd")
 
 
-def arch_finalize(mods_dev, nmod, wsum, sp_loss, depth, D, H, d, hidden, L, Cn, target_flops, w_flops, arch, dwsum):
-    check(lib().ofb_arch_finalize(ptr(mods_dev), nmod, ptr(wsum), ptr(sp_loss), depth, D, H, d, hidden, L, Cn,
+def arch_finalize(mods_dev, nmod, wsum, sp_loss, depth, D, H, d, hidden, L, Cn, target_flops, w_flops, arch, dwsum, d_active=0):
+    """D, H, d, hidden: original dims; d_active: current LayerNorm width after truncating prune events (0 = D)."""
+    check(lib().ofb_arch_finalize(ptr(mods_dev), nmod, ptr(wsum), ptr(sp_loss), depth, D, H, d, hidden, d_active, L, Cn,
                                   target_flops, w_flops, ptr(arch), ptr(dwsum), cur_stream()), "ofb_arch_finalize")
 
 

@@ -95,11 +95,25 @@ def proj_keep_index(plan: ModulePlan, d: int) -> torch.Tensor:
     return (plan.head_index.view(-1, 1) * d + plan.channel_index).reshape(-1)
 
 
-def gather_pruned(plans: Dict[str, ModulePlan], named: Dict[str, torch.Tensor], dims: Dict[str, dict], w_p: float):
+def gather_pruned(plans: Dict[str, ModulePlan], named: Dict[str, torch.Tensor], dims: Dict[str, dict], w_p: float,
+                  state: bool = False):
     """Every tensor of `named` (reference state_dict names, reference shapes, any device) in the shape the reference's
-    compress() leaves it in. dims[prefix] = {"heads": H, "dim": d} of the modules BEFORE the event."""
+    compress() leaves it in. dims[prefix] = {"heads": H, "dim": d} of the modules BEFORE the event.
+    state=True: `named` holds an Adam moment (exp_avg or exp_avg_sq) instead of the parameters; optim.AdamW.update
+    (optim.py:122-182) slices it with the same indices, except that the alpha of a module that executed a prune and a finalised
+    score restart from zero (initialize=True)."""
     out = {k: v for k, v in named.items()}
     dev = next(iter(named.values())).device
+    if state:
+        out_state = gather_pruned(plans, named, dims, w_p, state=False)
+        for prefix, pl in plans.items():
+            n_i, n_j = pl.switch.shape
+            a = named[prefix + ".alpha"]
+            out_state[prefix + ".alpha"] = torch.zeros(n_i, n_j, dtype=a.dtype, device=dev) if pl.executed \
+                else a.reshape(-1, a.shape[-1])[:n_i, :n_j].clone()
+            if pl.finalised:
+                out_state[prefix + ".score"] = torch.zeros_like(out_state[prefix + ".score"])
+        return out_state
 
     def sel(name, index, axis):
         out[name] = out[name].index_select(axis, index.to(dev))

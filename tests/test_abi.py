@@ -39,7 +39,7 @@ def test_struct_mirrors_match_header():
     from ofb_b200 import _lib
     assert _struct_fields("ofb_gemm_args") == [f[0] for f in _lib.GemmArgs._fields_]
     assert _struct_fields("ofb_bimask_module") == [f[0] for f in _lib.BimaskModule._fields_]
-    assert C.sizeof(_lib.BimaskModule) == 56
+    assert C.sizeof(_lib.BimaskModule) == 64
 
 
 def test_missing_library_fails_loudly(monkeypatch):

@@ -56,3 +56,66 @@ def test_oracle_pruned_step_matches_reference_golden(path):
             assert _rel(summarize(grads[key[5:]]).numpy(), g[key]) < tol, key
             n += 1
     assert n > 20
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", GOLD, ids=IDS)
+def test_engine_pruned_step_matches_reference_golden(cuda_dev, path):
+    """SearchStepEngine -> plan_prune -> rebuild_pruned (new engine on the truncated shapes, zero-padded layout) -> one
+    search step, against the generalised oracle (every gradient) and the reference's own outputs (golden)."""
+    from ofb_b200.engine import SearchStepEngine
+    from step_compare import BF16_TOL, DEC_TOL, FP32_TOL, GRAD_MAX_TOL, LOSS_TOL, rel, rel_l2
+    g, cfg, P0, inp = _case(path)
+    B, depth = inp.images.shape[0], cfg.depth
+    dpr, lr, ef = float(g["dpr"]), float(g["lr"]), float(g["epoch_frac"])
+    eng0 = SearchStepEngine(cfg.embed_dim, cfg.num_heads, depth, B, drop_path_rate=dpr, lr=lr)
+    eng0.load_params(P0)
+    eng0.set_schedule(ef)
+    img, lab, noise = inp.images.cuda(), inp.labels.cuda(), inp.noise.cuda()
+    drop_u = ((inp.drop_scale > 0).float().reshape(depth * 2, B) * 0.999).cuda()
+    eng0.step(img, lab, noise=noise, drop_u=drop_u, update=False)           # ranks for the plan
+    eng0.grads.zero_()
+    plans = eng0.plan_prune(0.2)
+    assert any(pl.truncated for pl in plans.values()) and not any(pl.finalised for pl in plans.values())
+    eng = eng0.rebuild_pruned(plans)
+    assert (eng.Dv, eng.heads, eng.hdims, eng.hids) == (int(g["embed"]), g["heads"].tolist(), g["head_dims"].tolist(),
+                                                        g["hiddens"].tolist())
+    scal = eng.step(img, lab, noise=noise, drop_u=drop_u, update=False)
+    torch.cuda.synchronize()
+    scal = scal.cpu()
+    assert eng.padding_is_clean()
+    # --- against the reference's own numbers ---
+    assert _rel(eng.logits.cpu().numpy(), g["logits"]) < BF16_TOL
+    assert _rel(float(scal[0]), g["loss_base"]) < LOSS_TOL
+    assert _rel(float(scal[1]), g["loss_arch"]) < 1e-3
+    assert _rel(float(scal[2]), g["loss_decoder"]) < LOSS_TOL
+    assert _rel(float(scal[3]), g["loss_total"]) < LOSS_TOL
+    assert _rel(float(eng.bimask.arch[5]), g["flops"][1]) < 1e-4 and _rel(float(eng.bimask.arch[6]), g["flops"][0]) < 1e-4
+    # --- every gradient against the oracle on the same pruned parameters ---
+    Pp = {k: v.detach().cpu().clone() for k, v in eng.named_parameters().items()}
+    Pp["alpha_patch"] = P0["alpha_patch"]
+    shape = pruned_shape_from_plans(cfg, plans)
+    out, grads = train_step(Pp, {}, inp, cfg, lr=lr, step=1, switches={k: pl.switch for k, pl in plans.items()}, shape=shape)
+    got = eng.named_grads()
+    worst_l2, worst_max = ("", 0.0), ("", 0.0)
+    for k, gr in grads.items():
+        if gr is None:
+            continue
+        e2, em = rel_l2(got[k], gr), rel(got[k], gr)
+        if k.startswith("decoder."):
+            assert max(e2, em) < DEC_TOL, k
+            continue
+        if k.endswith(".alpha") or k.endswith(".score"):
+            assert e2 < 5 * BF16_TOL, (k, e2)          # tiny tensors driven by bf16 column sums
+        worst_l2 = max(worst_l2, (k, e2), key=lambda kv: kv[1])
+        worst_max = max(worst_max, (k, em), key=lambda kv: kv[1])
+    print("worst L2", worst_l2, "worst max", worst_max)
+    assert worst_l2[1] < 1.5 * BF16_TOL and worst_max[1] < GRAD_MAX_TOL
+    for i, m in enumerate(eng.bimask.modules):
+        assert rel(eng.bimask.logical(i, eng.bimask.gate).reshape(-1), out.gates[m["prefix"]].reshape(-1)) < FP32_TOL
+    # the update keeps the padding clean and the engine can keep stepping (graph replay included)
+    eng.grads.zero_()
+    eng.step(img, lab, noise=noise, drop_u=drop_u)
+    eng.step_graphed(img, lab)
+    torch.cuda.synchronize()
+    assert eng.padding_is_clean() and torch.isfinite(eng.scal).all()
