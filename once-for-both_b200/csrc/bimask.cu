@@ -139,7 +139,9 @@ __global__ void __launch_bounds__(BM_THREADS) bimask_fwd_kernel(const BimaskModu
                 if (wj[jj] > r) t += a[ii * md.n_j + jj];
         }
         tsum += t;
-        gate[md.gate_off + h * md.stride + c] = w_p * sig[i] + (1.f - w_p) * t;
+        // a finished module (one cell left: its score has been finalised, layers.py:629 / 939 / 275) gates with the frozen score
+        // itself (layers.py:196-197, 518-521, 859-860)
+        gate[md.gate_off + h * md.stride + c] = alive > 1 ? w_p * sig[i] + (1.f - w_p) * t : s;
         rank[md.gate_off + h * md.stride + c] = hr * md.dim + r;
     }
     tsum = block_sum(tsum, red);
@@ -223,8 +225,12 @@ __global__ void __launch_bounds__(BM_THREADS) bimask_bwd_kernel(const BimaskModu
         const float dg = dgate[md.gate_off + ph];
         const float s = score[ph];
         const float sg = 1.f / (1.f + expf(-s));
-        const float dsig = dg * w_p + (alive > 1 ? md.loss_w * md.coef * grad_scale : 0.f);
-        grads[md.score_off + ph] += dsig * sg * (1.f - sg);
+        if (alive > 1) {
+            const float dsig = dg * w_p + md.loss_w * md.coef * grad_scale;
+            grads[md.score_off + ph] += dsig * sg * (1.f - sg);
+        } else {
+            grads[md.score_off + ph] += dg;                            // finished module: gate == score
+        }
         dtable[rank[md.gate_off + ph]] = dg * (1.f - w_p) + dws;
     }
     __syncthreads();

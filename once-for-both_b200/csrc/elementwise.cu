@@ -936,9 +936,9 @@ struct AdamSegs {
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                                                     float* __restrict__ v, __nv_bfloat16* __restrict__ shadow,
                                                     const float* __restrict__ hyper, AdamSegs segs, long long n4, int zero_grad) {
+    int s = 0;        // segment of the current element: monotone along the grid-stride loop, so the scan is amortised
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         const long long e = i * 4;
-        int s = 0;
         while (s < segs.nseg - 1 && e >= segs.end[s]) ++s;
         const float* h = hyper + s * 8;
         const float lr = h[0], wd = h[1], b1 = h[2], b2 = h[3], eps = h[4], bc1 = h[5], bc2 = h[6];

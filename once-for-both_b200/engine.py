@@ -228,7 +228,9 @@ class SearchStepEngine:
         # ---- parameter arenas ----
         self.ref_shapes = self._param_shapes()                       # reference (logical) shapes
         shapes = {k: self._padded_shape(k, v) for k, v in self.ref_shapes.items()}      # physical shapes (== logical when unpruned)
-        order = sorted(shapes, key=lambda k: GROUPS.index(param_group(k, shapes[k])))   # stable: keeps model order
+        # stable sort: keeps model order inside a group; the bi-mask scores go to the end of their (no-decay) group so that
+        # each can be its own AdamW segment (see below)
+        order = sorted(shapes, key=lambda k: (GROUPS.index(param_group(k, shapes[k])), k.endswith(".score")))
         self.offsets, self.shapes, off = {}, shapes, 0
         seg_end, cur = [], GROUPS[0]
         for k in order:
@@ -246,14 +248,22 @@ class SearchStepEngine:
         # AdamW segments: the four weight / decoder groups, then ONE SEGMENT PER ALPHA TENSOR - a prune event restarts the
         # optimizer state of the alphas it touches, step counter included (optim.AdamW.update(..., initialize=True),
         # optim.py:152-159), so every alpha carries its own bias-correction step
+        # ... and so does every score tensor: finalising a module re-initialises its score's state the same way (layers.py:631)
         self.alpha_names = [k for k in order if param_group(k, shapes[k]) == "arch"]
-        self.segments = [(gname, None) for gname in GROUPS[:4]] + [("arch", k) for k in self.alpha_names]
-        ends = list(seg_end[:4])
+        self.score_names = [k for k in order if k.endswith(".score")]
+        tend = lambda k: self.offsets[k] + (math.prod(shapes[k]) + T_PAD - 1) // T_PAD * T_PAD
+        self.segments, ends = [("param_nd", None)], [self.offsets[self.score_names[0]]]
+        for k in self.score_names:
+            self.segments.append(("param_nd", k)); ends.append(tend(k))
+        assert ends[-1] == seg_end[0], "scores must close the no-decay group"
+        for gi in (1, 2, 3):
+            self.segments.append((GROUPS[gi], None)); ends.append(seg_end[gi])
         for k in self.alpha_names:
-            ends.append(self.offsets[k] + (math.prod(shapes[k]) + T_PAD - 1) // T_PAD * T_PAD)
-        assert ends[-1] == off and len(ends) <= 64
+            self.segments.append(("arch", k)); ends.append(tend(k))
+        assert ends[-1] == off and len(ends) <= 64, "AdamW segment table (ofb_b200.h OFB_ADAMW_MAX_SEGMENTS)"
         self._seg_end_c = (C.c_int64 * len(ends))(*ends)
-        self.alpha_restart = {k: 0 for k in self.alpha_names}     # optimizer step at which the alpha's state was (re)started
+        # optimizer step at which a tensor's Adam state was (re)started by a prune event
+        self.alpha_restart = {k: 0 for k in self.alpha_names + self.score_names}
         self._wp_idx = len(self.segments) * 8
         f32 = dict(dtype=torch.float32, device=self.dev)
         bf = dict(dtype=torch.bfloat16, device=self.dev)
@@ -276,6 +286,9 @@ class SearchStepEngine:
                                                           dtype=torch.bool)
                 switches[f"blocks.{l}.mlp"] = torch.ones(1, len(hidden_widths(self.hid)), dtype=torch.bool)
         self.switches = switches
+        # finished embedding search -> standard pre-norm blocks (vision_transformer.py:193, 203-204); otherwise the residual is
+        # taken from the normalised input (the search-mode quirk)
+        self.prenorm = int(switches["patch_embed"].sum()) == 1
         self._loss_w = dict(w_attn=w_attn, w_mlp=w_mlp, w_embed=w_embed, w_flops=w_flops, target_flops=target_flops)
         self.bimask = BimaskTable(self.D0, self.H, depth, self.hid, switches, w_attn=w_attn, w_mlp=w_mlp, w_embed=w_embed,
                                   w_flops=w_flops, target_flops=target_flops, num_classes=num_classes, num_patches=self.L,
@@ -587,7 +600,7 @@ class SearchStepEngine:
             ops.attention_fwd(a["qkv"], a["o"], a["lse"], dp1, B, T, H, self.scale)
             ops.gemm(ops.EPI_STORE, a["o"], self.w(pre + "attn.proj.weight"), M=M, N=D, K=A, out0=a["x2"],
                      bias=self.p(pre + "attn.proj.bias"), rowscale=dp1, rows_per_scale=T, bias_rowscaled=True,
-                     res=a["x1"], bn=self.bn_nD)
+                     res=self.xs[l] if self.prenorm else a["x1"], bn=self.bn_nD)
             ops.layernorm_fwd(a["x2"], self.p(pre + "norm2.weight"), self.p(pre + "norm2.bias"), a["x3"], a["mean2"],
                               a["rstd2"], self.eps_ln, d_valid=Dv)
             # fc1 computes the transposed hidden activations u^T, h^T = [hidden, tokens] (weight is the M operand)
@@ -595,7 +608,7 @@ class SearchStepEngine:
                      bias=self.p(pre + "mlp.fc1.bias"), colscale=g_m, rowscale=dp2, rows_per_scale=T, bn=self.mlp_bn)
             ops.gemm(ops.EPI_STORE, a["h"], self.w(pre + "mlp.fc2.weight"), M=M, N=D, K=hid, out0=self.xs[l + 1],
                      bias=self.p(pre + "mlp.fc2.bias"), rowscale=dp2, rows_per_scale=T, bias_rowscaled=True,
-                     res=a["x3"], a_mn=True, bn=self.bn_nD)
+                     res=a["x2"] if self.prenorm else a["x3"], a_mn=True, bn=self.bn_nD)
         ops.layernorm_fwd(self.xs[self.depth], self.p("norm.weight"), self.p("norm.bias"), self.latent, self.meanf,
                           self.rstdf, self.eps_ln, d_valid=Dv)
         # head on the cls rows (row stride T*D), label-smoothing CE
@@ -672,14 +685,18 @@ class SearchStepEngine:
                         dict(part=self.cp1, R=self.mlp_parts, N=hid, out=self.g(pre + "mlp.fc1.bias"))]
             ops.gemm(ops.EPI_WGRAD, du, a["x3"], M=hid, N=D, K=M, out0=self.g(pre + "mlp.fc1.weight"), b_mn=True)
             G3 = spare.pop()
+            pn = self.prenorm         # pre-norm: the residual gradient bypasses the LayerNorm and joins inside its backward
             ops.gemm(ops.EPI_STORE, du, self.w(pre + "mlp.fc1.weight"), M=M, N=D, K=hid, out0=G3, a_mn=True, b_mn=True,
-                     res=G4, bn=self.bn_nD)
-            spare.append(G4)
+                     res=None if pn else G4, bn=self.bn_nD)
+            if not pn:
+                spare.append(G4)
             # LayerNorm 2 (+ proj bias grad)
             G2 = spare.pop()
             ops.layernorm_bwd(G3, a["x2"], a["mean2"], a["rstd2"], self.p(pre + "norm2.weight"), G2, self.pg_, self.pb_,
-                              self.pd_, dp1, T, d_valid=Dv)
+                              self.pd_, dp1, T, d_valid=Dv, dres=G4 if pn else None)
             spare.append(G3)
+            if pn:
+                spare.append(G4)
             # one launch finishes the column partials of the fc2 data-gradient GEMM and of this LayerNorm
             ops.reduce_partials_multi(mlp_jobs + [(self.pg_, R, D, self.g(pre + "norm2.weight")),
                                                   (self.pb_, R, D, self.g(pre + "norm2.bias")),
@@ -698,15 +715,18 @@ class SearchStepEngine:
                      b_mn=True)
             G1 = spare.pop()
             ops.gemm(ops.EPI_STORE, dqkv, self.w(pre + "attn.qkv.weight"), M=M, N=D, K=3 * A, out0=G1, b_mn=True,
-                     res=G2, bn=self.bn_nD)
-            spare.append(G2)
+                     res=None if pn else G2, bn=self.bn_nD)
+            if not pn:
+                spare.append(G2)
             # LayerNorm 1 (+ previous block's fc2 bias grad)
             G0 = spare.pop()
             has_prev = l > 0
             ops.layernorm_bwd(G1, self.xs[l], a["mean1"], a["rstd1"], self.p(pre + "norm1.weight"), G0, self.pg_,
                               self.pb_, self.pd_ if has_prev else None,
-                              self.drop_scale[2 * l - 1] if has_prev else None, T, d_valid=Dv)
+                              self.drop_scale[2 * l - 1] if has_prev else None, T, d_valid=Dv, dres=G2 if pn else None)
             spare.append(G1)
+            if pn:
+                spare.append(G2)
             ln1_jobs = [(self.pg_, R, D, self.g(pre + "norm1.weight")), (self.pb_, R, D, self.g(pre + "norm1.bias"))]
             if has_prev:
                 ln1_jobs.append((self.pd_, R, D, self.g(f"blocks.{l - 1}.mlp.fc2.bias")))
@@ -840,10 +860,9 @@ class SearchStepEngine:
         """The search engine after a TRUNCATING prune event (compress(), vision_transformer.py:785-950): a new engine on the
         sliced shapes with the gathered parameters and the sliced Adam state (optim.AdamW.update, optim.py:122-182: moments
         follow the same index gathers; the alphas of modules that executed a prune restart from zero with their own step
-        counter). Finalising events (a module left with one cell) are not supported yet."""
+        counter, and so do finalised scores). Finished modules gate with their frozen score; a finished embedding search switches
+        the blocks to standard pre-norm."""
         from . import prune
-        if any(pl.finalised for pl in plans.values()):
-            raise NotImplementedError("finalised modules (frozen gates) are not supported by the search engine yet")
         pruned, switches = self.pruned_config(plans)
         eng = SearchStepEngine(self.D0, self.H, self.depth, self.B, mlp_ratio=self.hid // self.D0, num_classes=self.C,
                                img=self.img, patch=self.P, drop_path_rate=self.drop_path_rate, lr=self.lr, weight_decay=self.wd,
@@ -861,6 +880,7 @@ class SearchStepEngine:
         eng.w_p, eng.keep_ratio = self.w_p, self.keep_ratio
         for pre, pl in plans.items():
             eng.alpha_restart[pre + ".alpha"] = self.step_count if pl.executed else self.alpha_restart[pre + ".alpha"]
+            eng.alpha_restart[pre + ".score"] = self.step_count if pl.finalised else self.alpha_restart[pre + ".score"]
         return eng
 
     def apply_prune(self, plans):

@@ -26,7 +26,20 @@ CASES = {
     "tiny_d2": dict(D=192, H=3, depth=2, B=2, epoch_frac=6.0, dpr=0.1, lr=1e-3, offset=0),
     "small_d3": dict(D=384, H=6, depth=3, B=2, epoch_frac=11.0, dpr=0.1, lr=1e-3, offset=1),
     "small_d2": dict(D=384, H=6, depth=2, B=3, epoch_frac=2.0, dpr=0.0, lr=1e-3, offset=2),
+    # mixed events incl. finalisation (make_golden_prune.script_alphas): finished modules gate with their frozen score, and a
+    # finished embedding search switches the blocks to standard pre-norm
+    "mixed_tiny_d2": dict(D=192, H=3, depth=2, B=2, epoch_frac=7.0, dpr=0.1, lr=1e-3, offset=0, mixed=True),
+    "mixed_small_d3": dict(D=384, H=6, depth=3, B=2, epoch_frac=12.0, dpr=0.1, lr=1e-3, offset=0, mixed=True),
+    "mixed_tiny_d3": dict(D=192, H=3, depth=3, B=2, epoch_frac=20.0, dpr=0.0, lr=1e-3, offset=3, mixed=True),
 }
+
+
+def script(P, c):
+    if c.get("mixed"):
+        from make_golden_prune import script_alphas
+        cfg = ModelCfg(embed_dim=c["D"], num_heads=c["H"], depth=c["depth"])
+        return script_alphas(P, cfg, offset=c["offset"])
+    return script_truncations(P, offset=c["offset"])
 
 
 def script_truncations(P, offset=0, seed=4):
@@ -75,7 +88,7 @@ def main():
     from ofb_b200 import prune
     for name, c in CASES.items():
         cfg = ModelCfg(embed_dim=c["D"], num_heads=c["H"], depth=c["depth"])
-        P0 = script_truncations(make_params(cfg, seed=0), offset=c["offset"])
+        P0 = script(make_params(cfg, seed=0), c)
         inp = make_inputs(cfg, c["B"], seed=1, epoch_frac=c["epoch_frac"], drop_path_rate=c["dpr"])
         sw0 = default_switches(cfg)
 
@@ -84,7 +97,7 @@ def main():
                 m.update_w(c["epoch_frac"], 20)
             with contextlib.redirect_stdout(io.StringIO()):
                 fin, ex, _, _, _ = model.compress(0.2, None, None, None)
-            assert ex and not fin and not any(m.finish_search for m in model.searchable_modules)
+            assert ex and not fin and (c.get("mixed") or not any(m.finish_search for m in model.searchable_modules))
 
         class AnyShape(dict):            # run_reference copies P0 by name before the hook: shapes still match there
             pass
@@ -116,6 +129,7 @@ def main():
                 "loss_decoder": ref["dec"].numpy(), "loss_total": ref["total"].numpy(), "flops": np.array(ref["flops"]),
                 "cfg": np.array([c["D"], c["H"], c["depth"], c["B"]]), "epoch_frac": np.array(c["epoch_frac"]),
                 "dpr": np.array(c["dpr"]), "lr": np.array(c["lr"]), "offset": np.array(c["offset"]),
+                "mixed": np.array(bool(c.get("mixed"))),
                 "embed": np.array(shape.embed), "heads": np.array(shape.heads), "head_dims": np.array(shape.head_dims),
                 "hiddens": np.array(shape.hiddens)}
         for k, g in ref["grads"].items():

@@ -121,6 +121,11 @@ def gate_1d(alpha, switch, score, widths: List[int], w_p: float):
     """MLP / embed gate (layers.py:847-858, 179-191).  alpha [1,n], score [1,dim].
     returns gate [dim], wr [dim] (= weight_restore), wsum (= weighted_mask.sum())."""
     dim = score.shape[-1]
+    if int(switch.sum()) == 1:
+        # finished module (layers.py:196-197, 859-860): the frozen gate is the (finalised) score itself, the weighted mask is
+        # the all-ones mask of the single surviving cell
+        g = score.reshape(-1)
+        return g, torch.ones_like(g), torch.tensor(float(dim), dtype=score.dtype, device=score.device)
     a = _alive_softmax(alpha, switch).reshape(-1)
     w = torch.tensor(widths, device=alpha.device)
     r = torch.arange(dim, device=alpha.device)
@@ -136,6 +141,8 @@ def gate_attn(alpha, switch, score, heads: List[int], widths: List[int], w_p: fl
     """joint head x channel gate (layers.py:494-509).  alpha [nh, nc], score [H, d].
     returns gate [H,d], wr [H,d], wsum."""
     H, d = score.shape
+    if int(switch.sum()) == 1:                  # finished module (layers.py:518-521): q, k, v *= score
+        return score, torch.ones_like(score), torch.tensor(float(H * d), dtype=score.dtype, device=score.device)
     a = _alive_softmax(alpha, switch)
     n_i = torch.tensor(heads, device=alpha.device)
     w_j = torch.tensor(widths, device=alpha.device)
@@ -282,9 +289,13 @@ def forward_step(P: Dict[str, torch.Tensor], inp: StepInputs, cfg: ModelCfg, swi
 
     # ---- blocks: search-mode normalised residual stream (vision_transformer.py:193-201) ----
     scale = d ** -0.5
+    # once the embedding search is finished the weighted embed mask has no fractional entry and MAEBlock takes its standard
+    # pre-norm branch (vision_transformer.py:193, 203-204); until then the residual is taken from the NORMALISED x (194-201)
+    prenorm = int(sw["patch_embed"].sum()) == 1
     attn_terms, mlp_terms, attn_wsum, mlp_wsum = [], [], [], []
     for l in range(cfg.depth):
         pre = f"blocks.{l}."
+        x_in = x
         x = _ln(x, P[pre + "norm1.weight"], P[pre + "norm1.bias"], cfg.eps)
         Hl, dl = (shape.heads[l], shape.head_dims[l]) if shape is not None else (H, d)
         wj_a, ni_a = sp(pre + "attn", (head_channel_widths(d), head_counts(H)))
@@ -296,14 +307,15 @@ def forward_step(P: Dict[str, torch.Tensor], inp: StepInputs, cfg: ModelCfg, swi
         att = torch.softmax((q @ k.transpose(-2, -1)) * scale, dim=-1)
         o = (att @ v).transpose(1, 2).reshape(B, N, Hl * dl)
         o = o @ P[pre + "attn.proj.weight"].t() + P[pre + "attn.proj.bias"]
-        x = x + inp.drop_scale[l, 0].reshape(B, 1, 1) * o
+        x = (x_in if prenorm else x) + inp.drop_scale[l, 0].reshape(B, 1, 1) * o
+        x_mid = x
         x = _ln(x, P[pre + "norm2.weight"], P[pre + "norm2.bias"], cfg.eps)
         g_m, _, ws_m = gate_1d(P[pre + "mlp.alpha"], sw[pre + "mlp"], P[pre + "mlp.score"],
                                sp(pre + "mlp", (hidden_widths(hid), []))[0], w_p)
         gates[pre + "mlp"] = g_m
         hdn = F.gelu((x @ P[pre + "mlp.fc1.weight"].t() + P[pre + "mlp.fc1.bias"]) * g_m)
         y = hdn @ P[pre + "mlp.fc2.weight"].t() + P[pre + "mlp.fc2.bias"]
-        x = x + inp.drop_scale[l, 1].reshape(B, 1, 1) * y
+        x = (x_mid if prenorm else x) + inp.drop_scale[l, 1].reshape(B, 1, 1) * y
         attn_wsum.append(ws_a)
         mlp_wsum.append(ws_m)
         if int(sw[pre + "attn"].sum()) > 1:

@@ -10,7 +10,7 @@ import pytest
 import torch
 
 from fixtures import make_inputs, make_params, pruned_shape_from_plans, summarize
-from make_golden_pruned_step import plan_on_cpu, script_truncations
+from make_golden_pruned_step import plan_on_cpu, script
 from ofb_oracle import ModelCfg, default_switches, train_step, w_p_schedule
 
 GOLD = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pruned_step", "*.npz")))
@@ -26,7 +26,8 @@ def _case(path):
     g = np.load(path)
     D, H, depth, B = (int(x) for x in g["cfg"])
     cfg = ModelCfg(embed_dim=D, num_heads=H, depth=depth)
-    P0 = script_truncations(make_params(cfg, seed=0), offset=int(g["offset"]))
+    c = dict(D=D, H=H, depth=depth, offset=int(g["offset"]), mixed=bool(g["mixed"]))
+    P0 = script(make_params(cfg, seed=0), c)
     inp = make_inputs(cfg, B, seed=1, epoch_frac=float(g["epoch_frac"]), drop_path_rate=float(g["dpr"]))
     return g, cfg, P0, inp
 
@@ -76,7 +77,8 @@ def test_engine_pruned_step_matches_reference_golden(cuda_dev, path):
     eng0.step(img, lab, noise=noise, drop_u=drop_u, update=False)           # ranks for the plan
     eng0.grads.zero_()
     plans = eng0.plan_prune(0.2)
-    assert any(pl.truncated for pl in plans.values()) and not any(pl.finalised for pl in plans.values())
+    assert any(pl.truncated for pl in plans.values())
+    assert any(pl.finalised for pl in plans.values()) == bool(g["mixed"])
     eng = eng0.rebuild_pruned(plans)
     assert (eng.Dv, eng.heads, eng.hdims, eng.hids) == (int(g["embed"]), g["heads"].tolist(), g["head_dims"].tolist(),
                                                         g["hiddens"].tolist())
