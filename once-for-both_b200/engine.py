@@ -883,13 +883,24 @@ class SearchStepEngine:
             eng.alpha_restart[pre + ".score"] = self.step_count if pl.finalised else self.alpha_restart[pre + ".score"]
         return eng
 
-    def apply_prune(self, plans):
-        """Apply a prune event in place. Events that only switch cells off (no physical slicing) are supported: new switch
-        cells, alpha <- where(alive, mean alpha, 0), Adam state of those alphas restarted (optim.py:152-159), step graphs
-        dropped. Truncating / finalising events need the search step on pruned shapes, which is not built yet."""
+    def prune_event(self, thresh=0.2):
+        """engine.py:201-213 (three times per epoch): model.compress(thresh, optimizers). Returns (engine to continue with,
+        finish_search, execute_prune): the same engine when the event slices nothing (switch-only events are applied in place),
+        a rebuilt engine on the sliced shapes otherwise. The caller drops its reference to the old engine."""
+        plans = self.plan_prune(thresh)
+        executed = any(pl.executed for pl in plans.values())
+        finished = all(pl.finished for pl in plans.values())
         if any(pl.truncated for pl in plans.values()):
-            raise NotImplementedError("this prune event slices tensors; post-prune search shapes are not built yet "
-                                      "(gather_pruned() returns the pruned tensors)")
+            return self.rebuild_pruned(plans), finished, executed
+        self.apply_prune(plans)
+        return self, finished, executed
+
+    def apply_prune(self, plans):
+        """Apply a prune event IN PLACE. Only events that switch cells off without slicing any tensor qualify: new switch
+        cells, alpha <- where(alive, mean alpha, 0), Adam state of those alphas restarted (optim.py:152-159), step graphs
+        dropped. Truncating / finalising events change shapes: use rebuild_pruned() (or prune_event(), which picks)."""
+        if any(pl.truncated for pl in plans.values()):
+            raise NotImplementedError("this prune event slices tensors: rebuild_pruned(plans) builds the engine on the new shapes")
         changed = False
         for pre, pl in plans.items():
             if not pl.executed:

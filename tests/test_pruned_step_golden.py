@@ -121,3 +121,67 @@ def test_engine_pruned_step_matches_reference_golden(cuda_dev, path):
     eng.step_graphed(img, lab)
     torch.cuda.synchronize()
     assert eng.padding_is_clean() and torch.isfinite(eng.scal).all()
+
+
+@pytest.mark.gpu
+def test_consecutive_prune_events(cuda_dev):
+    """A trajectory engine.py:201-213 style: steps, prune event, steps, second prune event ON THE ALREADY PRUNED ENGINE. The
+    second event's plan (alphas, switches, ranks read from the pruned engine's strided tables) must equal the CPU planner's
+    on the same parameters, and the twice-rebuilt engine must still match the oracle on its shapes."""
+    import ofb_b200  # noqa: F401
+    from fixtures import search_modules
+    from ofb_b200 import prune
+    from ofb_b200.engine import SearchStepEngine
+    from ofb_oracle import PrunedShape, _desc_rank, forward_step
+    from step_compare import BF16_TOL, FP32_TOL, LOSS_TOL, rel
+    cfg = ModelCfg(embed_dim=192, num_heads=3, depth=2)
+    c = dict(D=192, H=3, depth=2, offset=0, mixed=False)
+    P0 = script(make_params(cfg, seed=0), c)
+    B = 2
+    inp = make_inputs(cfg, B, seed=1, epoch_frac=6.0, drop_path_rate=0.0)
+    img, lab, noise = inp.images.cuda(), inp.labels.cuda(), inp.noise.cuda()
+    eng = SearchStepEngine(192, 3, 2, B, drop_path_rate=0.0, lr=1e-3)
+    eng.load_params(P0)
+    eng.set_schedule(6.0)
+    for _ in range(2):
+        eng.step(img, lab, noise=noise)
+    eng, finished, executed = eng.prune_event(0.2)
+    assert executed and not finished and eng.spaces is not None
+    for _ in range(2):
+        eng.step(img, lab, noise=noise)
+    # second event: kill the trailing columns of every remaining alpha table on the pruned engine
+    for name in eng.alpha_names:
+        a = eng.p(name)
+        if a.shape[-1] > 2:
+            a[..., -1:] = -9.0
+    eng.step(img, lab, noise=noise, update=False)
+    eng.grads.zero_()
+    plans = eng.plan_prune(0.2)
+    # CPU planner on the same (logical) parameters of the pruned engine
+    Pn = {k: v.detach().cpu().clone() for k, v in eng.named_parameters().items()}
+    for i, m in enumerate(eng.bimask.modules):
+        pre, H, dim = m["prefix"], m["heads"], m["dim"]
+        score = Pn[pre + ".score"].reshape(H, dim)
+        hr = _desc_rank(torch.sigmoid(score).sum(-1)) if H > 1 else torch.zeros(1, dtype=torch.long)
+        widths, counts = eng.spaces[pre]
+        ref_pl = prune.plan_module(pre, m["kind"], Pn[pre + ".alpha"], eng.switches[pre], list(widths), list(counts), hr,
+                                   _desc_rank(score), 0.2)
+        got = plans[pre]
+        assert torch.equal(got.switch, ref_pl.switch), pre
+        assert (got.truncated, got.finalised, got.width, got.head_num) == (ref_pl.truncated, ref_pl.finalised, ref_pl.width,
+                                                                          ref_pl.head_num), pre
+        if got.truncated:
+            assert torch.equal(got.channel_index, ref_pl.channel_index) and torch.equal(got.head_index, ref_pl.head_index), pre
+    assert any(pl.truncated for pl in plans.values())
+    eng2 = eng.rebuild_pruned(plans)
+    scal = eng2.step(img, lab, noise=noise, update=False)
+    torch.cuda.synchronize()
+    assert eng2.padding_is_clean()
+    P2 = {k: v.detach().cpu().clone() for k, v in eng2.named_parameters().items()}
+    P2["alpha_patch"] = P0["alpha_patch"]
+    shape = PrunedShape(embed=eng2.Dv, heads=eng2.heads, head_dims=eng2.hdims, hiddens=eng2.hids, spaces=eng2.spaces)
+    inp.w_p, inp.keep_ratio = eng2.w_p, eng2.keep_ratio
+    out = forward_step(P2, inp, cfg, {k: v for k, v in eng2.switches.items()}, shape)
+    assert rel(eng2.logits, out.logits) < BF16_TOL
+    assert rel(scal[0], out.loss_base) < LOSS_TOL and rel(scal[1], out.loss_arch) < 10 * FP32_TOL
+    assert rel(scal[3], out.loss_total) < LOSS_TOL
