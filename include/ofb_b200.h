@@ -111,6 +111,16 @@ int ofb_reduce_partials_multi(const ofb_reduce_job* jobs, int njobs, void* strea
  * token assembly (models/layers.py:177 im2col; vision_transformer.py:586-612 PMIM mask, 646-651 cls row; timm
  * DropPath used at vision_transformer.py:183) */
 int ofb_patchify(const float* images, void* patches_bf16, int B, int img, int patch, void* stream);
+/* timm.data.Mixup mode='batch' as applied by the post-search phase and the finetune loop (search.py:651-655, engine.py:98-99,
+ * finetune.py:360-366): images <- lam x + (1 - lam) x.flip(0), or (cutmix != 0) the box [yl,yh) x [xl,xh) pasted from
+ * x.flip(0). lam and the box are drawn on the host (numpy RNG, as timm does). out may alias images (in place, like timm).
+ * ofb_patchify_mixup is ofb_patchify of the mixed batch without materialising it; ofb_mixup_target builds timm's
+ * mixup_target: lam * smoothed one-hot(y) + (1 - lam) * smoothed one-hot(y.flip(0)), fp32 [B, C]. */
+int ofb_mixup_batch(const float* images, float* out, int B, int img, double lam, int cutmix, int yl, int yh, int xl, int xh,
+                    void* stream);
+int ofb_patchify_mixup(const float* images, void* patches_bf16, int B, int img, int patch, double lam, int cutmix, int yl,
+                       int yh, int xl, int xh, void* stream);
+int ofb_mixup_target(const int64_t* labels, float* target, int B, int C, double lam, double smoothing, void* stream);
 int ofb_pmim_mask(const float* noise, float* mask, int B, int L, int keep, void* stream);
 int ofb_droppath_scale(const float* u, const float* drop_prob, float* scale, int n_rows, int B, void* stream);
 int ofb_cls_rows(const float* cls, const float* pos, const float* gate, void* x_bf16, int B, int T, int D, void* stream);

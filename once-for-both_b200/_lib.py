@@ -51,7 +51,7 @@ class ReduceJob(C.Structure):
                 ("scale", C.c_float), ("accumulate", C.c_int32)]
 
 
-_P, _I, _F, _L = C.c_void_p, C.c_int, C.c_float, C.c_int64
+_P, _I, _F, _L, _D = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_double
 # every symbol include/ofb_b200.h declares, with its argument types
 SIGNATURES = {
     "ofb_version": [],
@@ -66,6 +66,9 @@ SIGNATURES = {
     "ofb_reduce_partials": [_P, _I, _I, _P, _F, _P, _I, _P],
     "ofb_reduce_partials_multi": [_P, _I, _P],
     "ofb_patchify": [_P, _P, _I, _I, _I, _P],
+    "ofb_mixup_batch": [_P, _P, _I, _I, _D, _I, _I, _I, _I, _I, _P],
+    "ofb_patchify_mixup": [_P, _P, _I, _I, _I, _D, _I, _I, _I, _I, _I, _P],
+    "ofb_mixup_target": [_P, _P, _I, _I, _D, _D, _P],
     "ofb_pmim_mask": [_P, _P, _I, _I, _I, _P],
     "ofb_droppath_scale": [_P, _P, _P, _I, _I, _P],
     "ofb_cls_rows": [_P, _P, _P, _P, _I, _I, _I, _P],

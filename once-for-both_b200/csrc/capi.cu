@@ -17,6 +17,9 @@ int launch_eval_metrics(const float*, const int64_t*, float*, int, int, cudaStre
 int launch_reduce_partials(const float*, int, int, float*, float, const float*, int, cudaStream_t);
 int launch_reduce_partials_multi(const void*, int, cudaStream_t);
 int launch_patchify(const float*, void*, int, int, int, cudaStream_t);
+int launch_mixup_batch(const float*, float*, int, int, double, int, int, int, int, int, cudaStream_t);
+int launch_patchify_mixup(const float*, void*, int, int, int, double, int, int, int, int, int, cudaStream_t);
+int launch_mixup_target(const long long*, float*, int, int, double, double, cudaStream_t);
 int launch_pmim_mask(const float*, float*, int, int, int, cudaStream_t);
 int launch_droppath_scale(const float*, const float*, float*, int, int, cudaStream_t);
 int launch_cls_rows(const float*, const float*, const float*, void*, int, int, int, cudaStream_t);
@@ -94,6 +97,17 @@ int ofb_reduce_partials_multi(const ofb_reduce_job* jobs, int njobs, void* strea
 }
 int ofb_patchify(const float* images, void* patches, int B, int img, int patch, void* stream) {
     return ofb::launch_patchify(images, patches, B, img, patch, ST(stream));
+}
+int ofb_mixup_batch(const float* images, float* out, int B, int img, double lam, int cutmix, int yl, int yh, int xl, int xh,
+                    void* stream) {
+    return ofb::launch_mixup_batch(images, out, B, img, lam, cutmix, yl, yh, xl, xh, ST(stream));
+}
+int ofb_patchify_mixup(const float* images, void* patches, int B, int img, int patch, double lam, int cutmix, int yl, int yh, int xl,
+                       int xh, void* stream) {
+    return ofb::launch_patchify_mixup(images, patches, B, img, patch, lam, cutmix, yl, yh, xl, xh, ST(stream));
+}
+int ofb_mixup_target(const int64_t* labels, float* target, int B, int C, double lam, double smoothing, void* stream) {
+    return ofb::launch_mixup_target(reinterpret_cast<const long long*>(labels), target, B, C, lam, smoothing, ST(stream));
 }
 int ofb_pmim_mask(const float* noise, float* mask, int B, int L, int keep, void* stream) {
     return ofb::launch_pmim_mask(noise, mask, B, L, keep, ST(stream));

@@ -619,6 +619,88 @@ __global__ void patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __
 }
 
 // =============================================================================================
+// Mixup / CutMix of a batch, timm.data.Mixup mode='batch' as the post-search phase applies it (search.py:651-655,
+// engine.py:98-99; finetune.py:360-366):  x <- lam x + (1 - lam) x.flip(0)   or   x[:, :, yl:yh, xl:xh] <- x.flip(0)[same box].
+// A thread owns 4 pixels of the PAIR (b, B-1-b): both images are read once and both results written (in place allowed; an
+// odd batch's middle image pairs with itself). fp32 arithmetic in timm's order: fl(fl(x lam) + fl(x' (1 - lam))).
+// =============================================================================================
+struct MixParams {
+    float lam, oml;            // lam and 1 - lam (both rounded from the host double, as torch does with a Python scalar)
+    int cutmix, yl, yh, xl, xh;
+};
+__device__ __forceinline__ void mix_pair4(const float4& a, const float4& b, int x0, int yy, const MixParams& mp, float4& oa, float4& ob) {
+    if (mp.cutmix) {
+        const bool row_in = yy >= mp.yl && yy < mp.yh;
+        const bool i0 = row_in && x0 >= mp.xl && x0 < mp.xh, i1 = row_in && x0 + 1 >= mp.xl && x0 + 1 < mp.xh;
+        const bool i2 = row_in && x0 + 2 >= mp.xl && x0 + 2 < mp.xh, i3 = row_in && x0 + 3 >= mp.xl && x0 + 3 < mp.xh;
+        oa = make_float4(i0 ? b.x : a.x, i1 ? b.y : a.y, i2 ? b.z : a.z, i3 ? b.w : a.w);
+        ob = make_float4(i0 ? a.x : b.x, i1 ? a.y : b.y, i2 ? a.z : b.z, i3 ? a.w : b.w);
+    } else {
+        oa = make_float4(__fadd_rn(__fmul_rn(a.x, mp.lam), __fmul_rn(b.x, mp.oml)), __fadd_rn(__fmul_rn(a.y, mp.lam), __fmul_rn(b.y, mp.oml)),
+                         __fadd_rn(__fmul_rn(a.z, mp.lam), __fmul_rn(b.z, mp.oml)), __fadd_rn(__fmul_rn(a.w, mp.lam), __fmul_rn(b.w, mp.oml)));
+        ob = make_float4(__fadd_rn(__fmul_rn(b.x, mp.lam), __fmul_rn(a.x, mp.oml)), __fadd_rn(__fmul_rn(b.y, mp.lam), __fmul_rn(a.y, mp.oml)),
+                         __fadd_rn(__fmul_rn(b.z, mp.lam), __fmul_rn(a.z, mp.oml)), __fadd_rn(__fmul_rn(b.w, mp.lam), __fmul_rn(a.w, mp.oml)));
+    }
+}
+__global__ void __launch_bounds__(256) mixup_batch_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int HW, MixParams mp) {
+    const int per_img = 3 * HW * HW / 4;
+    const int pairs = (B + 1) / 2;
+    const size_t total = size_t(pairs) * per_img;
+    for (size_t idx = blockIdx.x * size_t(blockDim.x) + threadIdx.x; idx < total; idx += size_t(gridDim.x) * blockDim.x) {
+        const int b = idx / per_img, r = idx % per_img;
+        const int f = B - 1 - b;
+        const int x0 = (r % (HW / 4)) * 4, yy = (r / (HW / 4)) % HW;
+        const float4 a = reinterpret_cast<const float4*>(in)[size_t(b) * per_img + r];
+        const float4 c = reinterpret_cast<const float4*>(in)[size_t(f) * per_img + r];
+        float4 oa, ob;
+        mix_pair4(a, c, x0, yy, mp, oa, ob);
+        reinterpret_cast<float4*>(out)[size_t(b) * per_img + r] = oa;
+        if (f != b) reinterpret_cast<float4*>(out)[size_t(f) * per_img + r] = ob;
+    }
+}
+// the same fused into the im2col: the mixed batch is never materialised (the post-search phase has no other consumer of the
+// images: PMIM is off, search.py:645)
+__global__ void __launch_bounds__(256) patchify_mixup_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int HW, int P,
+                                                             MixParams mp) {
+    const int G = HW / P;
+    const int per_img = 3 * HW * HW / 8;
+    const int pairs = (B + 1) / 2;
+    const size_t total = size_t(pairs) * per_img;
+    for (size_t idx = blockIdx.x * size_t(blockDim.x) + threadIdx.x; idx < total; idx += size_t(gridDim.x) * blockDim.x) {
+        const int b = idx / per_img;
+        const int f = B - 1 - b;
+        int r = idx % per_img;
+        const int x8 = r % (HW / 8); r /= (HW / 8);
+        const int yy = r % HW; const int c = r / HW;
+        const size_t off = (size_t(c) * HW + yy) * HW + x8 * 8;
+        const float4* sa = reinterpret_cast<const float4*>(img + size_t(b) * 3 * HW * HW + off);
+        const float4* sb = reinterpret_cast<const float4*>(img + size_t(f) * 3 * HW * HW + off);
+        const float4 a0 = __ldg(sa), a1 = __ldg(sa + 1), b0 = __ldg(sb), b1 = __ldg(sb + 1);
+        float4 oa0, oa1, ob0, ob1;
+        mix_pair4(a0, b0, x8 * 8, yy, mp, oa0, ob0);
+        mix_pair4(a1, b1, x8 * 8 + 4, yy, mp, oa1, ob1);
+        const int ph = yy / P, i = yy % P, pw = (x8 * 8) / P, j = (x8 * 8) % P;
+        const size_t col = size_t(c) * P * P + i * P + j;
+        const float fa[8] = {oa0.x, oa0.y, oa0.z, oa0.w, oa1.x, oa1.y, oa1.z, oa1.w};
+        *reinterpret_cast<uint4*>(out + (size_t(b) * G * G + ph * G + pw) * (3 * P * P) + col) = pack8(fa);
+        if (f != b) {
+            const float fb[8] = {ob0.x, ob0.y, ob0.z, ob0.w, ob1.x, ob1.y, ob1.z, ob1.w};
+            *reinterpret_cast<uint4*>(out + (size_t(f) * G * G + ph * G + pw) * (3 * P * P) + col) = pack8(fb);
+        }
+    }
+}
+// timm mixup_target: lam * smoothed one-hot(y) + (1 - lam) * smoothed one-hot(y.flip(0)), fp32 [B, C]
+__global__ void __launch_bounds__(256) mixup_target_kernel(const long long* __restrict__ labels, float* __restrict__ target, int B, int C, float lam,
+                                                           float oml, float on, float off) {
+    const size_t total = size_t(B) * C;
+    for (size_t idx = blockIdx.x * size_t(blockDim.x) + threadIdx.x; idx < total; idx += size_t(gridDim.x) * blockDim.x) {
+        const int b = idx / C, c = idx % C;
+        const float y1 = labels[b] == c ? on : off, y2 = labels[B - 1 - b] == c ? on : off;
+        target[idx] = __fadd_rn(__fmul_rn(y1, lam), __fmul_rn(y2, oml));
+    }
+}
+
+// =============================================================================================
 // PMIM mask + DropPath scales from uniform randoms
 //   mask[b,l] = 1 if noise[b,l] is NOT among the `keep` smallest of its row (vision_transformer.py:597-607)
 //   drop_scale[i] = floor(keep_i + u_i) / keep_i   (timm DropPath)
@@ -1157,6 +1239,43 @@ int launch_patchify(const float* img, void* out, int B, int HW, int P, cudaStrea
     const int cap = num_sms() * 16;
     if (grid > cap) grid = cap;
     patchify_kernel<<<grid, 256, 0, s>>>(img, reinterpret_cast<__nv_bfloat16*>(out), B, HW, P);
+    return err();
+}
+
+static bool mix_params(int HW, double lam, int cutmix, int yl, int yh, int xl, int xh, MixParams& mp) {
+    if (cutmix && (yl < 0 || yh > HW || xl < 0 || xh > HW || yl > yh || xl > xh)) return false;
+    mp.lam = float(lam); mp.oml = float(1.0 - lam);
+    mp.cutmix = cutmix; mp.yl = yl; mp.yh = yh; mp.xl = xl; mp.xh = xh;
+    return true;
+}
+int launch_mixup_batch(const float* in, float* out, int B, int HW, double lam, int cutmix, int yl, int yh, int xl, int xh, cudaStream_t s) {
+    MixParams mp;
+    if (HW % 4 != 0 || B < 1 || !mix_params(HW, lam, cutmix, yl, yh, xl, xh, mp)) return 1011;
+    const size_t total = size_t((B + 1) / 2) * 3 * HW * HW / 4;
+    int grid = int((total + 255) / 256);
+    const int cap = num_sms() * 16;
+    if (grid > cap) grid = cap;
+    mixup_batch_kernel<<<grid, 256, 0, s>>>(in, out, B, HW, mp);
+    return err();
+}
+int launch_patchify_mixup(const float* img, void* out, int B, int HW, int P, double lam, int cutmix, int yl, int yh, int xl, int xh,
+                          cudaStream_t s) {
+    MixParams mp;
+    if (HW % 8 != 0 || P % 8 != 0 || B < 1 || !mix_params(HW, lam, cutmix, yl, yh, xl, xh, mp)) return 1011;
+    const size_t total = size_t((B + 1) / 2) * 3 * HW * HW / 8;
+    int grid = int((total + 255) / 256);
+    const int cap = num_sms() * 16;
+    if (grid > cap) grid = cap;
+    patchify_mixup_kernel<<<grid, 256, 0, s>>>(img, reinterpret_cast<__nv_bfloat16*>(out), B, HW, P, mp);
+    return err();
+}
+int launch_mixup_target(const long long* labels, float* target, int B, int C, double lam, double smoothing, cudaStream_t s) {
+    if (B < 1 || C < 1) return 1011;
+    const double off = smoothing / C, on = 1.0 - smoothing + off;
+    int grid = int((size_t(B) * C + 255) / 256);
+    const int cap = num_sms() * 16;
+    if (grid > cap) grid = cap;
+    mixup_target_kernel<<<grid, 256, 0, s>>>(labels, target, B, C, float(lam), float(1.0 - lam), float(on), float(off));
     return err();
 }
 

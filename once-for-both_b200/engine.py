@@ -223,6 +223,9 @@ class SearchStepEngine:
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
         self.step_count = 0
         self.w_p, self.keep_ratio = 0.99, max_ratio
+        self._schedule_touched = False
+        self.decoder_frozen = False        # post-search phase (enter_post_search)
+        self._finish_cache = None
         self.drop_path_rate = drop_path_rate
 
         # ---- parameter arenas ----
@@ -524,24 +527,65 @@ class SearchStepEngine:
     # ------------------------------------------------------------------------------------------------------------
     def set_schedule(self, epoch_frac: float):
         """update_w (layers.py:484-486) and adjust_masking_ratio (vision_transformer.py:521-523)."""
-        e = min(epoch_frac, self.warmup_epochs)
+        if epoch_frac > self.warmup_epochs:
+            # both hooks only act while `epoch <= warmup_epochs`; later the last value stands - which is also what keeps
+            # reset_mask_ratio(1.0) of the post-search phase in force
+            if not self._schedule_touched:
+                epoch_frac = float(self.warmup_epochs)        # a run that starts past the warm-up: the warm-up end values
+            else:
+                return
+        self._schedule_touched = True
+        e = epoch_frac
         self.w_p = (0.1 - 0.99) / self.warmup_epochs * e + 0.99
         self.keep_ratio = self.max_ratio - (self.max_ratio - self.min_ratio) * e / self.warmup_epochs
+
+    @property
+    def finish_search(self) -> bool:
+        """Every searchable module is down to one cell: compress() returned finish_search=True (vision_transformer.py:785-950).
+        From then on the criterion returns the base loss alone (losses.py:105-106) and there is no architecture optimizer
+        (engine.py:206-208): the architecture loss is left out of the total and the alpha segments are not updated."""
+        if self._finish_cache is None:
+            self._finish_cache = all(int(sw.sum()) == 1 for sw in self.switches.values())
+        return self._finish_cache
+
+    def enter_post_search(self):
+        """The epoch-boundary switch of search.py:641-656 once the search has finished: reset_mask_ratio(1.0) (no PMIM masking
+        -> no decoder branch, vision_transformer.py:595-612, 719), freeze_decoder() (mask_token and the decoder get no gradient
+        and no update, vt:534-539; optimizer_decoder = None). The caller feeds Mixup soft targets from then on
+        (step(..., target=...), SoftTargetCrossEntropy, search.py:651-655)."""
+        assert self.finish_search, "search.py:642 enters this phase only with finish_search"
+        self.keep_ratio = 1.0
+        self._schedule_touched = True
+        self.decoder_frozen = True
+        # a frozen parameter is skipped by the optimizer (grad None, optim.py:70-71). Its gradient stays exactly zero here; with
+        # zeroed moments AdamW then leaves it bit-identical (0 / (0 + eps)), the decoder groups additionally get lr 0
+        for k in ("mask_token", "decoder.0.weight", "decoder.0.bias"):
+            self._view(self.adam_m, k).zero_()
+            self._view(self.adam_v, k).zero_()
+        self.release_graphs()
 
     def _fill_hyper(self, lrs=None):
         lrs = lrs or {}
         h = self.hyper_host
+        fin = self.finish_search
         for i, (gname, alpha_name) in enumerate(self.segments):
             t = self.step_count + 1 - (self.alpha_restart[alpha_name] if alpha_name else 0)
             b1, b2 = (0.5, 0.999) if gname == "arch" else (0.9, 0.999)
             lr = lrs.get(gname, self.lr)
             wd = 0.0 if gname.endswith("_nd") else self.wd
+            if (gname == "arch" and fin) or (gname.startswith("dec_") and self.decoder_frozen):
+                lr = wd = 0.0          # optimizer_arch = None after finish_search (engine.py:206-208); optimizer_decoder = None
             h[i * 8:i * 8 + 7] = torch.tensor([lr, wd, b1, b2, 1e-8, 1 - b1 ** t, 1 - b2 ** t])
         h[self._wp_idx] = self.w_p
 
     # ------------------------------------------------------------------------------------------------------------
-    def forward(self, images, labels, noise=None, drop_u=None, train=True):
+    def forward(self, images, labels, noise=None, drop_u=None, train=True, target=None, mix=None):
         """Forward + losses. images fp32 [B,3,224,224] (device), labels int64 [B].
+        target: fp32 [B, C] soft targets (Mixup, post-search phase) -> timm SoftTargetCrossEntropy instead of label smoothing.
+        mix: mixup.MixParams - `images` is the UNMIXED batch and the Mixup / CutMix blend is fused into the im2col (only when PMIM
+        is off: nothing else reads the images then).
+        With keep_ratio == 1 (enter_post_search) PMIM is off: no masking, no target normalisation, no decoder GEMM, decoder
+        loss 0 (vision_transformer.py:595-612, 719-730).
         train=False is the reference's eval mode while the search is running (engine.evaluate, engine.py:222-257 ->
         MIMVisionTransformer.forward with self.training False): same gates, no PMIM masking (vt:631-638), DropPath identity,
         no decoder branch (vt:719), and instead of the training losses the per-image {cross entropy, top-1, top-5} rows."""
@@ -558,16 +602,20 @@ class SearchStepEngine:
         with torch.cuda.stream(self._side):
             bm.forward(self.params, w_p_dev)
         # random draws stay in PyTorch (RNG parity with the reference's torch.rand), masks are built by our kernels
+        keep = int(L * self.keep_ratio)
+        pmim = train and keep != L                    # `len_keeps != [L]`, vision_transformer.py:595
+        self._pmim = pmim
+        assert mix is None or mix.identity or not pmim, "fused Mixup needs PMIM off; mix the batch with mixup.Mixup first"
         if train:
-            if noise is None:
-                noise = torch.rand(B, L, device=self.dev)
+            if pmim:
+                if noise is None:
+                    noise = torch.rand(B, L, device=self.dev)
+                ops.pmim_mask(noise, self.mask, keep)
             if drop_u is None:
                 drop_u = torch.rand(self.depth * 2, B, device=self.dev)
-            keep = int(L * self.keep_ratio)
-            ops.pmim_mask(noise, self.mask, keep)
             ops.droppath_scale(drop_u, self.drop_prob, self.drop_scale)
-        rowmask = self.mask if train else self.zero_mask
-        if train:
+        rowmask = self.mask if pmim else self.zero_mask
+        if pmim:
             # the PMIM targets (local normalisation of the masked patches) are only consumed by the decoder GEMM at the very
             # end of forward: a second branch, filling the tails of the block kernels instead of sitting on the critical path
             if self._side2 is None:
@@ -579,7 +627,10 @@ class SearchStepEngine:
                     ops.norm_targets(images, self.mask, self.tgt)
             else:
                 ops.norm_targets(images, self.mask, self.tgt)
-        ops.patchify(images, self.patches, self.P)
+        if mix is not None and not mix.identity:
+            ops.patchify_mixup(images, self.patches, mix.lam, mix.box, self.P)
+        else:
+            ops.patchify(images, self.patches, self.P)
         cur.wait_stream(self._side)
         g_e = bm.gate_of(0)
         x0 = self.xs[0]
@@ -619,14 +670,21 @@ class SearchStepEngine:
             ops.reduce_partials(self.eval_rows, B, 3, self.eval_out, scale=1.0 / B, accumulate=False)
             return self.eval_out
         gs = 1.0 / self.accum_iter
-        ops.ls_cross_entropy(self.logits, labels, self.loss_rows, self.dlogits, self.smoothing, gs)
+        if target is not None:
+            ops.soft_target_cross_entropy(self.logits, target, self.loss_rows, self.dlogits, gs)
+        else:
+            ops.ls_cross_entropy(self.logits, labels, self.loss_rows, self.dlogits, self.smoothing, gs)
+        arch = None if self.finish_search else bm.arch       # finish_search: the criterion returns the base loss alone
+        if not pmim:
+            ops.loss_finalize(self.loss_rows, None, None, arch, gs, self.scal)
+            return self.scal
         # PMIM decoder + masked L1 against the locally normalised pixels
         if side_targets:
             cur.wait_stream(self._side2)
         ops.gemm(ops.EPI_DECODER, self.latent, self.w("decoder.0.weight"), M=M, N=768, K=D, out0=self.sgn,
                  bias=self.p("decoder.0.bias"), rowmask=self.mask, target=self.tgt, tokens=L, colpart0=self.dec_part,
                  bn=self.dec_bn)
-        ops.loss_finalize(self.loss_rows, self.dec_part, self.mask, bm.arch, gs, self.scal)
+        ops.loss_finalize(self.loss_rows, self.dec_part, self.mask, arch, gs, self.scal)
         return self.scal
 
     # ------------------------------------------------------------------------------------------------------------
@@ -645,12 +703,17 @@ class SearchStepEngine:
 
         # ---- decoder + head ----
         dlat = self.gA
-        ops.gemm(ops.EPI_STORE, self.sgn, self.w("decoder.0.weight"), M=M, N=D, K=768, out0=dlat, b_mn=True,
-                 scale_ptr=dec_scale)
+        pmim = self._pmim
+        if pmim:
+            ops.gemm(ops.EPI_STORE, self.sgn, self.w("decoder.0.weight"), M=M, N=D, K=768, out0=dlat, b_mn=True,
+                     scale_ptr=dec_scale)
+        else:
+            dlat.zero_()                   # PMIM off: only the cls rows of the latent carry a gradient (the head's)
         ops.gemm(ops.EPI_STORE, self.dlogits, self.w("head.weight"), M=B, N=D, K=self.C, out0=dlat, ld0=T * D, b_mn=True)
-        ops.gemm(ops.EPI_WGRAD, self.sgn, self.latent, M=768, N=D, K=M, out0=self.g("decoder.0.weight").view(768, D),
-                 a_mn=True, b_mn=True, scale_ptr=dec_scale)
-        ops.colsum_bf16(self.sgn, M, 768, self.g("decoder.0.bias"), scale_dev=dec_scale)
+        if pmim and not self.decoder_frozen:
+            ops.gemm(ops.EPI_WGRAD, self.sgn, self.latent, M=768, N=D, K=M, out0=self.g("decoder.0.weight").view(768, D),
+                     a_mn=True, b_mn=True, scale_ptr=dec_scale)
+            ops.colsum_bf16(self.sgn, M, 768, self.g("decoder.0.bias"), scale_dev=dec_scale)
         ops.gemm(ops.EPI_WGRAD, self.dlogits, self.latent, M=self.C, N=D, K=B, out0=self.g("head.weight"), a_mn=True,
                  b_mn=True, ldb=T * D)
         ops.colsum_bf16(self.dlogits, B, self.C, self.g("head.bias"))
@@ -737,11 +800,15 @@ class SearchStepEngine:
 
         # ---- embed stage ----
         g_e = bm.gate_of(0)
-        ops.embed_bwd(G, self.xs[0], g_e, self.mask, self.dconv, self.e_gx, self.e_pos, self.e_mt, B, T, D)
-        ops.reduce_partials_multi([
+        ops.embed_bwd(G, self.xs[0], g_e, self.mask if pmim else self.zero_mask, self.dconv, self.e_gx, self.e_pos, self.e_mt,
+                      B, T, D)
+        embed_jobs = [
             dict(part=self.e_gx, R=T, N=D, out=self.dgate[0:D], div_by=g_e, accumulate=False),
             (self.e_pos, 1, T * D, self.g("pos_embed")), (self.e_pos, 1, D, self.g("cls_token")),
-            (self.e_mt, T, D, self.g("mask_token")), (self.e_pos[1:], L, D, self.g("patch_embed.proj.bias"))])
+            (self.e_pos[1:], L, D, self.g("patch_embed.proj.bias"))]
+        if pmim and not self.decoder_frozen:                 # freeze_decoder() also freezes the mask token (vt:535-536)
+            embed_jobs.append((self.e_mt, T, D, self.g("mask_token")))
+        ops.reduce_partials_multi(embed_jobs)
         ops.gemm(ops.EPI_WGRAD, self.dconv, self.patches, M=D, N=768, K=ML,
                  out0=self.g("patch_embed.proj.weight").view(D, 768), a_mn=True, b_mn=True)
         # ---- bi-mask: d gate (+ FLOPs / sparsity losses) -> d score, d alpha ----
@@ -759,7 +826,7 @@ class SearchStepEngine:
                   zero_grad=True)
         self.step_count += 1
 
-    def step_graphed(self, images, labels, lrs=None):
+    def step_graphed(self, images, labels, lrs=None, target=None):
         """One full search step replayed from a CUDA graph (forward, backward, AdamW; the whole step is ~270 launches of
         ~10-200 us, so per-launch host work would otherwise bound it). The graph is captured on first use for this
         (images buffer, labels buffer, PMIM keep count) and re-captured when the schedule changes the keep count; lr, AdamW
@@ -767,7 +834,8 @@ class SearchStepEngine:
         (PMIM noise, DropPath) come from torch's graph-safe generator. Multi-GPU: the all-reduce and the update stay
         outside the graph (see step())."""
         keep = int(self.L * self.keep_ratio)
-        key = (images.data_ptr(), labels.data_ptr(), keep)
+        key = (images.data_ptr(), labels.data_ptr() if labels is not None else 0, keep,
+               target.data_ptr() if target is not None else 0)
         self._fill_hyper(lrs)
         self.hyper.copy_(self.hyper_host, non_blocking=True)
         entry = self._graphs.get(key)
@@ -777,14 +845,14 @@ class SearchStepEngine:
             side = torch.cuda.Stream(device=self.dev)
             side.wait_stream(cur)
             with torch.cuda.stream(side):
-                self.forward(images, labels)
+                self.forward(images, labels, target=target)
                 self.backward(exchange=self.dp_overlap)      # also brings up the NCCL communicator before capture
                 self.grads.zero_()
             cur.wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             n0 = ops.LAUNCHES
             with torch.cuda.graph(graph):
-                self.forward(images, labels)
+                self.forward(images, labels, target=target)
                 self.backward(exchange=self.dp_overlap)      # overlapped exchange: the NCCL launches are graph nodes
                 if self.world <= 1 or self.dp_overlap:
                     ops.adamw(self.params, self.grads, self.adam_m, self.adam_v, self.shadow, self.hyper, self._seg_end_c,
@@ -878,6 +946,7 @@ class SearchStepEngine:
                 eng._view(arena_new, k).copy_(eng._pad(k, state[k].to(self.dev, torch.float32).reshape(eng.ref_shapes[k])))
         eng.step_count = self.step_count
         eng.w_p, eng.keep_ratio = self.w_p, self.keep_ratio
+        eng._schedule_touched, eng.decoder_frozen = self._schedule_touched, self.decoder_frozen
         for pre, pl in plans.items():
             eng.alpha_restart[pre + ".alpha"] = self.step_count if pl.executed else self.alpha_restart[pre + ".alpha"]
             eng.alpha_restart[pre + ".score"] = self.step_count if pl.finalised else self.alpha_restart[pre + ".score"]
@@ -907,6 +976,7 @@ class SearchStepEngine:
                 continue
             changed = True
             self.switches[pre] = pl.switch.clone()
+            self._finish_cache = None
             name = pre + ".alpha"
             self.p(name).copy_(pl.alpha.to(self.dev).reshape(self.shapes[name]))
             self._view(self.adam_m, name).zero_()
@@ -928,11 +998,13 @@ class SearchStepEngine:
         launches, and after a prune event changes shapes)."""
         self._graphs.clear()
 
-    def step(self, images, labels, noise=None, drop_u=None, update=True, lrs=None):
-        """One full search step; returns the device tensor scal = [base, arch, decoder, total, w_dec, ...]."""
+    def step(self, images, labels, noise=None, drop_u=None, update=True, lrs=None, target=None, mix=None):
+        """One full search step; returns the device tensor scal = [base, arch, decoder, total, w_dec, ...].
+        Post-search phase (after enter_post_search): target = Mixup soft targets [B, C]; mix = the MixParams when `images` is the
+        unmixed batch (blend fused into the im2col)."""
         self._fill_hyper(lrs)
         self.hyper.copy_(self.hyper_host, non_blocking=True)
-        self.forward(images, labels, noise, drop_u)
+        self.forward(images, labels, noise, drop_u, target=target, mix=mix)
         self.backward(exchange=update and self.dp_overlap)
         if update:
             if not self.dp_overlap:

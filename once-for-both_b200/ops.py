@@ -180,6 +180,32 @@ def patchify(images, patches, patch=16):
     check(lib().ofb_patchify(ptr(images), ptr(patches), B, HW, patch, cur_stream()), "ofb_patchify")
 
 
+def _box(box):
+    return (0, 0, 0, 0, 0) if box is None else (1,) + tuple(int(v) for v in box)
+
+
+def mixup_batch(images, out, lam, box=None):
+    """timm Mixup (batch mode) on the device: out <- lam x + (1-lam) x.flip(0), or the CutMix `box` = (yl, yh, xl, xh) pasted from
+    x.flip(0). out may be `images` itself (in place, as timm does)."""
+    _need_cuda(images, out)
+    B, _, HW, _ = images.shape
+    check(lib().ofb_mixup_batch(ptr(images), ptr(out), B, HW, float(lam), *_box(box), cur_stream()), "ofb_mixup_batch")
+
+
+def patchify_mixup(images, patches, lam, box=None, patch=16):
+    """patchify() of the mixed batch without materialising it."""
+    _need_cuda(images, patches)
+    B, _, HW, _ = images.shape
+    check(lib().ofb_patchify_mixup(ptr(images), ptr(patches), B, HW, patch, float(lam), *_box(box), cur_stream()),
+          "ofb_patchify_mixup")
+
+
+def mixup_target(labels, target, lam, smoothing):
+    _need_cuda(labels, target)
+    B, Cn = target.shape
+    check(lib().ofb_mixup_target(ptr(labels), ptr(target), B, Cn, float(lam), float(smoothing), cur_stream()), "ofb_mixup_target")
+
+
 def pmim_mask(noise, mask, keep):
     B, L = noise.shape
     check(lib().ofb_pmim_mask(ptr(noise), ptr(mask), B, L, keep, cur_stream()), "ofb_pmim_mask")

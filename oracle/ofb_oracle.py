@@ -207,6 +207,58 @@ def patchify_pixel_shuffle(t: torch.Tensor, P: int = 16) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------------------------------------------
+# Mixup / CutMix of the post-search phase (search.py:651-655, engine.py:98-99 `samples, targets = mixup_fn(samples, targets)`)
+# timm.data.Mixup is third-party code that is NOT under /root/reference (requirements.txt:4, an unpinned timm fork; timm is
+# not installed here either): this restates the published timm-0.4 `mode='batch'` algorithm (timm/data/mixup.py: Mixup.
+# _params_per_batch, _mix_batch, mixup_target, rand_bbox, cutmix_bbox_and_lam with correct_lam=True). PARITY UNPINNED for
+# this helper - no reference-side golden exists; the search-step goldens take the mixed batch as their input.
+# --------------------------------------------------------------------------------------------------------------------
+def mixup_draw(rng, img_hw=(224, 224), mixup_alpha=0.8, cutmix_alpha=1.0, prob=1.0, switch_prob=0.5):
+    """One batch-mode draw with a numpy RandomState-like `rng`, in timm's call order: (lam, box or None); box = (yl, yh, xl, xh)
+    with lam corrected to the clipped box area."""
+    import numpy as np
+    lam, use_cutmix = 1.0, False
+    if rng.rand() < prob:
+        if mixup_alpha > 0. and cutmix_alpha > 0.:
+            use_cutmix = rng.rand() < switch_prob
+            lam = float(rng.beta(cutmix_alpha, cutmix_alpha) if use_cutmix else rng.beta(mixup_alpha, mixup_alpha))
+        elif mixup_alpha > 0.:
+            lam = float(rng.beta(mixup_alpha, mixup_alpha))
+        elif cutmix_alpha > 0.:
+            use_cutmix, lam = True, float(rng.beta(cutmix_alpha, cutmix_alpha))
+    if lam == 1.0 or not use_cutmix:
+        return lam, None
+    H, W = img_hw
+    ratio = np.sqrt(1 - lam)
+    cut_h, cut_w = int(H * ratio), int(W * ratio)
+    cy, cx = rng.randint(0, H), rng.randint(0, W)
+    yl, yh = int(np.clip(cy - cut_h // 2, 0, H)), int(np.clip(cy + cut_h // 2, 0, H))
+    xl, xh = int(np.clip(cx - cut_w // 2, 0, W)), int(np.clip(cx + cut_w // 2, 0, W))
+    lam = 1. - (yh - yl) * (xh - xl) / float(H * W)
+    return lam, (yl, yh, xl, xh)
+
+
+def mixup_target(labels: torch.Tensor, num_classes: int, lam: float, smoothing: float) -> torch.Tensor:
+    off = smoothing / num_classes
+    on = 1. - smoothing + off
+    y1 = torch.full((labels.shape[0], num_classes), off).scatter_(1, labels.view(-1, 1), on)
+    y2 = torch.full((labels.shape[0], num_classes), off).scatter_(1, labels.flip(0).view(-1, 1), on)
+    return y1 * lam + y2 * (1. - lam)
+
+
+def mixup_batch(images: torch.Tensor, labels: torch.Tensor, lam: float, box, num_classes: int = 1000, smoothing: float = 0.1):
+    """(mixed images, soft targets): x <- lam x + (1 - lam) x.flip(0), or the CutMix box pasted from x.flip(0)."""
+    x = images.clone()
+    if lam != 1.0:
+        if box is not None:
+            yl, yh, xl, xh = box
+            x[:, :, yl:yh, xl:xh] = images.flip(0)[:, :, yl:yh, xl:xh]
+        else:
+            x = images * lam + images.flip(0) * (1. - lam)
+    return x, mixup_target(labels, num_classes, lam, smoothing)
+
+
+# --------------------------------------------------------------------------------------------------------------------
 # forward
 # --------------------------------------------------------------------------------------------------------------------
 @dataclass
@@ -217,6 +269,7 @@ class StepInputs:
     drop_scale: torch.Tensor        # [depth, 2, B] DropPath multipliers floor(keep+u)/keep (1.0 where drop prob = 0)
     w_p: float = 0.99
     keep_ratio: float = 0.95
+    soft_target: Optional[torch.Tensor] = None   # [B, C] Mixup targets of the post-search phase (search.py:651-655)
 
 
 @dataclass
@@ -255,13 +308,18 @@ def _sparsity_term(alpha, switch, score, coef):
     return loss
 
 
-def forward_step(P: Dict[str, torch.Tensor], inp: StepInputs, cfg: ModelCfg, switches=None, shape: Optional[PrunedShape] = None) -> StepOutputs:
+def forward_step(P: Dict[str, torch.Tensor], inp: StepInputs, cfg: ModelCfg, switches=None, shape: Optional[PrunedShape] = None,
+                 finish_search: bool = False) -> StepOutputs:
     """MIMVisionTransformer.forward (vision_transformer.py:614-669, 717-745) in search/training mode with embed,
     attention and MLP search active, followed by OFBSearchLOSS (losses.py:80-106) and the decoder-loss weighting of
     engine.search_one_epoch (engine.py:131-144).
     shape: the model after truncating prune events (tensors physically sliced, every module still searched). The attention
     scale and the ORIGINAL-FLOPs side of the FLOPs loss keep the unpruned dims (layers.py:418, 747-753); the
-    searched side uses the pruned LayerNorm width and head counts (vt:206-213 active_dim, layers.py:749 active_H)."""
+    searched side uses the pruned LayerNorm width and head counts (vt:206-213 active_dim, layers.py:749 active_H).
+    finish_search: every module is finalised - the criterion returns the base loss alone (losses.py:105-106), there is no
+    architecture optimizer any more (engine.py:206-208). With inp.keep_ratio == 1 (reset_mask_ratio(1.0), search.py:645) the
+    PMIM branch is off (vt:595-612, 719); inp.soft_target switches the base criterion to timm SoftTargetCrossEntropy on Mixup
+    targets (search.py:651-655)."""
     sw = switches or default_switches(cfg)
     D, H, d, hid, L = cfg.embed_dim, cfg.num_heads, cfg.head_dim, cfg.hidden, cfg.num_patches
     Dc = shape.embed if shape is not None else D                      # current (pruned) embedding width
@@ -338,7 +396,10 @@ def forward_step(P: Dict[str, torch.Tensor], inp: StepInputs, cfg: ModelCfg, swi
     # ---- losses ----
     logp = F.log_softmax(logits, dim=-1)
     nll = -logp.gather(1, inp.labels.unsqueeze(1)).squeeze(1)
-    loss_base = ((1 - cfg.smoothing) * nll + cfg.smoothing * (-logp.mean(-1))).mean()
+    if inp.soft_target is not None:
+        loss_base = (-inp.soft_target * logp).sum(-1).mean()        # timm SoftTargetCrossEntropy
+    else:
+        loss_base = ((1 - cfg.smoothing) * nll + cfg.smoothing * (-logp.mean(-1))).mean()
 
     zero = torch.zeros((), dtype=x.dtype)
     l_attn = sum(attn_terms) if attn_terms else zero
@@ -366,7 +427,7 @@ def forward_step(P: Dict[str, torch.Tensor], inp: StepInputs, cfg: ModelCfg, swi
     l_flops = ((f_s / 1e9 - cfg.target_flops) / (f_ori / 1e9)) ** 2
 
     loss_arch = cfg.w_attn * l_attn + cfg.w_mlp * l_mlp + cfg.w_embed * l_embed + cfg.w_flops * l_flops
-    loss_total = loss_base + loss_arch
+    loss_total = loss_base if finish_search else loss_base + loss_arch
     if mask is not None:
         w_dec = (loss_base / loss_dec).detach()          # engine.py:140-142
         loss_total = loss_total + w_dec * loss_dec
@@ -409,13 +470,16 @@ def adamw_step(p, g, m, v, step, lr, betas, eps, weight_decay):
 
 
 def train_step(P: Dict[str, torch.Tensor], state: Dict[str, Dict[str, torch.Tensor]], inp: StepInputs, cfg: ModelCfg,
-               lr: float, step: int, switches=None, frozen=("alpha_patch",), shape: Optional[PrunedShape] = None):
+               lr: float, step: int, switches=None, frozen=("alpha_patch",), shape: Optional[PrunedShape] = None,
+               finish_search: bool = False):
     """One full search step: forward, losses, backward, three AdamW updates (engine.py:131-184).
-    P entries are leaf tensors; returns (outputs, grads)."""
-    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in P.items() if k not in frozen}
-    out = forward_step(leaves, inp, cfg, switches, shape)
+    P entries are leaf tensors; returns (outputs, grads). `frozen` names get no gradient and no update (alpha_patch; in the
+    post-search phase mask_token and the decoder, vision_transformer.py:534-539; with finish_search the alphas, whose
+    optimizer is gone)."""
+    leaves = {k: (v.detach().clone().requires_grad_(True) if k not in frozen else v.detach()) for k, v in P.items()}
+    out = forward_step(leaves, inp, cfg, switches, shape, finish_search)
     out.loss_total.backward()
-    grads = {k: (v.grad if v.grad is not None else None) for k, v in leaves.items()}
+    grads = {k: (v.grad if v.grad is not None else None) for k, v in leaves.items() if k not in frozen}
     with torch.no_grad():
         for k, g in grads.items():
             if g is None:
