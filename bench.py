@@ -25,7 +25,8 @@ sys.path.insert(0, ROOT)
 
 MODELS = {"tiny": (192, 3), "small": (384, 6), "base": (768, 12)}
 METRIC = {"search": "images/sec DeiT-S bi-mask search step (fwd+bwd+update, PMIM on)",
-          "finetune": "images/sec finetune step of a physically pruned DeiT-S subnet (fwd+bwd+update)"}
+          "finetune": "images/sec finetune step of a physically pruned DeiT-S subnet (fwd+bwd+update)",
+          "post": "images/sec post-search step of the finalised DeiT-S subnet (Mixup/CutMix + soft-target CE, PMIM off, fwd+bwd+update)"}
 # algorithmic GFLOP / image of one search step: tiny 7.64, small 27.82, base 105.85
 STEP_GFLOP = {"tiny": 7.64, "small": 27.82, "base": 105.85}
 
@@ -42,9 +43,10 @@ def parse():
     ap.add_argument("--cpu-sample-batch", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying CUDA graphs")
-    ap.add_argument("--workload", default="search", choices=["search", "finetune"],
+    ap.add_argument("--workload", default="search", choices=["search", "finetune", "post"],
                     help="search: the bi-mask search step (BASELINE.json metric, default); finetune: the training step of a "
-                         "physically pruned DeiT-S subnet (BASELINE.json configs[4], extra configuration)")
+                         "physically pruned DeiT-S subnet (BASELINE.json configs[4], extra configuration); post: the post-search "
+                         "phase of the search loop (SURVEY 8f-3) on the same subnet shapes, reached through prune_event()")
     return ap.parse_args()
 
 
@@ -134,6 +136,72 @@ def cpu_ft_oracle_rate(sample_batch, steps=1, warmup=1):
     return sample_batch / dt, cores, dt
 
 
+def script_subnet_alphas(named, depth):
+    """Alphas that leave exactly the FT_SUBNET cell of every searchable module alive at the next prune event (DeiT-S search
+    space, layers.py:143-152, 425-462, 813-821): the synthetic stand-in for a finished search."""
+    import torch
+    D, d, hid = 384, 64, 1536
+    ew = [int((i / D) * D) for i in range(D // 2, D + 1, min(D // 32, 12))]
+    hc = list(range(2, 6 + 1, 2))
+    cw = [int(d * (i / d)) for i in range(d // 4, d + 1, max(d // 8, 1))]
+    hw = [int((i / hid) * hid) for i in range(hid // 4, hid + 1, hid // 8)]
+
+    def one(shape, idx):
+        a = torch.full(shape, -9.0)
+        a.view(-1)[idx] = 2.0
+        return a
+    out = dict(named)
+    out["patch_embed.alpha"] = one((1, len(ew)), ew.index(FT_SUBNET["embed_dim"]))
+    for l in range(depth):
+        out[f"blocks.{l}.attn.alpha"] = one((len(hc), len(cw)), hc.index(FT_SUBNET["heads"][l]) * len(cw)
+                                            + cw.index(FT_SUBNET["head_dims"][l]))
+        out[f"blocks.{l}.mlp.alpha"] = one((1, len(hw)), hw.index(FT_SUBNET["hiddens"][l]))
+    return out
+
+
+def subnet_step_gflop():
+    N, L, D, C = 197, 196, FT_SUBNET["embed_dim"], 1000
+    f = 2.0 * L * 768 * D + 2.0 * D * C
+    for H, d, hid in zip(FT_SUBNET["heads"], FT_SUBNET["head_dims"], FT_SUBNET["hiddens"]):
+        f += 2.0 * N * D * 3 * H * d + 2.0 * N * H * d * D + 4.0 * N * D * hid + 4.0 * H * N * N * d
+    return (3.0 * f - 2.0 * L * 768 * D) / 1e9
+
+
+def cpu_post_oracle_rate(sample_batch, steps=1, warmup=1):
+    """images/s of the CPU oracle on the post-search step (finalised subnet, Mixup soft targets, PMIM off, decoder frozen)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    from fixtures import make_inputs, make_params, pruned_shape_from_plans
+    from make_golden_post import FROZEN_P2
+    from make_golden_pruned_step import plan_on_cpu
+    from ofb_oracle import ModelCfg, default_switches, mixup_batch, train_step
+    import ofb_b200  # noqa: F401
+    from ofb_b200 import prune
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = ModelCfg(embed_dim=384, num_heads=6, depth=12)
+    P0 = script_subnet_alphas(make_params(cfg, seed=0), 12)
+    g = torch.Generator().manual_seed(3)
+    for k in sorted(k for k in P0 if k.endswith(".score")):
+        P0[k] = torch.randn(P0[k].shape, generator=g) * 0.2          # no ties (see oracle/make_golden_prune.py)
+    plans, dims = plan_on_cpu(cfg, P0, default_switches(cfg))
+    Pp = prune.gather_pruned(plans, {k: v for k, v in P0.items() if k != "alpha_patch"}, dims, 0.545)
+    Pp["alpha_patch"] = P0["alpha_patch"]
+    shape = pruned_shape_from_plans(cfg, plans)
+    sw = {k: pl.switch for k, pl in plans.items()}
+    inp = make_inputs(cfg, sample_batch, seed=1, epoch_frac=30.0, drop_path_rate=0.1, keep_ratio=1.0)
+    inp.images, inp.soft_target = mixup_batch(inp.images, inp.labels, 0.37, None)
+    state = {}
+    for i in range(warmup):
+        train_step(Pp, state, inp, cfg, lr=1e-3, step=i + 1, switches=sw, shape=shape, frozen=FROZEN_P2, finish_search=True)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        train_step(Pp, state, inp, cfg, lr=1e-3, step=warmup + i + 1, switches=sw, shape=shape, frozen=FROZEN_P2,
+                   finish_search=True)
+    dt = (time.perf_counter() - t0) / steps
+    return sample_batch / dt, cores, dt
+
+
 def cpu_oracle_rate(model, depth, sample_batch, steps=1, warmup=1):
     """images/s of the CPU oracle port (reference step restated, fp32, all host threads) on a bounded sample."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -163,6 +231,8 @@ def run_reference(args):
     D, H = MODELS[args.model]
     if args.workload == "finetune":
         rate, cores, dt = cpu_ft_oracle_rate(args.cpu_sample_batch, steps=max(1, min(args.steps, 3)), warmup=1)
+    elif args.workload == "post":
+        rate, cores, dt = cpu_post_oracle_rate(args.cpu_sample_batch, steps=max(1, min(args.steps, 3)), warmup=1)
     else:
         rate, cores, dt = cpu_oracle_rate(args.model, args.depth, args.cpu_sample_batch, steps=max(1, min(args.steps, 3)),
                                           warmup=max(1, min(args.warmup, 1)))
@@ -173,7 +243,9 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": (f"DeiT-{args.model} bi-mask search + PMIM step, depth {args.depth}, 224px, CPU sample"
                                 if args.workload == "search" else
-                                "finetune step of a pruned DeiT-S subnet (BASELINE.json configs[4]), 224px, CPU sample")},
+                                "finetune step of a pruned DeiT-S subnet (BASELINE.json configs[4]), 224px, CPU sample"
+                                if args.workload == "finetune" else
+                                "post-search step of the finalised DeiT-S subnet (SURVEY 8f-3), 224px, CPU sample")},
         "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -225,6 +297,36 @@ def main():
         workload = (f"finetune step of a pruned DeiT-S subnet (embed {FT_SUBNET['embed_dim']}, per-block heads / head dims / "
                     f"hidden widths fixed in bench.py FT_SUBNET), depth 12, batch {B}/GPU, 224px (BASELINE.json configs[4], "
                     "extra configuration)")
+    elif args.workload == "post":
+        # reach the post-search phase the way a run does: search engine -> the prune event that finalises every module (scripted
+        # alphas: the FT_SUBNET cells survive) -> rebuilt engine on the subnet shapes -> enter_post_search()
+        assert args.model == "small" and args.depth == 12, "the post workload is defined on the DeiT-S subnet of FT_SUBNET"
+        from ofb_b200.mixup import Mixup
+        eng0 = SearchStepEngine(D, H, args.depth, B, drop_path_rate=0.1, lr=lr, device=dev, process_group=pg)
+        eng0.init_params(seed=0)
+        eng0.load_params(script_subnet_alphas({k: v.clone() for k, v in eng0.named_parameters().items()}, args.depth))
+        eng0.set_schedule(10.0)
+        warm = torch.randn(B, 3, 224, 224, device=dev)
+        eng0.step(warm, torch.zeros(B, dtype=torch.int64, device=dev), update=False)       # ranks for the plan
+        eng0.grads.zero_()
+        t_ev = time.perf_counter()
+        eng, finished, executed = eng0.prune_event(0.2)
+        torch.cuda.synchronize()
+        prune_event_ms = (time.perf_counter() - t_ev) * 1e3
+        assert finished and executed and (eng.Dv, eng.heads, eng.hdims, eng.hids) == (
+            FT_SUBNET["embed_dim"], FT_SUBNET["heads"], FT_SUBNET["head_dims"], FT_SUBNET["hiddens"])
+        del eng0, warm
+        torch.cuda.empty_cache()
+        eng.enter_post_search()
+        import numpy as np
+        mixup_fn = Mixup(rng=np.random.RandomState(1 + rank))
+        soft = torch.empty(B, 1000, device=dev)
+        mixed = torch.empty(B, 3, 224, 224, device=dev)
+        step_gflop = subnet_step_gflop()
+        workload = (f"post-search step (search.py:641-656: Mixup/CutMix + soft-target CE, PMIM off, decoder frozen) of the DeiT-S "
+                    f"search engine after the finalising prune event (subnet of bench.py FT_SUBNET, embed {FT_SUBNET['embed_dim']}), "
+                    f"depth 12, batch {B}/GPU, 224px (SURVEY 8f-3, extra configuration); prune_event() itself took "
+                    f"{prune_event_ms:.0f} ms host wall")
     else:
         eng = SearchStepEngine(D, H, args.depth, B, drop_path_rate=0.1, lr=lr, device=dev, process_group=pg)
         eng.init_params(seed=0)                     # same initial weights on every rank (DDP broadcast equivalent)
@@ -247,6 +349,12 @@ def main():
             torch.cuda.synchronize()
 
     step = eng.step if args.no_graph else eng.step_graphed
+    if args.workload == "post":
+        inner = step
+
+        def step(images, labels):          # engine.py:98-99: `samples, targets = mixup_fn(samples, targets)`, then the step
+            mixup_fn(images, labels, soft, images_out=mixed)
+            return inner(mixed, None, target=soft)
 
     # ---------------- device-resident measurement ----------------
     mark("engine built")
@@ -286,7 +394,11 @@ def main():
         n_roof = min(3, args.steps)
         ops.GEMM_TIMING, ops.LN_TIMING = [], []
         for i in range(n_roof):
-            eng.step(dev_img[i % n_host], dev_lab[i % n_host])
+            if args.workload == "post":
+                mixup_fn(dev_img[i % n_host], dev_lab[i % n_host], soft, images_out=mixed)
+                eng.step(mixed, None, target=soft)
+            else:
+                eng.step(dev_img[i % n_host], dev_lab[i % n_host])
         sync_all()
         gemm_t, ln_t = ops.GEMM_TIMING, ops.LN_TIMING
         ops.GEMM_TIMING = ops.LN_TIMING = None
@@ -384,6 +496,8 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             if args.workload == "finetune":
                 rate, cores, dt = cpu_ft_oracle_rate(args.cpu_sample_batch)
+            elif args.workload == "post":
+                rate, cores, dt = cpu_post_oracle_rate(args.cpu_sample_batch)
             else:
                 rate, cores, dt = cpu_oracle_rate(args.model, args.depth, args.cpu_sample_batch)
             line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",

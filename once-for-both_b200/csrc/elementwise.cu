@@ -6,6 +6,7 @@
 #include "ptx.cuh"
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace ofb {
 
@@ -535,6 +536,205 @@ __global__ void __launch_bounds__(256) ln_bwd3_kernel(const __nv_bfloat16* __res
             const int idx = warp * (D / 2) + (lane + 32 * i) * W + j;
             sg[idx] = ag[i * W + j]; sb[idx] = ab[i * W + j]; sd[idx] = ad[i * W + j];
         }
+    __syncthreads();
+    const float* fg = reinterpret_cast<const float*>(sg);
+    const float* fb = reinterpret_cast<const float*>(sb);
+    const float* fd = reinterpret_cast<const float*>(sd);
+    for (int col = threadIdx.x; col < D; col += blockDim.x) {
+        float a = 0.f, b = 0.f, d = 0.f;
+#pragma unroll
+        for (int w = 0; w < WPB; ++w) { a += fg[w * D + col]; b += fb[w * D + col]; d += fd[w * D + col]; }
+        part_dgamma[size_t(blockIdx.x) * D + col] = a;
+        part_dbeta[size_t(blockIdx.x) * D + col] = b;
+        if (want_bias) part_dbias[size_t(blockIdx.x) * D + col] = d;
+    }
+}
+
+// =============================================================================================
+// Packed paths for ANY even width (the pruned embeddings of the search: multiples of 12, or 6 at DeiT-T, zero-padded to a
+// multiple of 8; configs[4] finetune, search steps after truncating prune events, post-search phase): a lane owns NW bf16x2
+// words at word index lane + 32 i. Only the last word slot is ragged, so lanes stay 81-100 % busy where the 16-byte-chunk
+// kernels above drop to 56 % at D = 288 (36 chunks over 64 slots) - and the arithmetic is packed fp32x2 like the 192 W paths.
+// D: physical row width (multiple of 8), Dv: real channels (even, D - 8 < Dv <= D); words >= Dv / 2 are zero padding that
+// stays out of the statistics and gets y = 0 / dx = dres.
+// =============================================================================================
+template <int NW>
+__global__ void __launch_bounds__(256) ln_fwdw_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
+                                                      float* __restrict__ mean, float* __restrict__ rstd, int M, int D, int Dv,
+                                                      float eps) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const int nw = D >> 1, nv = Dv >> 1;
+    float2 gam[NW], bet[NW];
+    bool ok[NW], sv[NW];
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+        const int w = lane + 32 * i;
+        ok[i] = w < nw; sv[i] = w < nv;
+        gam[i] = ok[i] ? __ldg(reinterpret_cast<const float2*>(gamma) + w) : splat2(0.f);
+        bet[i] = ok[i] ? __ldg(reinterpret_cast<const float2*>(beta) + w) : splat2(0.f);
+    }
+    const float inv = 1.f / Dv;
+    const int stride = gridDim.x * wpb;
+    int row = blockIdx.x * wpb + (threadIdx.x >> 5);
+    uint32_t cur[NW], nxt[NW];
+    if (row < M) {
+#pragma unroll
+        for (int i = 0; i < NW; ++i) cur[i] = ok[i] ? __ldg(reinterpret_cast<const uint32_t*>(x + size_t(row) * D) + lane + 32 * i) : 0u;
+    }
+    for (; row < M; row += stride) {
+        const int rn = row + stride;
+        if (rn < M) {
+#pragma unroll
+            for (int i = 0; i < NW; ++i) nxt[i] = ok[i] ? __ldg(reinterpret_cast<const uint32_t*>(x + size_t(rn) * D) + lane + 32 * i) : 0u;
+        }
+        float2 v[NW];
+        float2 s = splat2(0.f);
+#pragma unroll
+        for (int i = 0; i < NW; ++i) { v[i] = unpack_bf16x2(cur[i]); s = add2(s, v[i]); }
+        const float mu = warp_sum(s.x + s.y) * inv;
+        const float2 nmu = splat2(-mu);
+        float2 q = splat2(0.f);
+#pragma unroll
+        for (int i = 0; i < NW; ++i) { v[i] = sv[i] ? add2(v[i], nmu) : splat2(0.f); q = fma2(v[i], v[i], q); }
+        const float rs = rsqrtf(warp_sum(q.x + q.y) * inv + eps);
+        const float2 rs2 = splat2(rs);
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            v[i] = fma2(mul2(v[i], rs2), gam[i], bet[i]);
+            if (ok[i]) reinterpret_cast<uint32_t*>(y + size_t(row) * D)[lane + 32 * i] = pack_bf16x2(v[i].x, v[i].y);
+        }
+        if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+#pragma unroll
+        for (int i = 0; i < NW; ++i) cur[i] = nxt[i];
+    }
+}
+
+template <int NW>
+__global__ void __launch_bounds__(256) ln_bwdw_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                      const float* __restrict__ gamma, __nv_bfloat16* __restrict__ dx,
+                                                      float* __restrict__ part_dgamma, float* __restrict__ part_dbeta,
+                                                      float* __restrict__ part_dbias, const float* __restrict__ rowscale,
+                                                      int rows_per_scale, int M, int D, int Dv,
+                                                      const __nv_bfloat16* __restrict__ dres) {
+    constexpr int WPB = 8;
+    extern __shared__ __align__(128) uint8_t ln_smem_raw[];
+    // layout as in ln_bwd_kernel: ring [8 warps][LN_STAGES][2][D bf16] | barriers; the ring is reused as float [3][8][D] at the end
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nw = D >> 1, nv = Dv >> 1;
+    const uint32_t row_bytes = uint32_t(D) * 2u;
+    const uint32_t ring_bytes = WPB * LN_STAGES * 2 * row_bytes;
+    const uint32_t red_bytes = 3u * WPB * uint32_t(D) * 4u;
+    const uint32_t bar_off = (ring_bytes > red_bytes ? ring_bytes : red_bytes);
+    uint8_t* my_ring = ln_smem_raw + size_t(warp) * LN_STAGES * 2 * row_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem_raw + bar_off) + warp * LN_STAGES;
+    if (lane == 0) {
+        for (int sidx = 0; sidx < LN_STAGES; ++sidx) mbar_init(smem_u32(&bars[sidx]), 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+
+    float2 ag[NW], ab[NW], ad[NW], gam[NW];
+    bool ok[NW], sv[NW];
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+        const int w = lane + 32 * i;
+        ok[i] = w < nw; sv[i] = w < nv;
+        ag[i] = ab[i] = ad[i] = splat2(0.f);
+        gam[i] = ok[i] ? __ldg(reinterpret_cast<const float2*>(gamma) + w) : splat2(0.f);
+    }
+    const int row_stride = gridDim.x * WPB;
+    const int first = blockIdx.x * WPB + warp;
+    auto issue = [&](int row, int stage) {
+        const uint32_t b = smem_u32(&bars[stage]);
+        const uint32_t dst = smem_u32(my_ring + size_t(stage) * 2 * row_bytes);
+        mbar_arrive_expect_tx(b, 2 * row_bytes);
+        bulk_load_1d(dst, dy + size_t(row) * D, row_bytes, b);
+        bulk_load_1d(dst + row_bytes, x + size_t(row) * D, row_bytes, b);
+    };
+    if (lane == 0) {
+        for (int sidx = 0; sidx < LN_STAGES; ++sidx) {
+            const int row = first + sidx * row_stride;
+            if (row < M) issue(row, sidx);
+        }
+    }
+    const bool want_bias = part_dbias != nullptr, has_res = dres != nullptr;
+    auto row_stats = [&](int row, float& mu, float& rs, float& rsc) {
+        mu = __ldg(mean + row); rs = __ldg(rstd + row);
+        rsc = want_bias ? (rowscale != nullptr ? __ldg(rowscale + row / rows_per_scale) : 1.f) : 0.f;
+    };
+    auto load_res = [&](int row, uint32_t* r) {
+#pragma unroll
+        for (int i = 0; i < NW; ++i)
+            r[i] = (has_res && ok[i]) ? __ldg(reinterpret_cast<const uint32_t*>(dres + size_t(row) * D) + lane + 32 * i) : 0u;
+    };
+    const float inv = 1.f / Dv;
+    float mu = 0.f, rs = 0.f, rsc = 0.f;
+    uint32_t res[NW], res_n[NW];
+#pragma unroll
+    for (int i = 0; i < NW; ++i) res[i] = res_n[i] = 0u;
+    if (first < M) { row_stats(first, mu, rs, rsc); load_res(first, res); }
+    int k = 0;
+    for (int row = first; row < M; row += row_stride, ++k) {
+        const int stage = k % LN_STAGES;
+        const uint32_t parity = (k / LN_STAGES) & 1;
+        float mu_n = 0.f, rs_n = 0.f, rsc_n = 0.f;
+        if (row + row_stride < M) { row_stats(row + row_stride, mu_n, rs_n, rsc_n); load_res(row + row_stride, res_n); }   // one row ahead
+        mbar_wait(smem_u32(&bars[stage]), parity);
+        const uint32_t* sdy = reinterpret_cast<const uint32_t*>(my_ring + size_t(stage) * 2 * row_bytes);
+        const uint32_t* sx = reinterpret_cast<const uint32_t*>(my_ring + size_t(stage) * 2 * row_bytes + row_bytes);
+        float2 dyv[NW], xh[NW];
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            dyv[i] = ok[i] ? unpack_bf16x2(sdy[lane + 32 * i]) : splat2(0.f);
+            xh[i] = ok[i] ? unpack_bf16x2(sx[lane + 32 * i]) : splat2(0.f);
+        }
+        // the stage is consumed (values are in registers): refill it with the row LN_STAGES iterations ahead
+        __syncwarp();
+        if (lane == 0) {
+            const int nxt = row + LN_STAGES * row_stride;
+            if (nxt < M) { fence_proxy_async_smem(); issue(nxt, stage); }
+        }
+        const float2 rs2 = splat2(rs), nmr2 = splat2(-mu * rs);
+        float2 s1 = splat2(0.f), s2 = splat2(0.f);
+        float2 dg[NW];
+#pragma unroll
+        for (int j = 0; j < NW; ++j) {
+            xh[j] = sv[j] ? fma2(xh[j], rs2, nmr2) : splat2(0.f);
+            dg[j] = mul2(dyv[j], gam[j]);
+            s1 = add2(s1, dg[j]);
+            s2 = fma2(dg[j], xh[j], s2);
+            ag[j] = fma2(dyv[j], xh[j], ag[j]);
+            ab[j] = add2(ab[j], dyv[j]);
+        }
+        const float2 ss = warp_sum2(make_float2(s1.x + s1.y, s2.x + s2.y));
+        const float2 c1 = splat2(-ss.x * inv * rs), c2 = splat2(-ss.y * inv * rs);
+        const float2 rsc2 = splat2(rsc);
+#pragma unroll
+        for (int j = 0; j < NW; ++j) {
+            dg[j] = sv[j] ? fma2(xh[j], c2, fma2(dg[j], rs2, c1)) : splat2(0.f);          // rs * (dy*gamma - s1 - xhat*s2)
+            if (has_res) dg[j] = add2(dg[j], unpack_bf16x2(res[j]));
+            ad[j] = fma2(rsc2, dg[j], ad[j]);
+            if (ok[j]) reinterpret_cast<uint32_t*>(dx + size_t(row) * D)[lane + 32 * j] = pack_bf16x2(dg[j].x, dg[j].y);
+        }
+        mu = mu_n; rs = rs_n; rsc = rsc_n;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) res[i] = res_n[i];
+    }
+    // cross-warp reduction of the column accumulators (the ring is idle now: every issued copy has been consumed)
+    __syncthreads();
+    float2* sg = reinterpret_cast<float2*>(ln_smem_raw);
+    float2* sb = sg + WPB * nw;
+    float2* sd = sg + 2 * WPB * nw;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+        if (ok[i]) {
+            const int idx = warp * nw + lane + 32 * i;
+            sg[idx] = ag[i]; sb[idx] = ab[i]; sd[idx] = ad[i];
+        }
+    }
     __syncthreads();
     const float* fg = reinterpret_cast<const float*>(sg);
     const float* fb = reinterpret_cast<const float*>(sb);
@@ -1129,6 +1329,22 @@ static int ln_fwd3_inst(const void* x, const float* gamma, const float* beta, vo
     return err();
 }
 static bool ln_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static bool ln_word_path() {        // OFB_LN_WORDS=0 falls back to the 16-byte-chunk kernels (A/B measurements)
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("OFB_LN_WORDS"); on = (e == nullptr || e[0] != '0') ? 1 : 0; }
+    return on == 1;
+}
+template <int NW>
+static int ln_fwdw_inst(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M, int D, int Dv,
+                        float eps, cudaStream_t s) {
+    const int wpb = 8;
+    int grid = (M + wpb - 1) / wpb;
+    const int cap = num_sms() * 8;
+    if (grid > cap) grid = cap;
+    ln_fwdw_kernel<NW><<<grid, wpb * 32, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta,
+                                                 reinterpret_cast<__nv_bfloat16*>(y), mean, rstd, M, D, Dv, eps);
+    return err();
+}
 int launch_ln_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M, int D, float eps,
                   int Dv, cudaStream_t s) {
     if (D % 8 != 0 || D > 1024) return 1010;
@@ -1138,6 +1354,22 @@ int launch_ln_fwd(const void* x, const float* gamma, const float* beta, void* y,
         if (D == 192) return ln_fwd3_inst<1>(x, gamma, beta, y, mean, rstd, M, eps, s);
         if (D == 384) return ln_fwd3_inst<2>(x, gamma, beta, y, mean, rstd, M, eps, s);
         if (D == 768) return ln_fwd3_inst<4>(x, gamma, beta, y, mean, rstd, M, eps, s);
+    }
+    if (Dv % 2 == 0 && D <= 768 && ln_word_path()) {
+        switch ((D / 2 + 31) / 32) {
+            case 1: return ln_fwdw_inst<1>(x, gamma, beta, y, mean, rstd, M, D, Dv, eps, s);
+            case 2: return ln_fwdw_inst<2>(x, gamma, beta, y, mean, rstd, M, D, Dv, eps, s);
+            case 3: return ln_fwdw_inst<3>(x, gamma, beta, y, mean, rstd, M, D, Dv, eps, s);
+            case 4: return ln_fwdw_inst<4>(x, gamma, beta, y, mean, rstd, M, D, Dv, eps, s);
+            case 5: return ln_fwdw_inst<5>(x, gamma, beta, y, mean, rstd, M, D, Dv, eps, s);
+            case 6: return ln_fwdw_inst<6>(x, gamma, beta, y, mean, rstd, M, D, Dv, eps, s);
+            case 7: return ln_fwdw_inst<7>(x, gamma, beta, y, mean, rstd, M, D, Dv, eps, s);
+            case 8: return ln_fwdw_inst<8>(x, gamma, beta, y, mean, rstd, M, D, Dv, eps, s);
+            case 9: return ln_fwdw_inst<9>(x, gamma, beta, y, mean, rstd, M, D, Dv, eps, s);
+            case 10: return ln_fwdw_inst<10>(x, gamma, beta, y, mean, rstd, M, D, Dv, eps, s);
+            case 11: return ln_fwdw_inst<11>(x, gamma, beta, y, mean, rstd, M, D, Dv, eps, s);
+            default: return ln_fwdw_inst<12>(x, gamma, beta, y, mean, rstd, M, D, Dv, eps, s);
+        }
     }
     switch ((D + 255) / 256) {
         case 1: return ln_fwd_inst<1>(x, gamma, beta, y, mean, rstd, M, D, eps, Dv, s);
@@ -1194,6 +1426,28 @@ static int ln_bwd3_inst(const void* dy, const void* x, const float* mean, const 
                                                    part_dbias, rowscale, rows_per_scale > 0 ? rows_per_scale : 1, M);
     return err();
 }
+template <int NW>
+static int ln_bwdw_inst(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
+                        float* part_dgamma, float* part_dbeta, float* part_dbias, const float* rowscale, int rows_per_scale, int M, int D,
+                        int Dv, const void* dres, cudaStream_t s) {
+    const int wpb = 8;
+    const int grid = ln_bwd_grid(M);
+    const size_t ring = size_t(wpb) * LN_STAGES * 2 * D * 2, red = size_t(3) * wpb * D * sizeof(float);
+    const size_t smem = (ring > red ? ring : red) + wpb * LN_STAGES * 8;
+    static bool configured = false;
+    if (!configured) {
+        const int dmax = 64 * NW;
+        const size_t ring_max = size_t(wpb) * LN_STAGES * 2 * dmax * 2, red_max = size_t(3) * wpb * dmax * sizeof(float);
+        cudaFuncSetAttribute(ln_bwdw_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             int((ring_max > red_max ? ring_max : red_max) + wpb * LN_STAGES * 8));
+        configured = true;
+    }
+    ln_bwdw_kernel<NW><<<grid, wpb * 32, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x),
+                                                    mean, rstd, gamma, reinterpret_cast<__nv_bfloat16*>(dx), part_dgamma, part_dbeta,
+                                                    part_dbias, rowscale, rows_per_scale > 0 ? rows_per_scale : 1, M, D, Dv,
+                                                    reinterpret_cast<const __nv_bfloat16*>(dres));
+    return err();
+}
 int launch_ln_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx, float* part_dgamma,
                   float* part_dbeta, float* part_dbias, const float* rowscale, int rows_per_scale, int M, int D, int Dv, const void* dres,
                   cudaStream_t s) {
@@ -1206,6 +1460,17 @@ int launch_ln_bwd(const void* dy, const void* x, const float* mean, const float*
         if (D == 384) return ln_bwd3_inst<2>(dy, x, mean, rstd, gamma, dx, part_dgamma, part_dbeta, part_dbias, rowscale, rows_per_scale, M, s);
         if (D == 768) return ln_bwd3_inst<4>(dy, x, mean, rstd, gamma, dx, part_dgamma, part_dbeta, part_dbias, rowscale, rows_per_scale, M, s);
     }
+#define OFB_LN_BWDW(n) case n: return ln_bwdw_inst<n>(dy, x, mean, rstd, gamma, dx, part_dgamma, part_dbeta, part_dbias, rowscale, \
+                                                      rows_per_scale, M, D, Dv, dres, s)
+    if (Dv % 2 == 0 && D <= 768 && ln_word_path()) {
+        switch ((D / 2 + 31) / 32) {
+            OFB_LN_BWDW(1); OFB_LN_BWDW(2); OFB_LN_BWDW(3); OFB_LN_BWDW(4); OFB_LN_BWDW(5); OFB_LN_BWDW(6);
+            OFB_LN_BWDW(7); OFB_LN_BWDW(8); OFB_LN_BWDW(9); OFB_LN_BWDW(10); OFB_LN_BWDW(11);
+            default: return ln_bwdw_inst<12>(dy, x, mean, rstd, gamma, dx, part_dgamma, part_dbeta, part_dbias, rowscale,
+                                             rows_per_scale, M, D, Dv, dres, s);
+        }
+    }
+#undef OFB_LN_BWDW
     switch ((D + 255) / 256) {
         case 1: return ln_bwd_inst<1>(dy, x, mean, rstd, gamma, dx, part_dgamma, part_dbeta, part_dbias, rowscale, rows_per_scale, M, D, Dv, dres, s);
         case 2: return ln_bwd_inst<2>(dy, x, mean, rstd, gamma, dx, part_dgamma, part_dbeta, part_dbias, rowscale, rows_per_scale, M, D, Dv, dres, s);

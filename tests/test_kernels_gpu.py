@@ -164,6 +164,48 @@ def test_layernorm_fwd_bwd(cuda_dev, M, D):
     assert rel(out, 1 + 2.0 * pg.sum(0) / gamma) < 1e-5
 
 
+@pytest.mark.parametrize("M,D,Dv,with_res", [(1576, 288, 288, True), (788, 256, 252, True), (1576, 208, 204, False),
+                                              (394, 336, 336, False), (1000, 104, 102, True), (394, 376, 372, True),
+                                              (197, 72, 66, False), (394, 576, 576, True), (394, 200, 198, True)])
+def test_layernorm_pruned_widths(cuda_dev, M, D, Dv, with_res):
+    """LayerNorm over the Dv real channels of a zero-padded pruned embedding (physical width D = Dv rounded up to 8), forward and
+    backward incl. the residual-branch gradient of pre-norm blocks: the word-granular packed kernels (any even Dv)."""
+    from ofb_b200 import ops
+    torch.manual_seed(D + Dv)
+    x = rnd(M, D, s=2.0)
+    x[:, Dv:] = 0
+    gamma, beta = 1 + 0.1 * torch.randn(D, device="cuda"), 0.1 * torch.randn(D, device="cuda")
+    gamma[Dv:] = 0
+    beta[Dv:] = 0
+    y = torch.full_like(x, 7.0)
+    mean, rstd = torch.empty(M, device="cuda"), torch.empty(M, device="cuda")
+    ops.layernorm_fwd(x, gamma, beta, y, mean, rstd, 1e-6, d_valid=Dv)
+    xf = x[:, :Dv].float().requires_grad_(True)
+    gf, bf = gamma[:Dv].clone().requires_grad_(True), beta[:Dv].clone().requires_grad_(True)
+    ref = F.layer_norm(xf, (Dv,), gf, bf, 1e-6)
+    assert rel(y[:, :Dv], ref) < BF16_TOL and float(y[:, Dv:].abs().max() if Dv < D else 0) == 0.0
+    assert rel(mean, xf.mean(-1)) < 1e-4
+    assert rel(rstd, (xf.var(-1, unbiased=False) + 1e-6).rsqrt()) < 1e-4
+    dy = rnd(M, D)
+    dy[:, Dv:] = 0
+    ref.backward(dy[:, :Dv].float())
+    dres = rnd(M, D) if with_res else None
+    if dres is not None:
+        dres[:, Dv:] = 0
+    R = ops.layernorm_bwd_parts(M)
+    dx = torch.full_like(x, 7.0)
+    pg, pb, pd = (torch.zeros(R, D, device="cuda") for _ in range(3))
+    rs = torch.rand((M + 196) // 197, device="cuda")
+    ops.layernorm_bwd(dy, x, mean, rstd, gamma, dx, pg, pb, pd, rs, 197, dres=dres, d_valid=Dv)
+    want = xf.grad + (dres[:, :Dv].float() if dres is not None else 0)
+    assert rel(dx[:, :Dv], want) < BF16_TOL
+    assert float(dx[:, Dv:].abs().max() if Dv < D else 0) == 0.0            # padding stays exactly zero
+    assert rel(pg.sum(0)[:Dv], gf.grad) < 1e-3 and rel(pb.sum(0)[:Dv], bf.grad) < 1e-3
+    assert float(pg.sum(0)[Dv:].abs().max() if Dv < D else 0) == 0.0
+    rows = torch.arange(M, device="cuda") // 197
+    assert rel(pd.sum(0), (rs[rows, None] * dx.float()).sum(0)) < 1e-2
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # attention (layers.py:507-514) forward / backward incl. the bi-mask gate products
 # ---------------------------------------------------------------------------------------------------------------------
