@@ -422,11 +422,16 @@ def main():
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
 
+    # diagnostic only (never set for a reported number): "nocopy" skips the image H2D copy, "unused" copies but steps on the
+    # resident batch - separates copy/compute contention from stream dependencies when e2e lags the device-timed value
+    e2e_variant = os.environ.get("OFB_E2E_VARIANT", "")
+
     def prefetch(i):
         s = i % 2
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[s])
-            stage_img[s].copy_(host_img[i % n_host], non_blocking=True)
+            if e2e_variant != "nocopy":
+                stage_img[s].copy_(host_img[i % n_host], non_blocking=True)
             stage_lab[s].copy_(host_lab[i % n_host], non_blocking=True)
             ready[s].record(copy_stream)
 
@@ -439,7 +444,7 @@ def main():
                 prefetch(i + 1)
             s = i % 2
             torch.cuda.current_stream().wait_event(ready[s])
-            step(stage_img[s], stage_lab[s])
+            step(dev_img[s] if e2e_variant == "unused" else stage_img[s], stage_lab[s])
             consumed[s].record()
             loss_host.copy_(eng.scal, non_blocking=True)
         torch.cuda.current_stream().synchronize()

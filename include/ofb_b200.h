@@ -153,6 +153,9 @@ int ofb_loss_finalize(const float* loss_rows, int B, const float* dec_part, int 
 int ofb_adamw(float* p, float* g, float* m, float* v, void* shadow_bf16, const float* hyper, int nseg,
               const int64_t* seg_end, int64_t n, int zero_grad, void* stream);
 int ofb_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
+/* dst[0..n) = src[0..n) by a kernel; src may be pinned HOST memory (UVA). Used for the per-step hyper vector so that the upload
+ * never waits on a copy engine behind the bulk H2D copy of the next batch (engine.py:118-120 lr / schedule values). */
+int ofb_copy_f32(const float* src, float* dst, int n, void* stream);
 /* out[col] += scale * (scale_dev ? *scale_dev : 1) * sum_rows x[row, col]  (bias gradients of head / decoder) */
 int ofb_colsum_bf16(const void* x, int ld, int R, int N, float* out, float scale, const float* scale_dev, void* stream);
 

@@ -80,6 +80,7 @@ SIGNATURES = {
     "ofb_loss_finalize": [_P, _I, _P, _I, _P, _I, _P, _F, _P, _P],
     "ofb_adamw": [_P, _P, _P, _P, _P, _P, _I, _P, _L, _I, _P],
     "ofb_cast_bf16": [_P, _P, _L, _P],
+    "ofb_copy_f32": [_P, _P, _I, _P],
     "ofb_colsum_bf16": [_P, _I, _I, _I, _P, _F, _P, _P],
     "ofb_bimask_fwd": [_P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "ofb_arch_finalize": [_P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P, _P, _P],

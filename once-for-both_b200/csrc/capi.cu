@@ -17,6 +17,7 @@ int launch_eval_metrics(const float*, const int64_t*, float*, int, int, cudaStre
 int launch_reduce_partials(const float*, int, int, float*, float, const float*, int, cudaStream_t);
 int launch_reduce_partials_multi(const void*, int, cudaStream_t);
 int launch_patchify(const float*, void*, int, int, int, cudaStream_t);
+int launch_copy_f32(const float*, float*, int, cudaStream_t);
 int launch_mixup_batch(const float*, float*, int, int, double, int, int, int, int, int, cudaStream_t);
 int launch_patchify_mixup(const float*, void*, int, int, int, double, int, int, int, int, int, cudaStream_t);
 int launch_mixup_target(const long long*, float*, int, int, double, double, cudaStream_t);
@@ -147,6 +148,7 @@ int ofb_adamw(float* p, float* g, float* m, float* v, void* shadow, const float*
     for (int i = 0; i < nseg; ++i) ends[i] = seg_end[i];
     return ofb::launch_adamw(p, g, m, v, shadow, hyper, nseg, ends, n, zero_grad, ST(stream));
 }
+int ofb_copy_f32(const float* src, float* dst, int n, void* stream) { return ofb::launch_copy_f32(src, dst, n, ST(stream)); }
 int ofb_cast_bf16(const float* src, void* dst, int64_t n, void* stream) { return ofb::launch_cast_bf16(src, dst, n, ST(stream)); }
 int ofb_colsum_bf16(const void* x, int ld, int R, int N, float* out, float scale, const float* scale_dev, void* stream) {
     return ofb::launch_colsum_bf16(x, ld, R, N, out, scale, scale_dev, ST(stream));

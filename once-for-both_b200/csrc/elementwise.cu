@@ -1620,6 +1620,18 @@ int launch_adamw(float* p, float* g, float* m, float* v, void* shadow, const flo
     return err();
 }
 
+// Upload of a small fp32 vector by a kernel: src may be PINNED HOST memory (unified addressing makes it device-readable). The
+// per-step hyper-parameter vector (lr, bias corrections, w_p) goes this way instead of cudaMemcpyAsync so that it never queues on
+// a copy engine behind the bulk H2D copy of the next batch (measured: +2.7 ms per step when it did), and stays in stream order.
+__global__ void copy_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+int launch_copy_f32(const float* src, float* dst, int n, cudaStream_t s) {
+    if (n < 1) return 1011;
+    copy_f32_kernel<<<(n + 255) / 256 > 32 ? 32 : (n + 255) / 256, 256, 0, s>>>(src, dst, n);
+    return err();
+}
+
 int launch_cast_bf16(const float* src, void* dst, long long n, cudaStream_t s) {
     if (n % 4 != 0) return 1013;
     const long long n4 = n / 4;

@@ -277,7 +277,7 @@ class SearchStepEngine:
         self.shadow = torch.zeros(off, **bf)
         self.alpha_patch = torch.ones(1, 1, **f32)          # frozen when --patch_search is off
         nh = self._wp_idx + 8
-        self.hyper_host = torch.zeros(nh, dtype=torch.float32).pin_memory() if self.dev.type == "cuda" else torch.zeros(nh)
+        self._hyper_up = ops.HyperUploader(nh, self.dev)
         self.hyper = torch.zeros(nh, **f32)                    # [segments x 8 ..., w_p]
 
         # ---- bi-mask ----
@@ -566,7 +566,7 @@ class SearchStepEngine:
 
     def _fill_hyper(self, lrs=None):
         lrs = lrs or {}
-        h = self.hyper_host
+        h = self._hyper_up.begin()
         fin = self.finish_search
         for i, (gname, alpha_name) in enumerate(self.segments):
             t = self.step_count + 1 - (self.alpha_restart[alpha_name] if alpha_name else 0)
@@ -837,7 +837,7 @@ class SearchStepEngine:
         key = (images.data_ptr(), labels.data_ptr() if labels is not None else 0, keep,
                target.data_ptr() if target is not None else 0)
         self._fill_hyper(lrs)
-        self.hyper.copy_(self.hyper_host, non_blocking=True)
+        self._hyper_up.upload(self.hyper)
         entry = self._graphs.get(key)
         if entry is None:
             # warm-up outside capture: first launches configure kernel attributes and load modules
@@ -871,8 +871,8 @@ class SearchStepEngine:
     def evaluate(self, images, labels):
         """One evaluate() batch (engine.py:222-257) in the reference's eval mode of an unfinished search: returns the device
         tensor [mean cross entropy, top-1 fraction, top-5 fraction] of this batch; logits stay in self.logits."""
-        self.hyper_host[self._wp_idx] = self.w_p
-        self.hyper.copy_(self.hyper_host, non_blocking=True)
+        self._hyper_up.begin(keep=True)[self._wp_idx] = self.w_p
+        self._hyper_up.upload(self.hyper)
         return self.forward(images, labels, train=False)
 
     # ------------------------------------------------------------------------------------------------------------
@@ -1003,7 +1003,7 @@ class SearchStepEngine:
         Post-search phase (after enter_post_search): target = Mixup soft targets [B, C]; mix = the MixParams when `images` is the
         unmixed batch (blend fused into the im2col)."""
         self._fill_hyper(lrs)
-        self.hyper.copy_(self.hyper_host, non_blocking=True)
+        self._hyper_up.upload(self.hyper)
         self.forward(images, labels, noise, drop_u, target=target, mix=mix)
         self.backward(exchange=update and self.dp_overlap)
         if update:

@@ -92,7 +92,7 @@ class FinetuneStepEngine:
         self.adam_m, self.adam_v = torch.zeros(off, **f32), torch.zeros(off, **f32)
         self.shadow = torch.zeros(off, **bf)
         nh = len(self.groups) * 8
-        self.hyper_host = torch.zeros(nh, dtype=torch.float32).pin_memory() if self.dev.type == "cuda" else torch.zeros(nh)
+        self._hyper_up = ops.HyperUploader(nh, self.dev)
         self.hyper = torch.zeros(nh, **f32)
 
         # ---- activations ----
@@ -276,7 +276,7 @@ class FinetuneStepEngine:
     def _fill_hyper(self, lr=None):
         t = self.step_count + 1
         lr = self.lr if lr is None else lr
-        h = self.hyper_host
+        h = self._hyper_up.begin()
         for i, (lid, dec) in enumerate(self.groups):
             sc = self.layer_decay ** (self.depth + 1 - lid)
             h[i * 8:i * 8 + 7] = torch.tensor([lr * sc, self.wd if dec else 0.0, 0.9, 0.999, 1e-8, 1 - 0.9 ** t, 1 - 0.999 ** t])
@@ -417,7 +417,7 @@ class FinetuneStepEngine:
     def step(self, images, labels=None, target=None, drop_u=None, update=True, lr=None):
         """One train_one_epoch iteration; returns the device tensor scal (scal[0] = loss)."""
         self._fill_hyper(lr)
-        self.hyper.copy_(self.hyper_host, non_blocking=True)
+        self._hyper_up.upload(self.hyper)
         self.forward(images, labels, target, drop_u)
         self.backward()
         if update:
@@ -429,7 +429,7 @@ class FinetuneStepEngine:
         """The same step replayed from a CUDA graph (one graph per input-buffer set)."""
         key = (images.data_ptr(), labels.data_ptr() if labels is not None else 0, target.data_ptr() if target is not None else 0)
         self._fill_hyper(lr)
-        self.hyper.copy_(self.hyper_host, non_blocking=True)
+        self._hyper_up.upload(self.hyper)
         entry = self._graphs.get(key)
         if entry is None:
             cur = torch.cuda.current_stream(self.dev)

@@ -268,6 +268,44 @@ def colsum_bf16(x, R, N, out, scale=1.0, scale_dev=None, ld=None):
                                 cur_stream()), "ofb_colsum_bf16")
 
 
+class HyperUploader:
+    """Per-step upload of the small hyper-parameter vector (lr, AdamW bias corrections, w_p) from a RING of pinned host slots by
+    a kernel (ofb_copy_f32 reads the pinned slot directly). The ring keeps a host that runs several steps ahead of the GPU from
+    overwriting values an enqueued upload has not read yet (each slot's upload is fenced by an event before the slot is
+    refilled); the kernel keeps the upload off the copy engines, where it would queue behind the next batch's bulk H2D copy."""
+
+    def __init__(self, n, device, slots=8):
+        import torch
+        self.n, self.dev = n, device
+        cuda = torch.device(device).type == "cuda"
+        self.slots = [torch.zeros(n, dtype=torch.float32).pin_memory() if cuda else torch.zeros(n) for _ in range(slots)]
+        self.events = [None] * slots
+        self.cur = 0
+
+    @property
+    def host(self):
+        return self.slots[self.cur]
+
+    def begin(self, keep=False):
+        """Advance to the next slot (waiting, normally not at all, until its previous upload has been consumed) and return it;
+        keep=True starts from the previous slot's values."""
+        prev = self.slots[self.cur]
+        self.cur = (self.cur + 1) % len(self.slots)
+        if self.events[self.cur] is not None:
+            self.events[self.cur].synchronize()
+        if keep:
+            self.slots[self.cur].copy_(prev)
+        return self.slots[self.cur]
+
+    def upload(self, dst):
+        import torch
+        _need_cuda(dst)
+        check(lib().ofb_copy_f32(self.slots[self.cur].data_ptr(), ptr(dst), self.n, cur_stream()), "ofb_copy_f32")
+        if self.events[self.cur] is None:
+            self.events[self.cur] = torch.cuda.Event()
+        self.events[self.cur].record()
+
+
 def cast_bf16(src, dst):
     check(lib().ofb_cast_bf16(ptr(src), ptr(dst), src.numel(), cur_stream()), "ofb_cast_bf16")
 

@@ -488,3 +488,22 @@ def test_bimask_fwd_bwd_vs_oracle(cuda_dev, D, H, depth, dead):
         got = grads[offs[k]:offs[k] + P[k].numel()].cpu()
         want = leaves[k].grad.reshape(-1)
         assert rel(got, want) < 2e-4, k
+
+
+def test_hyper_uploader_ring(cuda_dev):
+    """ofb_copy_f32 reads a pinned HOST slot directly (no copy engine); the ring hands out a fresh slot per step so that values of
+    an enqueued upload are never overwritten by a host running ahead."""
+    from ofb_b200 import ops
+    up = ops.HyperUploader(300, "cuda", slots=3)
+    dst = torch.zeros(300, device="cuda")
+    seen = []
+    for step in range(7):
+        h = up.begin()
+        h.copy_(torch.arange(300, dtype=torch.float32) + 1000 * step)
+        up.upload(dst)
+        seen.append(dst.clone())                       # stream-ordered snapshot, no host sync between steps
+    h = up.begin(keep=True)
+    assert float(h[5]) == 6005.0
+    torch.cuda.synchronize()
+    for step, t in enumerate(seen):
+        assert torch.equal(t.cpu(), torch.arange(300, dtype=torch.float32) + 1000 * step)

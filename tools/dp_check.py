@@ -47,7 +47,7 @@ def grads_once(overlap):
     eng.init_params(seed=0)
     eng.set_schedule(0.0)
     eng._fill_hyper()
-    eng.hyper.copy_(eng.hyper_host)
+    eng._hyper_up.upload(eng.hyper)
     eng.forward(img, lab, noise, drop_u)
     eng.backward(exchange=overlap)
     if not overlap:
