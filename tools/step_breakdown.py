@@ -23,15 +23,24 @@ ap.add_argument("--depth", type=int, default=12)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--set", action="append", default=[], help="engine attribute override, e.g. bn_nD=128")
 ap.add_argument("--out", default=None)
+ap.add_argument("--workload", default="search", choices=["search", "finetune"],
+                help="finetune: FinetuneStepEngine on the pruned subnet of bench.py FT_SUBNET (BASELINE configs[4])")
 args = ap.parse_args()
 
 D, H = MODELS[args.model]
-eng = SearchStepEngine(D, H, args.depth, args.batch, drop_path_rate=0.1, lr=2.5e-4)
+if args.workload == "finetune":
+    from bench import FT_SUBNET
+    from ofb_b200.finetune_engine import FinetuneStepEngine
+    eng = FinetuneStepEngine(batch=args.batch, lr=2.5e-4, **FT_SUBNET)
+    args.model = "pruned-subnet"
+else:
+    eng = SearchStepEngine(D, H, args.depth, args.batch, drop_path_rate=0.1, lr=2.5e-4)
 for kv in args.set:
     k, v = kv.split("=")
     setattr(eng, k, int(v))
 eng.init_params(seed=0)
-eng.set_schedule(0.0)
+if args.workload == "search":
+    eng.set_schedule(0.0)
 g = torch.Generator(device="cpu").manual_seed(1)
 img = torch.randn(args.batch, 3, 224, 224, generator=g).cuda()
 lab = torch.randint(0, 1000, (args.batch,), generator=g).cuda()
