@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libofb_b200.so")
+# OFB_B200_LIB: load another build of the same sources instead (debug builds only, e.g. the phase-trace build of tools/attn_trace.py)
+LIB_PATH = os.environ.get("OFB_B200_LIB") or os.path.join(_HERE, "libofb_b200.so")
 
 _lib = None
 

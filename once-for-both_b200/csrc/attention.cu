@@ -319,21 +319,29 @@ __device__ __forceinline__ float bfly16(float (&v)[16]) {
 // epilogue of one 16-column slice of dQ / dK / dV for one token row: multiply by the gate (d pre-gate) and store; the row's
 // gate products are accumulated in registers (ag, reduced once per item), the bias column sums are reduced across the 32
 // rows of the warp right away and added to the shared-memory accumulators. x0/x1 = the row's 16 gated q/k/v values.
-__device__ __forceinline__ void dqkv_slice16(float (&v)[16], bool ok, const uint4& x0, const uint4& x1, __nv_bfloat16* dy,
-                                             const float* gate16, float2 (&ag)[8], float* cs_bias) {
+// AGW: weight of this slice's sum_rows x * dx in the d gate accumulator. q, k and v share one gate; since S = scale q k^T is
+// bilinear, sum_t q[t,c] dq[t,c] == sum_kv k[kv,c] dk[kv,c] (both are sum_{t,kv} q[t,c] dS[t,kv] k[kv,c]), so the k slices
+// carry weight 2 and the q slices none - the dQ epilogue then needs no operand rows at all.
+template <int AGW>
+__device__ __forceinline__ void dqkv_slice16(float (&v)[16], bool ok, const uint4& x0, const uint4& x1, uint32_t stage_row,
+                                             uint32_t chunk, const float* gate16, float2 (&ag)[8], float* cs_bias) {
+    // stage_row: shared-memory address of this token row inside a [32 rows][128 B] SWIZZLE_128B slab (rows of one TMEM lane
+    // quarter); the slab leaves through one TMA store, which clips rows >= T, so rows that are not `ok` may hold anything
     if (ok) {
         const uint32_t xw[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
         uint32_t ow[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float2 vv = make_float2(v[2 * j], v[2 * j + 1]);
-            ag[j] = fma2(unpack_bf16x2(xw[j]), vv, ag[j]);
+            if (AGW == 1) ag[j] = fma2(unpack_bf16x2(xw[j]), vv, ag[j]);
+            if (AGW == 2) ag[j] = fma2(unpack_bf16x2(xw[j]), add2(vv, vv), ag[j]);
             const float2 o = mul2(vv, __ldg(reinterpret_cast<const float2*>(gate16) + j));
             v[2 * j] = o.x; v[2 * j + 1] = o.y;
             ow[j] = pack_bf16x2(o.x, o.y);
         }
-        reinterpret_cast<uint4*>(dy)[0] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-        reinterpret_cast<uint4*>(dy)[1] = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+        const uint32_t sw = lane_id() & 7u;
+        st_shared_v4(stage_row + (((chunk) ^ sw) << 4), make_uint4(ow[0], ow[1], ow[2], ow[3]));
+        st_shared_v4(stage_row + (((chunk + 1) ^ sw) << 4), make_uint4(ow[4], ow[5], ow[6], ow[7]));
     } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = 0.f;
@@ -350,21 +358,37 @@ __device__ __forceinline__ float dot8(const uint4& x, const uint4& y) {
     return d.x + d.y;
 }
 
+// Optional phase trace of the backward kernel (tools/attn_trace.py; compiled only with -DOFB_ATTN_TRACE into a separate debug
+// library): SM clock stamps of compute warps 0 / 15 and of the MMA warp of CTA 0 for items 2..5, plus accumulated barrier waits.
+#ifdef OFB_ATTN_TRACE
+__device__ long long g_attn_trace[3 * 4 * 32];
+#define TRC_ON(role) (blockIdx.x == 0 && lane == 0 && it >= 2 && it < 6 && (role) >= 0)
+#define TRC(role, slot) do { if (TRC_ON(role)) g_attn_trace[((role) * 4 + (it - 2)) * 32 + (slot)] = clock64(); } while (0)
+#define TRC_ACC(role, slot, t0) do { if (TRC_ON(role)) g_attn_trace[((role) * 4 + (it - 2)) * 32 + (slot)] += clock64() - (t0); } while (0)
+#define TRC_NOW() clock64()
+#else
+#define TRC(role, slot) do { } while (0)
+#define TRC_ACC(role, slot, t0) do { } while (0)
+#define TRC_NOW() 0ll
+#endif
+
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
-                const __grid_constant__ CUtensorMap tm_do, const AttnArgs a) {
+                const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_out,
+                const __grid_constant__ CUtensorMap tm_o, const AttnArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sQ = smem_u32(smem);                   // 2 q tiles
     const uint32_t sDO = sQ + 2 * TILE_B;                 // 2 q tiles
     const uint32_t sK = sDO + 2 * TILE_B;
     const uint32_t sV = sK + KV_B;
     const uint32_t sP = sV + KV_B;                        // 2 buffers (even / odd sub-tiles), P then dS in place
-    uint8_t* tail = smem + 4 * TILE_B + 2 * KV_B + 2 * PB_B;
+    const uint32_t sST = sP + 2 * PB_B;                   // 2 staging tiles [128 rows][64 bf16] of the d qkv epilogues (TMA stores)
+    uint8_t* tail = smem + 4 * TILE_B + 2 * KV_B + 2 * PB_B + 2 * TILE_B;
     float* cs = reinterpret_cast<float*>(tail);                 // [2 parities][256]: gate[64] | bias q,k,v [3][64]
     const uint32_t sXD = smem_u32(tail + 2048);                 // [2 q tiles][4 column groups][128 rows] delta partials
     uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 2048 + 4096);
     enum { QK_FULL = 0, DOV_FULL, ITEM_EMPTY, S_FULL, P_FULL = S_FULL + 2, DP_FULL = P_FULL + 2, DS_FULL = DP_FULL + 2,
-           PB_FREE = DS_FULL + 2, ACC_FULL = PB_FREE + 2, ACC_EMPTY, DQ_FULL, DQ_EMPTY, NBAR };
+           PB_FREE = DS_FULL + 2, ACC_FULL = PB_FREE + 2, ACC_EMPTY, DQ_FULL, DQ_EMPTY, XREAD, NBAR };
     auto bar = [&](int k) { return smem_u32(&bars[k]); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[NBAR]);
 
@@ -384,6 +408,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             mbar_init(bar(DS_FULL + s2), BWD_CW); mbar_init(bar(PB_FREE + s2), 1);
         }
         mbar_init(bar(ACC_FULL), 1); mbar_init(bar(ACC_EMPTY), BWD_CW); mbar_init(bar(DQ_FULL), 1); mbar_init(bar(DQ_EMPTY), BWD_CW);
+        mbar_init(bar(XREAD), BWD_CW);
         mbar_fence_init();
     }
     if (warp == BWD_CW + 1) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
@@ -399,11 +424,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     if (warp == BWD_CW) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_kv); tma_prefetch_desc(&tm_do);
+            tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_kv); tma_prefetch_desc(&tm_do); tma_prefetch_desc(&tm_out);
             int it = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
                 const int b = item / a.H, h = item % a.H;
                 mbar_wait(bar(ITEM_EMPTY), (it & 1) ^ 1);        // every MMA of the previous item has retired
+                mbar_wait(bar(XREAD), (it & 1) ^ 1);             // ... and its epilogues have read their q / k / v rows out of the tiles
                 mbar_arrive_expect_tx(bar(QK_FULL), nh * TILE_B + KV_B);
                 tma_load_5d(sQ, &tm_q, bar(QK_FULL), 0, 0, h, 0, b);
                 tma_load_5d(sK, &tm_kv, bar(QK_FULL), 0, 0, h, 1, b);
@@ -421,7 +447,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     for (int i = 0; i < nh; ++i) {
                         tma_prefetch_5d(&tm_q, 0, i * QT, h2, 0, b2);
                         tma_prefetch_4d(&tm_do, h2 * HD, i * QT, b2, 0);
+                        // the forward output rows and the LSE feed the per-row statistics at the very start of the item, read by
+                        // plain loads: without this they come from HBM and every compute warp idles ~4k clocks per item
+                        tma_prefetch_4d(&tm_o, h2 * HD, i * QT, b2, 0);
                     }
+                    const char* lse2 = reinterpret_cast<const char*>(a.lse + (size_t(b2) * a.H + h2) * a.T);
+                    for (int off = 0; off < a.T * 4 + 127; off += 128)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(lse2 + off));
                 }
             }
         }
@@ -447,7 +479,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             int it = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
                 const uint32_t pi = it & 1;
+                TRC(2, 0);
                 mbar_wait(bar(QK_FULL), pi);
+                TRC(2, 1);
                 tc_fence_after();
                 issue_s(0);
                 if (nt > 1) issue_s(1);
@@ -462,9 +496,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     for (int i = 0; i < np; ++i) {
                         const uint32_t par = (i == 0 ? use0 : use1) & 1u;
                         const uint32_t pbuf = sP + i * PB_B, doa = sDO + i * TILE_B;
-                        mbar_wait(bar(P_FULL + i), par);
+                        { const long long tw = TRC_NOW(); mbar_wait(bar(P_FULL + i), par); TRC_ACC(2, 8, tw); }
                         if (t0 == 0 && i == 0) mbar_wait(bar(DOV_FULL), pi);
-                        if (i == 0) { mbar_wait(bar(ACC_EMPTY), (n_acc & 1u) ^ 1u); ++n_acc; }   // previous dK / dV read out
+                        if (i == 0) { const long long tw = TRC_NOW(); mbar_wait(bar(ACC_EMPTY), (n_acc & 1u) ^ 1u); ++n_acc; TRC_ACC(2, 9, tw); }   // previous dK / dV read out
                         tc_fence_after();
 #pragma unroll
                         for (int k = 0; k < QT / 16; ++k)
@@ -484,8 +518,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                         const uint32_t par = (i == 0 ? use0 : use1) & 1u;
                         if (i == 0) ++use0; else ++use1;
                         const uint32_t pbuf = sP + i * PB_B, qa = sQ + i * TILE_B;
-                        mbar_wait(bar(DS_FULL + i), par);
-                        if (t0 == 0 && i == 0) mbar_wait(bar(DQ_EMPTY), pi ^ 1u);       // previous item's dQ read out
+                        { const long long tw = TRC_NOW(); mbar_wait(bar(DS_FULL + i), par); TRC_ACC(2, 10, tw); }
+                        if (t0 == 0 && i == 0) { const long long tw = TRC_NOW(); mbar_wait(bar(DQ_EMPTY), pi ^ 1u); TRC_ACC(2, 11, tw); }       // previous item's dQ read out
                         tc_fence_after();
                         if (t0 + 2 + i < nt) issue_s(t0 + 2 + i);
                         for (uint32_t k = 0; k < nj / 16; ++k)
@@ -501,6 +535,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 }
                 umma_commit(bar(DQ_FULL));
                 umma_commit(bar(ITEM_EMPTY));
+                TRC(2, 2);
             }
         }
     } else {
@@ -513,13 +548,29 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         float v[32];
         uint32_t use0 = 0, use1 = 0;
         uint32_t n_acc = 0;
+        // per-row scalars of an item (LSE of this thread's two q rows, DropPath multiplier of the image): fetched one item ahead,
+        // inside the previous item's wait for its last MMAs - read at the item start they were two serialised global-load
+        // latencies (~3k clocks) that every compute warp sat through
+        auto row_scalars = [&](int item, float& l0, float& l1, float& dp) {
+            const int b = item / a.H, h = item % a.H;
+            const float* lp = a.lse + (size_t(b) * a.H + h) * a.T;
+            l0 = __ldg(lp + min(r, a.T - 1));
+            l1 = __ldg(lp + min(QT + r, a.T - 1));
+            dp = a.drop_scale != nullptr ? __ldg(a.drop_scale + b) : 1.f;
+        };
+        float lse_n0 = 0.f, lse_n1 = 0.f, dps_n = 1.f;
+        if (int(blockIdx.x) < n_items) row_scalars(blockIdx.x, lse_n0, lse_n1, dps_n);
         int it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const int b = item / a.H, h = item % a.H;
             const uint32_t pi = it & 1;
+#ifdef OFB_ATTN_TRACE
+            const int trole = warp == 0 ? 0 : (warp == 15 ? 1 : -1);
+#endif
+            TRC(trole, 0);
             float* cs_gate = cs + pi * 256 + cg * BWD_EC;
             float* cs_bias = cs + pi * 256 + 64 + cg * BWD_EC;
-            const float dps = a.drop_scale != nullptr ? __ldg(a.drop_scale + b) : 1.f;
+            const float dps = dps_n;
             const float inv_dps = dps != 0.f ? 1.f / dps : 0.f;
             const float* gate16 = a.gate + h * HD + cg * BWD_EC;
             float2 ag[8];
@@ -527,45 +578,63 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             for (int j = 0; j < 8; ++j) ag[j] = make_float2(0.f, 0.f);
             // ---- per-row statistics of both q tiles: LSE and delta = rowsum(dO * O) / droppath ----
             float nlse2_0 = -INFINITY, nlse2_1 = -INFINITY, ndsc_0 = 0.f, ndsc_1 = 0.f;   // rows >= T: exp2(-inf) = 0 everywhere
-            {
-                uint4 ov[2][2];
+            // delta: 8 lanes share a row (one 16-byte chunk each), so a warp instruction reads 4 whole 128-byte rows of O - with one
+            // row per lane (the TMEM mapping used everywhere else) every load instruction cost 32 LSU wavefronts. Thread tid -> row
+            // (tid >> 3) + 64 * pass, chunk tid & 7. The loads are issued here and consumed only after the first P phases
+            // (stats_finish): delta is not needed before the first dS phase, and the O rows take ~2.5k clocks to arrive.
+            const int tid = threadIdx.x, ch = tid & 7;
+            uint4 ov[2][2];
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const int t = i * QT + r;
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) ov[i][c] = make_uint4(0, 0, 0, 0);
-                    if (i < nh && t < a.T) {
-                        const float l2 = -__ldg(a.lse + (size_t(b) * a.H + h) * a.T + t) * 1.4426950408889634f;
-                        if (i == 0) nlse2_0 = l2; else nlse2_1 = l2;
-                        const uint4* po = reinterpret_cast<const uint4*>(a.o_in + (size_t(b) * a.T + t) * D + h * HD + cg * BWD_EC);
-#pragma unroll
-                        for (int c = 0; c < 2; ++c) ov[i][c] = __ldg(po + c);
-                    }
+            for (int i = 0; i < 2; ++i) {
+                const int t = i * QT + r;
+                if (i < nh && t < a.T) {
+                    const float l2 = -(i == 0 ? lse_n0 : lse_n1) * 1.4426950408889634f;
+                    if (i == 0) nlse2_0 = l2; else nlse2_1 = l2;
                 }
+#pragma unroll
+                for (int ps = 0; ps < 2; ++ps) {
+                    const int t2 = i * QT + ps * 64 + (tid >> 3);
+                    ov[i][ps] = make_uint4(0, 0, 0, 0);
+                    if (i < nh && t2 < a.T)
+                        ov[i][ps] = __ldg(reinterpret_cast<const uint4*>(a.o_in + (size_t(b) * a.T + t2) * D + h * HD) + ch);
+                }
+            }
+            TRC(trole, 15);
+            TRC(trole, 1);
+            auto stats_finish = [&]() {
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int ps = 0; ps < 2; ++ps)   // pins the unpacking of the loaded words below this point (it is pure ALU work
+                                                     // and would otherwise be hoisted above the P phases, stalling them on the loads)
+                        asm volatile("" : "+r"(ov[i][ps].x), "+r"(ov[i][ps].y), "+r"(ov[i][ps].z), "+r"(ov[i][ps].w));
                 mbar_wait(bar(DOV_FULL), pi);
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     if (i < nh) {
-                        float d = 0.f;
 #pragma unroll
-                        for (int c = 0; c < 2; ++c) d += dot8(ov[i][c], ld_shared_v4(sDO + i * TILE_B + sw128_offset(r, cg * 2 + c)));
-                        st_shared_f32(sXD + ((i * 4 + cg) * 128 + r) * 4, d * inv_dps);
+                        for (int ps = 0; ps < 2; ++ps) {
+                            const int row = ps * 64 + (tid >> 3);
+                            float d = dot8(ov[i][ps], ld_shared_v4(sDO + i * TILE_B + sw128_offset(row, ch)));
+                            d += __shfl_xor_sync(0xffffffffu, d, 1);
+                            d += __shfl_xor_sync(0xffffffffu, d, 2);
+                            d += __shfl_xor_sync(0xffffffffu, d, 4);
+                            if (ch == 0) st_shared_f32(sXD + (i * 128 + row) * 4, d * inv_dps);
+                        }
                     }
                 }
-                named_bar_sync(2 + q, 128);                      // the four warps (column groups) of this row quarter
-                ndsc_0 = -((ld_shared_f32(sXD + r * 4) + ld_shared_f32(sXD + (128 + r) * 4)) +
-                           (ld_shared_f32(sXD + (256 + r) * 4) + ld_shared_f32(sXD + (384 + r) * 4))) * a.scale;
-                if (nh == 2) ndsc_1 = -((ld_shared_f32(sXD + (512 + r) * 4) + ld_shared_f32(sXD + (640 + r) * 4)) +
-                                        (ld_shared_f32(sXD + (768 + r) * 4) + ld_shared_f32(sXD + (896 + r) * 4))) * a.scale;
-            }
+                named_bar_sync(1, BWD_CT);                       // rows are spread over all compute warps here
+                ndsc_0 = -ld_shared_f32(sXD + r * 4) * a.scale;
+                if (nh == 2) ndsc_1 = -ld_shared_f32(sXD + (128 + r) * 4) * a.scale;
+            };
             // ---- P = exp(S*scale - LSE) of sub-tile (q tile i, kv half j) over this warp's 32 kv columns ----
             auto phase_p = [&](int i, int j) {
                 const uint32_t par = (i == 0 ? use0 : use1) & 1u;
                 const uint32_t tR = tmem + i * 128 + lane_base;
                 const uint32_t pbuf = sP + i * PB_B;
                 const float2 nl2 = splat2(i == 0 ? nlse2_0 : nlse2_1);
-                mbar_wait(bar(S_FULL + i), par);
-                mbar_wait(bar(PB_FREE + i), par ^ 1u);            // the MMAs that read this buffer one pair ago have retired
+                { const long long tw = TRC_NOW(); mbar_wait(bar(S_FULL + i), par); TRC_ACC(trole, 20, tw); }
+                { const long long tw = TRC_NOW(); mbar_wait(bar(PB_FREE + i), par ^ 1u); TRC_ACC(trole, 21, tw); }   // the MMAs that read this buffer one pair ago have retired
                 tc_fence_after();
                 {
                     const int col = cg * BWD_PC;                  // column inside the sub-tile
@@ -601,7 +670,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 const uint32_t tR = tmem + i * 128 + lane_base;
                 const uint32_t pbuf = sP + i * PB_B;
                 const float2 nd2 = splat2(i == 0 ? ndsc_0 : ndsc_1);
-                mbar_wait(bar(DP_FULL + i), par);
+                { const long long tw = TRC_NOW(); mbar_wait(bar(DP_FULL + i), par); TRC_ACC(trole, 22, tw); }
                 tc_fence_after();
                 {
                     const int col = cg * BWD_PC;
@@ -636,57 +705,91 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar(DS_FULL + i));
             };
-            // ---- dK_j / dV_j epilogue of a finished kv half (kv row = j*128 + r, head-dim columns [32 cg, 32 cg + 32)) ----
-            auto epi_kv = [&](int j) {
+            // ---- epilogues: d q / d k / d v rows leave through shared memory. Each TMEM lane quarter (the 4 warps with the same
+            //      q) owns a [32 rows][128 B] swizzled slab of each staging tile and stores it with ONE bulk tensor copy (rows >= T
+            //      are clipped by the hardware) - per-lane 32-byte global stores cost 32 LSU wavefronts per instruction and made
+            //      the three epilogues half of the item time. The gated q / k / v values of the row (for the d gate products)
+            //      are read from the operand tiles still in shared memory; XREAD tells the producer when the last such read is
+            //      done so that the next item's tiles may land.
+            const uint32_t slab0 = sST + q * 4096 + lane * 128, slab1 = slab0 + TILE_B;
+            const bool issuer = cg == 0 && lane == 0;
+            auto stage_open = [&]() {                            // the previous round's stores have read the slabs
+                if (issuer) bulk_wait_read<0>();
+                named_bar_sync(2 + q, 128);
+            };
+            auto stage_close = [&](int which0, int row0, int which1, int row1) {
+                fence_proxy_async_smem();
+                named_bar_sync(2 + q, 128);
+                if (issuer) {
+                    if (row0 + q * 32 < a.T) tma_store_5d(&tm_out, sST + q * 4096, 0, row0 + q * 32, h, which0, b);
+                    if (row1 + q * 32 < a.T) tma_store_5d(&tm_out, sST + TILE_B + q * 4096, 0, row1 + q * 32, h, which1, b);
+                    bulk_commit();
+                }
+            };
+            // ---- dK_j / dV_j epilogue of a finished kv half (kv row = j*128 + r, head-dim columns [16 cg, 16 cg + 16)) ----
+            auto epi_kv = [&](int j, bool last) {
                 const int kv = j * QT + r;
                 const bool kv_ok = kv < a.T;
-                const size_t off = ((size_t(b) * a.T + (kv_ok ? kv : 0)) * 3 + 1) * D + h * HD + cg * BWD_EC;
-                const uint4 k0 = __ldg(reinterpret_cast<const uint4*>(a.qkv + off)), k1 = __ldg(reinterpret_cast<const uint4*>(a.qkv + off) + 1);
-                const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(a.qkv + off + D)), v1 = __ldg(reinterpret_cast<const uint4*>(a.qkv + off + D) + 1);
-                mbar_wait(bar(ACC_FULL), n_acc & 1u);
+                const uint4 k0 = ld_shared_v4(sK + sw128_offset(kv, cg * 2)), k1 = ld_shared_v4(sK + sw128_offset(kv, cg * 2 + 1));
+                const uint4 v0 = ld_shared_v4(sV + sw128_offset(kv, cg * 2)), v1 = ld_shared_v4(sV + sw128_offset(kv, cg * 2 + 1));
+                if (last) {          // last reads of this item's operand tiles: the producer may refill them once the MMAs retire
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar(XREAD));
+                    if (item + int(gridDim.x) < n_items) row_scalars(item + gridDim.x, lse_n0, lse_n1, dps_n);
+                }
+                { const long long tw = TRC_NOW(); mbar_wait(bar(ACC_FULL), n_acc & 1u); TRC_ACC(trole, 23, tw); }
                 ++n_acc;
                 tc_fence_after();
-                float w1[16], w2[16];
+                // dK then dV, one 16-column slice in registers at a time (the kernel sits at its 96-register ceiling)
+                float w1[16];
                 tmem_ld16(tDK + lane_base + cg * BWD_EC, w1);
-                tmem_ld16(tDV + lane_base + cg * BWD_EC, w2);
+                tmem_ld_wait();
+                stage_open();
+                dqkv_slice16<2>(w1, kv_ok, k0, k1, slab0, cg * 2, gate16, ag, cs_bias + 64);
+                tmem_ld16(tDV + lane_base + cg * BWD_EC, w1);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar(ACC_EMPTY));
-                dqkv_slice16(w1, kv_ok, k0, k1, a.dqkv + off, gate16, ag, cs_bias + 64);
-                dqkv_slice16(w2, kv_ok, v0, v1, a.dqkv + off + D, gate16, ag, cs_bias + 128);
+                dqkv_slice16<1>(w1, kv_ok, v0, v1, slab1, cg * 2, gate16, ag, cs_bias + 128);
+                stage_close(1, j * QT, 2, j * QT);
             };
+            TRC(trole, 2);
             if (nt == 1) {
                 phase_p(0, 0);
+                stats_finish();
                 phase_ds(0, 0);
             } else {
-                phase_p(0, 0); phase_p(1, 0);
-                phase_ds(0, 0); phase_ds(1, 0);
-                phase_p(0, 1);
-                epi_kv(0);                                       // its TMEM reads release dK / dV for the second kv half
-                phase_p(1, 1);
-                phase_ds(0, 1); phase_ds(1, 1);
+                phase_p(0, 0); TRC(trole, 3); phase_p(1, 0);
+                stats_finish(); TRC(trole, 4);
+                phase_ds(0, 0); TRC(trole, 5); phase_ds(1, 0); TRC(trole, 6);
+                phase_p(0, 1); TRC(trole, 7);
+                epi_kv(0, false);                                // its TMEM reads release dK / dV for the second kv half
+                TRC(trole, 8);
+                phase_p(1, 1); TRC(trole, 9);
+                phase_ds(0, 1); TRC(trole, 10); phase_ds(1, 1); TRC(trole, 11);
             }
-            epi_kv(nh - 1);
+            epi_kv(nh - 1, true);
+            TRC(trole, 12);
             // ---- dQ epilogue of both q tiles ----
             {
-                mbar_wait(bar(DQ_FULL), pi);
+                { const long long tw = TRC_NOW(); mbar_wait(bar(DQ_FULL), pi); TRC_ACC(trole, 24, tw); }
                 tc_fence_after();
-#pragma unroll 1
-                for (int i = 0; i < nh; ++i) {
-                    const int t = i * QT + r;
-                    const size_t qoff = ((size_t(b) * a.T + (t < a.T ? t : 0)) * 3 + 0) * D + h * HD + cg * BWD_EC;
-                    const uint4 x0 = __ldg(reinterpret_cast<const uint4*>(a.qkv + qoff)), x1 = __ldg(reinterpret_cast<const uint4*>(a.qkv + qoff) + 1);
-                    float w1[16];
-                    tmem_ld16(tDQ + i * HD + lane_base + cg * BWD_EC, w1);
+                float w1[16];
+                tmem_ld16(tDQ + lane_base + cg * BWD_EC, w1);
+                tmem_ld_wait();
+                stage_open();
+                const uint4 none = make_uint4(0, 0, 0, 0);
+                dqkv_slice16<0>(w1, r < a.T, none, none, slab0, cg * 2, gate16, ag, cs_bias);
+                if (nh == 2) {
+                    tmem_ld16(tDQ + HD + lane_base + cg * BWD_EC, w1);
                     tmem_ld_wait();
-                    if (i == nh - 1) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bar(DQ_EMPTY));
-                    }
-                    dqkv_slice16(w1, t < a.T, x0, x1, a.dqkv + qoff, gate16, ag, cs_bias);
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(DQ_EMPTY));
+                if (nh == 2) dqkv_slice16<0>(w1, QT + r < a.T, none, none, slab1, cg * 2, gate16, ag, cs_bias);
+                stage_close(0, 0, 0, nh == 2 ? QT : a.T);
             }
             // d gate: q, k and v contributions of all rows of this warp
             {
@@ -696,8 +799,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 const float sg = bfly16(tsum);
                 if ((lane & 1) == 0) atomicAdd(cs_gate + (lane >> 1), sg);
             }
+            TRC(trole, 13);
             // ---- per-item column sums -> global partials; the accumulator of this parity is re-zeroed for item it+2 ----
             named_bar_sync(1, BWD_CT);
+            TRC(trole, 14);
             {
                 const int tid = threadIdx.x;   // 0..511
                 if (tid < 256) {
@@ -710,6 +815,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             }
         }
     }
+    if (warp < BWD_CW && (warp >> 2) == 0 && lane == 0) bulk_wait<0>();      // this quarter's last stores have completed
     tc_fence_before();
     __syncthreads();
     if (warp == BWD_CW + 1) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem, 512); }
@@ -719,7 +825,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 // host
 // ---------------------------------------------------------------------------------------------
 static constexpr int FWD_SMEM = 2 * TILE_B + 2 * KV_B + 2 * PBUF_B + 4096 + 256;
-static constexpr int BWD_SMEM = 4 * TILE_B + 2 * KV_B + 2 * PB_B + 2048 + 4096 + 256;
+static constexpr int BWD_SMEM = 4 * TILE_B + 2 * KV_B + 2 * PB_B + 2 * TILE_B + 2048 + 4096 + 256;
 
 static int make_qkv_maps(const void* qkv, int B, int T, int H, CUtensorMap* tq, CUtensorMap* tkv) {
     const uint64_t D = uint64_t(H) * HD;
@@ -760,15 +866,26 @@ int launch_attn_bwd(const void* qkv, const void* o, const void* d_o, const float
         if (e != cudaSuccess) return int(e);
         configured = true;
     }
-    CUtensorMap tq, tkv, tdo;
+    CUtensorMap tq, tkv, tdo, tout, to;
     int r = make_qkv_maps(qkv, B, T, H, &tq, &tkv);
     if (r) return r;
+    {
+        // d qkv leaves in [32 rows][64 columns] slabs (one per TMEM lane quarter), same 5-D geometry as the qkv input
+        const uint64_t D = uint64_t(H) * HD;
+        uint64_t dims[5] = {HD, uint64_t(T), uint64_t(H), 3, uint64_t(B)};
+        uint64_t str[5] = {1, 3 * D, HD, D, uint64_t(T) * 3 * D};
+        uint32_t box[5] = {HD, 32, 1, 1, 1};
+        r = make_tmap_bf16(&tout, dqkv, 5, dims, str, box);
+        if (r) return r;
+    }
     {
         const uint64_t D = uint64_t(H) * HD;
         uint64_t dims[4] = {D, uint64_t(T), uint64_t(B), 1};
         uint64_t str[4] = {1, D, uint64_t(T) * D, uint64_t(B) * T * D};
         uint32_t box[4] = {HD, QT, 1, 1};
         r = make_tmap_bf16(&tdo, d_o, 4, dims, str, box);
+        if (r) return r;
+        r = make_tmap_bf16(&to, o, 4, dims, str, box);          // L2 prefetch of the forward output rows only
         if (r) return r;
     }
     AttnArgs a{};
@@ -782,8 +899,25 @@ int launch_attn_bwd(const void* qkv, const void* o, const void* d_o, const float
     a.part_gate = part_gate; a.part_bias = part_bias;
     const int items = B * H;
     const int grid = items < num_sms() ? items : num_sms();
-    attn_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM, s>>>(tq, tkv, tdo, a);
+    attn_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM, s>>>(tq, tkv, tdo, tout, to, a);
     return int(cudaGetLastError());
 }
 
+#ifdef OFB_ATTN_TRACE
 }  // namespace ofb
+extern "C" int ofb_debug_attn_trace(long long* out, int n, int reset);
+namespace ofb {
+int attn_trace_read(long long* out, int n, int reset) {
+    const size_t bytes = sizeof(long long) * size_t(n < 3 * 4 * 32 ? n : 3 * 4 * 32);
+    cudaDeviceSynchronize();
+    if (out != nullptr && cudaMemcpyFromSymbol(out, g_attn_trace, bytes) != cudaSuccess) return 1;
+    if (reset) { static long long zeros[3 * 4 * 32]; cudaMemcpyToSymbol(g_attn_trace, zeros, sizeof(zeros)); }
+    return 0;
+}
+#endif
+
+}  // namespace ofb
+
+#ifdef OFB_ATTN_TRACE
+extern "C" int ofb_debug_attn_trace(long long* out, int n, int reset) { return ofb::attn_trace_read(out, n, reset); }
+#endif
