@@ -84,7 +84,8 @@ __device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
 }
 
 __global__ void __launch_bounds__(FWD_THREADS, 1)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, const AttnArgs a) {
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
+                const __grid_constant__ CUtensorMap tm_o, const AttnArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sQ = smem_u32(smem);                       // 2 tiles
     const uint32_t sK = sQ + 2 * TILE_B;
@@ -213,6 +214,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             mx = fmaxf(mx, ld_shared_f32(x_other));
             const float mxs = mx * sl2;
             // ---- pass 2: P = exp(S*scale - max), row sums, P -> shared memory (bf16, swizzled K-major A operand) ----
+            // (the first 64 kv columns of these rows double as the O staging slab of the previous item: its bulk store, issued
+            //  by lane 0 of this very warp when hf == 0, must have read the slab before P overwrites it)
+            if (hf == 0) {
+                if (lane == 0) bulk_wait_read<0>();
+                __syncwarp();
+            }
             float sum = 0.f;
 #pragma unroll 1
             for (int c = 0; c < n32 + 1; ++c) {
@@ -256,19 +263,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(slot_bar(s, 3));
-            if (t < a.T) {
+            // O rows leave through shared memory: the two warps of a row quarter fill a [32 rows][128 B] swizzled slab (in the P
+            // buffer of the slot, free now that the P V MMA has retired) and one bulk tensor store writes it, clipping rows >= T -
+            // a 64-byte global store per lane costs 32 LSU wavefronts per instruction
+            {
                 const float inv = dps / sum;
-                uint4* dst = reinterpret_cast<uint4*>(a.o + (size_t(b) * a.T + t) * (a.H * HD) + h * HD + hf * 32);
+                const uint32_t slab = pS + q * 4096 + lane * 128;
+                const uint32_t sw = lane & 7u;
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) {
                     uint4 pk;
                     pk.x = pack_bf16x2(v[q4 * 8 + 0] * inv, v[q4 * 8 + 1] * inv); pk.y = pack_bf16x2(v[q4 * 8 + 2] * inv, v[q4 * 8 + 3] * inv);
                     pk.z = pack_bf16x2(v[q4 * 8 + 4] * inv, v[q4 * 8 + 5] * inv); pk.w = pack_bf16x2(v[q4 * 8 + 6] * inv, v[q4 * 8 + 7] * inv);
-                    dst[q4] = pk;
+                    st_shared_v4(slab + (((hf * 4 + q4) ^ sw) << 4), pk);
                 }
-                if (hf == 0) a.lse[(size_t(b) * a.H + h) * a.T + t] = mx * a.scale + logf(sum);
+                if (t < a.T && hf == 0) a.lse[(size_t(b) * a.H + h) * a.T + t] = mx * a.scale + logf(sum);
+                fence_proxy_async_smem();
+                named_bar_sync(pair_bar, 64);
+                if (hf == 0 && lane == 0 && s * QT + q * 32 < a.T) {
+                    tma_store_4d(&tm_o, pS + q * 4096, h * HD, s * QT + q * 32, b, 0);
+                    bulk_commit();
+                }
             }
         }
+        if (hf == 0 && lane == 0) bulk_wait<0>();
     }
     tc_fence_before();
     __syncthreads();
@@ -845,15 +863,24 @@ int launch_attn_fwd(const void* qkv, void* o, float* lse, const float* drop_scal
         if (e != cudaSuccess) return int(e);
         configured = true;
     }
-    CUtensorMap tq, tkv;
+    CUtensorMap tq, tkv, to;
     int r = make_qkv_maps(qkv, B, T, H, &tq, &tkv);
     if (r) return r;
+    {
+        // O leaves in [32 rows][64 columns] slabs (one per TMEM lane quarter of a q tile)
+        const uint64_t D = uint64_t(H) * HD;
+        uint64_t dims[4] = {D, uint64_t(T), uint64_t(B), 1};
+        uint64_t str[4] = {1, D, uint64_t(T) * D, uint64_t(B) * T * D};
+        uint32_t box[4] = {HD, 32, 1, 1};
+        r = make_tmap_bf16(&to, o, 4, dims, str, box);
+        if (r) return r;
+    }
     AttnArgs a{};
     a.B = B; a.T = T; a.H = H; a.scale = scale; a.drop_scale = drop_scale;
     a.o = reinterpret_cast<__nv_bfloat16*>(o); a.lse = lse;
     const int items = B * H;
     const int grid = items < num_sms() ? items : num_sms();
-    attn_fwd_kernel<<<grid, FWD_THREADS, FWD_SMEM, s>>>(tq, tkv, a);
+    attn_fwd_kernel<<<grid, FWD_THREADS, FWD_SMEM, s>>>(tq, tkv, to, a);
     return int(cudaGetLastError());
 }
 
