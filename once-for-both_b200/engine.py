@@ -993,6 +993,46 @@ class SearchStepEngine:
             self.release_graphs()
         return changed
 
+    # ------------------------------------------------------------------------------------------------------------
+    # checkpoint / resume in a state-dict format with shape metadata. The reference pickles the whole model object
+    # plus three optimizer state_dicts (search.py:671-740) and unpickles it in resume() (search.py:302-372) because compress()
+    # changes shapes; here the shapes travel as metadata next to the tensors, which keep the reference's names and shapes.
+    def state_dict(self):
+        named = lambda arena: {k: self._unpad(k, self._view(arena, k)).detach().cpu().clone() for k in self.offsets}
+        pruned = None if self.spaces is None else dict(embed=self.Dv, heads=list(self.heads), head_dims=list(self.hdims),
+                                                       hiddens=list(self.hids),
+                                                       spaces={k: (list(v[0]), list(v[1])) for k, v in self.spaces.items()})
+        return dict(
+            format="ofb_b200.search/1",
+            config=dict(embed_dim=self.D0, num_heads=self.H, depth=self.depth, mlp_ratio=self.hid // self.D0, num_classes=self.C,
+                        img=self.img, patch=self.P, drop_path_rate=self.drop_path_rate, lr=self.lr, weight_decay=self.wd,
+                        eps_ln=self.eps_ln, smoothing=self.smoothing, accum_iter=self.accum_iter, warmup_epochs=self.warmup_epochs,
+                        max_ratio=self.max_ratio, min_ratio=self.min_ratio, **self._loss_w),
+            pruned=pruned, switches={k: v.clone().cpu() for k, v in self.switches.items()},
+            params=named(self.params), adam_m=named(self.adam_m), adam_v=named(self.adam_v),
+            step_count=self.step_count, alpha_restart=dict(self.alpha_restart), w_p=self.w_p, keep_ratio=self.keep_ratio,
+            schedule_touched=self._schedule_touched, decoder_frozen=self.decoder_frozen)
+
+    @classmethod
+    def from_state_dict(cls, sd, batch, device="cuda", process_group=None):
+        """Rebuild the engine a state_dict() was taken from (any batch size): same shapes (pruned or not), switch cells, parameters,
+        Adam moments with their per-tensor restart steps, schedule and post-search state."""
+        if sd.get("format") != "ofb_b200.search/1":
+            raise ValueError(f"not a SearchStepEngine checkpoint: format {sd.get('format')!r}")
+        eng = cls(batch=batch, device=device, process_group=process_group, switches={k: v.clone() for k, v in sd["switches"].items()},
+                  pruned=sd["pruned"], **sd["config"])
+        if set(sd["params"]) != set(eng.offsets):
+            raise ValueError("checkpoint tensors do not match the engine's parameter set")
+        eng.load_params(sd["params"])
+        for arena, key in ((eng.adam_m, "adam_m"), (eng.adam_v, "adam_v")):
+            for k in eng.offsets:
+                eng._view(arena, k).copy_(eng._pad(k, sd[key][k].to(eng.dev, torch.float32).reshape(eng.ref_shapes[k])))
+        eng.step_count = int(sd["step_count"])
+        eng.alpha_restart.update(sd["alpha_restart"])
+        eng.w_p, eng.keep_ratio = float(sd["w_p"]), float(sd["keep_ratio"])
+        eng._schedule_touched, eng.decoder_frozen = bool(sd["schedule_touched"]), bool(sd["decoder_frozen"])
+        return eng
+
     def release_graphs(self):
         """Drop every captured step graph (required before the process group is destroyed when the graphs hold NCCL
         launches, and after a prune event changes shapes)."""
