@@ -62,6 +62,11 @@ __global__ void __launch_bounds__(BM_THREADS) bimask_fwd_kernel(const BimaskModu
     const BimaskModule md = mods[blockIdx.x];
     const int tid = threadIdx.x;
     const int n = md.heads * md.dim;
+    // blockIdx.y: a module's units are split over gridDim.y CTAs (the rank of a unit is a count over the whole row: 1536^2
+    // comparisons for an MLP module, which one CTA per module turned into a 120 us kernel at the head of every step). Every part
+    // loads all scores (cheap); part 0 alone writes the per-module outputs.
+    const int part = blockIdx.y, per_part = (n + int(gridDim.y) - 1) / int(gridDim.y);
+    const int i_begin = part * per_part, i_end = min(n, i_begin + per_part);
     const int ncell = md.n_i * md.n_j;
     const float* alpha = params + md.alpha_off;
     const float* score = params + md.score_off;
@@ -90,8 +95,10 @@ __global__ void __launch_bounds__(BM_THREADS) bimask_fwd_kernel(const BimaskModu
             const float sigma = var / (1.f - 1.f / alive);
             l = ent + tanf(1.5707963267948966f - 3.14159265358979323846f * sigma) / alive;
         }
-        sp_loss[blockIdx.x] = l;     // score-norm term added below
-        for (int k = 0; k < ncell; ++k) aprob[blockIdx.x * MAX_CELLS + k] = a[k];
+        if (part == 0) {
+            sp_loss[blockIdx.x] = l;     // score-norm term added below
+            for (int k = 0; k < ncell; ++k) aprob[blockIdx.x * MAX_CELLS + k] = a[k];
+        }
         s_alive = alive;
     }
     float ssum = 0.f;
@@ -104,7 +111,7 @@ __global__ void __launch_bounds__(BM_THREADS) bimask_fwd_kernel(const BimaskModu
     }
     ssum = block_sum(ssum, red);   // includes __syncthreads -> a[], sig[], sc[] visible
     const int alive = s_alive;
-    if (tid == 0 && alive > 1) sp_loss[blockIdx.x] += md.coef * ssum;
+    if (tid == 0 && part == 0 && alive > 1) sp_loss[blockIdx.x] += md.coef * ssum;
 
     // ---- head ranks (attention): descending by sum_c sigmoid(score[h,c]) ----
     if (md.kind == 2) {
@@ -123,8 +130,7 @@ __global__ void __launch_bounds__(BM_THREADS) bimask_fwd_kernel(const BimaskModu
     }
 
     // ---- per-channel rank (within head), table lookup, gate ----
-    float tsum = 0.f;
-    for (int i = tid; i < n; i += BM_THREADS) {
+    for (int i = i_begin + tid; i < i_end; i += BM_THREADS) {
         const int h = i / md.dim, c = i % md.dim;
         const float s = sc[i];
         const float* row = sc + h * md.dim;
@@ -138,14 +144,24 @@ __global__ void __launch_bounds__(BM_THREADS) bimask_fwd_kernel(const BimaskModu
             for (int jj = 0; jj < md.n_j; ++jj)
                 if (wj[jj] > r) t += a[ii * md.n_j + jj];
         }
-        tsum += t;
         // a finished module (one cell left: its score has been finalised, layers.py:629 / 939 / 275) gates with the frozen score
         // itself (layers.py:196-197, 518-521, 859-860)
         gate[md.gate_off + h * md.stride + c] = alive > 1 ? w_p * sig[i] + (1.f - w_p) * t : s;
         rank[md.gate_off + h * md.stride + c] = hr * md.dim + r;
     }
-    tsum = block_sum(tsum, red);
-    if (tid == 0) wsum[blockIdx.x] = tsum;   // == weighted_mask.sum()
+    // weighted_mask.sum(): the ranks of a row are a permutation of 0..dim-1, so the sum over units of table[head rank][rank] does
+    // not depend on the scores: sum_h sum_ii [n_i > head rank] sum_jj a[ii][jj] * min(w_jj, dim)
+    if (tid == 0 && part == 0) {
+        float tsum = 0.f;
+        for (int h = 0; h < md.heads; ++h) {
+            const int hr = (md.kind == 2) ? rank_h[h] : 0;
+            for (int ii = 0; ii < md.n_i; ++ii) {
+                if (md.kind == 2 && !(ni[ii] > hr)) continue;
+                for (int jj = 0; jj < md.n_j; ++jj) tsum += a[ii * md.n_j + jj] * float(min(wj[jj], md.dim));
+            }
+        }
+        wsum[blockIdx.x] = tsum;
+    }
 }
 
 // ---- FLOPs loss + total architecture loss + d loss / d wsum (vision_transformer.py:759-783, losses.py:93-102) ----
@@ -276,8 +292,9 @@ int launch_bimask_fwd(const void* mods, int nmod, int max_n, const float* params
                       const float* w_p_ptr, float* gate, int* rank, float* aprob, float* wsum, float* sp_loss, cudaStream_t s) {
     const size_t smem = size_t(2) * max_n * sizeof(float);
     if (smem > 48 * 1024) return 1020;
-    bimask_fwd_kernel<<<nmod, BM_THREADS, smem, s>>>(reinterpret_cast<const BimaskModule*>(mods), params, switches, widths, w_p_ptr, gate,
-                                                     rank, aprob, wsum, sp_loss);
+    const int parts = max_n > 512 ? 8 : (max_n > 256 ? 2 : 1);
+    bimask_fwd_kernel<<<dim3(nmod, parts), BM_THREADS, smem, s>>>(reinterpret_cast<const BimaskModule*>(mods), params, switches, widths,
+                                                                 w_p_ptr, gate, rank, aprob, wsum, sp_loss);
     return int(cudaGetLastError());
 }
 
