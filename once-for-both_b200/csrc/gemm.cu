@@ -50,7 +50,9 @@ struct GemmCfg {
     // issued a whole tile time before its use (HBM latency is ~3 panel times). Two pipelines: two slots each.
     static constexpr int AUX_SLOTS = (TMA_OUT != 2) ? 0 : (NPIPE == 2 ? 4 : (BN == 128 ? 3 : (BN == 192 ? 4 : ((BN == 256 && EPI == EPI_FC2_DGRAD) ? 3 : 2))));
     static constexpr int AUX_BYTES = AUX_SLOTS * PANEL_BYTES;
-    static constexpr int SCRATCH_BYTES = 0;
+    // weight-gradient epilogue: 2 KB per epilogue warp to regroup a [32 rows][16 columns] fp32 block so that 4 lanes share a row
+    // segment of the red.global.add (it fits in what the operand ring leaves over: the stage count is unchanged for BN >= 192)
+    static constexpr int SCRATCH_BYTES = (EPI == EPI_WGRAD) ? EW * 2048 : 0;
     // per-column epilogue vectors, double-buffered by tile parity (the transposed-hidden epilogues use per-thread scalars)
     static constexpr int VEC_BYTES = (EPI == EPI_FC1 || EPI == EPI_FC2_DGRAD) ? 0 : 2 * 2 * BN * 4;
     static constexpr int BAR_BYTES = 256;
@@ -624,20 +626,39 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         acc_db += cdb2.x + cdb2.y;
                     }
                 } else if (EPI == EPI_WGRAD) {
-                    if (row_ok && nvalid > 0) {
-                        float* dst = reinterpret_cast<float*>(g.out0) + size_t(row) * g.ld0 + col0;
-                        if (nvalid >= 32) {
+                    if (nvalid >= 32) {
+                        // One row per lane (the TMEM mapping) makes every red.global.add.v4 touch 32 different gradient rows = 32
+                        // LSU wavefronts. The warp regroups its [32 rows][16 columns] half-chunk through 2 KB of shared memory
+                        // (float4 slots swizzled by (row >> 1) & 3: conflict-free both ways) so that 4 lanes cover 64 contiguous
+                        // bytes of a row: 8 wavefronts per instruction.
+                        float* sc = reinterpret_cast<float*>(auxbuf + Cfg::AUX_BYTES) + (etid >> 5) * 512;
+                        float* out = reinterpret_cast<float*>(g.out0);
+                        const int rbase = m_blk * BM + q * 32;
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * i),
-                                             "f"(v[4 * i] * gs), "f"(v[4 * i + 1] * gs), "f"(v[4 * i + 2] * gs), "f"(v[4 * i + 3] * gs)
-                                             : "memory");
+                        for (int hv = 0; hv < 2; ++hv) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                *reinterpret_cast<float4*>(sc + lane * 16 + ((i ^ ((lane >> 1) & 3)) << 2)) =
+                                    make_float4(v[hv * 16 + 4 * i] * gs, v[hv * 16 + 4 * i + 1] * gs, v[hv * 16 + 4 * i + 2] * gs,
+                                                v[hv * 16 + 4 * i + 3] * gs);
+                            __syncwarp();
+#pragma unroll
+                            for (int ps = 0; ps < 4; ++ps) {
+                                const int rl = ps * 8 + (lane >> 2), idx = lane & 3;
+                                const float4 w = *reinterpret_cast<const float4*>(sc + rl * 16 + ((idx ^ ((rl >> 1) & 3)) << 2));
+                                if (rbase + rl < g.M) {
+                                    float* dst = out + size_t(rbase + rl) * g.ld0 + col0 + hv * 16 + idx * 4;
+                                    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(w.x), "f"(w.y),
+                                                 "f"(w.z), "f"(w.w) : "memory");
+                                }
                             }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                if (i < nvalid) atomicAdd(dst + i, v[i] * gs);
+                            __syncwarp();
                         }
+                    } else if (row_ok && nvalid > 0) {
+                        float* dst = reinterpret_cast<float*>(g.out0) + size_t(row) * g.ld0 + col0;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (i < nvalid) atomicAdd(dst + i, v[i] * gs);
                     }
                 } else if (EPI == EPI_PATCH) {
                     // rows are (image b, patch l); output row skips the cls slot of each image.
