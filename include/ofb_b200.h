@@ -96,7 +96,7 @@ int ofb_layernorm_bwd_ex(const void* dy, const void* x, const float* mean, const
 /* out[col] (+)= scale * sum_r part[r,col] / (div_by ? div_by[col] : 1) */
 int ofb_reduce_partials(const float* part, int R, int N, float* out, float scale, const float* div_by, int accumulate,
                         void* stream);
-/* up to 8 such reductions in one launch (the gradient pieces that fall out of one backward kernel) */
+/* up to 12 such reductions in one launch (the gradient pieces that fall out of the backward kernels of one block) */
 typedef struct ofb_reduce_job {
     const float* part;
     float* out;

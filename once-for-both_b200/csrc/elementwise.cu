@@ -774,7 +774,7 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, int R, in
 // several independent reductions in one launch (blockIdx.y = job): the gradient pieces that fall out of one backward
 // kernel (LayerNorm: d gamma, d beta, d bias; fc2 dgrad: d gate, d bias; ...) are finished together.
 struct ReduceJob { const float* part; float* out; const float* div_by; int R, N; float scale; int accumulate; };
-struct ReduceJobs { ReduceJob j[8]; };
+struct ReduceJobs { ReduceJob j[12]; };
 __global__ void reduce_partials_multi_kernel(const ReduceJobs jobs) {
     const ReduceJob jb = jobs.j[blockIdx.y];
     const int col = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -1486,7 +1486,7 @@ int launch_reduce_partials(const float* part, int R, int N, float* out, float sc
 }
 
 int launch_reduce_partials_multi(const void* jobs_host, int njobs, cudaStream_t s) {
-    if (njobs < 1 || njobs > 8) return 1015;
+    if (njobs < 1 || njobs > 12) return 1015;
     ReduceJobs jobs;
     memset(&jobs, 0, sizeof(jobs));
     const ReduceJob* src = reinterpret_cast<const ReduceJob*>(jobs_host);

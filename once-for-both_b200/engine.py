@@ -343,6 +343,8 @@ class SearchStepEngine:
         self.dconv = torch.empty(ML, D, **bf)
         self.ln_parts = ops.layernorm_bwd_parts(M)
         self.pg_, self.pb_, self.pd_ = (torch.empty(self.ln_parts, D, **f32) for _ in range(3))
+        # second set: the partials of a block's LayerNorm 2 are finished together with those of its LayerNorm 1 (one launch per block)
+        self.pg2_, self.pb2_, self.pd2_ = (torch.empty(self.ln_parts, D, **f32) for _ in range(3))
         mt = (M + 127) // 128
         self.cp0, self.cp1 = torch.empty(self.mlp_parts, hid, **f32), torch.empty(self.mlp_parts, hid, **f32)
         self.att_pg, self.att_pb = torch.empty(B, Amax, **f32), torch.empty(B, 3 * Amax, **f32)
@@ -755,15 +757,15 @@ class SearchStepEngine:
                 spare.append(G4)
             # LayerNorm 2 (+ proj bias grad)
             G2 = spare.pop()
-            ops.layernorm_bwd(G3, a["x2"], a["mean2"], a["rstd2"], self.p(pre + "norm2.weight"), G2, self.pg_, self.pb_,
-                              self.pd_, dp1, T, d_valid=Dv, dres=G4 if pn else None)
+            ops.layernorm_bwd(G3, a["x2"], a["mean2"], a["rstd2"], self.p(pre + "norm2.weight"), G2, self.pg2_, self.pb2_,
+                              self.pd2_, dp1, T, d_valid=Dv, dres=G4 if pn else None)
             spare.append(G3)
             if pn:
                 spare.append(G4)
-            # one launch finishes the column partials of the fc2 data-gradient GEMM and of this LayerNorm
-            ops.reduce_partials_multi(mlp_jobs + [(self.pg_, R, D, self.g(pre + "norm2.weight")),
-                                                  (self.pb_, R, D, self.g(pre + "norm2.bias")),
-                                                  (self.pd_, R, D, self.g(pre + "attn.proj.bias"))])
+            # the column partials of the fc2 data-gradient GEMM and of this LayerNorm are finished at the end of the block, in the
+            # same launch as the attention / LayerNorm 1 partials (nothing in between reads their results)
+            mlp_jobs += [(self.pg2_, R, D, self.g(pre + "norm2.weight")), (self.pb2_, R, D, self.g(pre + "norm2.bias")),
+                         (self.pd2_, R, D, self.g(pre + "attn.proj.bias"))]
             # proj
             ops.gemm(ops.EPI_WGRAD, G2, a["o"], M=D, N=A, K=M, out0=self.g(pre + "attn.proj.weight"), a_mn=True, b_mn=True)
             ops.gemm(ops.EPI_STORE, G2, self.w(pre + "attn.proj.weight"), M=M, N=A, K=D, out0=dO, b_mn=True, rowscale=dp1,
@@ -793,7 +795,7 @@ class SearchStepEngine:
             ln1_jobs = [(self.pg_, R, D, self.g(pre + "norm1.weight")), (self.pb_, R, D, self.g(pre + "norm1.bias"))]
             if has_prev:
                 ln1_jobs.append((self.pd_, R, D, self.g(f"blocks.{l - 1}.mlp.fc2.bias")))
-            ops.reduce_partials_multi(attn_jobs + ln1_jobs)
+            ops.reduce_partials_multi(mlp_jobs + attn_jobs + ln1_jobs)
             G = G0
             if red is not None:
                 red.on_block_done(l)

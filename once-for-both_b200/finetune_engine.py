@@ -131,6 +131,7 @@ class FinetuneStepEngine:
         self.dconv = torch.empty(ML, Dp, **bf)
         self.ln_parts = ops.layernorm_bwd_parts(M)
         self.pg_, self.pb_, self.pd_ = (torch.empty(self.ln_parts, Dp, **f32) for _ in range(3))
+        self.pg2_, self.pb2_, self.pd2_ = (torch.empty(self.ln_parts, Dp, **f32) for _ in range(3))    # LayerNorm 2 (see backward)
         self.cp0, self.cp1 = torch.empty(self.mlp_parts, hmax, **f32), torch.empty(self.mlp_parts, hmax, **f32)
         self.att_pg, self.att_pb = torch.empty(B, Amax, **f32), torch.empty(B, 3 * Amax, **f32)
         self.e_gx, self.e_pos, self.e_mt = (torch.empty(T, Dp, **f32) for _ in range(3))
@@ -371,13 +372,13 @@ class FinetuneStepEngine:
             G3 = spare.pop()                                   # d LN2 output
             ops.gemm(ops.EPI_STORE, du, self.w(pre + "mlp.fc1.weight"), M=M, N=Dp, K=hid, out0=G3, a_mn=True, b_mn=True)
             G2 = spare.pop()                                   # d x2 (total) = LN2 backward + the residual branch G4
-            ops.layernorm_bwd(G3, a["x2"], a["mean2"], a["rstd2"], self.p(pre + "norm2.weight"), G2, self.pg_, self.pb_,
-                              self.pd_, dp1, T, dres=G4, d_valid=Dv)
+            ops.layernorm_bwd(G3, a["x2"], a["mean2"], a["rstd2"], self.p(pre + "norm2.weight"), G2, self.pg2_, self.pb2_,
+                              self.pd2_, dp1, T, dres=G4, d_valid=Dv)
             spare.append(G3)
             spare.append(G4)
-            ops.reduce_partials_multi(mlp_jobs + [(self.pg_, R, Dp, self.g(pre + "norm2.weight")),
-                                                  (self.pb_, R, Dp, self.g(pre + "norm2.bias")),
-                                                  (self.pd_, R, Dp, self.g(pre + "attn.proj.bias"))])
+            # finished at the end of the block together with the attention / LayerNorm 1 partials (one launch per block)
+            mlp_jobs += [(self.pg2_, R, Dp, self.g(pre + "norm2.weight")), (self.pb2_, R, Dp, self.g(pre + "norm2.bias")),
+                         (self.pd2_, R, Dp, self.g(pre + "attn.proj.bias"))]
             ops.gemm(ops.EPI_WGRAD, G2, a["o"], M=Dp, N=A, K=M, out0=self.g(pre + "attn.proj.weight"), a_mn=True, b_mn=True)
             ops.gemm(ops.EPI_STORE, G2, self.w(pre + "attn.proj.weight"), M=M, N=A, K=Dp, out0=dO, b_mn=True, rowscale=dp1,
                      rows_per_scale=T)
@@ -397,7 +398,7 @@ class FinetuneStepEngine:
             ln1_jobs = [(self.pg_, R, Dp, self.g(pre + "norm1.weight")), (self.pb_, R, Dp, self.g(pre + "norm1.bias"))]
             if has_prev:
                 ln1_jobs.append((self.pd_, R, Dp, self.g(f"blocks.{l - 1}.mlp.fc2.bias")))
-            ops.reduce_partials_multi(attn_jobs + ln1_jobs)
+            ops.reduce_partials_multi(mlp_jobs + attn_jobs + ln1_jobs)
             G = G0
         # ---- embedding: x0 = [cls + pos_0 ; conv(patches) + bias + pos_{1..L}] ----
         ops.embed_bwd(G, self.xs[0], ones, self.zero_mask, self.dconv, self.e_gx, self.e_pos, self.e_mt, B, T, Dp)
