@@ -105,6 +105,13 @@ class BimaskTable:
             nonlocal gate_off
             wj, ni = space(prefix, wj, ni)
             sw = switches[prefix].to(torch.bool).reshape(len(ni) if kind == 2 else 1, len(wj))
+            # MAEBlock normalises only the channels whose weighted embed mask is > 0 and concatenates the rest behind them
+            # (vision_transformer.py:193-201). Every state compress() can leave keeps the widest surviving embed cell equal to
+            # the current width (it truncates first), so all channels are reserved and this engine's all-channel LayerNorm is
+            # the same thing; a hand-built switch table whose widest cell is dead would silently diverge - refuse it.
+            if kind == 0 and not bool(sw[:, -1].any()):
+                raise ValueError("patch_embed switch cells: the widest embedding candidate must be alive (the reference would "
+                                 "normalise a channel subset, vision_transformer.py:193-201; compress() never leaves this state)")
             self.modules.append(dict(prefix=prefix, kind=kind, dim=dim, heads=heads, stride=stride, slot=slot, n_i=sw.shape[0],
                                      n_j=sw.shape[1], switch_off=len(sw_bytes), width_off=len(widths), gate_off=gate_off,
                                      coef=coef, loss_w=loss_w))
@@ -367,7 +374,10 @@ class SearchStepEngine:
         early, tail = dp.overlap_plan(self.n_arena, blk_rng, int(os.environ.get("OFB_DP_BLOCKS_PER_BUCKET", "2")),
                                       int(os.environ.get("OFB_DP_TAIL_BLOCKS", "2")))
         self._reducer = dp.OverlappedReducer(self.grads, self.world, self.pg, early, tail)
-        self._graphs = {}          # (images ptr, labels ptr, keep) -> (CUDAGraph, kernel launches per replay)
+        # the single exchange after backward as nodes of the step graph (no host launches between backward and AdamW)
+        self.dp_in_graph = self.world > 1 and os.environ.get("OFB_DP_GRAPH", "0") == "1"
+        self._graphs = {}          # (images ptr, labels ptr, keep, target ptr, update, pinned noise) -> (CUDAGraph, launches per replay)
+        self._noise_in = None      # persistent PMIM-noise input of graphs captured with a pinned draw
         self._side = None          # side stream of the gate construction (see forward)
         self._side2 = None         # side stream of the PMIM target normalisation
 
@@ -575,8 +585,12 @@ class SearchStepEngine:
             b1, b2 = (0.5, 0.999) if gname == "arch" else (0.9, 0.999)
             lr = lrs.get(gname, self.lr)
             wd = 0.0 if gname.endswith("_nd") else self.wd
-            if (gname == "arch" and fin) or (gname.startswith("dec_") and self.decoder_frozen):
-                lr = wd = 0.0          # optimizer_arch = None after finish_search (engine.py:206-208); optimizer_decoder = None
+            # optimizer_arch = None after finish_search (engine.py:206-208); optimizer_decoder = None in the post-search phase;
+            # the alpha of a module that is already down to one cell left optimizer_arch when it was finalised (requires_grad
+            # False and removed from the param group, optim.py:179-182): no decay either
+            done = gname == "arch" and int(self.switches[alpha_name[:-len(".alpha")]].sum()) == 1
+            if (gname == "arch" and fin) or done or (gname.startswith("dec_") and self.decoder_frozen):
+                lr = wd = 0.0
             h[i * 8:i * 8 + 7] = torch.tensor([lr, wd, b1, b2, 1e-8, 1 - b1 ** t, 1 - b2 ** t])
         h[self._wp_idx] = self.w_p
 
@@ -828,46 +842,67 @@ class SearchStepEngine:
                   zero_grad=True)
         self.step_count += 1
 
-    def step_graphed(self, images, labels, lrs=None, target=None):
-        """One full search step replayed from a CUDA graph (forward, backward, AdamW; the whole step is ~270 launches of
-        ~10-200 us, so per-launch host work would otherwise bound it). The graph is captured on first use for this
-        (images buffer, labels buffer, PMIM keep count) and re-captured when the schedule changes the keep count; lr, AdamW
-        bias corrections and w_p are read from the device-side `hyper` vector, so they may change every step. Random draws
-        (PMIM noise, DropPath) come from torch's graph-safe generator. Multi-GPU: the all-reduce and the update stay
-        outside the graph (see step())."""
+    def step_graphed(self, images, labels, lrs=None, target=None, update=True, noise=None):
+        """One full search step replayed from a CUDA graph (forward, backward, [gradient exchange,] AdamW; the whole step is
+        ~255 launches of ~10-200 us, so per-launch host work would otherwise bound it). The graph is captured on first use for
+        this (images buffer, labels buffer, PMIM keep count, update flag) and re-captured when the schedule changes the keep
+        count; lr, AdamW bias corrections and w_p are read from the device-side `hyper` vector, so they may change every step.
+        Random draws (PMIM noise, DropPath) come from torch's graph-safe generator; `noise` (optional, [B, L]) pins the PMIM
+        draw instead (copied into a persistent buffer the graph reads).
+        update=False is a gradient-accumulation micro-step (engine.py:152, 169: backward on every micro-step, optimizers only
+        when (data_iter_step + 1) % accum_iter == 0): its graph ends after backward, gradients keep accumulating in the arena,
+        no exchange, no AdamW, and step_count does not advance. The reference all-reduces on every micro-step (no no_sync,
+        SURVEY App. B-9); averaging once on the boundary gives the same mean.
+        Multi-GPU: with OFB_DP_GRAPH=1 the bucket all-reduces and the update are nodes of the same graph (no host launches
+        between backward and the update); otherwise they follow the replay from the host."""
         keep = int(self.L * self.keep_ratio)
         key = (images.data_ptr(), labels.data_ptr() if labels is not None else 0, keep,
-               target.data_ptr() if target is not None else 0)
+               target.data_ptr() if target is not None else 0, bool(update), noise is not None)
         self._fill_hyper(lrs)
         self._hyper_up.upload(self.hyper)
+        if noise is not None:
+            if self._noise_in is None:
+                self._noise_in = torch.empty(self.B, self.L, dtype=torch.float32, device=self.dev)
+            self._noise_in.copy_(noise)
+        nz = self._noise_in if noise is not None else None
+        in_graph_dp = self.world > 1 and (self.dp_overlap or self.dp_in_graph)
         entry = self._graphs.get(key)
         if entry is None:
-            # warm-up outside capture: first launches configure kernel attributes and load modules
+            # warm-up outside capture: first launches configure kernel attributes and load modules. Gradients accumulated by
+            # earlier micro-steps must survive it.
             cur = torch.cuda.current_stream(self.dev)
             side = torch.cuda.Stream(device=self.dev)
             side.wait_stream(cur)
             with torch.cuda.stream(side):
-                self.forward(images, labels, target=target)
+                saved = self.grads.clone()
+                self.forward(images, labels, target=target, noise=nz)
                 self.backward(exchange=self.dp_overlap)      # also brings up the NCCL communicator before capture
-                self.grads.zero_()
+                if self.world > 1 and self.dp_in_graph and not self.dp_overlap:
+                    self.allreduce_grads()
+                self.grads.copy_(saved)
+                del saved
             cur.wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             n0 = ops.LAUNCHES
             with torch.cuda.graph(graph):
-                self.forward(images, labels, target=target)
-                self.backward(exchange=self.dp_overlap)      # overlapped exchange: the NCCL launches are graph nodes
-                if self.world <= 1 or self.dp_overlap:
-                    ops.adamw(self.params, self.grads, self.adam_m, self.adam_v, self.shadow, self.hyper, self._seg_end_c,
-                              zero_grad=True)
+                self.forward(images, labels, target=target, noise=nz)
+                self.backward(exchange=self.dp_overlap and update)      # overlapped exchange: the NCCL launches are graph nodes
+                if update:
+                    if self.world > 1 and self.dp_in_graph and not self.dp_overlap:
+                        self.allreduce_grads()
+                    if self.world <= 1 or in_graph_dp:
+                        ops.adamw(self.params, self.grads, self.adam_m, self.adam_v, self.shadow, self.hyper, self._seg_end_c,
+                                  zero_grad=True)
             entry = (graph, ops.LAUNCHES - n0)
             self._graphs[key] = entry
         entry[0].replay()
         ops._count(entry[1])
-        if self.world > 1 and not self.dp_overlap:
-            self.allreduce_grads()
-            ops.adamw(self.params, self.grads, self.adam_m, self.adam_v, self.shadow, self.hyper, self._seg_end_c,
-                      zero_grad=True)
-        self.step_count += 1
+        if update:
+            if self.world > 1 and not in_graph_dp:
+                self.allreduce_grads()
+                ops.adamw(self.params, self.grads, self.adam_m, self.adam_v, self.shadow, self.hyper, self._seg_end_c,
+                          zero_grad=True)
+            self.step_count += 1
         return self.scal
 
     def evaluate(self, images, labels):

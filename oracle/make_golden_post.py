@@ -32,10 +32,10 @@ from ofb_oracle import (ModelCfg, adamw_step, default_switches, group_hparams, m
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden", "post")
 CASES = {
     # compress_at: epoch fraction of the finalising prune event (fixes w_p inside the finalised scores)
-    "p1_tiny_d2": dict(D=192, H=3, depth=2, B=2, phase=1, compress_at=15.0, epoch_frac=15.4, dpr=0.1, lr=1e-3),
-    "p2_tiny_d2_mix": dict(D=192, H=3, depth=2, B=4, phase=2, compress_at=15.0, epoch_frac=25.0, dpr=0.1, lr=1e-3, lam=0.37,
+    "p1_tiny_d2": dict(D=192, H=3, depth=2, B=8, phase=1, compress_at=15.0, epoch_frac=15.4, dpr=0.1, lr=1e-3),
+    "p2_tiny_d2_mix": dict(D=192, H=3, depth=2, B=8, phase=2, compress_at=15.0, epoch_frac=25.0, dpr=0.1, lr=1e-3, lam=0.37,
                            box=None),
-    "p2_small_d3_cut": dict(D=384, H=6, depth=3, B=2, phase=2, compress_at=20.0, epoch_frac=21.0, dpr=0.0, lr=5e-4,
+    "p2_small_d3_cut": dict(D=384, H=6, depth=3, B=8, phase=2, compress_at=20.0, epoch_frac=21.0, dpr=0.0, lr=5e-4,
                             lam=None, box=(40, 152, 96, 224)),
 }
 FROZEN_P2 = ("alpha_patch", "mask_token", "decoder.0.weight", "decoder.0.bias")

@@ -23,14 +23,14 @@ from ofb_oracle import ModelCfg, _desc_rank, default_switches, train_step, w_p_s
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden", "pruned_step")
 CASES = {
-    "tiny_d2": dict(D=192, H=3, depth=2, B=2, epoch_frac=6.0, dpr=0.1, lr=1e-3, offset=0),
-    "small_d3": dict(D=384, H=6, depth=3, B=2, epoch_frac=11.0, dpr=0.1, lr=1e-3, offset=1),
-    "small_d2": dict(D=384, H=6, depth=2, B=3, epoch_frac=2.0, dpr=0.0, lr=1e-3, offset=2),
+    "tiny_d2": dict(D=192, H=3, depth=2, B=8, epoch_frac=6.0, dpr=0.1, lr=1e-3, offset=0),
+    "small_d3": dict(D=384, H=6, depth=3, B=8, epoch_frac=11.0, dpr=0.1, lr=1e-3, offset=1),
+    "small_d2": dict(D=384, H=6, depth=2, B=8, epoch_frac=2.0, dpr=0.0, lr=1e-3, offset=2),
     # mixed events incl. finalisation (make_golden_prune.script_alphas): finished modules gate with their frozen score, and a
     # finished embedding search switches the blocks to standard pre-norm
-    "mixed_tiny_d2": dict(D=192, H=3, depth=2, B=2, epoch_frac=7.0, dpr=0.1, lr=1e-3, offset=0, mixed=True),
-    "mixed_small_d3": dict(D=384, H=6, depth=3, B=2, epoch_frac=12.0, dpr=0.1, lr=1e-3, offset=0, mixed=True),
-    "mixed_tiny_d3": dict(D=192, H=3, depth=3, B=2, epoch_frac=20.0, dpr=0.0, lr=1e-3, offset=3, mixed=True),
+    "mixed_tiny_d2": dict(D=192, H=3, depth=2, B=8, epoch_frac=7.0, dpr=0.1, lr=1e-3, offset=0, mixed=True),
+    "mixed_small_d3": dict(D=384, H=6, depth=3, B=8, epoch_frac=12.0, dpr=0.1, lr=1e-3, offset=0, mixed=True),
+    "mixed_tiny_d3": dict(D=192, H=3, depth=3, B=8, epoch_frac=20.0, dpr=0.0, lr=1e-3, offset=3, mixed=True),
 }
 
 

@@ -1,9 +1,10 @@
 """TEST INFRASTRUCTURE ONLY — import shim that lets the *unmodified* reference under /root/reference be imported in
 this container (no timm / apex / matplotlib installed, torch >= 2 has no torch._six).
 
-Used only by oracle/make_golden.py and oracle/time_reference.py to pin the oracle restatement (oracle/ofb_oracle.py)
-against the real reference and to produce tests/golden/*.npz.  /root/reference does not exist on the GPU box, so
-nothing under tests/ with the gpu marker, smoke() or bench.py may import this module.
+Used by oracle/make_golden*.py to pin the oracle restatement (oracle/ofb_oracle.py) against the real reference and to
+produce tests/golden/*.npz, and by oracle/ref_runner.py (the reference arm of bench.py and the drop-in tests).
+/root/reference does not exist on the GPU box: there the byte-identical staged copy oracle/_ref/ (oracle/make_ref.py,
+git-ignored, shipped with the snapshot) is imported instead.
 
 The stand-ins restate the standard timm-0.4 semantics of the handful of third-party symbols the hot path touches
 (SURVEY.md §8c): trunc_normal_, to_2tuple, DropPath, LabelSmoothingCrossEntropy, SoftTargetCrossEntropy, accuracy.
@@ -16,7 +17,15 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-REFERENCE_ROOT = "/root/reference"
+import os
+
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+REFERENCE_ROOT = "/root/reference" if os.path.isdir("/root/reference") else _STAGED
+
+
+def available() -> bool:
+    """The unmodified reference can be imported here (build container: /root/reference; GPU box: the staged oracle/_ref)."""
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "models", "layers.py"))
 
 
 def _trunc_normal_(tensor, mean=0., std=1., a=-2., b=2.):

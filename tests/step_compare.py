@@ -1,17 +1,23 @@
-"""TEST INFRASTRUCTURE — run one full search step on the GPU engine and on the CPU oracle with identical seeded
+"""TEST INFRASTRUCTURE — run one full search step on the GPU engine and on the fp32 oracle with identical seeded
 parameters, inputs and random draws, and compare logits, every loss term, every gradient and the AdamW update.
 
-Tolerance (written here once, used by tests and smoke): the GPU path computes in bf16 with fp32 accumulation, the
-oracle in fp32 -> rel 2e-2 (BASELINE.json north_star, "bf16 rel 2e-2").
-  * logits, gates, losses: max|a-b| / max|b| per tensor (logits 2e-2; loss scalars, being reductions over many elements,
-    5e-3; the pure-fp32 pieces - gates, architecture loss, AdamW - 1e-4).
-  * gradients: relative L2 error ||a-b|| / ||b|| per tensor < 2e-2, AND the worst element max|a-b| / max|b| < 4e-2.
-    The engine keeps the residual gradient stream in bf16 ("precision"): every residual join and LayerNorm
-    backward rounds it once, ~4 roundings per block, so single elements of small-fan-in gradients (mask_token, LayerNorm
-    weights) sit at 1-2.5e-2 from the fp32 oracle while the tensors as a whole are within ~5e-3. PyTorch's own bf16
-    autocast of the same algorithm (fp32 residual stream) is measured alongside; where even that exceeds 2e-2 on some
-    tensor (it does: ~2e-2 on mask_token, whose gradient sums only the few masked tokens), the bound becomes 1.5 x its
-    worst error (same L2 metric) - the extra margin is what the bf16 gradient stream costs over autocast's fp32 stream."""
+Tolerance (written here once, used by tests and smoke; BASELINE.json north_star: "fp32 rel 1e-4; bf16 rel 2e-2"). The GPU
+path computes in bf16 with fp32 accumulation, the oracle in fp32:
+  * logits: max|a-b| / max|b| < 2e-2; loss scalars (reductions over many elements) 5e-3; the pure-fp32 pieces - gates,
+    architecture loss, AdamW - 1e-4; PMIM mask and index sets exact.
+  * EVERY gradient tensor, decoder included: relative L2 error ||a-b|| / ||b|| < 2e-2.  Fixed: no yardstick-derived
+    escape, no per-tensor multipliers.  The worst single element (max|a-b| / max|b|) is reported next to it and held to
+    2 x 2e-2.
+What the bound needs: a batch that is not degenerate.  Three gradients are sums over a handful of terms at toy batches -
+mask_token (the ~10 masked tokens of each image), decoder.0.weight / bias (an L1 loss: the gradient is sign(x_rec - target)
+over those same tokens, and a sign flips wherever |x_rec - target| is below the bf16 error of x_rec).  tests/precision_study.py
+emulates the engine's rounding points inside the oracle: at batch 2 even PyTorch's own bf16 autocast (fp32 residual stream,
+only the GEMM operands rounded) is 1.7e-2 / 1.9e-2 away from fp32 on mask_token / the decoder weight, at batch >= 8 every
+variant is below 1.3e-2 (depth 2) and the averages keep shrinking with 1/sqrt(batch).  So the step-parity cases run at
+batch >= 8 (the benchmark configurations at their real batch: 256 / 128 / 1024 with the fp32 oracle on the GPU), and the
+smallest batch any case uses is stated in its id.
+The same study shows where the distance comes from: GEMM operands in bf16 (inherent, ~5e-3 median), the bf16 forward
+residual stream (+3e-3), the bf16 gradient stream (+1e-3) - see DESIGN.md "Precision"."""
 import os
 import sys
 
@@ -25,15 +31,11 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
 BF16_TOL = 2e-2
 LOSS_TOL = 5e-3
 FP32_TOL = 1e-4
-# The PMIM loss is an L1 (vision_transformer.py:728): its gradient is sign(x_rec - target), discontinuous at 0. A bf16
-# x_rec flips that sign wherever |x_rec - target| is below the bf16 rounding error (~1 % of the entries); with the
-# handful of masked patches of a test-sized batch (10 per image at keep 0.95) one flip moves a decoder-weight gradient
-# entry by ~1/n_masked. The decoder gradients are therefore held to DEC_TOL here; tests/test_kernels_gpu.py checks that
-# the sign matrix is exact away from 0 and that the GEMMs consuming it are exact given the same signs.
-DEC_TOL = 1.5e-1
-
-
-GRAD_MAX_TOL = 2 * BF16_TOL
+GRAD_MAX_TOL = 2 * BF16_TOL        # worst single element of a gradient tensor, relative to the tensor's largest element
+MIN_BATCH = 8                      # smallest batch the fixed gradient bound is asserted at (see header)
+# ONLY for fixtures recorded at batch <= 4 (reference goldens of the pruned / post-search steps): the decoder gradient is a
+# sum of sign(x_rec - target) over ~10 masked tokens per image, one flipped sign moves an entry by ~1/n_masked
+DEC_TOL_TOY_BATCH = 1.5e-1
 
 
 def rel(a, b):
@@ -46,66 +48,88 @@ def rel_l2(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
-def autocast_reference_errors(P, inp, cfg, sw, grads_fp32):
-    """How far PyTorch's own bf16 autocast of the same algorithm lands from the fp32 oracle (per-gradient rel error).
-    Deep configurations are additionally held to this yardstick: bf16 rounding of ~100 chained activations reaches a
-    few 1e-2 on some gradients no matter who implements it."""
-    from ofb_oracle import StepInputs, forward_step
-    dev = torch.device("cuda")
-    leaves = {k: v.detach().to(dev).clone().requires_grad_(True) for k, v in P.items() if k != "alpha_patch"}
-    inp_d = StepInputs(images=inp.images.to(dev), labels=inp.labels.to(dev), noise=inp.noise.to(dev),
-                       drop_scale=inp.drop_scale.to(dev), w_p=inp.w_p, keep_ratio=inp.keep_ratio)
+def _to(inp, dev):
+    from ofb_oracle import StepInputs
+    return StepInputs(images=inp.images.to(dev), labels=inp.labels.to(dev), noise=inp.noise.to(dev),
+                      drop_scale=inp.drop_scale.to(dev), w_p=inp.w_p, keep_ratio=inp.keep_ratio)
+
+
+def oracle_step(P, inps, cfg, sw, lr, device="cpu"):
+    """fp32 oracle gradients of `len(inps)` accumulated micro-steps (engine.py:152, 169: loss_total /= accum_iter, backward on
+    every micro-step, optimizer step on the last) on `device`. Returns (outputs of the LAST micro-step, grads on the CPU)."""
+    from ofb_oracle import forward_step
+    dev = torch.device(device)
+    if dev.type == "cuda":
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+    leaves = {k: (v.detach().to(dev).clone().requires_grad_(True) if k != "alpha_patch" else v.detach().to(dev))
+              for k, v in P.items()}
     sw_d = {k: v.to(dev) for k, v in sw.items()}
-    with torch.autocast("cuda", dtype=torch.bfloat16):
-        out = forward_step(leaves, inp_d, cfg, sw_d)
-    out.loss_total.float().backward()
-    return {k: rel_l2(leaves[k].grad, g) for k, g in grads_fp32.items() if g is not None and leaves[k].grad is not None}
+    out = None
+    for inp in inps:
+        out = forward_step(leaves, _to(inp, dev), cfg, sw_d)
+        (out.loss_total / len(inps)).backward()
+    grads = {k: (v.grad.detach().cpu() if v.grad is not None else None) for k, v in leaves.items() if k != "alpha_patch"}
+    return out, grads
 
 
-def compare_step_with_oracle(embed_dim=192, num_heads=3, depth=2, batch=2, epoch_frac=0.0, drop_path_rate=0.1, lr=1e-3,
-                             switches=None, verbose=False, autocast_yardstick=False):
+def compare_step_with_oracle(embed_dim=192, num_heads=3, depth=2, batch=8, epoch_frac=0.0, drop_path_rate=0.1, lr=1e-3,
+                             switches=None, verbose=False, oracle_device="cpu", accum_iter=1, graphed=False):
+    """accum_iter > 1: `accum_iter` micro-batches through step(update=False) ... step(update=True) against the oracle's
+    accumulated gradient. graphed: drive the engine through step_graphed (CUDA-graph replay; the random draws then come from
+    torch's generator, so only configurations without DropPath / with the noise fed through a fixed seed are comparable -
+    used by the accumulation test with drop_path_rate 0 and the PMIM noise taken from the engine)."""
     import ofb_b200  # noqa: F401
     from fixtures import make_inputs, make_params
-    from ofb_b200.engine import GROUPS, SearchStepEngine, param_group
-    from ofb_oracle import ModelCfg, adamw_step, default_switches, group_hparams, train_step
+    from ofb_b200.engine import SearchStepEngine, param_group
+    from ofb_oracle import ModelCfg, adamw_step, default_switches, group_hparams
 
     cfg = ModelCfg(embed_dim=embed_dim, num_heads=num_heads, depth=depth)
     P = make_params(cfg, seed=0)
-    inp = make_inputs(cfg, batch, seed=1, epoch_frac=epoch_frac, drop_path_rate=drop_path_rate)
+    inps = [make_inputs(cfg, batch, seed=1 + i, epoch_frac=epoch_frac, drop_path_rate=drop_path_rate) for i in range(accum_iter)]
     sw = switches or default_switches(cfg)
 
-    eng = SearchStepEngine(embed_dim, num_heads, depth, batch, drop_path_rate=drop_path_rate, lr=lr, switches=sw)
+    eng = SearchStepEngine(embed_dim, num_heads, depth, batch, drop_path_rate=drop_path_rate, lr=lr, switches=sw,
+                           accum_iter=accum_iter)
     eng.load_params(P)
     eng.set_schedule(epoch_frac)
-    assert abs(eng.w_p - inp.w_p) < 1e-9 and abs(eng.keep_ratio - inp.keep_ratio) < 1e-9
-    # the oracle takes DropPath multipliers; the engine takes the uniform draws -> invert: u = scale>0 ? 1 : 0 works
-    # because floor(keep+u) is 1 iff u >= p; feed u = 1-eps (kept) or 0 (dropped)
-    drop_u = (inp.drop_scale > 0).float().reshape(depth * 2, batch) * 0.999
-    scal = eng.step(inp.images.cuda(), inp.labels.cuda(), noise=inp.noise.cuda(), drop_u=drop_u.cuda(), update=False)
+    assert abs(eng.w_p - inps[0].w_p) < 1e-9 and abs(eng.keep_ratio - inps[0].keep_ratio) < 1e-9
+    p_before = {k: eng.p(k).detach().cpu().clone() for k in eng.offsets}
+    g_engine = None
+    for i, inp in enumerate(inps):
+        last = i == accum_iter - 1
+        # the oracle takes DropPath multipliers; the engine takes the uniform draws -> invert: u = scale>0 ? 1 : 0 works
+        # because floor(keep+u) is 1 iff u >= p; feed u = 1-eps (kept) or 0 (dropped)
+        drop_u = (inp.drop_scale > 0).float().reshape(depth * 2, batch) * 0.999
+        if last:
+            # gradients are read before the update: run the last micro-step without it, then the optimizer alone
+            scal = eng.step(inp.images.cuda(), inp.labels.cuda(), noise=inp.noise.cuda(), drop_u=drop_u.cuda(), update=False)
+        else:
+            eng.step(inp.images.cuda(), inp.labels.cuda(), noise=inp.noise.cuda(), drop_u=drop_u.cuda(), update=False)
     torch.cuda.synchronize()
     scal = scal.cpu()
+    g_engine = {k: eng.g(k).detach().cpu().clone() for k in eng.offsets}
+    logits_e, mask_e = eng.logits.detach().cpu().clone(), eng.mask.detach().cpu().clone()
+    gates_e = [eng.bimask.gate_of(i).detach().cpu().clone() for i in range(len(eng.bimask.modules))]
 
-    Pc = {k: v.clone() for k, v in P.items()}
-    out, grads = train_step(Pc, {}, inp, cfg, lr=lr, step=1, switches=sw)
+    out, grads = oracle_step(P, inps, cfg, sw, lr, oracle_device)
 
     errs = {}
-    errs["mask"] = float((eng.mask.cpu() - out.mask).abs().max())
-    errs["logits"] = rel(eng.logits, out.logits)
+    errs["mask"] = float((mask_e - out.mask.cpu()).abs().max())
+    errs["logits"] = rel(logits_e, out.logits)
     errs["loss_base"] = rel(scal[0], out.loss_base)
     errs["loss_arch"] = rel(scal[1], out.loss_arch)
     errs["loss_decoder"] = rel(scal[2], out.loss_decoder)
     errs["loss_total"] = rel(scal[3], out.loss_total)
     for i, m in enumerate(eng.bimask.modules):
-        errs["gate:" + m["prefix"]] = rel(eng.bimask.gate_of(i), out.gates[m["prefix"]].reshape(-1))
+        errs["gate:" + m["prefix"]] = rel(gates_e[i], out.gates[m["prefix"]].reshape(-1))
     gerrs, gmax = {}, {}
     for k, g in grads.items():
         if g is None:
             continue
-        gerrs[k] = rel_l2(eng.g(k), g)
-        gmax[k] = rel(eng.g(k), g)
+        gerrs[k] = rel_l2(g_engine[k], g)
+        gmax[k] = rel(g_engine[k], g)
     # AdamW: apply the fused kernel to the engine's own gradients and the oracle's AdamW to the same gradients
-    g_engine = {k: eng.g(k).detach().cpu().clone() for k in eng.offsets}
-    p_before = {k: eng.p(k).detach().cpu().clone() for k in eng.offsets}
     eng.optimizer_step()
     torch.cuda.synchronize()
     aerrs = {}
@@ -115,29 +139,34 @@ def compare_step_with_oracle(embed_dim=192, num_heads=3, depth=2, batch=2, epoch
         aerrs[k] = rel(eng.p(k), pk)
     grads_zeroed = float(eng.grads.abs().max()) == 0.0
 
-    dec_errs = {k: max(gerrs.pop(k), gmax.pop(k)) for k in list(gerrs) if k.startswith("decoder.")}
-    worst_m = max(gmax.items(), key=lambda kv: kv[1])
-    grad_tol, yard = BF16_TOL, None
-    if autocast_yardstick:
-        yard = autocast_reference_errors(P, inp, cfg, sw, grads)
-        yard_worst = max(v for k, v in yard.items() if not k.startswith("decoder."))
-        grad_tol = max(BF16_TOL, 1.5 * yard_worst)
     worst_g = max(gerrs.items(), key=lambda kv: kv[1])
-    worst_d = max(dec_errs.items(), key=lambda kv: kv[1])
+    worst_m = max(gmax.items(), key=lambda kv: kv[1])
     worst_a = max(aerrs.items(), key=lambda kv: kv[1])
     gate_worst = max(v for k, v in errs.items() if k.startswith("gate:"))
     ok = (errs["mask"] == 0 and errs["logits"] < BF16_TOL and errs["loss_base"] < LOSS_TOL
           and errs["loss_arch"] < FP32_TOL * 10 and errs["loss_decoder"] < LOSS_TOL and errs["loss_total"] < LOSS_TOL
-          and gate_worst < FP32_TOL and worst_g[1] < grad_tol and worst_m[1] < max(GRAD_MAX_TOL, grad_tol)
-          and worst_d[1] < DEC_TOL and worst_a[1] < FP32_TOL and grads_zeroed)
-    summary = (f"D{embed_dim} H{num_heads} depth{depth} B{batch} e{epoch_frac}: logits {errs['logits']:.2e} "
-               f"base {errs['loss_base']:.2e} arch {errs['loss_arch']:.2e} dec {errs['loss_decoder']:.2e} "
-               f"total {errs['loss_total']:.2e} gate {gate_worst:.2e} worst-grad(L2) {worst_g[0]} {worst_g[1]:.2e} "
-               f"(tol {grad_tol:.2e}) worst-grad(max) {worst_m[0]} {worst_m[1]:.2e} (tol {max(GRAD_MAX_TOL, grad_tol):.2e}) "
-               f"decoder-grad {worst_d[1]:.2e} "
+          and gate_worst < FP32_TOL and worst_g[1] < BF16_TOL and worst_m[1] < GRAD_MAX_TOL
+          and worst_a[1] < FP32_TOL and grads_zeroed)
+    med = sorted(gerrs.values())[len(gerrs) // 2]
+    summary = (f"D{embed_dim} H{num_heads} depth{depth} B{batch} e{epoch_frac} accum{accum_iter} oracle@{oracle_device}: "
+               f"logits {errs['logits']:.2e} base {errs['loss_base']:.2e} arch {errs['loss_arch']:.2e} "
+               f"dec {errs['loss_decoder']:.2e} total {errs['loss_total']:.2e} gate {gate_worst:.2e} "
+               f"worst-grad(L2) {worst_g[0]} {worst_g[1]:.2e} (tol {BF16_TOL:.2e}) median-grad(L2) {med:.2e} "
+               f"worst-grad(max) {worst_m[0]} {worst_m[1]:.2e} (tol {GRAD_MAX_TOL:.2e}) "
                f"worst-adamw {worst_a[0]} {worst_a[1]:.2e} mask_exact {errs['mask'] == 0} ok={ok}")
     if verbose:
-        for k, v in sorted(gmax.items(), key=lambda kv: -kv[1])[:12]:
+        for k, v in sorted(gerrs.items(), key=lambda kv: -kv[1])[:8]:
+            print(f"   grad {k}: l2-rel {v:.3e}  max-rel {gmax[k]:.3e}")
+        for k, v in sorted(gmax.items(), key=lambda kv: -kv[1])[:4]:
             print(f"   grad {k}: max-rel {v:.3e}  l2-rel {gerrs[k]:.3e}")
-    return dict(ok=ok, summary=summary, errs=errs, grad_errs=gerrs, dec_errs=dec_errs, adamw_errs=aerrs,
+    return dict(ok=ok, summary=summary, errs=errs, grad_errs=gerrs, grad_max=gmax, adamw_errs=aerrs,
                 losses=dict(base=float(scal[0]), arch=float(scal[1]), dec=float(scal[2]), total=float(scal[3])))
+
+
+if __name__ == "__main__":
+    # python tests/step_compare.py D H depth B [epoch_frac] [oracle_device] [accum]
+    a = sys.argv[1:]
+    r = compare_step_with_oracle(int(a[0]), int(a[1]), int(a[2]), int(a[3]), epoch_frac=float(a[4]) if len(a) > 4 else 0.0,
+                                 oracle_device=a[5] if len(a) > 5 else "cpu", accum_iter=int(a[6]) if len(a) > 6 else 1,
+                                 verbose=True)
+    print(r["summary"])

@@ -65,7 +65,7 @@ def test_engine_pruned_step_matches_reference_golden(cuda_dev, path):
     """SearchStepEngine -> plan_prune -> rebuild_pruned (new engine on the truncated shapes, zero-padded layout) -> one
     search step, against the generalised oracle (every gradient) and the reference's own outputs (golden)."""
     from ofb_b200.engine import SearchStepEngine
-    from step_compare import BF16_TOL, DEC_TOL, FP32_TOL, GRAD_MAX_TOL, LOSS_TOL, rel, rel_l2
+    from step_compare import BF16_TOL, FP32_TOL, GRAD_MAX_TOL, LOSS_TOL, rel, rel_l2
     g, cfg, P0, inp = _case(path)
     B, depth = inp.images.shape[0], cfg.depth
     dpr, lr, ef = float(g["dpr"]), float(g["lr"]), float(g["epoch_frac"])
@@ -104,15 +104,11 @@ def test_engine_pruned_step_matches_reference_golden(cuda_dev, path):
         if gr is None:
             continue
         e2, em = rel_l2(got[k], gr), rel(got[k], gr)
-        if k.startswith("decoder."):
-            assert max(e2, em) < DEC_TOL, k
-            continue
-        if k.endswith(".alpha") or k.endswith(".score"):
-            assert e2 < 5 * BF16_TOL, (k, e2)          # tiny tensors driven by bf16 column sums
         worst_l2 = max(worst_l2, (k, e2), key=lambda kv: kv[1])
         worst_max = max(worst_max, (k, em), key=lambda kv: kv[1])
     print("worst L2", worst_l2, "worst max", worst_max)
-    assert worst_l2[1] < 1.5 * BF16_TOL and worst_max[1] < GRAD_MAX_TOL
+    # fixed bound of step_compare.py for EVERY gradient tensor (decoder, alphas and scores included)
+    assert worst_l2[1] < BF16_TOL and worst_max[1] < GRAD_MAX_TOL
     for i, m in enumerate(eng.bimask.modules):
         assert rel(eng.bimask.logical(i, eng.bimask.gate).reshape(-1), out.gates[m["prefix"]].reshape(-1)) < FP32_TOL
     # the update keeps the padding clean and the engine can keep stepping (graph replay included)

@@ -7,21 +7,78 @@ import numpy as np
 import pytest
 import torch
 
-from step_compare import BF16_TOL, DEC_TOL, LOSS_TOL, compare_step_with_oracle
+from step_compare import BF16_TOL, GRAD_MAX_TOL, LOSS_TOL, compare_step_with_oracle
 
 pytestmark = pytest.mark.gpu
 GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz"))
               if not os.path.basename(p).startswith("ft_"))       # ft_*: finetune-step fixtures (test_ft_*.py)
 
 
-@pytest.mark.parametrize("D,H,depth,B,ef,dpr", [(192, 3, 2, 2, 0.0, 0.1), (192, 3, 12, 4, 10.0, 0.1),
-                                                (384, 6, 3, 3, 5.0, 0.1), (768, 12, 2, 2, 20.0, 0.0)])
+@pytest.mark.parametrize("D,H,depth,B,ef,dpr", [(192, 3, 2, 8, 0.0, 0.1), (192, 3, 12, 16, 10.0, 0.1),
+                                                (384, 6, 3, 8, 5.0, 0.1), (768, 12, 2, 8, 20.0, 0.0)])
 def test_step_matches_oracle(cuda_dev, D, H, depth, B, ef, dpr):
-    # every configuration is also measured against PyTorch's own bf16 autocast of the oracle (see step_compare)
-    res = compare_step_with_oracle(D, H, depth, B, epoch_frac=ef, drop_path_rate=dpr, verbose=True,
-                                   autocast_yardstick=True)
+    """Fixed tolerance (step_compare.py header): every gradient tensor rel-L2 < 2e-2 against the fp32 CPU oracle."""
+    res = compare_step_with_oracle(D, H, depth, B, epoch_frac=ef, drop_path_rate=dpr, verbose=True)
     print(res["summary"])
     assert res["ok"], res["summary"]
+
+
+# The BENCHMARKED configurations at their real batch (BASELINE.json configs[1], [3], [2]): M = 50 432 token rows means
+# multi-wave persistent scheduling, automatic split-K at K = 50 432, ragged last tiles and the full mlp_parts partial buffers -
+# none of which the small cases reach. The fp32 oracle runs on the same GPU (TF32 off) so that it finishes in seconds.
+@pytest.mark.parametrize("D,H,depth,B,ef", [(384, 6, 12, 256, 0.0), (384, 6, 12, 256, 10.0), (768, 12, 12, 128, 5.0),
+                                            (192, 3, 12, 1024, 0.0)],
+                         ids=["deit_s_b256_e0", "deit_s_b256_e10", "deit_b_b128", "deit_t_b1024"])
+def test_step_matches_oracle_at_benchmark_config(cuda_dev, D, H, depth, B, ef):
+    res = compare_step_with_oracle(D, H, depth, B, epoch_frac=ef, drop_path_rate=0.1, verbose=True, oracle_device="cuda")
+    print(res["summary"])
+    assert res["ok"], res["summary"]
+
+
+@pytest.mark.parametrize("D,H,depth,B,accum,dev", [(192, 3, 2, 8, 4, "cpu"), (384, 6, 12, 64, 4, "cuda")],
+                         ids=["tiny_d2_accum4", "deit_s_b64_accum4"])
+def test_gradient_accumulation(cuda_dev, D, H, depth, B, accum, dev):
+    """accum_iter = 4 (the reference's only documented run, exp_sh/run_exp.sh:4-15; engine.py:152, 169-184): four micro-steps
+    without update accumulate loss/4 gradients, compared with four oracle micro-steps; then one AdamW update."""
+    res = compare_step_with_oracle(D, H, depth, B, epoch_frac=3.0, drop_path_rate=0.1, verbose=True, oracle_device=dev,
+                                   accum_iter=accum)
+    print(res["summary"])
+    assert res["ok"], res["summary"]
+
+
+def test_graphed_accumulation_matches_eager(cuda_dev):
+    """step_graphed(update=False/True) - the benchmarked path - accumulates and updates exactly like the eager step():
+    same micro-batches, DropPath off and the PMIM noise pinned through the generator seed, parameters after two optimizer
+    steps of accum_iter = 2 compared (bit-level differences only from the atomically accumulated weight gradients)."""
+    from fixtures import make_inputs, make_params
+    from ofb_b200.engine import SearchStepEngine
+    from ofb_oracle import ModelCfg
+    cfg = ModelCfg(embed_dim=192, num_heads=3, depth=2)
+    P = make_params(cfg, seed=0)
+    B = 8
+    batches = [make_inputs(cfg, B, seed=10 + i, drop_path_rate=0.0) for i in range(4)]
+    out = []
+    for graphed in (False, True):
+        eng = SearchStepEngine(192, 3, 2, B, drop_path_rate=0.0, lr=1e-3, accum_iter=2)
+        eng.load_params(P)
+        eng.set_schedule(2.0)
+        torch.manual_seed(5)
+        torch.cuda.manual_seed(5)
+        if graphed:
+            img, lab = torch.empty(B, 3, 224, 224, device="cuda"), torch.empty(B, dtype=torch.int64, device="cuda")
+        for i, b in enumerate(batches):
+            upd = i % 2 == 1
+            if graphed:
+                img.copy_(b.images); lab.copy_(b.labels)
+                eng.step_graphed(img, lab, update=upd, noise=b.noise.cuda())
+            else:
+                eng.step(b.images.cuda(), b.labels.cuda(), noise=b.noise.cuda(), update=upd)
+        torch.cuda.synchronize()
+        assert eng.step_count == 2
+        out.append({k: v.detach().cpu().clone() for k, v in eng.named_parameters().items()})
+    for k in out[0]:
+        d = float((out[0][k] - out[1][k]).abs().max())
+        assert d <= 2e-5 * max(1.0, float(out[0][k].abs().max())), (k, d)
 
 
 @pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
@@ -65,12 +122,8 @@ def test_step_matches_reference_golden(cuda_dev, path):
             got = summarize(eng.g(key[5:]).cpu()).numpy()
             # strided samples of the gradient, relative to the gradient's max-norm scale (l2 / sqrt(n) is too lenient)
             e = float(np.abs(got[3:] - g[key][3:]).max() / (np.abs(g[key][3:]).max() + 1e-30))
-            if key.startswith("gsum:decoder."):      # L1 sign discontinuity, see step_compare.DEC_TOL
-                assert e < DEC_TOL, key
-                continue
             worst = max(worst, (key, e), key=lambda kv: kv[1])
             assert abs(got[2] - g[key][2]) / (g[key][2] + 1e-30) < BF16_TOL, key     # l2 norm
     print("worst sampled gradient error:", worst)
-    # sampled entries (48 per tensor): single elements are held to the element-wise bound of step_compare (2 x 2e-2; the
-    # bf16 residual gradient stream, see step_compare's header); 12-block gradients to the autocast-yardstick level
-    assert worst[1] < (2.5 if depth >= 12 else 2.0) * BF16_TOL
+    # sampled entries (48 per tensor): single elements are held to the element-wise bound of step_compare (2 x 2e-2)
+    assert worst[1] < GRAD_MAX_TOL
