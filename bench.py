@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--cpu-sample-batch", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying CUDA graphs")
+    ap.add_argument("--no-eager", action="store_true", help="skip the same-box GPU baseline (unmodified reference, PyTorch eager)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short runs of the other BASELINE.json configurations")
     ap.add_argument("--workload", default="search", choices=["search", "finetune", "post"],
                     help="search: the bi-mask search step (BASELINE.json metric, default); finetune: the training step of a "
                          "physically pruned DeiT-S subnet (BASELINE.json configs[4], extra configuration); post: the post-search "
@@ -224,71 +226,135 @@ def cpu_oracle_rate(model, depth, sample_batch, steps=1, warmup=1):
     return sample_batch / dt, cores, dt
 
 
+def reference_available():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    try:
+        import ref_shim
+        return ref_shim.available()
+    except Exception:
+        return False
+
+
+def cpu_reference_rate(model, depth, sample_batch, steps=1, warmup=1):
+    """images/s of the UNMODIFIED reference step (oracle/_ref or /root/reference through oracle/ref_runner.py: the reference's
+    own model, criterion and optimizers; fp32, all host threads) on a bounded sample of the workload."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_runner
+    D, H = MODELS[model]
+    rate, dt, cores = ref_runner.time_reference(D, H, depth, sample_batch, device="cpu", steps=steps, warmup=warmup)
+    return rate, cores, dt
+
+
+def cpu_arm(args, steps=1, warmup=1):
+    """(rate, cores, s/step, kind) of the CPU arm: the unmodified reference when it is staged (search workload), else the
+    oracle port."""
+    if args.workload == "finetune":
+        return cpu_ft_oracle_rate(args.cpu_sample_batch, steps, warmup) + ("port",)
+    if args.workload == "post":
+        return cpu_post_oracle_rate(args.cpu_sample_batch, steps, warmup) + ("port",)
+    if reference_available():
+        return cpu_reference_rate(args.model, args.depth, args.cpu_sample_batch, steps, warmup) + ("reference",)
+    return cpu_oracle_rate(args.model, args.depth, args.cpu_sample_batch, steps, warmup) + ("port",)
+
+
+def gpu_eager_baseline(model, depth, batch, steps=3, warmup=2):
+    """The same-box GPU yardstick of SURVEY 2.2 / 8(d): the UNMODIFIED reference (PyTorch eager: cuBLAS / cuDNN / ATen kernels)
+    on this B200, fp32 as the reference runs by default and under torch.autocast(bf16)."""
+    if not reference_available():
+        return {"unavailable": "oracle/_ref not staged (run oracle/make_ref.py in the build container)"}
+    import torch
+    import ref_runner
+    D, H = MODELS[model]
+    out = {"kind": "reference (unmodified, PyTorch eager on the same GPU)", "batch": batch, "steps": steps, "warmup": warmup,
+           "unit": "images/s"}
+    for name, ac in (("fp32", None), ("autocast_bf16", torch.bfloat16)):
+        try:
+            torch.backends.cuda.matmul.allow_tf32 = False
+            rate, dt, _ = ref_runner.time_reference(D, H, depth, batch, device="cuda", steps=steps, warmup=warmup, autocast=ac)
+            out[name] = rate
+            out[name + "_ms_per_step"] = dt * 1e3
+        except Exception as e:                      # noqa: BLE001 - a baseline that cannot run is reported, not fatal
+            out[name] = None
+            out[name + "_error"] = f"{type(e).__name__}: {str(e)[:200]}"
+        torch.cuda.empty_cache()
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    D, H = MODELS[args.model]
-    if args.workload == "finetune":
-        rate, cores, dt = cpu_ft_oracle_rate(args.cpu_sample_batch, steps=max(1, min(args.steps, 3)), warmup=1)
-    elif args.workload == "post":
-        rate, cores, dt = cpu_post_oracle_rate(args.cpu_sample_batch, steps=max(1, min(args.steps, 3)), warmup=1)
-    else:
-        rate, cores, dt = cpu_oracle_rate(args.model, args.depth, args.cpu_sample_batch, steps=max(1, min(args.steps, 3)),
-                                          warmup=max(1, min(args.warmup, 1)))
-    sample = f"{args.cpu_sample_batch} images / step of the same DeiT-{args.model} {args.workload} step, fp32, {cores} threads"
+    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    rate, cores, dt, kind = cpu_arm(args, steps, warmup)
+    what = "unmodified reference (oracle/_ref)" if kind == "reference" else "oracle port"
+    sample = (f"{args.cpu_sample_batch} images / step of the same DeiT-{args.model} {args.workload} step, {what}, fp32, "
+              f"{cores} threads, {steps} steps after {warmup} warm-up")
     line = {
         "impl": "reference", "metric": METRIC[args.workload], "value": rate,
-        "unit": "images/s", "n_gpus": args.gpus, "steps": max(1, min(args.steps, 3)), "warmup": 1, "ms_per_step": dt * 1e3,
+        "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": (f"DeiT-{args.model} bi-mask search + PMIM step, depth {args.depth}, 224px, CPU sample"
+        "config": {"workload": (f"DeiT-{args.model} bi-mask search + PMIM step, depth {args.depth}, 224px, CPU sample of "
+                                f"{args.cpu_sample_batch} images / step"
                                 if args.workload == "search" else
                                 "finetune step of a pruned DeiT-S subnet (BASELINE.json configs[4]), 224px, CPU sample"
                                 if args.workload == "finetune" else
                                 "post-search step of the finalised DeiT-S subnet (SURVEY 8f-3), 224px, CPU sample")},
-        "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def main():
-    args = parse()
-    if args.impl == "reference":
-        return run_reference(args)
-    # stray writes to fd 1 (NCCL prints its version banner there) must not end up next to the JSON line: everything but
-    # the result goes to stderr
-    out_fd = os.dup(1)
-    os.dup2(2, 1)
-    trace = os.environ.get("OFB_BENCH_TRACE")
-    if trace:          # debugging aid: stage markers on stderr and a Python stack dump if a stage hangs
-        import faulthandler
-        faulthandler.dump_traceback_later(int(trace), repeat=False, exit=False)
+# kernel families of the step, by substring of the kernel name
+FAMILIES = (("gemm", ("gemm_kernel",)), ("attn_bwd", ("attn_bwd",)), ("attn_fwd", ("attn_fwd",)), ("ln", ("ln_fwd", "ln_bwd")),
+            ("adamw", ("adamw_kernel",)), ("reduce", ("reduce_partials",)), ("nccl", ("nccl",)))
 
-    def mark(what):
-        if trace:
-            print(f"[bench rank {os.environ.get('RANK', '0')}] {what}", file=sys.stderr, flush=True)
 
+def family_of(name):
+    for fam, keys in FAMILIES:
+        if any(k in name for k in keys):
+            return fam
+    return "other"
+
+
+def kernel_breakdown(run_steps, n):
+    """Per-kernel device durations of `n` steps from CUPTI activity records (torch.profiler): independent of how fast the host
+    launches (the timed steps are CUDA-graph replays - an event pair around a host launch would time host gaps instead).
+    Returns ({family: ms per step}, {kernel name: (ms per step, launches per step)}) or (None, why)."""
     import torch
-    import torch.distributed as dist
-    import ofb_b200  # noqa: F401
-    from ofb_b200 import ops
-    from ofb_b200.engine import SearchStepEngine
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            run_steps(n)
+            torch.cuda.synchronize()
+        fam, kern = {}, {}
+        for ev in prof.key_averages():
+            dt = getattr(ev, "device_time_total", None)
+            if dt is None:
+                dt = getattr(ev, "cuda_time_total", 0.0)
+            if not dt or str(getattr(ev, "device_type", "")).endswith("CPU"):
+                continue
+            ms = float(dt) / 1e3 / n
+            kern[ev.key] = (ms, ev.count / n)
+            f = family_of(ev.key)
+            fam[f] = fam.get(f, 0.0) + ms
+        if not kern:
+            return None, "torch.profiler returned no device activity records"
+        return fam, kern
+    except Exception as e:                      # noqa: BLE001
+        return None, f"{type(e).__name__}: {str(e)[:200]}"
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    pg = None
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        pg = dist.group.WORLD
-    dev = torch.device("cuda", local)
+
+def build_workload(args, dev, pg, world, rank):
+    """Engine + step callable + description of one bench workload."""
+    import torch
+    from ofb_b200.engine import SearchStepEngine
     D, H = MODELS[args.model]
     B = args.batch
-    eff = B * world
-    lr = 2.5e-4 * eff / 256                     # search.py:509-518
+    lr = 2.5e-4 * B * world / 256                     # search.py:509-518
+    ctx = {}
     if args.workload == "finetune":
         from ofb_b200.finetune_engine import FinetuneStepEngine
         eng = FinetuneStepEngine(batch=B, lr=lr, device=dev, process_group=pg, **FT_SUBNET)
@@ -319,9 +385,9 @@ def main():
         torch.cuda.empty_cache()
         eng.enter_post_search()
         import numpy as np
-        mixup_fn = Mixup(rng=np.random.RandomState(1 + rank))
-        soft = torch.empty(B, 1000, device=dev)
-        mixed = torch.empty(B, 3, 224, 224, device=dev)
+        ctx["mixup_fn"] = Mixup(rng=np.random.RandomState(1 + rank))
+        ctx["soft"] = torch.empty(B, 1000, device=dev)
+        ctx["mixed"] = torch.empty(B, 3, 224, 224, device=dev)
         step_gflop = subnet_step_gflop()
         workload = (f"post-search step (search.py:641-656: Mixup/CutMix + soft-target CE, PMIM off, decoder frozen) of the DeiT-S "
                     f"search engine after the finalising prune event (subnet of bench.py FT_SUBNET, embed {FT_SUBNET['embed_dim']}), "
@@ -334,6 +400,88 @@ def main():
         step_gflop = STEP_GFLOP.get(args.model)
         workload = (f"DeiT-{args.model} bi-mask search + PMIM step, depth {args.depth}, batch {B}/GPU, 224px "
                     + ("(BASELINE.json configs[1])" if args.model == "small" else "(BASELINE.json parity / extra configuration)"))
+
+    inner = eng.step if args.no_graph else eng.step_graphed
+    eager = eng.step
+    if args.workload == "post":
+        def step(images, labels):          # engine.py:98-99: `samples, targets = mixup_fn(samples, targets)`, then the step
+            ctx["mixup_fn"](images, labels, ctx["soft"], images_out=ctx["mixed"])
+            return inner(ctx["mixed"], None, target=ctx["soft"])
+
+        def eager_step(images, labels):
+            ctx["mixup_fn"](images, labels, ctx["soft"], images_out=ctx["mixed"])
+            return eager(ctx["mixed"], None, target=ctx["soft"], update=False)
+    else:
+        step = inner
+
+        def eager_step(images, labels):
+            return eager(images, labels, update=False)
+    return eng, step, eager_step, step_gflop, workload
+
+
+def extra_config(model, batch, workload, dev, steps=5, warmup=3):
+    """Short device-timed run of another BASELINE.json configuration (same engine, same timing rules, fewer steps)."""
+    import torch
+    ns = argparse.Namespace(model=model, batch=batch, depth=12, workload=workload, no_graph=False)
+    try:
+        eng, step, _, step_gflop, desc = build_workload(ns, dev, None, 1, 0)
+        g = torch.Generator(device="cpu").manual_seed(7)
+        img = [torch.randn(batch, 3, 224, 224, generator=g).to(dev) for _ in range(2)]
+        lab = [torch.randint(0, 1000, (batch,), generator=g).to(dev) for _ in range(2)]
+        for i in range(warmup):
+            step(img[i % 2], lab[i % 2])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step(img[i % 2], lab[i % 2])
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out = {"workload": desc, "value": batch / (ms / 1e3), "unit": "images/s", "ms_per_step": ms, "steps": steps,
+               "warmup": warmup, "step_tflops": (step_gflop or 0) * batch / ms}
+        eng.release_graphs()
+        del eng, step, img, lab
+    except Exception as e:                      # noqa: BLE001
+        out = {"workload": f"DeiT-{model} {workload} batch {batch}", "error": f"{type(e).__name__}: {str(e)[:200]}"}
+    torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    # stray writes to fd 1 (NCCL prints its version banner there) must not end up next to the JSON line: everything but
+    # the result goes to stderr
+    out_fd = os.dup(1)
+    os.dup2(2, 1)
+    trace = os.environ.get("OFB_BENCH_TRACE")
+    if trace:          # debugging aid: stage markers on stderr and a Python stack dump if a stage hangs
+        import faulthandler
+        faulthandler.dump_traceback_later(int(trace), repeat=False, exit=False)
+
+    def mark(what):
+        if trace:
+            print(f"[bench rank {os.environ.get('RANK', '0')}] {what}", file=sys.stderr, flush=True)
+
+    import torch
+    import torch.distributed as dist
+    import ofb_b200  # noqa: F401
+    from ofb_b200 import ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        pg = dist.group.WORLD
+    dev = torch.device("cuda", local)
+    B = args.batch
+    eff = B * world
+    eng, step, eager_step, step_gflop, workload = build_workload(args, dev, pg, world, rank)
 
     g = torch.Generator(device="cpu").manual_seed(1 + rank)
     n_host = 2
@@ -348,13 +496,15 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    step = eng.step if args.no_graph else eng.step_graphed
-    if args.workload == "post":
-        inner = step
-
-        def step(images, labels):          # engine.py:98-99: `samples, targets = mixup_fn(samples, targets)`, then the step
-            mixup_fn(images, labels, soft, images_out=mixed)
-            return inner(mixed, None, target=soft)
+    # ---------------- algorithmic work of one step (GEMM / attention FLOPs, LayerNorm bytes): one logged eager pass ----------------
+    ops.WORK_LOG = []
+    eager_step(dev_img[0], dev_lab[0])
+    work_log, ops.WORK_LOG = ops.WORK_LOG, None
+    eng.grads.zero_()
+    work = {}
+    for fam, fl, nb in work_log:
+        w = work.setdefault(fam, [0.0, 0.0, 0])
+        w[0] += fl; w[1] += nb; w[2] += 1
 
     # ---------------- device-resident measurement ----------------
     mark("engine built")
@@ -368,9 +518,6 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ln_t = []
-    if args.no_graph:
-        ops.GEMM_TIMING, ops.LN_TIMING = [], []
     launches0 = ops.LAUNCHES
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -381,38 +528,19 @@ def main():
     ms = e0.elapsed_time(e1)
     mark("timed region done")
     launches = ops.LAUNCHES - launches0
-    gemm_t = ops.GEMM_TIMING
-    if args.no_graph:
-        ln_t = ops.LN_TIMING
-    ops.GEMM_TIMING = ops.LN_TIMING = None
     clocks = sampler.stop() if rank == 0 else None
-    n_roof = args.steps
-    if gemm_t is None:
-        # the timed steps were CUDA-graph replays (no per-kernel events possible): time every GEMM launch of a few more,
-        # host-launched steps of the same workload with CUDA events on the launching stream (the stream stays saturated:
-        # ~270 launches of ~60 us per step, so an event pair brackets exactly one kernel)
-        n_roof = min(3, args.steps)
-        ops.GEMM_TIMING, ops.LN_TIMING = [], []
-        for i in range(n_roof):
-            if args.workload == "post":
-                mixup_fn(dev_img[i % n_host], dev_lab[i % n_host], soft, images_out=mixed)
-                eng.step(mixed, None, target=soft)
-            else:
-                eng.step(dev_img[i % n_host], dev_lab[i % n_host])
-        sync_all()
-        gemm_t, ln_t = ops.GEMM_TIMING, ops.LN_TIMING
-        ops.GEMM_TIMING = ops.LN_TIMING = None
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     value = eff * args.steps / (ms / 1e3)
-    gemm_ms = sum(a.elapsed_time(b) for a, b, _, _ in gemm_t)
-    gemm_flops = sum(f for _, _, f, _ in gemm_t)
-    ln_ms = sum(a.elapsed_time(b) for a, b, _ in ln_t)
-    ln_bytes = sum(nb for _, _, nb in ln_t)
     scal = eng.scal.cpu().tolist()
 
+    # ---------------- per-kernel durations of the same replayed steps (CUPTI) ----------------
+    n_prof = min(4, args.steps)
+    fam_ms, kern = (None, "skipped") if rank != 0 else kernel_breakdown(
+        lambda n: [step(dev_img[i % n_host], dev_lab[i % n_host]) for i in range(n)], n_prof)
+    sync_all()
     mark("roofline pass done")
     # ---------------- end to end: host buffers -> step -> loss on host ----------------
     copy_stream = torch.cuda.Stream(device=dev)
@@ -465,11 +593,34 @@ def main():
     if rank == 0:
         pk = peaks()
         tr = gemm_traffic()
-        achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+        step_ms = ms / args.steps
+        timed_over = f"{n_prof} CUDA-graph replays of the timed step, CUPTI kernel records (torch.profiler), grouped by kernel family"
+        if fam_ms is None:
+            timed_over = f"unavailable ({kern})"
+            fam_ms, kern = {}, {}
+
+        def fam(name):
+            return fam_ms.get(name, 0.0)
+
+        def frac(x, peak):
+            return x / peak if x is not None else None
+        gemm_tf = work.get("gemm", [0, 0, 0])[0] / (fam("gemm") / 1e3) / 1e12 if fam("gemm") > 0 else None
+        attn = {}
+        for k in ("attn_fwd", "attn_bwd"):
+            fl, nb, n = work.get(k, [0.0, 0.0, 0])
+            if fam(k) > 0:
+                attn[k] = {"us_per_launch": fam(k) * 1e3 / max(n, 1), "launches_per_step": n,
+                           "tflops": fl / (fam(k) / 1e3) / 1e12, "frac_tensor": fl / (fam(k) / 1e3) / 1e12 / pk["tflops"],
+                           "gbs": nb / (fam(k) / 1e3) / 1e9, "frac_hbm": nb / (fam(k) / 1e3) / 1e9 / pk["hbm"],
+                           "share_of_step": fam(k) / step_ms}
+        ln_b = work.get("ln", [0, 0, 0])
+        ln_gbs = ln_b[1] / (fam("ln") / 1e3) / 1e9 if fam("ln") > 0 else None
+        step_tf = (step_gflop or 0) * value / 1e3 / world
+        ksum = sum(fam_ms.values())
         line = {
             "metric": METRIC[args.workload],
             "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload, "global_batch": eff, "parallelism": f"dp{world}",
                        "l2": "activations per step (>7 GB) exceed the 126 MB L2; no explicit flush",
@@ -478,36 +629,52 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32},
             "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "kernel": "ofb::gemm_kernel (tcgen05, all epilogues)", "achieved": achieved,
-                         "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
+            # dominant kernel family: the tcgen05 GEMM (all fused epilogues). achieved = algorithmic FLOPs of a step's GEMM
+            # launches (2 M N K, unpadded) / their summed device durations in the replayed graph
+            "roofline": {"bound": "tensor", "kernel": "ofb::gemm_kernel (tcgen05, all epilogues)", "achieved": gemm_tf,
+                         "peak": pk["tflops"], "unit": "TFLOP/s", "frac": frac(gemm_tf, pk["tflops"]),
                          "traffic": (tr["dram_bytes_per_launch"] if tr and args.workload == "search" and args.model == "small"
                                      and B == 256 and args.depth == 12 else None),
-                         "traffic_note": "DRAM bytes per GEMM launch (mean over the 152 launches of a step), ncu --set full, "
-                                         "profiles/r01_gemm_traffic.json; algorithmic FLOPs per launch = "
-                                         f"{gemm_flops / max(len(gemm_t), 1):.4g}",
-                         "peak_source": pk["src"], "launches_per_step": len(gemm_t) / max(n_roof, 1),
-                         "share_of_step": (gemm_ms / n_roof) / (ms / args.steps) if ms > 0 else None,
-                         "timed_over": f"{n_roof} host-launched steps, one CUDA-event pair per GEMM launch",
-                         "step_tflops": (step_gflop or 0) * value / 1e3 / world},
+                         "traffic_note": "DRAM bytes per GEMM launch (mean over the launches of a step), ncu --set full, "
+                                         "profiles/r01_gemm_traffic.json",
+                         "peak_source": pk["src"], "launches_per_step": work.get("gemm", [0, 0, 0])[2],
+                         "ms_per_step": fam("gemm"), "share_of_step": fam("gemm") / step_ms if step_ms > 0 else None,
+                         "timed_over": timed_over},
+            # the whole step against the tensor roofline (north_star: >= 0.60): algorithmic FLOPs of the step / step time
+            "roofline_step": {"bound": "tensor", "achieved": step_tf, "peak": pk["tflops"], "unit": "TFLOP/s",
+                              "frac": step_tf / pk["tflops"], "target_frac": 0.60},
+            # attention kernels: tensor work AND algorithmic HBM bytes (q, k, v, o [, dO, dq, dk, dv]); the smaller time floor is HBM
+            "roofline_attention": attn,
             # the HBM-bound kernel family of the step: LayerNorm forward / backward, algorithmic bytes (bf16 rows
-            # read + written) over CUDA-event durations of the same host-launched steps, against the measured copy bandwidth
+            # read + written) over device durations, against the measured copy bandwidth
             "roofline_hbm": {"bound": "hbm", "kernel": "ofb::ln_fwd*/ln_bwd* (LayerNorm forward + backward)",
-                             "achieved": (ln_bytes / (ln_ms / 1e3) / 1e9) if ln_ms > 0 else None, "peak": pk["hbm"],
-                             "unit": "GB/s", "frac": (ln_bytes / (ln_ms / 1e3) / 1e9 / pk["hbm"]) if ln_ms > 0 else None,
-                             "launches_per_step": len(ln_t) / max(n_roof, 1),
-                             "share_of_step": (ln_ms / n_roof) / (ms / args.steps) if ms > 0 else None, "traffic": None},
+                             "achieved": ln_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": frac(ln_gbs, pk["hbm"]),
+                             "launches_per_step": ln_b[2], "ms_per_step": fam("ln"),
+                             "share_of_step": fam("ln") / step_ms if step_ms > 0 else None, "traffic": None},
+            # every kernel family of the replayed step: ms per step and share of the device-timed step (branches of the graph
+            # overlap, so the shares can add up to slightly more than 1)
+            "kernel_shares": {k: {"ms_per_step": v, "share_of_step": v / step_ms} for k, v in sorted(fam_ms.items(),
+                                                                                                      key=lambda kv: -kv[1])},
+            "kernel_sum_ms": ksum,
+            "top_kernels": [{"name": k[:96], "ms_per_step": v[0], "launches_per_step": v[1]}
+                            for k, v in sorted(kern.items(), key=lambda kv: -kv[1][0])[:12]],
             "losses": {"base": scal[0], "arch": scal[1], "decoder": scal[2], "total": scal[3]},
         }
+        if world == 1:
+            eng.release_graphs()
+            del eng, step, eager_step, stage_img, dev_img
+            torch.cuda.empty_cache()
         if world == 1 and not args.no_cpu_baseline:
-            if args.workload == "finetune":
-                rate, cores, dt = cpu_ft_oracle_rate(args.cpu_sample_batch)
-            elif args.workload == "post":
-                rate, cores, dt = cpu_post_oracle_rate(args.cpu_sample_batch)
-            else:
-                rate, cores, dt = cpu_oracle_rate(args.model, args.depth, args.cpu_sample_batch)
-            line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
+            rate, cores, dt, kind = cpu_arm(args)
+            what = "unmodified reference, oracle/_ref" if kind == "reference" else "oracle port"
+            line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": cores, "kind": kind,
                                     "sample": f"{args.cpu_sample_batch} images / step of the same DeiT-{args.model} {args.workload} "
-                                              f"step (oracle port, fp32, {cores} threads, {dt:.1f} s/step)"}
+                                              f"step ({what}, fp32, {cores} threads, {dt:.1f} s/step)"}
+        if world == 1 and not args.no_eager and args.workload == "search":
+            line["gpu_eager_baseline"] = gpu_eager_baseline(args.model, args.depth, B)
+        if world == 1 and not args.no_extra and args.workload == "search" and args.model == "small":
+            line["extra_configs"] = [extra_config("tiny", 1024, "search", dev), extra_config("base", 256, "search", dev),
+                                     extra_config("small", 256, "finetune", dev)]
         sys.stdout.flush()
         os.write(out_fd, (json.dumps(line) + "\n").encode())
     mark("result written")

@@ -109,7 +109,7 @@ class BimaskTable:
             # (vision_transformer.py:193-201). Every state compress() can leave keeps the widest surviving embed cell equal to
             # the current width (it truncates first), so all channels are reserved and this engine's all-channel LayerNorm is
             # the same thing; a hand-built switch table whose widest cell is dead would silently diverge - refuse it.
-            if kind == 0 and not bool(sw[:, -1].any()):
+            if kind == 0 and int(sw.sum()) > 1 and not bool(sw[:, -1].any()):
                 raise ValueError("patch_embed switch cells: the widest embedding candidate must be alive (the reference would "
                                  "normalise a channel subset, vision_transformer.py:193-201; compress() never leaves this state)")
             self.modules.append(dict(prefix=prefix, kind=kind, dim=dim, heads=heads, stride=stride, slot=slot, n_i=sw.shape[0],
@@ -704,9 +704,11 @@ class SearchStepEngine:
         return self.scal
 
     # ------------------------------------------------------------------------------------------------------------
-    def backward(self, exchange=False):
+    def backward(self, exchange=False, loss_grads=True):
         """Backward of the step. exchange=True: the data-parallel bucket all-reduces are launched from inside (each bucket
-        as soon as backward has passed its blocks) and joined at the end, so the gradients are averaged on return."""
+        as soon as backward has passed its blocks) and joined at the end, so the gradients are averaged on return.
+        loss_grads=False: d score / d alpha carry the network path only - the sparsity / FLOPs loss terms are left to the caller
+        (modules.py: under the reference's own training loop OFBSearchLOSS computes them with autograd)."""
         B, D, H, T, L, M, ML, hid = self.B, self.D, self.H, self.T, self.L, self.M, self.ML, self.hid
         bm = self.bimask
         red = self._reducer if (exchange and self.world > 1) else None
@@ -828,7 +830,7 @@ class SearchStepEngine:
         ops.gemm(ops.EPI_WGRAD, self.dconv, self.patches, M=D, N=768, K=ML,
                  out0=self.g("patch_embed.proj.weight").view(D, 768), a_mn=True, b_mn=True)
         # ---- bi-mask: d gate (+ FLOPs / sparsity losses) -> d score, d alpha ----
-        bm.backward(self.params, self.hyper[self._wp_idx:self._wp_idx + 1], self.dgate, gs, self.grads)
+        bm.backward(self.params, self.hyper[self._wp_idx:self._wp_idx + 1], self.dgate, gs if loss_grads else 0.0, self.grads)
         if red is not None:
             red.finish()
 

@@ -19,7 +19,18 @@ GEMM_TIMING = None
 LN_TIMING = None
 
 
+# optional algorithmic-work log (bench.py roofline): set to a list -> the GEMM / attention / LayerNorm wrappers append
+# (kernel family, algorithmic FLOPs, algorithmic HBM bytes) per launch; durations come from CUPTI kernel records of graph replays
+WORK_LOG = None
+
+
+def _work(family, flops, nbytes):
+    if WORK_LOG is not None:
+        WORK_LOG.append((family, float(flops), float(nbytes)))
+
+
 def _ln_timed(call, nbytes):
+    _work("ln", 0.0, nbytes)
     if LN_TIMING is None:
         return call()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -99,6 +110,7 @@ def gemm(epi, A, B, *, M, N, K, out0=None, ld0=0, out1=None, ld1=0, out_fp32=Fal
     ldb = ldb if ldb is not None else B.stride(0)
     global _TAG
     _TAG = f"epi{epi} M{M} N{N} K{K} a{int(a_mn)}b{int(b_mn)}"
+    _work("gemm", 2.0 * M * N * K, 2.0 * (M * K + N * K + M * N * (2 if epi == EPI_FC1 else 1)))
     if GEMM_TIMING is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -334,10 +346,14 @@ def bimask_bwd(mods_dev, nmod, max_n, params, switches, widths, w_p_dev, dgate, 
 # attention
 # ---------------------------------------------------------------------------------------------------------------------
 def attention_fwd(qkv, o, lse, drop_scale, B, T, H, scale):
+    # algorithmic work: 4 H T^2 d FLOPs per image; HBM: read q, k, v, write o (bf16) + lse
+    _work("attn_fwd", 4.0 * B * H * T * T * 64, 2.0 * B * T * H * 64 * 4 + 4.0 * B * H * T)
     check(lib().ofb_attention_fwd(ptr(qkv), ptr(o), ptr(lse), ptr(drop_scale), B, T, H, scale, cur_stream()),
           "ofb_attention_fwd")
 
 
 def attention_bwd(qkv, o, d_o, lse, gate, drop_scale, dqkv, part_gate, part_bias, B, T, H, scale):
+    # backward = 2.5 x forward FLOPs (S recomputed, dP, dV, dK, dQ); HBM: read q, k, v, o, dO, write dq, dk, dv
+    _work("attn_bwd", 10.0 * B * H * T * T * 64, 2.0 * B * T * H * 64 * 8 + 4.0 * B * H * T)
     check(lib().ofb_attention_bwd(ptr(qkv), ptr(o), ptr(d_o), ptr(lse), ptr(gate), ptr(drop_scale), ptr(dqkv),
                                   ptr(part_gate), ptr(part_bias), B, T, H, scale, cur_stream()), "ofb_attention_bwd")

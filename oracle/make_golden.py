@@ -185,6 +185,7 @@ def main():
         for k, g in ref["grads"].items():
             if g is not None:
                 gold["gsum:" + k] = summarize(g).numpy()
+                gold["gmax:" + k] = np.array(float(g.abs().max()))      # scale of the sampled-entry comparison
                 gold["psum:" + k] = summarize(ref["new_params"][k]).numpy()
         for k, gt in ref["gates"].items():
             gold["gate:" + k] = gt.numpy()

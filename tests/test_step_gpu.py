@@ -14,11 +14,12 @@ GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(os.path.abspath(
               if not os.path.basename(p).startswith("ft_"))       # ft_*: finetune-step fixtures (test_ft_*.py)
 
 
-@pytest.mark.parametrize("D,H,depth,B,ef,dpr", [(192, 3, 2, 8, 0.0, 0.1), (192, 3, 12, 16, 10.0, 0.1),
-                                                (384, 6, 3, 8, 5.0, 0.1), (768, 12, 2, 8, 20.0, 0.0)])
-def test_step_matches_oracle(cuda_dev, D, H, depth, B, ef, dpr):
-    """Fixed tolerance (step_compare.py header): every gradient tensor rel-L2 < 2e-2 against the fp32 CPU oracle."""
-    res = compare_step_with_oracle(D, H, depth, B, epoch_frac=ef, drop_path_rate=dpr, verbose=True)
+@pytest.mark.parametrize("D,H,depth,B,ef,dpr,dev", [(192, 3, 2, 16, 0.0, 0.1, "cpu"), (192, 3, 12, 16, 10.0, 0.1, "cuda"),
+                                                    (384, 6, 3, 16, 5.0, 0.1, "cuda"), (768, 12, 2, 16, 20.0, 0.0, "cuda")])
+def test_step_matches_oracle(cuda_dev, D, H, depth, B, ef, dpr, dev):
+    """Fixed tolerance (step_compare.py header): every gradient tensor rel-L2 < 2e-2 against the fp32 oracle (on the CPU for
+    the first case, on the GPU with TF32 off for the rest)."""
+    res = compare_step_with_oracle(D, H, depth, B, epoch_frac=ef, drop_path_rate=dpr, verbose=True, oracle_device=dev)
     print(res["summary"])
     assert res["ok"], res["summary"]
 
@@ -48,37 +49,48 @@ def test_gradient_accumulation(cuda_dev, D, H, depth, B, accum, dev):
 
 def test_graphed_accumulation_matches_eager(cuda_dev):
     """step_graphed(update=False/True) - the benchmarked path - accumulates and updates exactly like the eager step():
-    same micro-batches, DropPath off and the PMIM noise pinned through the generator seed, parameters after two optimizer
-    steps of accum_iter = 2 compared (bit-level differences only from the atomically accumulated weight gradients)."""
+    same micro-batches, DropPath off, the PMIM noise pinned. The accumulated gradients of two micro-steps are compared before
+    any update (they differ only by the order of the atomically accumulated weight-gradient partials), then the boundary
+    micro-step: one AdamW update, gradients zeroed, step_count advanced once."""
     from fixtures import make_inputs, make_params
     from ofb_b200.engine import SearchStepEngine
     from ofb_oracle import ModelCfg
+    from step_compare import rel_l2
     cfg = ModelCfg(embed_dim=192, num_heads=3, depth=2)
     P = make_params(cfg, seed=0)
     B = 8
-    batches = [make_inputs(cfg, B, seed=10 + i, drop_path_rate=0.0) for i in range(4)]
-    out = []
+    batches = [make_inputs(cfg, B, seed=10 + i, drop_path_rate=0.0) for i in range(3)]
+    grads, params = [], []
     for graphed in (False, True):
-        eng = SearchStepEngine(192, 3, 2, B, drop_path_rate=0.0, lr=1e-3, accum_iter=2)
+        eng = SearchStepEngine(192, 3, 2, B, drop_path_rate=0.0, lr=1e-3, accum_iter=3)
         eng.load_params(P)
         eng.set_schedule(2.0)
-        torch.manual_seed(5)
-        torch.cuda.manual_seed(5)
-        if graphed:
-            img, lab = torch.empty(B, 3, 224, 224, device="cuda"), torch.empty(B, dtype=torch.int64, device="cuda")
-        for i, b in enumerate(batches):
-            upd = i % 2 == 1
+        img, lab = torch.empty(B, 3, 224, 224, device="cuda"), torch.empty(B, dtype=torch.int64, device="cuda")
+
+        def run(b, upd):
+            img.copy_(b.images); lab.copy_(b.labels)
             if graphed:
-                img.copy_(b.images); lab.copy_(b.labels)
                 eng.step_graphed(img, lab, update=upd, noise=b.noise.cuda())
             else:
-                eng.step(b.images.cuda(), b.labels.cuda(), noise=b.noise.cuda(), update=upd)
+                eng.step(img, lab, noise=b.noise.cuda(), update=upd)
+        run(batches[0], False)
+        run(batches[1], False)
         torch.cuda.synchronize()
-        assert eng.step_count == 2
-        out.append({k: v.detach().cpu().clone() for k, v in eng.named_parameters().items()})
-    for k in out[0]:
-        d = float((out[0][k] - out[1][k]).abs().max())
-        assert d <= 2e-5 * max(1.0, float(out[0][k].abs().max())), (k, d)
+        assert eng.step_count == 0
+        grads.append({k: v.detach().cpu().clone() for k, v in eng.named_grads().items()})
+        run(batches[2], True)
+        torch.cuda.synchronize()
+        assert eng.step_count == 1 and float(eng.grads.abs().max()) == 0.0
+        params.append({k: v.detach().cpu().clone() for k, v in eng.named_parameters().items()})
+    for k in grads[0]:
+        assert float(grads[0][k].abs().max()) > 0 or k.endswith("alpha_patch"), k
+        assert rel_l2(grads[1][k], grads[0][k]) < 1e-5, (k, rel_l2(grads[1][k], grads[0][k]))
+    # Adam's first step moves a parameter by lr * sign(g): entries whose gradient is numerical noise around zero (the k part of
+    # qkv.bias is mathematically zero) can land 2 lr apart, everything else agrees to rounding - hence the median
+    assert not torch.equal(params[0]["head.weight"], P["head.weight"])
+    for k in params[0]:
+        d = (params[0][k] - params[1][k]).abs()
+        assert float(d.median()) < 1e-6 and float(d.max()) <= 2.1e-3, (k, float(d.median()), float(d.max()))
 
 
 @pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
@@ -120,8 +132,9 @@ def test_step_matches_reference_golden(cuda_dev, path):
             assert rel(eng.bimask.gate_of(i).cpu().numpy(), g[key]) < 1e-4, key
         if key.startswith("gsum:"):
             got = summarize(eng.g(key[5:]).cpu()).numpy()
-            # strided samples of the gradient, relative to the gradient's max-norm scale (l2 / sqrt(n) is too lenient)
-            e = float(np.abs(got[3:] - g[key][3:]).max() / (np.abs(g[key][3:]).max() + 1e-30))
+            # strided samples of the gradient, relative to the gradient's max-norm scale (l2 / sqrt(n) is too lenient; the
+            # largest SAMPLED entry is not a scale either: pos_embed's gradient is dominated 10^4 : 1 by its cls row)
+            e = float(np.abs(got[3:] - g[key][3:]).max() / (float(g["gmax:" + key[5:]]) + 1e-30))
             worst = max(worst, (key, e), key=lambda kv: kv[1])
             assert abs(got[2] - g[key][2]) / (g[key][2] + 1e-30) < BF16_TOL, key     # l2 norm
     print("worst sampled gradient error:", worst)
