@@ -14,6 +14,7 @@
 // q,k,v are read straight out of the token-major qkv GEMM output [B, T, 3, H, 64] through a 5-D tensor map, so the
 // reference's reshape/permute/contiguous copy (layers.py:491) never happens; TMA zero-fills tokens >= T.
 #include "ptx.cuh"
+#include "launch.cuh"
 #include <math.h>
 
 namespace ofb {
@@ -86,6 +87,7 @@ __device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                 const __grid_constant__ CUtensorMap tm_o, const AttnArgs a) {
+    pdl_trigger();
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sQ = smem_u32(smem);                       // 2 tiles
     const uint32_t sK = sQ + 2 * TILE_B;
@@ -114,6 +116,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_wait();
     constexpr uint32_t IDESC_S = make_idesc_bf16(128, KVP, 0, 0);
     constexpr uint32_t IDESC_O = make_idesc_bf16(128, HD, 0, 1);
 
@@ -138,7 +141,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
     } else if (warp == FWD_CW + 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // the whole warp runs the loop (uniform operands stay in uniform registers); one elected lane issues the tcgen05 instructions
+        {
             int it = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
                 const uint32_t ph = it & 1;
@@ -146,24 +150,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 for (int s = 0; s < 2; ++s) {
                     mbar_wait(slot_bar(s, 3), ph ^ 1);          // slot's TMEM free (previous item's O read out)
                     tc_fence_after();
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < HD / 16; ++k)
-                        umma_bf16(tmem + s * 256, make_smem_desc_sw128(sQ + s * TILE_B + k * 32, 0, 1024),
-                                  make_smem_desc_sw128(sK + k * 32, 0, 1024), IDESC_S, k > 0);
-                    umma_commit(slot_bar(s, 0));
+                        for (int k = 0; k < HD / 16; ++k)
+                            umma_bf16(tmem + s * 256, make_smem_desc_sw128(sQ + s * TILE_B + k * 32, 0, 1024),
+                                      make_smem_desc_sw128(sK + k * 32, 0, 1024), IDESC_S, k > 0);
+                        umma_commit(slot_bar(s, 0));
+                        if (s == 1) umma_commit(qk_empty);      // Q / K may be overwritten by the next item's loads
+                    }
+                    __syncwarp();
                 }
-                umma_commit(qk_empty);                          // Q / K may be overwritten by the next item's loads
                 mbar_wait(v_full, ph);
                 for (int s = 0; s < 2; ++s) {
                     mbar_wait(slot_bar(s, 1), ph);              // P of this slot is in shared memory, S fully consumed
                     tc_fence_after();
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < KVP / 16; ++k)
-                        umma_bf16(tmem + s * 256, make_smem_desc_sw128(sP + s * PBUF_B + (k >> 2) * TILE_B + (k & 3) * 32, 0, 1024),
-                                  make_smem_desc_sw128(sV + k * 2048, 0, 1024), IDESC_O, k > 0);
-                    umma_commit(slot_bar(s, 2));
+                        for (int k = 0; k < KVP / 16; ++k)
+                            umma_bf16(tmem + s * 256, make_smem_desc_sw128(sP + s * PBUF_B + (k >> 2) * TILE_B + (k & 3) * 32, 0, 1024),
+                                      make_smem_desc_sw128(sV + k * 2048, 0, 1024), IDESC_O, k > 0);
+                        umma_commit(slot_bar(s, 2));
+                        if (s == 1) umma_commit(v_empty);
+                    }
+                    __syncwarp();
                 }
-                umma_commit(v_empty);
             }
         }
     } else {
@@ -394,6 +404,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                 const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_out,
                 const __grid_constant__ CUtensorMap tm_o, const AttnArgs a) {
+    pdl_trigger();
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sQ = smem_u32(smem);                   // 2 q tiles
     const uint32_t sDO = sQ + 2 * TILE_B;                 // 2 q tiles
@@ -435,6 +446,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_wait();
     const uint32_t tDQ = tmem + 256, tDK = tmem + 384, tDV = tmem + 448;
     constexpr uint32_t IDESC_DQ = make_idesc_bf16(128, HD, 0, 1);     // dQ     : dS K-major, K MN-major
     constexpr uint32_t IDESC_KV = make_idesc_bf16(128, HD, 1, 1);     // dK, dV : MN-major x MN-major
@@ -480,11 +492,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         // Sub-tiles are processed in pairs (t0, t0+1) = the two q tiles of one kv half; the compute warps run
         //   P(t0) P(t0+1) dS(t0) dS(t0+1)
         // so that every MMA -> mbarrier -> compute round trip of one sub-tile is covered by compute work on the other one.
-        if (lane == 0) {
+        // The whole warp runs the loop (uniform operands stay in uniform registers: a `lane == 0` region made the compiler
+        // broadcast every descriptor through an R2UR waterfall in front of each UTCHMMA, ~130 MMAs per item); one elected lane
+        // issues the tcgen05 instructions.
+        {
             uint32_t use0 = 0, use1 = 0;       // completed uses of the per-slot barriers (slot = sub-tile parity)
             uint32_t n_acc = 0;                // kv halves started (ACC_EMPTY waits)
             const uint32_t n_kv0 = uint32_t(min(kvp, QT));
-            auto issue_s = [&](int t) {
+            auto issue_s = [&](int t) {        // (elected lane only)
                 const int j = (nh == 2) ? (t >> 1) : 0, i = (nh == 2) ? (t & 1) : 0;
                 const uint32_t idesc = make_idesc_bf16(128, j == 0 ? n_kv0 : uint32_t(n_kv1), 0, 0);
                 const uint32_t qa = sQ + i * TILE_B, kb = sK + j * (QT * 128);
@@ -501,8 +516,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 mbar_wait(bar(QK_FULL), pi);
                 TRC(2, 1);
                 tc_fence_after();
-                issue_s(0);
-                if (nt > 1) issue_s(1);
+                if (elect_one()) {
+                    issue_s(0);
+                    if (nt > 1) issue_s(1);
+                }
+                __syncwarp();
 #pragma unroll 1
                 for (int t0 = 0; t0 < nt; t0 += 2) {
                     const int np = min(2, nt - t0);
@@ -518,16 +536,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                         if (t0 == 0 && i == 0) mbar_wait(bar(DOV_FULL), pi);
                         if (i == 0) { const long long tw = TRC_NOW(); mbar_wait(bar(ACC_EMPTY), (n_acc & 1u) ^ 1u); ++n_acc; TRC_ACC(2, 9, tw); }   // previous dK / dV read out
                         tc_fence_after();
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < QT / 16; ++k)
-                            umma_bf16(tDV, make_smem_desc_sw128(pbuf + k * 2048, TILE_B, 1024),
-                                      make_smem_desc_sw128(doa + k * 2048, 0, 1024), IDESC_KV, (i > 0 || k > 0) ? 1u : 0u);
-                        const uint32_t idesc = make_idesc_bf16(128, nj, 0, 0);
+                            for (int k = 0; k < QT / 16; ++k)
+                                umma_bf16(tDV, make_smem_desc_sw128(pbuf + k * 2048, TILE_B, 1024),
+                                          make_smem_desc_sw128(doa + k * 2048, 0, 1024), IDESC_KV, (i > 0 || k > 0) ? 1u : 0u);
+                            const uint32_t idesc = make_idesc_bf16(128, nj, 0, 0);
 #pragma unroll
-                        for (int k = 0; k < HD / 16; ++k)
-                            umma_bf16(tmem + i * 128, make_smem_desc_sw128(doa + k * 32, 0, 1024),
-                                      make_smem_desc_sw128(vb + k * 32, 0, 1024), idesc, k > 0);
-                        umma_commit(bar(DP_FULL + i));
+                            for (int k = 0; k < HD / 16; ++k)
+                                umma_bf16(tmem + i * 128, make_smem_desc_sw128(doa + k * 32, 0, 1024),
+                                          make_smem_desc_sw128(vb + k * 32, 0, 1024), idesc, k > 0);
+                            umma_commit(bar(DP_FULL + i));
+                        }
+                        __syncwarp();
                     }
                     // ---- once dS of a sub-tile is in place: S of the sub-tile two ahead (its TMEM region is free now), then
                     //      dQ_i (+)= dS K_j and dK_j (+)= dS^T Q_i ----
@@ -539,20 +560,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                         { const long long tw = TRC_NOW(); mbar_wait(bar(DS_FULL + i), par); TRC_ACC(2, 10, tw); }
                         if (t0 == 0 && i == 0) { const long long tw = TRC_NOW(); mbar_wait(bar(DQ_EMPTY), pi ^ 1u); TRC_ACC(2, 11, tw); }       // previous item's dQ read out
                         tc_fence_after();
-                        if (t0 + 2 + i < nt) issue_s(t0 + 2 + i);
-                        for (uint32_t k = 0; k < nj / 16; ++k)
-                            umma_bf16(tDQ + i * HD, make_smem_desc_sw128(pbuf + (k >> 2) * TILE_B + (k & 3) * 32, 0, 1024),
-                                      make_smem_desc_sw128(kb + k * 2048, 0, 1024), IDESC_DQ, (j > 0 || k > 0) ? 1u : 0u);
+                        if (elect_one()) {
+                            if (t0 + 2 + i < nt) issue_s(t0 + 2 + i);
+                            for (uint32_t k = 0; k < nj / 16; ++k)
+                                umma_bf16(tDQ + i * HD, make_smem_desc_sw128(pbuf + (k >> 2) * TILE_B + (k & 3) * 32, 0, 1024),
+                                          make_smem_desc_sw128(kb + k * 2048, 0, 1024), IDESC_DQ, (j > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
-                        for (int k = 0; k < QT / 16; ++k)
-                            umma_bf16(tDK, make_smem_desc_sw128(pbuf + k * 2048, TILE_B, 1024),
-                                      make_smem_desc_sw128(qa + k * 2048, 0, 1024), IDESC_KV, (i > 0 || k > 0) ? 1u : 0u);
-                        umma_commit(bar(PB_FREE + i));
+                            for (int k = 0; k < QT / 16; ++k)
+                                umma_bf16(tDK, make_smem_desc_sw128(pbuf + k * 2048, TILE_B, 1024),
+                                          make_smem_desc_sw128(qa + k * 2048, 0, 1024), IDESC_KV, (i > 0 || k > 0) ? 1u : 0u);
+                            umma_commit(bar(PB_FREE + i));
+                            if (i == np - 1) {
+                                umma_commit(bar(ACC_FULL));
+                                if (t0 + 2 >= nt) { umma_commit(bar(DQ_FULL)); umma_commit(bar(ITEM_EMPTY)); }
+                            }
+                        }
+                        __syncwarp();
                     }
-                    umma_commit(bar(ACC_FULL));
                 }
-                umma_commit(bar(DQ_FULL));
-                umma_commit(bar(ITEM_EMPTY));
                 TRC(2, 2);
             }
         }
@@ -880,8 +905,7 @@ int launch_attn_fwd(const void* qkv, void* o, float* lse, const float* drop_scal
     a.o = reinterpret_cast<__nv_bfloat16*>(o); a.lse = lse;
     const int items = B * H;
     const int grid = items < num_sms() ? items : num_sms();
-    attn_fwd_kernel<<<grid, FWD_THREADS, FWD_SMEM, s>>>(tq, tkv, to, a);
-    return int(cudaGetLastError());
+    return int(launch_k(attn_fwd_kernel, dim3(grid), dim3(FWD_THREADS), size_t(FWD_SMEM), s, 1, tq, tkv, to, a));
 }
 
 int launch_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, const float* gate, const float* drop_scale,
@@ -926,8 +950,7 @@ int launch_attn_bwd(const void* qkv, const void* o, const void* d_o, const float
     a.part_gate = part_gate; a.part_bias = part_bias;
     const int items = B * H;
     const int grid = items < num_sms() ? items : num_sms();
-    attn_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM, s>>>(tq, tkv, tdo, tout, to, a);
-    return int(cudaGetLastError());
+    return int(launch_k(attn_bwd_kernel, dim3(grid), dim3(BWD_THREADS), size_t(BWD_SMEM), s, 1, tq, tkv, tdo, tout, to, a));
 }
 
 #ifdef OFB_ATTN_TRACE

@@ -8,6 +8,7 @@
 //   * double argsort + gather                   ==  rank by counting (ties: lower index first)
 // one CTA per module, fp32 throughout, FLOPs polynomial in double.
 #include "ptx.cuh"
+#include "launch.cuh"
 #include <math.h>
 
 namespace ofb {
@@ -53,6 +54,7 @@ __global__ void __launch_bounds__(BM_THREADS) bimask_fwd_kernel(const BimaskModu
                                                                 const float* __restrict__ w_p_ptr, float* __restrict__ gate,
                                                                 int* __restrict__ rank, float* __restrict__ aprob, float* __restrict__ wsum,
                                                                 float* __restrict__ sp_loss) {
+    pdl_wait();
     extern __shared__ float bsm[];
     __shared__ float a[MAX_CELLS];
     __shared__ float red[BM_THREADS / 32];
@@ -170,6 +172,7 @@ __global__ void __launch_bounds__(BM_THREADS) bimask_fwd_kernel(const BimaskModu
 //      arch[5] = searched GFLOPs, arch[6] = original GFLOPs
 __global__ void arch_finalize_kernel(const BimaskModule* __restrict__ mods, int nmod, const float* __restrict__ wsum,
                                      const float* __restrict__ sp_loss, ArchDims ad, float* __restrict__ arch, float* __restrict__ dwsum) {
+    pdl_wait();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const double n = ad.L, D = ad.D, H = ad.H, d = ad.d, hid = ad.hidden, C = ad.C, Da = ad.D_active;
     const double ae = wsum[0];
@@ -218,6 +221,7 @@ __global__ void __launch_bounds__(BM_THREADS) bimask_bwd_kernel(const BimaskModu
                                                                 const float* __restrict__ w_p_ptr, const float* __restrict__ dgate,
                                                                 const int* __restrict__ rank, const float* __restrict__ aprob,
                                                                 const float* __restrict__ dwsum, float grad_scale, float* __restrict__ grads) {
+    pdl_wait();
     extern __shared__ float bsm[];
     __shared__ float red[BM_THREADS / 32];
     __shared__ float da[MAX_CELLS];
@@ -293,7 +297,7 @@ int launch_bimask_fwd(const void* mods, int nmod, int max_n, const float* params
     const size_t smem = size_t(2) * max_n * sizeof(float);
     if (smem > 48 * 1024) return 1020;
     const int parts = max_n > 512 ? 8 : (max_n > 256 ? 2 : 1);
-    bimask_fwd_kernel<<<dim3(nmod, parts), BM_THREADS, smem, s>>>(reinterpret_cast<const BimaskModule*>(mods), params, switches, widths,
+    OFB_LAUNCH(bimask_fwd_kernel, dim3(nmod, parts), BM_THREADS, smem, s, reinterpret_cast<const BimaskModule*>(mods), params, switches, widths,
                                                                  w_p_ptr, gate, rank, aprob, wsum, sp_loss);
     return int(cudaGetLastError());
 }
@@ -301,7 +305,7 @@ int launch_bimask_fwd(const void* mods, int nmod, int max_n, const float* params
 int launch_arch_finalize(const void* mods, int nmod, const float* wsum, const float* sp_loss, int depth, int D, int H, int d, int hidden,
                          int D_active, int L, int C, float target_flops, float w_flops, float* arch, float* dwsum, cudaStream_t s) {
     ArchDims ad{depth, D, H, d, hidden, L, C, D_active > 0 ? D_active : D, target_flops, w_flops};
-    arch_finalize_kernel<<<1, 32, 0, s>>>(reinterpret_cast<const BimaskModule*>(mods), nmod, wsum, sp_loss, ad, arch, dwsum);
+    OFB_LAUNCH(arch_finalize_kernel, 1, 32, 0, s, reinterpret_cast<const BimaskModule*>(mods), nmod, wsum, sp_loss, ad, arch, dwsum);
     return int(cudaGetLastError());
 }
 
@@ -310,7 +314,7 @@ int launch_bimask_bwd(const void* mods, int nmod, int max_n, const float* params
                       float grad_scale, float* grads, cudaStream_t s) {
     const size_t smem = size_t(max_n) * sizeof(float);
     if (smem > 48 * 1024) return 1020;
-    bimask_bwd_kernel<<<nmod, BM_THREADS, smem, s>>>(reinterpret_cast<const BimaskModule*>(mods), params, switches, widths, w_p_ptr, dgate,
+    OFB_LAUNCH(bimask_bwd_kernel, nmod, BM_THREADS, smem, s, reinterpret_cast<const BimaskModule*>(mods), params, switches, widths, w_p_ptr, dgate,
                                                      rank, aprob, dwsum, grad_scale, grads);
     return int(cudaGetLastError());
 }

@@ -4,6 +4,7 @@
 // loss finalisation, column-partial reduction, fused multi-segment AdamW (+ bf16 shadow weights + grad zeroing).
 // All are vectorised (16-byte accesses), warp-shuffle reduced, grid-strided over 148 SMs.
 #include "ptx.cuh"
+#include "launch.cuh"
 #include <math.h>
 #include <string.h>
 #include <stdlib.h>
@@ -39,6 +40,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const __nv_bfloat16* __rest
                                                      const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
                                                      float* __restrict__ mean, float* __restrict__ rstd, int M, int D, float eps,
                                                      int Dv) {
+    pdl_wait();          // programmatic dependent launch: inputs of the previous kernel are complete from here on (launch.cuh)
     // Dv <= D: number of real channels; columns [Dv, D) are zero padding of a physically pruned embedding (they hold zeros,
     // carry gamma = beta = 0 and must not enter the statistics: the reference normalises over Dv channels)
     const int lane = threadIdx.x & 31;
@@ -113,6 +115,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
                                                      float* __restrict__ part_dbias, const float* __restrict__ rowscale,
                                                      int rows_per_scale, int M, int D, int Dv,
                                                      const __nv_bfloat16* __restrict__ dres) {
+    pdl_wait();          // programmatic dependent launch: inputs of the previous kernel are complete from here on (launch.cuh)
     // Dv: real channels (see ln_fwd_kernel); dres (optional): gradient arriving over the residual connection that bypasses
     // this LayerNorm (pre-norm blocks, vision_transformer.py:157-160), added to dx before it is stored / column-summed
     extern __shared__ __align__(128) uint8_t ln_smem_raw[];
@@ -293,6 +296,7 @@ template <int W>
 __global__ void __launch_bounds__(256) ln_fwd3_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                                                       const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
                                                       float* __restrict__ mean, float* __restrict__ rstd, int M, float eps) {
+    pdl_wait();          // programmatic dependent launch: inputs of the previous kernel are complete from here on (launch.cuh)
     using V = typename WordVec<W>::T;
     constexpr int D = 192 * W, NP = 3 * W;
     const int lane = threadIdx.x & 31;
@@ -348,6 +352,7 @@ template <int W>
 __global__ void __launch_bounds__(256) ln_fwd3x2_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
                                                         float* __restrict__ mean, float* __restrict__ rstd, int M, float eps) {
+    pdl_wait();          // programmatic dependent launch: inputs of the previous kernel are complete from here on (launch.cuh)
     using V = typename WordVec<W>::T;
     constexpr int D = 192 * W, NP = 3 * W, RB = 2;
     const int lane = threadIdx.x & 31;
@@ -432,6 +437,7 @@ __global__ void __launch_bounds__(256) ln_bwd3_kernel(const __nv_bfloat16* __res
                                                       float* __restrict__ part_dgamma, float* __restrict__ part_dbeta,
                                                       float* __restrict__ part_dbias, const float* __restrict__ rowscale,
                                                       int rows_per_scale, int M) {
+    pdl_wait();          // programmatic dependent launch: inputs of the previous kernel are complete from here on (launch.cuh)
     using V = typename WordVec<W>::T;
     constexpr int D = 192 * W, NP = 3 * W, WPB = 8;
     extern __shared__ __align__(128) uint8_t ln_smem_raw[];
@@ -563,6 +569,7 @@ __global__ void __launch_bounds__(256) ln_fwdw_kernel(const __nv_bfloat16* __res
                                                       const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
                                                       float* __restrict__ mean, float* __restrict__ rstd, int M, int D, int Dv,
                                                       float eps) {
+    pdl_wait();          // programmatic dependent launch: inputs of the previous kernel are complete from here on (launch.cuh)
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     const int nw = D >> 1, nv = Dv >> 1;
@@ -619,6 +626,7 @@ __global__ void __launch_bounds__(256) ln_bwdw_kernel(const __nv_bfloat16* __res
                                                       float* __restrict__ part_dbias, const float* __restrict__ rowscale,
                                                       int rows_per_scale, int M, int D, int Dv,
                                                       const __nv_bfloat16* __restrict__ dres) {
+    pdl_wait();          // programmatic dependent launch: inputs of the previous kernel are complete from here on (launch.cuh)
     constexpr int WPB = 8;
     extern __shared__ __align__(128) uint8_t ln_smem_raw[];
     // layout as in ln_bwd_kernel: ring [8 warps][LN_STAGES][2][D bf16] | barriers; the ring is reused as float [3][8][D] at the end
@@ -754,6 +762,7 @@ __global__ void __launch_bounds__(256) ln_bwdw_kernel(const __nv_bfloat16* __res
 // =============================================================================================
 __global__ void reduce_partials_kernel(const float* __restrict__ part, int R, int N, float* __restrict__ out, float scale,
                                        const float* __restrict__ inv_colscale, int accumulate) {
+    pdl_wait();          // programmatic dependent launch: inputs of the previous kernel are complete from here on (launch.cuh)
     const int col = blockIdx.x * 32 + (threadIdx.x & 31);
     const int ty = threadIdx.x >> 5, ny = blockDim.x >> 5;
     __shared__ float sm[32][33];
@@ -776,6 +785,7 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, int R, in
 struct ReduceJob { const float* part; float* out; const float* div_by; int R, N; float scale; int accumulate; };
 struct ReduceJobs { ReduceJob j[12]; };
 __global__ void reduce_partials_multi_kernel(const ReduceJobs jobs) {
+    pdl_wait();          // programmatic dependent launch: inputs of the previous kernel are complete from here on (launch.cuh)
     const ReduceJob jb = jobs.j[blockIdx.y];
     const int col = blockIdx.x * 32 + (threadIdx.x & 31);
     if (blockIdx.x * 32 >= jb.N) return;
@@ -800,6 +810,7 @@ __global__ void reduce_partials_multi_kernel(const ReduceJobs jobs) {
 // (the im2col of the 16x16/16 conv, layers.py:177)
 // =============================================================================================
 __global__ void patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int HW, int P) {
+    pdl_wait();          // programmatic dependent launch: inputs of the previous kernel are complete from here on (launch.cuh)
     // one thread = 8 consecutive pixels of one patch row
     const int G = HW / P;                       // 14
     const int per_img = 3 * HW * HW / 8;
@@ -843,6 +854,7 @@ __device__ __forceinline__ void mix_pair4(const float4& a, const float4& b, int 
     }
 }
 __global__ void __launch_bounds__(256) mixup_batch_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int HW, MixParams mp) {
+    pdl_wait();          // programmatic dependent launch: inputs of the previous kernel are complete from here on (launch.cuh)
     const int per_img = 3 * HW * HW / 4;
     const int pairs = (B + 1) / 2;
     const size_t total = size_t(pairs) * per_img;
@@ -862,6 +874,7 @@ __global__ void __launch_bounds__(256) mixup_batch_kernel(const float* __restric
 // images: PMIM is off, search.py:645)
 __global__ void __launch_bounds__(256) patchify_mixup_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int HW, int P,
                                                              MixParams mp) {
+    pdl_wait();          // programmatic dependent launch: inputs of the previous kernel are complete from here on (launch.cuh)
     const int G = HW / P;
     const int per_img = 3 * HW * HW / 8;
     const int pairs = (B + 1) / 2;
@@ -892,6 +905,7 @@ __global__ void __launch_bounds__(256) patchify_mixup_kernel(const float* __rest
 // timm mixup_target: lam * smoothed one-hot(y) + (1 - lam) * smoothed one-hot(y.flip(0)), fp32 [B, C]
 __global__ void __launch_bounds__(256) mixup_target_kernel(const long long* __restrict__ labels, float* __restrict__ target, int B, int C, float lam,
                                                            float oml, float on, float off) {
+    pdl_wait();          // programmatic dependent launch: inputs of the previous kernel are complete from here on (launch.cuh)
     const size_t total = size_t(B) * C;
     for (size_t idx = blockIdx.x * size_t(blockDim.x) + threadIdx.x; idx < total; idx += size_t(gridDim.x) * blockDim.x) {
         const int b = idx / C, c = idx % C;
@@ -906,6 +920,7 @@ __global__ void __launch_bounds__(256) mixup_target_kernel(const long long* __re
 //   drop_scale[i] = floor(keep_i + u_i) / keep_i   (timm DropPath)
 // =============================================================================================
 __global__ void pmim_mask_kernel(const float* __restrict__ noise, float* __restrict__ mask, int L, int keep) {
+    pdl_wait();          // programmatic dependent launch: inputs of the previous kernel are complete from here on (launch.cuh)
     extern __shared__ float nz[];
     const int b = blockIdx.x;
     for (int i = threadIdx.x; i < L; i += blockDim.x) nz[i] = noise[size_t(b) * L + i];
@@ -919,6 +934,7 @@ __global__ void pmim_mask_kernel(const float* __restrict__ noise, float* __restr
 }
 __global__ void droppath_scale_kernel(const float* __restrict__ u, const float* __restrict__ drop_prob, float* __restrict__ scale,
                                       int n_layers2, int B) {
+    pdl_wait();          // programmatic dependent launch: inputs of the previous kernel are complete from here on (launch.cuh)
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < n_layers2 * B) {
         const float p = drop_prob[idx / B];
@@ -932,6 +948,7 @@ __global__ void droppath_scale_kernel(const float* __restrict__ u, const float* 
 // =============================================================================================
 __global__ void cls_rows_kernel(const float* __restrict__ cls, const float* __restrict__ pos, const float* __restrict__ gate,
                                 __nv_bfloat16* __restrict__ x, int B, int T, int D) {
+    pdl_wait();          // programmatic dependent launch: inputs of the previous kernel are complete from here on (launch.cuh)
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < B * D) {
         const int b = idx / D, c = idx % D;
@@ -954,6 +971,7 @@ __global__ void __launch_bounds__(512) embed_bwd_kernel(const __nv_bfloat16* __r
                                  const float* __restrict__ gate, const float* __restrict__ mask, __nv_bfloat16* __restrict__ dconv,
                                  float* __restrict__ part_gx, float* __restrict__ part_pos, float* __restrict__ part_mt, int B, int T,
                                  int D, int G) {
+    pdl_wait();          // programmatic dependent launch: inputs of the previous kernel are complete from here on (launch.cuh)
     extern __shared__ float eb_red[];                  // [G][D]
     const int t = blockIdx.x;
     const int VC = D >> 3;
@@ -1015,6 +1033,7 @@ __global__ void __launch_bounds__(512) embed_bwd_kernel(const __nv_bfloat16* __r
 static constexpr int NT_P = 16, NT_K = 47, NT_R = 23, NT_W = NT_P + 2 * NT_R;  // 62
 __global__ void __launch_bounds__(256) norm_targets_kernel(const float* __restrict__ img, const float* __restrict__ mask,
                                                            float* __restrict__ tgt, int HW) {
+    pdl_wait();          // programmatic dependent launch: inputs of the previous kernel are complete from here on (launch.cuh)
     const int G = HW / NT_P;
     const int patch = blockIdx.x;             // b*L + l
     const int c = blockIdx.y;
@@ -1065,6 +1084,7 @@ __global__ void __launch_bounds__(256) norm_targets_kernel(const float* __restri
 __global__ void __launch_bounds__(128) ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels,
                                                  float* __restrict__ loss_rows, __nv_bfloat16* __restrict__ dlogits, int C,
                                                  float smoothing, float gscale_over_B) {
+    pdl_wait();          // programmatic dependent launch: inputs of the previous kernel are complete from here on (launch.cuh)
     const int b = blockIdx.x;
     const float* lr = logits + size_t(b) * C;
     __shared__ float red[4];
@@ -1107,6 +1127,7 @@ __global__ void __launch_bounds__(128) ce_kernel(const float* __restrict__ logit
 __global__ void __launch_bounds__(128) soft_ce_kernel(const float* __restrict__ logits, const float* __restrict__ target,
                                                       float* __restrict__ loss_rows, __nv_bfloat16* __restrict__ dlogits, int C,
                                                       float gscale_over_B) {
+    pdl_wait();          // programmatic dependent launch: inputs of the previous kernel are complete from here on (launch.cuh)
     const int b = blockIdx.x;
     const float* lr = logits + size_t(b) * C;
     const float* tr = target + size_t(b) * C;
@@ -1142,6 +1163,7 @@ __global__ void __launch_bounds__(128) soft_ce_kernel(const float* __restrict__ 
 // =============================================================================================
 __global__ void __launch_bounds__(128) eval_metrics_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels,
                                                            float* __restrict__ out_rows, int C) {
+    pdl_wait();          // programmatic dependent launch: inputs of the previous kernel are complete from here on (launch.cuh)
     const int b = blockIdx.x;
     const float* lr = logits + size_t(b) * C;
     __shared__ float red[4];
@@ -1182,6 +1204,7 @@ __global__ void __launch_bounds__(128) eval_metrics_kernel(const float* __restri
 __global__ void __launch_bounds__(1024) loss_finalize_kernel(const float* __restrict__ loss_rows, int B, const float* __restrict__ dec_part,
                                                             int n_dec_part, const float* __restrict__ mask, int n_mask,
                                                             const float* __restrict__ arch_loss, float grad_scale, float* __restrict__ scal) {
+    pdl_wait();          // programmatic dependent launch: inputs of the previous kernel are complete from here on (launch.cuh)
     __shared__ float red[3][32];          // one CTA of 32 warps: the kernel sits on the critical path between forward and backward
     float a = 0.f, d = 0.f, m = 0.f;
     for (int i = threadIdx.x; i < B; i += blockDim.x) a += loss_rows[i];
@@ -1218,6 +1241,7 @@ struct AdamSegs {
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                                                     float* __restrict__ v, __nv_bfloat16* __restrict__ shadow,
                                                     const float* __restrict__ hyper, AdamSegs segs, long long n4, int zero_grad) {
+    pdl_wait();          // programmatic dependent launch: inputs of the previous kernel are complete from here on (launch.cuh)
     int s = 0;        // segment of the current element: monotone along the grid-stride loop, so the scan is amortised
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         const long long e = i * 4;
@@ -1255,6 +1279,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float
 }
 
 __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n4) {
+    pdl_wait();          // programmatic dependent launch: inputs of the previous kernel are complete from here on (launch.cuh)
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         const float4 a = reinterpret_cast<const float4*>(src)[i];
         uint2 o;
@@ -1269,6 +1294,7 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
 // =============================================================================================
 __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int ld, int R, int N, float* __restrict__ out, float scale,
                                    const float* __restrict__ scale_dev) {
+    pdl_wait();          // programmatic dependent launch: inputs of the previous kernel are complete from here on (launch.cuh)
     __shared__ float2 sm[8][32];
     const int col = (blockIdx.x * 32 + threadIdx.x) * 2;
     float2 acc = make_float2(0.f, 0.f);
@@ -1297,7 +1323,7 @@ int launch_colsum_bf16(const void* x, int ld, int R, int N, float* out, float sc
     if (splits > 64) splits = 64;
     if (splits < 1) splits = 1;
     dim3 grid((N + 63) / 64, splits), block(32, 8);
-    colsum_bf16_kernel<<<grid, block, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, R, N, out, scale, scale_dev);
+    OFB_LAUNCH(colsum_bf16_kernel, grid, block, 0, s, reinterpret_cast<const __nv_bfloat16*>(x), ld, R, N, out, scale, scale_dev);
     return int(cudaGetLastError());
 }
 
@@ -1309,7 +1335,7 @@ static int ln_fwd_inst(const void* x, const float* gamma, const float* beta, voi
     int grid = (M + wpb - 1) / wpb;
     const int cap = num_sms() * 8;
     if (grid > cap) grid = cap;
-    ln_fwd_kernel<MAXC><<<grid, wpb * 32, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta,
+    OFB_LAUNCH(ln_fwd_kernel<MAXC>, grid, wpb * 32, 0, s, reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta,
                                                   reinterpret_cast<__nv_bfloat16*>(y), mean, rstd, M, D, eps, Dv);
     return err();
 }
@@ -1321,10 +1347,10 @@ static int ln_fwd3_inst(const void* x, const float* gamma, const float* beta, vo
     const int cap = num_sms() * 8;
     if (grid > cap) grid = cap;
     if (W == 1)
-        ln_fwd3x2_kernel<W><<<grid, wpb * 32, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta,
+        OFB_LAUNCH(ln_fwd3x2_kernel<W>, grid, wpb * 32, 0, s, reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta,
                                                       reinterpret_cast<__nv_bfloat16*>(y), mean, rstd, M, eps);
     else
-        ln_fwd3_kernel<W><<<grid, wpb * 32, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta,
+        OFB_LAUNCH(ln_fwd3_kernel<W>, grid, wpb * 32, 0, s, reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta,
                                                     reinterpret_cast<__nv_bfloat16*>(y), mean, rstd, M, eps);
     return err();
 }
@@ -1341,7 +1367,7 @@ static int ln_fwdw_inst(const void* x, const float* gamma, const float* beta, vo
     int grid = (M + wpb - 1) / wpb;
     const int cap = num_sms() * 8;
     if (grid > cap) grid = cap;
-    ln_fwdw_kernel<NW><<<grid, wpb * 32, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta,
+    OFB_LAUNCH(ln_fwdw_kernel<NW>, grid, wpb * 32, 0, s, reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta,
                                                  reinterpret_cast<__nv_bfloat16*>(y), mean, rstd, M, D, Dv, eps);
     return err();
 }
@@ -1402,7 +1428,7 @@ static int ln_bwd_inst(const void* dy, const void* x, const float* mean, const f
                              int((ring_max > red_max ? ring_max : red_max) + wpb * LN_STAGES * 8));
         configured = true;
     }
-    ln_bwd_kernel<MAXC><<<grid, wpb * 32, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x),
+    OFB_LAUNCH(ln_bwd_kernel<MAXC>, grid, wpb * 32, smem, s, reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x),
                                                      mean, rstd, gamma, reinterpret_cast<__nv_bfloat16*>(dx), part_dgamma, part_dbeta,
                                                      part_dbias, rowscale, rows_per_scale > 0 ? rows_per_scale : 1, M, D, Dv,
                                                      reinterpret_cast<const __nv_bfloat16*>(dres));
@@ -1421,7 +1447,7 @@ static int ln_bwd3_inst(const void* dy, const void* x, const float* mean, const 
         cudaFuncSetAttribute(ln_bwd3_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         configured = true;
     }
-    ln_bwd3_kernel<W><<<grid, wpb * 32, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x),
+    OFB_LAUNCH(ln_bwd3_kernel<W>, grid, wpb * 32, smem, s, reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x),
                                                    mean, rstd, gamma, reinterpret_cast<__nv_bfloat16*>(dx), part_dgamma, part_dbeta,
                                                    part_dbias, rowscale, rows_per_scale > 0 ? rows_per_scale : 1, M);
     return err();
@@ -1442,7 +1468,7 @@ static int ln_bwdw_inst(const void* dy, const void* x, const float* mean, const 
                              int((ring_max > red_max ? ring_max : red_max) + wpb * LN_STAGES * 8));
         configured = true;
     }
-    ln_bwdw_kernel<NW><<<grid, wpb * 32, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x),
+    OFB_LAUNCH(ln_bwdw_kernel<NW>, grid, wpb * 32, smem, s, reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x),
                                                     mean, rstd, gamma, reinterpret_cast<__nv_bfloat16*>(dx), part_dgamma, part_dbeta,
                                                     part_dbias, rowscale, rows_per_scale > 0 ? rows_per_scale : 1, M, D, Dv,
                                                     reinterpret_cast<const __nv_bfloat16*>(dres));
@@ -1481,7 +1507,7 @@ int launch_ln_bwd(const void* dy, const void* x, const float* mean, const float*
 
 int launch_reduce_partials(const float* part, int R, int N, float* out, float scale, const float* inv_colscale, int accumulate,
                            cudaStream_t s) {
-    reduce_partials_kernel<<<(N + 31) / 32, 32 * 32, 0, s>>>(part, R, N, out, scale, inv_colscale, accumulate);
+    OFB_LAUNCH(reduce_partials_kernel, (N + 31) / 32, 32 * 32, 0, s, part, R, N, out, scale, inv_colscale, accumulate);
     return err();
 }
 
@@ -1493,7 +1519,7 @@ int launch_reduce_partials_multi(const void* jobs_host, int njobs, cudaStream_t 
     int maxn = 0;
     for (int i = 0; i < njobs; ++i) { jobs.j[i] = src[i]; if (src[i].N > maxn) maxn = src[i].N; }
     dim3 grid((maxn + 31) / 32, njobs);
-    reduce_partials_multi_kernel<<<grid, 32 * 32, 0, s>>>(jobs);
+    OFB_LAUNCH(reduce_partials_multi_kernel, grid, 32 * 32, 0, s, jobs);
     return err();
 }
 
@@ -1503,7 +1529,7 @@ int launch_patchify(const float* img, void* out, int B, int HW, int P, cudaStrea
     int grid = int((total + 255) / 256);
     const int cap = num_sms() * 16;
     if (grid > cap) grid = cap;
-    patchify_kernel<<<grid, 256, 0, s>>>(img, reinterpret_cast<__nv_bfloat16*>(out), B, HW, P);
+    OFB_LAUNCH(patchify_kernel, grid, 256, 0, s, img, reinterpret_cast<__nv_bfloat16*>(out), B, HW, P);
     return err();
 }
 
@@ -1520,7 +1546,7 @@ int launch_mixup_batch(const float* in, float* out, int B, int HW, double lam, i
     int grid = int((total + 255) / 256);
     const int cap = num_sms() * 16;
     if (grid > cap) grid = cap;
-    mixup_batch_kernel<<<grid, 256, 0, s>>>(in, out, B, HW, mp);
+    OFB_LAUNCH(mixup_batch_kernel, grid, 256, 0, s, in, out, B, HW, mp);
     return err();
 }
 int launch_patchify_mixup(const float* img, void* out, int B, int HW, int P, double lam, int cutmix, int yl, int yh, int xl, int xh,
@@ -1531,7 +1557,7 @@ int launch_patchify_mixup(const float* img, void* out, int B, int HW, int P, dou
     int grid = int((total + 255) / 256);
     const int cap = num_sms() * 16;
     if (grid > cap) grid = cap;
-    patchify_mixup_kernel<<<grid, 256, 0, s>>>(img, reinterpret_cast<__nv_bfloat16*>(out), B, HW, P, mp);
+    OFB_LAUNCH(patchify_mixup_kernel, grid, 256, 0, s, img, reinterpret_cast<__nv_bfloat16*>(out), B, HW, P, mp);
     return err();
 }
 int launch_mixup_target(const long long* labels, float* target, int B, int C, double lam, double smoothing, cudaStream_t s) {
@@ -1540,23 +1566,23 @@ int launch_mixup_target(const long long* labels, float* target, int B, int C, do
     int grid = int((size_t(B) * C + 255) / 256);
     const int cap = num_sms() * 16;
     if (grid > cap) grid = cap;
-    mixup_target_kernel<<<grid, 256, 0, s>>>(labels, target, B, C, float(lam), float(1.0 - lam), float(on), float(off));
+    OFB_LAUNCH(mixup_target_kernel, grid, 256, 0, s, labels, target, B, C, float(lam), float(1.0 - lam), float(on), float(off));
     return err();
 }
 
 int launch_pmim_mask(const float* noise, float* mask, int B, int L, int keep, cudaStream_t s) {
-    pmim_mask_kernel<<<B, 256, L * sizeof(float), s>>>(noise, mask, L, keep);
+    OFB_LAUNCH(pmim_mask_kernel, B, 256, L * sizeof(float), s, noise, mask, L, keep);
     return err();
 }
 
 int launch_droppath_scale(const float* u, const float* drop_prob, float* scale, int n_layers2, int B, cudaStream_t s) {
     const int n = n_layers2 * B;
-    droppath_scale_kernel<<<(n + 255) / 256, 256, 0, s>>>(u, drop_prob, scale, n_layers2, B);
+    OFB_LAUNCH(droppath_scale_kernel, (n + 255) / 256, 256, 0, s, u, drop_prob, scale, n_layers2, B);
     return err();
 }
 
 int launch_cls_rows(const float* cls, const float* pos, const float* gate, void* x, int B, int T, int D, cudaStream_t s) {
-    cls_rows_kernel<<<(B * D + 255) / 256, 256, 0, s>>>(cls, pos, gate, reinterpret_cast<__nv_bfloat16*>(x), B, T, D);
+    OFB_LAUNCH(cls_rows_kernel, (B * D + 255) / 256, 256, 0, s, cls, pos, gate, reinterpret_cast<__nv_bfloat16*>(x), B, T, D);
     return err();
 }
 
@@ -1569,7 +1595,7 @@ int launch_embed_bwd(const void* g0, const void* x0, const float* gate, const fl
     if (G > B) G = B;
     if (G < 1) return 1011;
     const int threads = ((VC * G + 31) / 32) * 32;
-    embed_bwd_kernel<<<T, threads, size_t(G) * D * sizeof(float), s>>>(reinterpret_cast<const __nv_bfloat16*>(g0),
+    OFB_LAUNCH(embed_bwd_kernel, T, threads, size_t(G) * D * sizeof(float), s, reinterpret_cast<const __nv_bfloat16*>(g0),
         reinterpret_cast<const __nv_bfloat16*>(x0), gate, mask, reinterpret_cast<__nv_bfloat16*>(dconv), part_gx, part_pos, part_mt, B, T, D, G);
     return err();
 }
@@ -1578,28 +1604,28 @@ int launch_norm_targets(const float* img, const float* mask, float* tgt, int B, 
     if (HW % NT_P != 0) return 1012;
     const int L = (HW / NT_P) * (HW / NT_P);
     dim3 grid(B * L, 3);
-    norm_targets_kernel<<<grid, 256, 0, s>>>(img, mask, tgt, HW);
+    OFB_LAUNCH(norm_targets_kernel, grid, 256, 0, s, img, mask, tgt, HW);
     return err();
 }
 
 int launch_ce(const float* logits, const int64_t* labels, float* loss_rows, void* dlogits, int B, int C, float smoothing, float gscale,
               cudaStream_t s) {
-    ce_kernel<<<B, 128, 0, s>>>(logits, labels, loss_rows, reinterpret_cast<__nv_bfloat16*>(dlogits), C, smoothing, gscale / B);
+    OFB_LAUNCH(ce_kernel, B, 128, 0, s, logits, labels, loss_rows, reinterpret_cast<__nv_bfloat16*>(dlogits), C, smoothing, gscale / B);
     return err();
 }
 
 int launch_soft_ce(const float* logits, const float* target, float* loss_rows, void* dlogits, int B, int C, float gscale, cudaStream_t s) {
-    soft_ce_kernel<<<B, 128, 0, s>>>(logits, target, loss_rows, reinterpret_cast<__nv_bfloat16*>(dlogits), C, gscale / B);
+    OFB_LAUNCH(soft_ce_kernel, B, 128, 0, s, logits, target, loss_rows, reinterpret_cast<__nv_bfloat16*>(dlogits), C, gscale / B);
     return err();
 }
 int launch_eval_metrics(const float* logits, const int64_t* labels, float* out_rows, int B, int C, cudaStream_t s) {
-    eval_metrics_kernel<<<B, 128, 0, s>>>(logits, labels, out_rows, C);
+    OFB_LAUNCH(eval_metrics_kernel, B, 128, 0, s, logits, labels, out_rows, C);
     return err();
 }
 
 int launch_loss_finalize(const float* loss_rows, int B, const float* dec_part, int n_dec_part, const float* mask, int n_mask,
                          const float* arch_loss, float grad_scale, float* scal, cudaStream_t s) {
-    loss_finalize_kernel<<<1, 1024, 0, s>>>(loss_rows, B, dec_part, n_dec_part, mask, n_mask, arch_loss, grad_scale, scal);
+    OFB_LAUNCH(loss_finalize_kernel, 1, 1024, 0, s, loss_rows, B, dec_part, n_dec_part, mask, n_mask, arch_loss, grad_scale, scal);
     return err();
 }
 
@@ -1616,7 +1642,7 @@ int launch_adamw(float* p, float* g, float* m, float* v, void* shadow, const flo
     long long grid = (n4 + 255) / 256;
     const long long cap = (long long)num_sms() * 16;
     if (grid > cap) grid = cap;
-    adamw_kernel<<<int(grid), 256, 0, s>>>(p, g, m, v, reinterpret_cast<__nv_bfloat16*>(shadow), hyper, segs, n4, zero_grad);
+    OFB_LAUNCH(adamw_kernel, int(grid), 256, 0, s, p, g, m, v, reinterpret_cast<__nv_bfloat16*>(shadow), hyper, segs, n4, zero_grad);
     return err();
 }
 
@@ -1624,11 +1650,12 @@ int launch_adamw(float* p, float* g, float* m, float* v, void* shadow, const flo
 // per-step hyper-parameter vector (lr, bias corrections, w_p) goes this way instead of cudaMemcpyAsync so that it never queues on
 // a copy engine behind the bulk H2D copy of the next batch (measured: +2.7 ms per step when it did), and stays in stream order.
 __global__ void copy_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int n) {
+    pdl_wait();          // programmatic dependent launch: inputs of the previous kernel are complete from here on (launch.cuh)
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
 }
 int launch_copy_f32(const float* src, float* dst, int n, cudaStream_t s) {
     if (n < 1) return 1011;
-    copy_f32_kernel<<<(n + 255) / 256 > 32 ? 32 : (n + 255) / 256, 256, 0, s>>>(src, dst, n);
+    OFB_LAUNCH(copy_f32_kernel, ((n + 255) / 256 > 32 ? 32 : (n + 255) / 256), 256, 0, s, src, dst, n);
     return err();
 }
 
@@ -1638,7 +1665,7 @@ int launch_cast_bf16(const float* src, void* dst, long long n, cudaStream_t s) {
     long long grid = (n4 + 255) / 256;
     const long long cap = (long long)num_sms() * 16;
     if (grid > cap) grid = cap;
-    cast_bf16_kernel<<<int(grid), 256, 0, s>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n4);
+    OFB_LAUNCH(cast_bf16_kernel, int(grid), 256, 0, s, src, reinterpret_cast<__nv_bfloat16*>(dst), n4);
     return err();
 }
 

@@ -15,6 +15,7 @@
 // (vision_transformer.py:723), the head (vision_transformer.py:744) and their autograd backward (engine.py:169).
 #include "ptx.cuh"
 #include "gemm.cuh"
+#include "launch.cuh"
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -27,6 +28,18 @@ static constexpr int EPI_THREADS = EPI_WARPS * 32;
 static constexpr int GEMM_THREADS = 64 + EPI_THREADS;     // warp0 TMA, warp1 MMA (+TMEM alloc), warps2-9 epilogue
 static constexpr int SMEM_LIMIT = 232448;                 // 227 KB
 static constexpr int PANEL_BYTES = BM * 128;              // one [128 rows][64 bf16] SWIZZLE_128B output panel
+
+// Bound-finding experiments (tools/gemm_bound.py; compiled only with -DOFB_GEMM_DEBUG into a separate debug library, never the
+// product): bit 0 = the producer stops issuing TMA loads once the operand ring has been filled (the MMAs then run on stale
+// shared memory: main loop + epilogue without any L2 -> SM operand feed), bit 1 = the epilogue skips its global / TMA stores,
+// bit 2 = the epilogue skips the TMA loads of residual / saved-activation panels, bit 3 = no epilogue at all (the accumulator
+// stage is handed straight back: pure main-loop rate).
+#ifdef OFB_GEMM_DEBUG
+__device__ int g_gemm_dbg = 0;
+#define GEMM_DBG(bit) ((g_gemm_dbg >> (bit)) & 1)
+#else
+#define GEMM_DBG(bit) 0
+#endif
 
 // CG = CTAs per tile: 1, or 2 for a CTA pair (cta_group::2) that shares one 256-row UMMA: each CTA stages its own 128 rows of A
 // but only HALF of the B tile, which cuts the L2 -> shared-memory operand traffic per MAC from (128 + BN) / (128 BN) to
@@ -201,6 +214,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             const __grid_constant__ CUtensorMap tma_o0, const __grid_constant__ CUtensorMap tma_o1,
             const __grid_constant__ CUtensorMap tma_aux, const GemmArgs g) {
     using Cfg = GemmCfg<BN, EPI, TMA_OUT, CG>;
+    pdl_trigger();          // one CTA (pair) per SM: the next kernel's CTAs may take over each SM as soon as this one's leave it
     constexpr int STAGES = Cfg::STAGES;
     constexpr uint32_t IDESC = make_idesc_bf16(BM * CG, BN, A_MN, B_MN);
     // CTA pair: rank in the cluster (0 = leader, issues the MMAs), pair index / pair count replace the CTA index / grid size
@@ -262,6 +276,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     if (CG == 2) cluster_sync_all();          // the peer's barriers are initialised before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();             // prologue done (barriers, TMEM, descriptor prefetch): from here on the previous kernel's outputs are read
 
     const int m_tiles = (g.M + BM - 1) / BM;              // 128-row tiles (epilogue granularity)
     const int mt = (CG == 2) ? (m_tiles + 1) / 2 : m_tiles;   // scheduled row tiles (128 CG rows each)
@@ -293,6 +308,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
                     const uint32_t sa = smem_u32(smem_a + stage * Cfg::A_BYTES);
                     const uint32_t sb = smem_u32(smem_b + stage * Cfg::B_BYTES);
+#ifdef OFB_GEMM_DEBUG
+                    if (GEMM_DBG(0) && (phase != 0 || t != cta_first || kb - kb0 >= STAGES)) {
+                        // stale operands: complete the stage's transaction count without moving any bytes
+                        if (CG == 2) { if (rank == 0) mbar_arrive_expect_tx(smem_u32(&full_bar[stage]), 0); }
+                        else mbar_arrive_expect_tx(smem_u32(&full_bar[stage]), 0);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
+#endif
                     if (CG == 2) {
                         // both CTAs' copies complete on the LEADER's full barrier, which expects the bytes of the pair
                         const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
@@ -331,7 +355,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (pair: the leader CTA only) =====================
-        if (lane == 0 && rank == 0) {
+        // The whole warp runs the loop (uniform control flow, uniform operands); one elected lane issues the tcgen05 instructions.
+        if (rank == 0) {
             int stage = 0; uint32_t phase = 0;
             int it = 0;
             for (int t = cta_first; t < total_tiles; t += cta_stride) {
@@ -350,24 +375,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem_a + stage * Cfg::A_BYTES);
                     const uint32_t sb = smem_u32(smem_b + stage * Cfg::B_BYTES);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        // K-major: advance 16 bf16 (32 B) inside the 128-B swizzle row.
-                        // MN-major: advance 16 k-rows of 128 B; 64-wide MN atoms are BK*128 B apart (LBO).
-                        const uint64_t da = A_MN ? make_smem_desc_sw128(sa + k * 2048, BK * 128, 1024)
-                                                 : make_smem_desc_sw128(sa + k * 32, 0, 1024);
-                        const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * 2048, BK * 128, 1024)
-                                                 : make_smem_desc_sw128(sb + k * 32, 0, 1024);
-                        if (CG == 2) umma_bf16_cg2(d_tmem, da, db, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
-                        else umma_bf16(d_tmem, da, db, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < BK / 16; ++k) {
+                            // K-major: advance 16 bf16 (32 B) inside the 128-B swizzle row.
+                            // MN-major: advance 16 k-rows of 128 B; 64-wide MN atoms are BK*128 B apart (LBO).
+                            const uint64_t da = A_MN ? make_smem_desc_sw128(sa + k * 2048, BK * 128, 1024)
+                                                     : make_smem_desc_sw128(sa + k * 32, 0, 1024);
+                            const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * 2048, BK * 128, 1024)
+                                                     : make_smem_desc_sw128(sb + k * 32, 0, 1024);
+                            if (CG == 2) umma_bf16_cg2(d_tmem, da, db, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+                            else umma_bf16(d_tmem, da, db, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+                        }
+                        if (CG == 2) {
+                            umma_commit_cg2(smem_u32(&empty_bar[stage]));          // frees the stage in both CTAs
+                            if (kb == kb1 - 1) umma_commit_cg2(smem_u32(&tfull_bar[acc]));
+                        } else {
+                            umma_commit(smem_u32(&empty_bar[stage]));
+                            if (kb == kb1 - 1) umma_commit(smem_u32(&tfull_bar[acc]));
+                        }
                     }
-                    if (CG == 2) {
-                        umma_commit_cg2(smem_u32(&empty_bar[stage]));          // frees the stage in both CTAs
-                        if (kb == kb1 - 1) umma_commit_cg2(smem_u32(&tfull_bar[acc]));
-                    } else {
-                        umma_commit(smem_u32(&empty_bar[stage]));
-                        if (kb == kb1 - 1) umma_commit(smem_u32(&tfull_bar[acc]));
-                    }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -394,6 +422,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             int s2, m2, n2;                                           // k_splits == 1 for these epilogues
             decode(int(t2), s2, m2, n2);
             const uint32_t fb = smem_u32(&aux_full[P % AUX_SLOTS]);
+            if (GEMM_DBG(2)) { mbar_arrive_expect_tx(fb, 0); return; }
             mbar_arrive_expect_tx(fb, PANEL_BYTES);
             tma_load_2d(smem_u32(auxbuf) + (P % AUX_SLOTS) * PANEL_BYTES, &tma_aux, fb, n2 * BN + int(P % NPT) * 64, m2 * BM);
         };
@@ -477,6 +506,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             if (Cfg::VEC_BYTES > 0) named_bar_sync(1, EPI_THREADS);       // epilogue vectors visible
             mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
             tc_fence_after();
+#ifdef OFB_GEMM_DEBUG
+            if (GEMM_DBG(3)) {            // no epilogue at all: hand the accumulator stage straight back (pure main-loop rate)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CG == 2) mbar_arrive_cluster(tempty_remote0 + acc * 8);
+                    else mbar_arrive(smem_u32(&tempty_bar[acc]));
+                }
+                continue;
+            }
+#endif
 
             float loss_acc = 0.f;
 #pragma unroll
@@ -709,7 +749,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     fence_proxy_async_smem();
                     if (NPIPE == 1 && elected) bulk_wait_read<0>();          // the other slot's previous store has been read out
                     named_bar_sync(2 + pp, 256);
-                    if (elected && n0 + pj * 64 < g.N) {
+                    if (elected && n0 + pj * 64 < g.N && !GEMM_DBG(1)) {
                         tma_store_2d(&tma_o0, panel0, n0 + pj * 64, m_blk * BM);
                         if (Cfg::NOUT == 2) tma_store_2d(&tma_o1, panel0 + PANEL_BYTES, n0 + pj * 64, m_blk * BM);
                         bulk_commit();
@@ -847,17 +887,7 @@ static int launch_gemm_inst(const void* A, int lda, const void* B, int ldb, cons
     const int total = mt * n_tiles * (g.k_splits > 0 ? g.k_splits : 1);
     const int slots = num_sms() / CG;
     const int grid = (total < slots ? total : slots) * CG;
-    if (CG == 1) {
-        kfn<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, to0, to1, tx, g);
-        return int(cudaGetLastError());
-    }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(Cfg::THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    return int(cudaLaunchKernelEx(&cfg, kfn, ta, tb, to0, to1, tx, g));
+    return int(launch_k(kfn, dim3(grid), dim3(Cfg::THREADS), size_t(Cfg::SMEM_BYTES), stream, CG, ta, tb, to0, to1, tx, g));
 }
 
 // pick the N tile: fewest (waves x tile width) with a penalty for narrow tiles (shared-memory bandwidth per MMA)
@@ -993,4 +1023,12 @@ int launch_gemm(int epi, int a_mn, int b_mn, int bn_hint, const void* A, int lda
     }
 }
 
+#ifdef OFB_GEMM_DEBUG
+int gemm_debug_flags(int flags) { return int(cudaMemcpyToSymbol(g_gemm_dbg, &flags, sizeof(int))); }
+#endif
+
 }  // namespace ofb
+
+#ifdef OFB_GEMM_DEBUG
+extern "C" int ofb_debug_gemm_flags(int flags) { return ofb::gemm_debug_flags(flags); }
+#endif
