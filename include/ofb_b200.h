@@ -58,6 +58,7 @@ typedef struct ofb_gemm_args {
     const float* rowmask;
     const float* target;
     int32_t tokens;
+    float* splitk_ws;          /* WGRAD, deterministic split-K: [k_splits][M][N] fp32 workspace or null (see ofb_splitk_reduce) */
 } ofb_gemm_args;
 
 /* a_mn / b_mn: 0 = operand is [rows, K] row-major (K-major), 1 = operand is [K, rows] row-major (MN-major).
@@ -93,6 +94,21 @@ int ofb_layernorm_bwd(const void* dy, const void* x, const float* mean, const fl
 int ofb_layernorm_bwd_ex(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
                          const void* dres, void* dx, float* part_dgamma, float* part_dbeta, float* part_dbias,
                          const float* rowscale, int rows_per_scale, int M, int D, int D_valid, void* stream);
+/* Deterministic split-K of the weight-gradient GEMMs (the reference's autograd sums weight gradients in a fixed order;
+ * red.global.add does not). With args->splitk_ws set, OFB_EPI_WGRAD stores each split's partial tile into
+ * splitk_ws[split][M][N] instead of accumulating atomically; args->k_splits must be ofb_gemm_wgrad_splits(M, N, K, b_mn,
+ * bn_hint) (the factor the library would pick itself; value, not an error code). ofb_splitk_reduce then does
+ * out[i] += sum_s ws[s][i] (s ascending) for up to 8 GEMMs in one launch; n4 = M*N/4 (N % 4 == 0, out dense). */
+int ofb_gemm_wgrad_splits(int M, int N, int K, int b_mn, int bn_hint);
+typedef struct ofb_splitk_job {
+    const float* ws;
+    float* out;
+    int64_t n4;
+    int32_t splits;
+    int32_t pad_;
+} ofb_splitk_job;
+int ofb_splitk_reduce(const ofb_splitk_job* jobs, int njobs, void* stream);
+
 /* out[col] (+)= scale * sum_r part[r,col] / (div_by ? div_by[col] : 1) */
 int ofb_reduce_partials(const float* part, int R, int N, float* out, float scale, const float* div_by, int accumulate,
                         void* stream);

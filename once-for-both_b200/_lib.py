@@ -32,6 +32,7 @@ class GemmArgs(C.Structure):
         ("scale_ptr", C.c_void_p),
         ("pos", C.c_void_p), ("mask_token", C.c_void_p), ("rowmask", C.c_void_p), ("target", C.c_void_p),
         ("tokens", C.c_int32),
+        ("splitk_ws", C.c_void_p),
     ]
 
 
@@ -44,6 +45,11 @@ class BimaskModule(C.Structure):
         ("alpha_off", C.c_int64), ("score_off", C.c_int64),
         ("coef", C.c_float), ("loss_w", C.c_float),
     ]
+
+
+class SplitkJob(C.Structure):
+    """Mirror of ``ofb_splitk_job``."""
+    _fields_ = [("ws", C.c_void_p), ("out", C.c_void_p), ("n4", C.c_int64), ("splits", C.c_int32), ("pad_", C.c_int32)]
 
 
 class ReduceJob(C.Structure):
@@ -66,6 +72,8 @@ SIGNATURES = {
     "ofb_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "ofb_reduce_partials": [_P, _I, _I, _P, _F, _P, _I, _P],
     "ofb_reduce_partials_multi": [_P, _I, _P],
+    "ofb_gemm_wgrad_splits": [_I, _I, _I, _I, _I],
+    "ofb_splitk_reduce": [_P, _I, _P],
     "ofb_patchify": [_P, _P, _I, _I, _I, _P],
     "ofb_mixup_batch": [_P, _P, _I, _I, _D, _I, _I, _I, _I, _I, _P],
     "ofb_patchify_mixup": [_P, _P, _I, _I, _I, _D, _I, _I, _I, _I, _I, _P],

@@ -346,13 +346,13 @@ __device__ __forceinline__ float bfly16(float (&v)[16]) {
 
 // epilogue of one 16-column slice of dQ / dK / dV for one token row: multiply by the gate (d pre-gate) and store; the row's
 // gate products are accumulated in registers (ag, reduced once per item), the bias column sums are reduced across the 32
-// rows of the warp right away and added to the shared-memory accumulators. x0/x1 = the row's 16 gated q/k/v values.
+// rows of the warp right away and accumulated in a register. x0/x1 = the row's 16 gated q/k/v values.
 // AGW: weight of this slice's sum_rows x * dx in the d gate accumulator. q, k and v share one gate; since S = scale q k^T is
 // bilinear, sum_t q[t,c] dq[t,c] == sum_kv k[kv,c] dk[kv,c] (both are sum_{t,kv} q[t,c] dS[t,kv] k[kv,c]), so the k slices
 // carry weight 2 and the q slices none - the dQ epilogue then needs no operand rows at all.
 template <int AGW>
 __device__ __forceinline__ void dqkv_slice16(float (&v)[16], bool ok, const uint4& x0, const uint4& x1, uint32_t stage_row,
-                                             uint32_t chunk, const float* gate16, float2 (&ag)[8], float* cs_bias) {
+                                             uint32_t chunk, const float* gate16, float2 (&ag)[8], float& bias_acc) {
     // stage_row: shared-memory address of this token row inside a [32 rows][128 B] SWIZZLE_128B slab (rows of one TMEM lane
     // quarter); the slab leaves through one TMA store, which clips rows >= T, so rows that are not `ok` may hold anything
     if (ok) {
@@ -374,9 +374,10 @@ __device__ __forceinline__ void dqkv_slice16(float (&v)[16], bool ok, const uint
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = 0.f;
     }
-    const float sb = bfly16(v);
-    const uint32_t lane = lane_id();
-    if ((lane & 1u) == 0) atomicAdd(cs_bias + (lane >> 1), sb);
+    // column sums over the 32 rows of the warp (even lanes: column lane >> 1), accumulated in a register over the item's slices
+    // and combined across warps in FIXED order at the end of the item (shared-memory atomics made d bias / d gate differ from run
+    // to run)
+    bias_acc += bfly16(v);
 }
 __device__ __forceinline__ float dot8(const uint4& x, const uint4& y) {
     float2 d = mul2(unpack_bf16x2(x.x), unpack_bf16x2(y.x));
@@ -413,9 +414,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const uint32_t sP = sV + KV_B;                        // 2 buffers (even / odd sub-tiles), P then dS in place
     const uint32_t sST = sP + 2 * PB_B;                   // 2 staging tiles [128 rows][64 bf16] of the d qkv epilogues (TMA stores)
     uint8_t* tail = smem + 4 * TILE_B + 2 * KV_B + 2 * PB_B + 2 * TILE_B;
-    float* cs = reinterpret_cast<float*>(tail);                 // [2 parities][256]: gate[64] | bias q,k,v [3][64]
-    const uint32_t sXD = smem_u32(tail + 2048);                 // [2 q tiles][4 column groups][128 rows] delta partials
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 2048 + 4096);
+    float* cs = reinterpret_cast<float*>(tail);                 // [2 parities][16 warps][4: gate | bias q,k,v][16 columns] per-warp partials
+    const uint32_t sXD = smem_u32(tail + 8192);                 // [2 q tiles][4 column groups][128 rows] delta partials
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 8192 + 4096);
     enum { QK_FULL = 0, DOV_FULL, ITEM_EMPTY, S_FULL, P_FULL = S_FULL + 2, DP_FULL = P_FULL + 2, DS_FULL = DP_FULL + 2,
            PB_FREE = DS_FULL + 2, ACC_FULL = PB_FREE + 2, ACC_EMPTY, DQ_FULL, DQ_EMPTY, XREAD, NBAR };
     auto bar = [&](int k) { return smem_u32(&bars[k]); };
@@ -441,7 +442,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         mbar_fence_init();
     }
     if (warp == BWD_CW + 1) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
-    for (int i = threadIdx.x; i < 512; i += BWD_THREADS) cs[i] = 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -611,8 +611,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             const int trole = warp == 0 ? 0 : (warp == 15 ? 1 : -1);
 #endif
             TRC(trole, 0);
-            float* cs_gate = cs + pi * 256 + cg * BWD_EC;
-            float* cs_bias = cs + pi * 256 + 64 + cg * BWD_EC;
+            float* cs_warp = cs + (pi * BWD_CW + warp) * 64;     // this warp's [gate | bias q | bias k | bias v][16] partial sums
+            float bs_q = 0.f, bs_k = 0.f, bs_v = 0.f;            // bias column sums of this warp's rows (even lanes)
             const float dps = dps_n;
             const float inv_dps = dps != 0.f ? 1.f / dps : 0.f;
             const float* gate16 = a.gate + h * HD + cg * BWD_EC;
@@ -788,13 +788,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 tmem_ld16(tDK + lane_base + cg * BWD_EC, w1);
                 tmem_ld_wait();
                 stage_open();
-                dqkv_slice16<2>(w1, kv_ok, k0, k1, slab0, cg * 2, gate16, ag, cs_bias + 64);
+                dqkv_slice16<2>(w1, kv_ok, k0, k1, slab0, cg * 2, gate16, ag, bs_k);
                 tmem_ld16(tDV + lane_base + cg * BWD_EC, w1);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar(ACC_EMPTY));
-                dqkv_slice16<1>(w1, kv_ok, v0, v1, slab1, cg * 2, gate16, ag, cs_bias + 128);
+                dqkv_slice16<1>(w1, kv_ok, v0, v1, slab1, cg * 2, gate16, ag, bs_v);
                 stage_close(1, j * QT, 2, j * QT);
             };
             TRC(trole, 2);
@@ -823,7 +823,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 tmem_ld_wait();
                 stage_open();
                 const uint4 none = make_uint4(0, 0, 0, 0);
-                dqkv_slice16<0>(w1, r < a.T, none, none, slab0, cg * 2, gate16, ag, cs_bias);
+                dqkv_slice16<0>(w1, r < a.T, none, none, slab0, cg * 2, gate16, ag, bs_q);
                 if (nh == 2) {
                     tmem_ld16(tDQ + HD + lane_base + cg * BWD_EC, w1);
                     tmem_ld_wait();
@@ -831,7 +831,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar(DQ_EMPTY));
-                if (nh == 2) dqkv_slice16<0>(w1, QT + r < a.T, none, none, slab1, cg * 2, gate16, ag, cs_bias);
+                if (nh == 2) dqkv_slice16<0>(w1, QT + r < a.T, none, none, slab1, cg * 2, gate16, ag, bs_q);
                 stage_close(0, 0, 0, nh == 2 ? QT : a.T);
             }
             // d gate: q, k and v contributions of all rows of this warp
@@ -840,20 +840,23 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < 8; ++j) { tsum[2 * j] = ag[j].x; tsum[2 * j + 1] = ag[j].y; }
                 const float sg = bfly16(tsum);
-                if ((lane & 1) == 0) atomicAdd(cs_gate + (lane >> 1), sg);
+                if ((lane & 1) == 0) {
+                    const int c = lane >> 1;
+                    cs_warp[c] = sg; cs_warp[16 + c] = bs_q; cs_warp[32 + c] = bs_k; cs_warp[48 + c] = bs_v;
+                }
             }
             TRC(trole, 13);
-            // ---- per-item column sums -> global partials; the accumulator of this parity is re-zeroed for item it+2 ----
+            // ---- per-item column sums -> global partials: the four row quarters of a column group are added in fixed order ----
             named_bar_sync(1, BWD_CT);
             TRC(trole, 14);
             {
                 const int tid = threadIdx.x;   // 0..511
                 if (tid < 256) {
-                    float* src = cs + pi * 256 + tid;
-                    const float val = *src;
-                    *src = 0.f;
-                    if (tid < 64) a.part_gate[size_t(b) * D + h * HD + tid] = val;
-                    else a.part_bias[size_t(b) * 3 * D + ((tid - 64) / 64) * D + h * HD + ((tid - 64) % 64)] = val;
+                    const int which = tid >> 6, col = tid & 63;          // 0 = gate, 1..3 = bias of q, k, v
+                    const float* src = cs + (pi * BWD_CW + (col >> 4) * 4) * 64 + which * 16 + (col & 15);   // warp = cg * 4 + quarter
+                    const float val = ((src[0] + src[64]) + src[128]) + src[192];
+                    if (which == 0) a.part_gate[size_t(b) * D + h * HD + col] = val;
+                    else a.part_bias[size_t(b) * 3 * D + (which - 1) * D + h * HD + col] = val;
                 }
             }
         }
@@ -868,7 +871,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 // host
 // ---------------------------------------------------------------------------------------------
 static constexpr int FWD_SMEM = 2 * TILE_B + 2 * KV_B + 2 * PBUF_B + 4096 + 256;
-static constexpr int BWD_SMEM = 4 * TILE_B + 2 * KV_B + 2 * PB_B + 2 * TILE_B + 2048 + 4096 + 256;
+static constexpr int BWD_SMEM = 4 * TILE_B + 2 * KV_B + 2 * PB_B + 2 * TILE_B + 8192 + 4096 + 256;
 
 static int make_qkv_maps(const void* qkv, int B, int T, int H, CUtensorMap* tq, CUtensorMap* tkv) {
     const uint64_t D = uint64_t(H) * HD;

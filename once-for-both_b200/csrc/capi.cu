@@ -16,6 +16,8 @@ int launch_soft_ce(const float*, const float*, float*, void*, int, int, float, c
 int launch_eval_metrics(const float*, const int64_t*, float*, int, int, cudaStream_t);
 int launch_reduce_partials(const float*, int, int, float*, float, const float*, int, cudaStream_t);
 int launch_reduce_partials_multi(const void*, int, cudaStream_t);
+int launch_splitk_reduce(const void*, int, cudaStream_t);
+int wgrad_plan(int M, int N, int K, int b_mn, int bn_hint);
 int launch_patchify(const float*, void*, int, int, int, cudaStream_t);
 int launch_copy_f32(const float*, float*, int, cudaStream_t);
 int launch_mixup_batch(const float*, float*, int, int, double, int, int, int, int, int, cudaStream_t);
@@ -63,6 +65,7 @@ int ofb_gemm_bf16(int epilogue, int a_mn, int b_mn, int bn_hint, const void* A, 
     g.colpart0 = a->colpart0; g.colpart1 = a->colpart1; g.scale_ptr = a->scale_ptr;
     g.pos = a->pos; g.mask_token = a->mask_token; g.rowmask = a->rowmask; g.target = a->target;
     g.tokens = a->tokens > 0 ? a->tokens : 1;
+    g.splitk_ws = a->splitk_ws;
     return ofb::launch_gemm(epilogue, a_mn, b_mn, bn_hint, A, lda, B, ldb, g, reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -90,6 +93,12 @@ int ofb_layernorm_bwd_ex(const void* dy, const void* x, const float* mean, const
 }
 int ofb_reduce_partials(const float* part, int R, int N, float* out, float scale, const float* div_by, int accumulate, void* stream) {
     return ofb::launch_reduce_partials(part, R, N, out, scale, div_by, accumulate, ST(stream));
+}
+int ofb_gemm_wgrad_splits(int M, int N, int K, int b_mn, int bn_hint) { return ofb::wgrad_plan(M, N, K, b_mn, bn_hint); }
+int ofb_splitk_reduce(const ofb_splitk_job* jobs, int njobs, void* stream) {
+    static_assert(sizeof(ofb_splitk_job) == 32, "ofb_splitk_job layout");
+    if (jobs == nullptr) return 1000;
+    return ofb::launch_splitk_reduce(jobs, njobs, ST(stream));
 }
 int ofb_reduce_partials_multi(const ofb_reduce_job* jobs, int njobs, void* stream) {
     static_assert(sizeof(ofb_reduce_job) == 40, "ofb_reduce_job layout");

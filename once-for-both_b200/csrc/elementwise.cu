@@ -806,6 +806,30 @@ __global__ void reduce_partials_multi_kernel(const ReduceJobs jobs) {
 }
 
 // =============================================================================================
+// deterministic split-K finish of the weight-gradient GEMMs: out[i] += sum_s ws[s][i], s ascending - the run-to-run order of
+// red.global.add is gone, two runs of a step are bit-identical. Up to 8 GEMMs (one block's four weight gradients, or the
+// embed / head / decoder ones) per launch; float4 columns, the splits of a column stay in registers.
+// =============================================================================================
+struct SplitkJob { const float* ws; float* out; long long n4; int splits; int pad_; };
+struct SplitkJobs { SplitkJob j[8]; };
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const SplitkJobs jobs) {
+    pdl_wait();
+    const SplitkJob jb = jobs.j[blockIdx.y];
+    const float4* ws = reinterpret_cast<const float4*>(jb.ws);
+    float4* out = reinterpret_cast<float4*>(jb.out);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < jb.n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 a = ws[i];
+        for (int s = 1; s < jb.splits; ++s) {
+            const float4 b = ws[s * jb.n4 + i];
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        float4 o = out[i];
+        o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+        out[i] = o;
+    }
+}
+
+// =============================================================================================
 // patchify + cast: images fp32 [B,3,224,224] -> bf16 [B*196, 768] with column c*256 + i*16 + j
 // (the im2col of the 16x16/16 conv, layers.py:177)
 // =============================================================================================
@@ -1291,11 +1315,18 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
 
 // =============================================================================================
 // out[col] += scale * sum_rows x[row, col]   (x bf16 [R, N], N even).  grid (ceil(N/64), row splits), block (32, 8)
+// Deterministic: the row splits of a column block park their partial sums in a device-side scratch and the split that
+// arrives last (ticket per column block) adds them in ascending split order - no floating-point atomics. The scratch is
+// shared by all launches: they are stream-ordered in every caller (one stream per process issues the colsum launches).
 // =============================================================================================
+static constexpr int COLSUM_MAX_SPLITS = 64, COLSUM_MAX_N = 4096;
+__device__ float g_colsum_part[COLSUM_MAX_SPLITS * COLSUM_MAX_N];
+__device__ unsigned int g_colsum_ticket[COLSUM_MAX_N / 64];
 __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int ld, int R, int N, float* __restrict__ out, float scale,
                                    const float* __restrict__ scale_dev) {
     pdl_wait();          // programmatic dependent launch: inputs of the previous kernel are complete from here on (launch.cuh)
     __shared__ float2 sm[8][32];
+    __shared__ int s_last;
     const int col = (blockIdx.x * 32 + threadIdx.x) * 2;
     float2 acc = make_float2(0.f, 0.f);
     if (col < N) {
@@ -1308,9 +1339,22 @@ __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int ld, 
     __syncthreads();
     if (threadIdx.y == 0 && col < N) {
         for (int i = 1; i < 8; ++i) { acc.x += sm[i][threadIdx.x].x; acc.y += sm[i][threadIdx.x].y; }
+        *reinterpret_cast<float2*>(g_colsum_part + size_t(blockIdx.y) * N + col) = acc;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) s_last = atomicInc(&g_colsum_ticket[blockIdx.x], gridDim.y - 1) == gridDim.y - 1;
+    __syncthreads();
+    if (s_last && threadIdx.y == 0 && col < N) {
+        __threadfence();
+        float2 t = make_float2(0.f, 0.f);
+        for (unsigned sp = 0; sp < gridDim.y; ++sp) {
+            const float* pp = g_colsum_part + size_t(sp) * N + col;      // other CTAs wrote these: bypass L1
+            t.x += __ldcg(pp); t.y += __ldcg(pp + 1);
+        }
         const float s = scale * (scale_dev != nullptr ? *scale_dev : 1.f);
-        atomicAdd(out + col, acc.x * s);
-        if (col + 1 < N) atomicAdd(out + col + 1, acc.y * s);
+        out[col] += t.x * s;
+        if (col + 1 < N) out[col + 1] += t.y * s;
     }
 }
 
@@ -1318,7 +1362,7 @@ __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int ld, 
 // launchers
 // =============================================================================================
 int launch_colsum_bf16(const void* x, int ld, int R, int N, float* out, float scale, const float* scale_dev, cudaStream_t s) {
-    if (N % 2 != 0 || ld % 2 != 0) return 1014;
+    if (N % 2 != 0 || ld % 2 != 0 || N > COLSUM_MAX_N) return 1014;
     int splits = (R + 255) / 256;
     if (splits > 64) splits = 64;
     if (splits < 1) splits = 1;
@@ -1520,6 +1564,24 @@ int launch_reduce_partials_multi(const void* jobs_host, int njobs, cudaStream_t 
     for (int i = 0; i < njobs; ++i) { jobs.j[i] = src[i]; if (src[i].N > maxn) maxn = src[i].N; }
     dim3 grid((maxn + 31) / 32, njobs);
     OFB_LAUNCH(reduce_partials_multi_kernel, grid, 32 * 32, 0, s, jobs);
+    return err();
+}
+
+int launch_splitk_reduce(const void* jobs_host, int njobs, cudaStream_t s) {
+    if (njobs < 1 || njobs > 8) return 1015;
+    SplitkJobs jobs;
+    memset(&jobs, 0, sizeof(jobs));
+    const SplitkJob* src = reinterpret_cast<const SplitkJob*>(jobs_host);
+    long long maxn = 0;
+    for (int i = 0; i < njobs; ++i) {
+        if (src[i].ws == nullptr || src[i].out == nullptr || src[i].splits < 1 || src[i].n4 < 1) return 1015;
+        jobs.j[i] = src[i];
+        if (src[i].n4 > maxn) maxn = src[i].n4;
+    }
+    long long gx = (maxn + 255) / 256;
+    const long long cap = (long long)num_sms() * 8 / njobs + 1;
+    if (gx > cap) gx = cap;
+    OFB_LAUNCH(splitk_reduce_kernel, dim3(unsigned(gx), unsigned(njobs)), 256, 0, s, jobs);
     return err();
 }
 

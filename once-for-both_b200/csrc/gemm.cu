@@ -672,7 +672,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         // (float4 slots swizzled by (row >> 1) & 3: conflict-free both ways) so that 4 lanes cover 64 contiguous
                         // bytes of a row: 8 wavefronts per instruction.
                         float* sc = reinterpret_cast<float*>(auxbuf + Cfg::AUX_BYTES) + (etid >> 5) * 512;
-                        float* out = reinterpret_cast<float*>(g.out0);
+                        // deterministic split-K: this split's partial tile goes to its own slice of the workspace (plain stores)
+                        const bool det = g.splitk_ws != nullptr;
+                        float* out = det ? g.splitk_ws + size_t(split) * g.M * g.N : reinterpret_cast<float*>(g.out0);
+                        const int ldo = det ? g.N : g.ld0;
                         const int rbase = m_blk * BM + q * 32;
 #pragma unroll
                         for (int hv = 0; hv < 2; ++hv) {
@@ -687,18 +690,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                                 const int rl = ps * 8 + (lane >> 2), idx = lane & 3;
                                 const float4 w = *reinterpret_cast<const float4*>(sc + rl * 16 + ((idx ^ ((rl >> 1) & 3)) << 2));
                                 if (rbase + rl < g.M) {
-                                    float* dst = out + size_t(rbase + rl) * g.ld0 + col0 + hv * 16 + idx * 4;
-                                    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(w.x), "f"(w.y),
-                                                 "f"(w.z), "f"(w.w) : "memory");
+                                    float* dst = out + size_t(rbase + rl) * ldo + col0 + hv * 16 + idx * 4;
+                                    if (det) *reinterpret_cast<float4*>(dst) = w;
+                                    else asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(w.x), "f"(w.y),
+                                                      "f"(w.z), "f"(w.w) : "memory");
                                 }
                             }
                             __syncwarp();
                         }
                     } else if (row_ok && nvalid > 0) {
-                        float* dst = reinterpret_cast<float*>(g.out0) + size_t(row) * g.ld0 + col0;
+                        if (g.splitk_ws != nullptr) {
+                            float* dst = g.splitk_ws + (size_t(split) * g.M + row) * g.N + col0;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (i < nvalid) atomicAdd(dst + i, v[i] * gs);
+                            for (int i = 0; i < 32; ++i)
+                                if (i < nvalid) dst[i] = v[i] * gs;
+                        } else {
+                            float* dst = reinterpret_cast<float*>(g.out0) + size_t(row) * g.ld0 + col0;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (i < nvalid) atomicAdd(dst + i, v[i] * gs);
+                        }
                     }
                 } else if (EPI == EPI_PATCH) {
                     // rows are (image b, patch l); output row skips the cls slot of each image.
@@ -932,6 +943,22 @@ static bool pair_ok(int epi, int M, int bn, bool b_mn) {
     return ((pair_mask() >> epi) & 1) && M > BM && bn >= 128 && (!b_mn || bn % 128 == 0);
 }
 
+// split-K factor of a weight-gradient GEMM (reduction over K tokens): fills the SMs with (tiles x splits) work items and leaves
+// no split without a k block. Exported (ofb_gemm_wgrad_splits) so that the caller can size the deterministic split-K workspace.
+int wgrad_plan(int M, int N, int K, int b_mn, int bn_hint) {
+    const int bn = bn_hint > 0 ? bn_hint : pick_bn(M, N, true);
+    // same predicate as launch_gemm_bn: a CTA pair covers 256 rows and there are num_sms / 2 pairs
+    const bool pair = pair_ok(EPI_WGRAD, M, bn, b_mn != 0);
+    const int m_tiles = (M + BM - 1) / BM;
+    const int tiles = (pair ? (m_tiles + 1) / 2 : m_tiles) * ((N + bn - 1) / bn);
+    int s = (pair ? num_sms() / 2 : num_sms()) / tiles;
+    const int kb = (K + BK - 1) / BK;
+    if (s < 1) s = 1;
+    if (s > kb) s = kb;
+    const int per = (kb + s - 1) / s;
+    return (kb + per - 1) / per;              // splits that actually own k blocks
+}
+
 template <int A_MN, int B_MN, int EPI, int TMA_OUT>
 static int launch_gemm_bn(int bn, const void* A, int lda, const void* B, int ldb, const GemmArgs& g, cudaStream_t s) {
     const bool pair = pair_ok(EPI, g.M, bn, B_MN != 0);
@@ -969,16 +996,13 @@ int launch_gemm(int epi, int a_mn, int b_mn, int bn_hint, const void* A, int lda
     // situ at N = 384: K = 1536 94 -> 79 us, K = 1152 75 -> 65 us; K = 384 is epilogue-bound and stays on 192)
     if (bn_hint <= 0 && epi == EPI_STORE && b_mn && g.K >= 768 && g.N > 128 && pair_ok(EPI_STORE, g.M, 256, true)) bn = 256;
     if (epi == EPI_WGRAD) {
-        if (g.k_splits <= 0) {
-            // same predicate as launch_gemm_bn: a CTA pair covers 256 rows and there are num_sms / 2 pairs
-            const bool pair = pair_ok(EPI_WGRAD, g.M, bn, b_mn != 0);
-            const int m_tiles = (g.M + BM - 1) / BM;
-            const int tiles = (pair ? (m_tiles + 1) / 2 : m_tiles) * ((g.N + bn - 1) / bn);
-            int s = (pair ? num_sms() / 2 : num_sms()) / tiles;
+        if (g.k_splits <= 0) g.k_splits = wgrad_plan(g.M, g.N, g.K, b_mn, bn_hint);
+        if (g.splitk_ws != nullptr) {
+            // every split must own at least one k block (an empty split would leave its workspace slice unwritten) and the
+            // vectorised partial stores need 16-byte aligned rows
             const int kb = (g.K + BK - 1) / BK;
-            if (s < 1) s = 1;
-            if (s > kb) s = kb;
-            g.k_splits = s;
+            const int per = (kb + g.k_splits - 1) / g.k_splits;
+            if ((g.k_splits - 1) * per >= kb || g.N % 4 != 0) return 1006;
         }
         // the reduction runs over tokens; operands are either token-major activations (MN-major here) or transposed
         // hidden activations [hidden, tokens] (K-major here)

@@ -39,6 +39,10 @@ struct GemmArgs {
     const float* rowmask;    // [B*tokens] PMIM mask (1 = masked/removed)
     const float* target;     // EPI_DECODER: [B*tokens, N] normalised pixel targets, patch-major
     int tokens;              // patches per image (196)
+    // EPI_WGRAD, deterministic split-K: when non-null every (split, tile) stores its fp32 partial tile to
+    // splitk_ws[split][M][N] (dense, plain stores) instead of red.global.add into out0; launch_splitk_reduce then adds the
+    // splits in fixed order. k_splits must then be the value wgrad_plan() returns (no empty split).
+    float* splitk_ws;
 };
 
 }  // namespace ofb

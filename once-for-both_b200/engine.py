@@ -709,6 +709,11 @@ class SearchStepEngine:
         as soon as backward has passed its blocks) and joined at the end, so the gradients are averaged on return.
         loss_grads=False: d score / d alpha carry the network path only - the sparsity / FLOPs loss terms are left to the caller
         (modules.py: under the reference's own training loop OFBSearchLOSS computes them with autograd)."""
+        # the split-K partials of the weight-gradient GEMMs are finished in fixed order, one reduction launch per block
+        with ops.wgrad_batch():
+            self._backward(exchange, loss_grads)
+
+    def _backward(self, exchange, loss_grads):
         B, D, H, T, L, M, ML, hid = self.B, self.D, self.H, self.T, self.L, self.M, self.ML, self.hid
         bm = self.bimask
         red = self._reducer if (exchange and self.world > 1) else None
@@ -812,6 +817,7 @@ class SearchStepEngine:
             if has_prev:
                 ln1_jobs.append((self.pd_, R, D, self.g(f"blocks.{l - 1}.mlp.fc2.bias")))
             ops.reduce_partials_multi(mlp_jobs + attn_jobs + ln1_jobs)
+            ops.wgrad_flush()
             G = G0
             if red is not None:
                 red.on_block_done(l)
@@ -831,6 +837,7 @@ class SearchStepEngine:
                  out0=self.g("patch_embed.proj.weight").view(D, 768), a_mn=True, b_mn=True)
         # ---- bi-mask: d gate (+ FLOPs / sparsity losses) -> d score, d alpha ----
         bm.backward(self.params, self.hyper[self._wp_idx:self._wp_idx + 1], self.dgate, gs if loss_grads else 0.0, self.grads)
+        ops.wgrad_flush()
         if red is not None:
             red.finish()
 

@@ -337,6 +337,11 @@ class FinetuneStepEngine:
 
     # ------------------------------------------------------------------------------------------------------------
     def backward(self):
+        # split-K partials of the weight-gradient GEMMs are finished in fixed order, one reduction launch per block
+        with ops.wgrad_batch():
+            self._backward()
+
+    def _backward(self):
         B, T, L, M, ML, Dp, Dv = self.B, self.T, self.L, self.M, self.ML, self.Dp, self.Dv
         use_dp = self.training_mode and self.drop_path_rate > 0
         R = self.ln_parts
@@ -399,6 +404,7 @@ class FinetuneStepEngine:
             if has_prev:
                 ln1_jobs.append((self.pd_, R, Dp, self.g(f"blocks.{l - 1}.mlp.fc2.bias")))
             ops.reduce_partials_multi(mlp_jobs + attn_jobs + ln1_jobs)
+            ops.wgrad_flush()
             G = G0
         # ---- embedding: x0 = [cls + pos_0 ; conv(patches) + bias + pos_{1..L}] ----
         ops.embed_bwd(G, self.xs[0], ones, self.zero_mask, self.dconv, self.e_gx, self.e_pos, self.e_mt, B, T, Dp)

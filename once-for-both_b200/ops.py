@@ -3,6 +3,7 @@
 Every function launches on the current torch CUDA stream and never synchronises.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -70,6 +71,81 @@ def lib():  # noqa: F811  (shadows the import on purpose: same object unless OP_
     return _TimedLib(_raw_lib()) if OP_TIMING is not None else _raw_lib()
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# deterministic split-K of the weight-gradient GEMMs (default on; OFB_DETERMINISTIC=0 restores red.global.add accumulation)
+# ---------------------------------------------------------------------------------------------------------------------
+DETERMINISTIC = os.environ.get("OFB_DETERMINISTIC", "1") == "1"
+
+
+class _WgradPool:
+    """Workspace of the split partial tiles + the pending fixed-order reductions. Inside `batch()` (the engines' backward) the
+    reductions of several GEMMs are finished together by flush() - one launch per block; outside it every weight-gradient GEMM
+    is finished right away. The workspace is bump-allocated and recycled at every flush (stream order keeps that safe)."""
+
+    def __init__(self):
+        self.buf = {}           # device -> fp32 tensor
+        self.retired = []
+        self.cursor = 0
+        self.batch_total = 0
+        self.jobs = []
+        self.batching = False
+
+    def take(self, dev, nfloat):
+        # batch_total counts everything taken since the last EXPLICIT flush: the buffer is kept large enough for a whole batch,
+        # so that a pass that was run eagerly once (growing the buffer, possibly splitting a batch to do so) can be captured in
+        # a CUDA graph afterwards without any allocation
+        need = max(self.cursor, self.batch_total) + nfloat
+        buf = self.buf.get(dev)
+        if buf is None or buf.numel() < need:
+            if torch.cuda.is_current_stream_capturing():
+                raise _lib.OfbError("split-K workspace would have to grow during CUDA-graph capture: run one eager step first")
+            if self.jobs:                       # pending partials live in the old buffer: finish them before it is replaced
+                self._reduce()
+            if buf is not None:
+                self.retired.append(buf)        # CUDA graphs captured earlier still write their partials here: never freed
+            buf = torch.empty(max(need, 1 << 22) * 2, dtype=torch.float32, device=dev)
+            self.buf[dev] = buf
+        off = self.cursor
+        step = (nfloat + 3) // 4 * 4
+        self.cursor += step
+        self.batch_total += step
+        return buf[off:off + nfloat]
+
+    def _reduce(self):
+        jobs, self.jobs, self.cursor = self.jobs, [], 0
+        for i in range(0, len(jobs), 8):
+            chunk = jobs[i:i + 8]
+            arr = (_lib.SplitkJob * len(chunk))()
+            for a, (ws, out, n4, splits) in zip(arr, chunk):
+                a.ws, a.out, a.n4, a.splits = ws, out, n4, splits
+            check(lib().ofb_splitk_reduce(C.cast(arr, C.c_void_p), len(chunk), cur_stream()), "ofb_splitk_reduce")
+
+    def flush(self):
+        self._reduce()
+        self.batch_total = 0
+
+
+_WG = _WgradPool()
+
+
+class wgrad_batch:
+    """with ops.wgrad_batch(): ... ops.wgrad_flush() ... - defer the split-K reductions to explicit flush points."""
+
+    def __enter__(self):
+        self.prev, _WG.batching = _WG.batching, True
+        return self
+
+    def __exit__(self, *exc):
+        _WG.batching = self.prev
+        if not _WG.batching and exc[0] is None:
+            _WG.flush()
+        return False
+
+
+def wgrad_flush():
+    _WG.flush()
+
+
 def _count(n=1):
     global LAUNCHES
     LAUNCHES += n
@@ -111,6 +187,14 @@ def gemm(epi, A, B, *, M, N, K, out0=None, ld0=0, out1=None, ld1=0, out_fp32=Fal
     global _TAG
     _TAG = f"epi{epi} M{M} N{N} K{K} a{int(a_mn)}b{int(b_mn)}"
     _work("gemm", 2.0 * M * N * K, 2.0 * (M * K + N * K + M * N * (2 if epi == EPI_FC1 else 1)))
+    det = False
+    if epi == EPI_WGRAD and DETERMINISTIC and k_splits == 0 and N % 4 == 0 and g.ld0 == N:
+        splits = _raw_lib().ofb_gemm_wgrad_splits(M, N, K, int(b_mn), bn)
+        if splits > 1:          # a single split adds every element exactly once: already deterministic
+            ws = _WG.take(out0.device, splits * M * N)
+            g.k_splits, g.splitk_ws = splits, ptr(ws)
+            _WG.jobs.append((ptr(ws), ptr(out0), M * N // 4, splits))
+            det = True
     if GEMM_TIMING is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -120,6 +204,8 @@ def gemm(epi, A, B, *, M, N, K, out0=None, ld0=0, out1=None, ld1=0, out_fp32=Fal
         e1.record()
         GEMM_TIMING.append((e0, e1, 2.0 * M * N * K, epi))
     _TAG = ""
+    if det and not _WG.batching:
+        _WG.flush()
 
 
 # ---------------------------------------------------------------------------------------------------------------------

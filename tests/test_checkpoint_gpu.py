@@ -22,9 +22,8 @@ def _roundtrip(sd):
 
 
 def _same(a, b, tol_abs, what):
-    # the kernels accumulate some gradients with atomics (split-K weight gradients, attention bias / gate partials), so two runs of
-    # the same step agree to fp32 summation order, not bit for bit: the bound is a small fraction of one AdamW update (lr = 1e-3;
-    # a restore that lost optimizer state or a step counter would be off by ~lr on every element)
+    # every gradient reduction of the step runs in a fixed order (deterministic split-K weight gradients, per-warp column sums of
+    # the attention backward combined in order, ticketed bf16 column sums): a restored engine continues BIT FOR BIT
     worst = max(((float((a.p(k).float() - b.p(k).float()).abs().max()), k) for k in a.offsets))
     assert worst[0] <= tol_abs, (what, worst)
 
@@ -67,8 +66,12 @@ def test_resume_continues_identically(cuda_dev, mode):
         e.step(img, lab, noise=noise, target=soft)
         e.step_graphed(img, lab, target=soft) if mode == "post" else e.step(img, lab, noise=noise)
     torch.cuda.synchronize()
-    _same(res, eng, 1e-4, "after two more steps")
-    assert float((res.scal[:4] - eng.scal[:4]).abs().max()) < 1e-4 * float(eng.scal[3].abs())
+    if mode == "post":
+        # the post-search leg replays a CUDA graph, whose PMIM / DropPath draws come from torch's generator (different offsets in
+        # the two engines' histories do not matter here: PMIM is off and the DropPath rate is 0)
+        pass
+    _same(res, eng, 0.0, "after two more steps")
+    assert torch.equal(res.scal[:4], eng.scal[:4])
 
 
 def test_rejects_foreign_checkpoint(cuda_dev):

@@ -93,6 +93,37 @@ def test_graphed_accumulation_matches_eager(cuda_dev):
         assert float(d.median()) < 1e-6 and float(d.max()) <= 2.1e-3, (k, float(d.median()), float(d.max()))
 
 
+def test_gradients_are_run_to_run_deterministic(cuda_dev):
+    """Split-K weight gradients are finished in a fixed order (workspace partials + ofb_splitk_reduce; SURVEY 7 asked for a
+    deterministic reduction order): two executions of the same step give bit-identical weight gradients, at a size where
+    every weight-gradient GEMM really splits K over many CTAs (M = 12 608 token rows)."""
+    from fixtures import make_inputs, make_params
+    from ofb_b200 import ops
+    from ofb_b200.engine import SearchStepEngine
+    from ofb_oracle import ModelCfg
+    assert ops.DETERMINISTIC
+    cfg = ModelCfg(embed_dim=384, num_heads=6, depth=2)
+    P = make_params(cfg, seed=0)
+    B = 64
+    inp = make_inputs(cfg, B, seed=3, drop_path_rate=0.1)
+    eng = SearchStepEngine(384, 6, 2, B, drop_path_rate=0.1)
+    eng.load_params(P)
+    eng.set_schedule(1.0)
+    img, lab, noise = inp.images.cuda(), inp.labels.cuda(), inp.noise.cuda()
+    drop_u = ((inp.drop_scale > 0).float().reshape(4, B) * 0.999).cuda()
+    runs = []
+    for _ in range(3):
+        eng.grads.zero_()
+        eng.step(img, lab, noise=noise, drop_u=drop_u, update=False)
+        torch.cuda.synchronize()
+        runs.append({k: v.detach().clone() for k, v in eng.named_grads().items()})
+    differing = [k for k in runs[0] if not (torch.equal(runs[0][k], runs[1][k]) and torch.equal(runs[0][k], runs[2][k]))]
+    print("tensors that differ between runs:", differing)
+    # every gradient, not only the split-K ones: the attention backward combines its per-warp column sums in fixed order and
+    # the bf16 column sums finish through a ticketed fixed-order reduction - nothing in the step accumulates with fp atomics
+    assert not differing, differing
+
+
 @pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
 def test_step_matches_reference_golden(cuda_dev, path):
     """Same seeded parameters / inputs as oracle/make_golden.py fed to the engine; compare with the reference's own

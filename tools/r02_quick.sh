@@ -2,7 +2,7 @@
 # quick GPU iteration: kernel + step parity, then a bench without the baselines; prints the essentials
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_step_gpu.py -m gpu -q -x 2>&1 | tail -3
-for pdl in ${PDLS:-1}; do
+for pdl in ${PDLS:-0}; do
 OFB_PDL=$pdl timeout 600 python bench.py --no-eager --no-extra --no-cpu-baseline > gpurun_out/bench_q.json 2> gpurun_out/bench_q.err || tail -5 gpurun_out/bench_q.err
 python - <<PY
 import json
