@@ -198,73 +198,90 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             mbar_wait(slot_bar(s, 0), ph);
             tc_fence_after();
             float v[32];
-            // ---- pass 1: row maximum over this warp's columns ----
-            float mx = -INFINITY;
+            // Softmax in ONE pass over the S accumulator: P = exp2(S * scale * log2e) without subtracting the row maximum. The
+            // result of softmax does not depend on the reference point, bf16 / fp32 keep their relative precision at any
+            // magnitude, and attention logits stay far inside the fp32 exponent range (|S * scale| < 88); TMEM reads run at
+            // 64 B/clk per SM, so the separate maximum pass over the 128 x 208 fp32 tile cost as much as the softmax itself.
+            // Guard: a row whose sum left [1e-30, 1e30] (logits beyond +-69) sends BOTH warps of its row quarter through the
+            // classic two-pass path below (the vote is taken on the combined sum, identical in the two warps).
+            float mx = 0.f, sum = 0.f;
+            bool two_pass = false;
+            while (true) {
+                if (two_pass) {
+                    // ---- row maximum over this warp's columns, exchanged with the warp of the other kv half ----
+                    mx = -INFINITY;
 #pragma unroll 1
-            for (int c = 0; c < n32; ++c) {
-                const int col = c_begin + c * 32;
-                tmem_ld32(tS + col, v);
-                tmem_ld_wait();
-                if (col + 32 <= a.T) {
+                    for (int c = 0; c < n32; ++c) {
+                        const int col = c_begin + c * 32;
+                        tmem_ld32(tS + col, v);
+                        tmem_ld_wait();
+                        if (col + 32 <= a.T) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, v[j]);
-                } else {
+                            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, v[j]);
+                        } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, col + j < a.T ? v[j] : -INFINITY);
+                            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, col + j < a.T ? v[j] : -INFINITY);
+                        }
+                    }
+                    if (hf == 0) {
+                        tmem_ld16(tS + 96, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) mx = fmaxf(mx, 96 + j < a.T ? v[j] : -INFINITY);
+                    }
+                    st_shared_f32(x_mine, mx);
+                    named_bar_sync(pair_bar, 64);
+                    mx = fmaxf(mx, ld_shared_f32(x_other));
                 }
-            }
-            if (hf == 0) {
-                tmem_ld16(tS + 96, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 16; ++j) mx = fmaxf(mx, 96 + j < a.T ? v[j] : -INFINITY);
-            }
-            st_shared_f32(x_mine, mx);
-            named_bar_sync(pair_bar, 64);
-            mx = fmaxf(mx, ld_shared_f32(x_other));
-            const float mxs = mx * sl2;
-            // ---- pass 2: P = exp(S*scale - max), row sums, P -> shared memory (bf16, swizzled K-major A operand) ----
-            // (the first 64 kv columns of these rows double as the O staging slab of the previous item: its bulk store, issued
-            //  by lane 0 of this very warp when hf == 0, must have read the slab before P overwrites it)
-            if (hf == 0) {
-                if (lane == 0) bulk_wait_read<0>();
-                __syncwarp();
-            }
-            float sum = 0.f;
+                const float mxs = mx * sl2;
+                // ---- P = exp(S*scale - reference), row sums, P -> shared memory (bf16, swizzled K-major A operand) ----
+                // (the first 64 kv columns of these rows double as the O staging slab of the previous item: its bulk store, issued
+                //  by lane 0 of this very warp when hf == 0, must have read the slab before P overwrites it)
+                if (hf == 0 && !two_pass) {
+                    if (lane == 0) bulk_wait_read<0>();
+                    __syncwarp();
+                }
+                sum = 0.f;
 #pragma unroll 1
-            for (int c = 0; c < n32 + 1; ++c) {
-                const int col = c_begin + c * 32;
-                const int nj = c < n32 ? 32 : (hf == 0 ? 16 : 0);
-                if (nj == 0) break;
-                if (nj == 32) tmem_ld32(tS + col, v);
-                else tmem_ld16(tS + col, v);
-                tmem_ld_wait();
-                if (col + nj <= a.T) {
+                for (int c = 0; c < n32 + 1; ++c) {
+                    const int col = c_begin + c * 32;
+                    const int nj = c < n32 ? 32 : (hf == 0 ? 16 : 0);
+                    if (nj == 0) break;
+                    if (nj == 32) tmem_ld32(tS + col, v);
+                    else tmem_ld16(tS + col, v);
+                    tmem_ld_wait();
+                    if (col + nj <= a.T) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < nj) { v[j] = fast_ex2(fmaf(v[j], sl2, -mxs)); sum += v[j]; }
-                } else {
+                        for (int j = 0; j < 32; ++j)
+                            if (j < nj) { v[j] = fast_ex2(fmaf(v[j], sl2, -mxs)); sum += v[j]; }
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < nj) { v[j] = col + j < a.T ? fast_ex2(fmaf(v[j], sl2, -mxs)) : 0.f; sum += v[j]; }
-                }
+                        for (int j = 0; j < 32; ++j)
+                            if (j < nj) { v[j] = col + j < a.T ? fast_ex2(fmaf(v[j], sl2, -mxs)) : 0.f; sum += v[j]; }
+                    }
 #pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                    if (q4 * 8 < nj) {
-                        uint4 pk;
-                        pk.x = pack_bf16x2(v[q4 * 8 + 0], v[q4 * 8 + 1]); pk.y = pack_bf16x2(v[q4 * 8 + 2], v[q4 * 8 + 3]);
-                        pk.z = pack_bf16x2(v[q4 * 8 + 4], v[q4 * 8 + 5]); pk.w = pack_bf16x2(v[q4 * 8 + 6], v[q4 * 8 + 7]);
-                        st_shared_v4(pbuf_addr(pS, r, (col >> 3) + q4), pk);
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        if (q4 * 8 < nj) {
+                            uint4 pk;
+                            pk.x = pack_bf16x2(v[q4 * 8 + 0], v[q4 * 8 + 1]); pk.y = pack_bf16x2(v[q4 * 8 + 2], v[q4 * 8 + 3]);
+                            pk.z = pack_bf16x2(v[q4 * 8 + 4], v[q4 * 8 + 5]); pk.w = pack_bf16x2(v[q4 * 8 + 6], v[q4 * 8 + 7]);
+                            st_shared_v4(pbuf_addr(pS, r, (col >> 3) + q4), pk);
+                        }
                     }
                 }
+                st_shared_f32(x_mine + 2048, sum);
+                named_bar_sync(pair_bar, 64);
+                sum += ld_shared_f32(x_other + 2048);
+                if (two_pass) break;
+                const bool bad = !(sum > 1e-30f && sum < 1e30f) && t < a.T;
+                if (!__any_sync(0xffffffffu, bad)) break;
+                two_pass = true;
+                named_bar_sync(pair_bar, 64);        // both warps have read the other's sum before the exchange slots are reused
             }
-            st_shared_f32(x_mine + 2048, sum);
             fence_proxy_async_smem();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(slot_bar(s, 1));
-            named_bar_sync(pair_bar, 64);
-            sum += ld_shared_f32(x_other + 2048);
             // ---- epilogue: O / rowsum * droppath; this warp owns head-dim columns [32 hf, 32 hf + 32) ----
             mbar_wait(slot_bar(s, 2), ph);
             tc_fence_after();
@@ -442,6 +459,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         mbar_fence_init();
     }
     if (warp == BWD_CW + 1) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
+    // P / dS buffers start as zeros: the chunks of q rows >= T are skipped by the compute warps for the whole kernel
+    for (int i = threadIdx.x; i < 2 * PB_B / 16; i += BWD_THREADS) st_shared_v4(sP + i * 16, make_uint4(0, 0, 0, 0));
+    fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -679,7 +699,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 { const long long tw = TRC_NOW(); mbar_wait(bar(S_FULL + i), par); TRC_ACC(trole, 20, tw); }
                 { const long long tw = TRC_NOW(); mbar_wait(bar(PB_FREE + i), par ^ 1u); TRC_ACC(trole, 21, tw); }   // the MMAs that read this buffer one pair ago have retired
                 tc_fence_after();
-                {
+                // a chunk whose 32 q rows or 32 kv columns all lie past T is never read where it matters (its P / dS entries only
+                // reach clipped output rows, or multiply zero-filled dO / Q rows - the P buffers are zeroed once at kernel start so
+                // that those products are 0 x 0): 15 of the 64 chunks of an item at T = 197. Skipping them takes their TMEM reads
+                // and exponentials off the column groups' schedulers.
+                if (j * QT + cg * BWD_PC < a.T && i * QT + q * 32 < a.T) {
                     const int col = cg * BWD_PC;                  // column inside the sub-tile
                     const int kv0 = j * QT + col;                 // kv index of the chunk
                     tmem_ld32(tR + col, v);
@@ -715,7 +739,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 const float2 nd2 = splat2(i == 0 ? ndsc_0 : ndsc_1);
                 { const long long tw = TRC_NOW(); mbar_wait(bar(DP_FULL + i), par); TRC_ACC(trole, 22, tw); }
                 tc_fence_after();
-                {
+                if (j * QT + cg * BWD_PC < a.T && i * QT + q * 32 < a.T) {
                     const int col = cg * BWD_PC;
                     const int kv0 = j * QT + col;
                     tmem_ld32(tR + col, v);

@@ -243,6 +243,34 @@ def test_attention_fwd_bwd(cuda_dev, B, H, T):
     assert rel(pb.sum(0), (g * gview).sum((0, 1)).reshape(-1)) < BF16_TOL
 
 
+@pytest.mark.parametrize("amp,shift", [(1.0, 0.0), (6.0, 0.0), (1.0, 14.0), (1.0, -14.0)],
+                         ids=["normal", "wide_logits", "logits_plus_200", "logits_minus_200"])
+def test_attention_fwd_single_pass_guard(cuda_dev, amp, shift):
+    """The forward softmax runs in one pass without subtracting the row maximum; rows whose sum leaves the safe exponent range
+    fall back to the two-pass path. Logits of ordinary size, a +-150 spread, and rows pushed to +-200 (where exp over / under
+    flows without a reference point) must all match torch's softmax."""
+    from ofb_b200 import ops
+    torch.manual_seed(11)
+    B, H, T, d = 2, 3, 197, 64
+    D = H * d
+    qkv = torch.randn(B, T, 3, H, d, device="cuda") * amp
+    # constant component along one channel: q . k gets an additive shift of 64 * shift^2 / 8 in half of the rows
+    qkv[:, ::2, 0, :, 0] += shift * 8.0
+    qkv[:, :, 1, :, 0] += abs(shift) * 8.0 if shift else 0.0
+    qkv = qkv.to(torch.bfloat16)
+    o = torch.empty(B, T, D, device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(B, H, T, device="cuda")
+    ops.attention_fwd(qkv, o, lse, None, B, T, H, d ** -0.5)
+    q, k, v = qkv.float().permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-2, -1)) * d ** -0.5
+    if shift:
+        assert float(s.abs().max()) > 150
+    oref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B, T, D)
+    assert torch.isfinite(o.float()).all() and torch.isfinite(lse).all()
+    assert rel(o, oref) < BF16_TOL
+    assert float((lse - torch.logsumexp(s, -1)).abs().max()) < 1e-3 * max(1.0, float(s.abs().max()))
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # token assembly, PMIM, targets
 # ---------------------------------------------------------------------------------------------------------------------
