@@ -347,6 +347,35 @@ def kernel_breakdown(run_steps, n):
         return None, f"{type(e).__name__}: {str(e)[:200]}"
 
 
+def cublas_same_shapes(gemm_shapes, dev, iters=6):
+    """cuBLAS (torch.matmul, bf16, fp32 accumulate) on exactly the GEMM shapes / operand layouts of one step, each timed in
+    isolation: ms per step if every GEMM of the step were a plain library GEMM (no fused epilogue: the gate / GELU / residual
+    / gradient-reduction passes would come on top). The yardstick for "how good is the tensor main loop on THESE shapes"."""
+    import torch
+    total, worst = 0.0, None
+    for (M, N, K, a_mn, b_mn), count in gemm_shapes.items():
+        if M * N * K < 1 << 24:
+            continue
+        try:
+            A = torch.randn((K, M) if a_mn else (M, K), device=dev, dtype=torch.bfloat16)
+            B = torch.randn((K, N) if b_mn else (N, K), device=dev, dtype=torch.bfloat16)
+            Am, Bm = (A.t() if a_mn else A), (B if b_mn else B.t())
+            out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+            for _ in range(2):
+                torch.matmul(Am, Bm, out=out)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                torch.matmul(Am, Bm, out=out)
+            e1.record()
+            torch.cuda.synchronize()
+            total += e0.elapsed_time(e1) / iters * count
+            del A, B, out
+        except Exception as e:                      # noqa: BLE001
+            worst = f"{type(e).__name__}: {str(e)[:120]}"
+    return total, worst
+
+
 def build_workload(args, dev, pg, world, rank):
     """Engine + step callable + description of one bench workload."""
     import torch
@@ -501,10 +530,12 @@ def main():
     eager_step(dev_img[0], dev_lab[0])
     work_log, ops.WORK_LOG = ops.WORK_LOG, None
     eng.grads.zero_()
-    work = {}
-    for fam, fl, nb in work_log:
+    work, gemm_shapes = {}, {}
+    for fam, fl, nb, dims in work_log:
         w = work.setdefault(fam, [0.0, 0.0, 0])
         w[0] += fl; w[1] += nb; w[2] += 1
+        if fam == "gemm" and dims is not None:
+            gemm_shapes[dims[:5]] = gemm_shapes.get(dims[:5], 0) + 1
 
     # ---------------- device-resident measurement ----------------
     mark("engine built")
@@ -664,6 +695,12 @@ def main():
             eng.release_graphs()
             del eng, step, eager_step, stage_img, dev_img
             torch.cuda.empty_cache()
+            cb_ms, cb_err = cublas_same_shapes(gemm_shapes, dev)
+            line["roofline"]["cublas_same_shapes"] = {
+                "ms_per_step": cb_ms, "ours_ms_per_step": fam("gemm"), "ours_over_cublas_time": (fam("gemm") / cb_ms) if cb_ms else None,
+                "note": "torch.matmul bf16 on the step's GEMM shapes and operand layouts, each timed in isolation, plain store "
+                        "(no fused gate / GELU / residual / d-gate / split-K epilogue); our figure includes those epilogues",
+                "error": cb_err}
         if world == 1 and not args.no_cpu_baseline:
             rate, cores, dt, kind = cpu_arm(args)
             what = "unmodified reference, oracle/_ref" if kind == "reference" else "oracle port"

@@ -25,9 +25,9 @@ LN_TIMING = None
 WORK_LOG = None
 
 
-def _work(family, flops, nbytes):
+def _work(family, flops, nbytes, dims=None):
     if WORK_LOG is not None:
-        WORK_LOG.append((family, float(flops), float(nbytes)))
+        WORK_LOG.append((family, float(flops), float(nbytes), dims))
 
 
 def _ln_timed(call, nbytes):
@@ -186,7 +186,7 @@ def gemm(epi, A, B, *, M, N, K, out0=None, ld0=0, out1=None, ld1=0, out_fp32=Fal
     ldb = ldb if ldb is not None else B.stride(0)
     global _TAG
     _TAG = f"epi{epi} M{M} N{N} K{K} a{int(a_mn)}b{int(b_mn)}"
-    _work("gemm", 2.0 * M * N * K, 2.0 * (M * K + N * K + M * N * (2 if epi == EPI_FC1 else 1)))
+    _work("gemm", 2.0 * M * N * K, 2.0 * (M * K + N * K + M * N * (2 if epi == EPI_FC1 else 1)), (M, N, K, int(a_mn), int(b_mn), epi))
     det = False
     if epi == EPI_WGRAD and DETERMINISTIC and k_splits == 0 and N % 4 == 0 and g.ld0 == N:
         splits = _raw_lib().ofb_gemm_wgrad_splits(M, N, K, int(b_mn), bn)
