@@ -820,6 +820,7 @@ class SearchStepEngine:
             ops.wgrad_flush()
             G = G0
             if red is not None:
+                ops.wgrad_join()          # the bucket all-reduce of this block reads the finished weight gradients
                 red.on_block_done(l)
 
         # ---- embed stage ----
@@ -838,6 +839,7 @@ class SearchStepEngine:
         # ---- bi-mask: d gate (+ FLOPs / sparsity losses) -> d score, d alpha ----
         bm.backward(self.params, self.hyper[self._wp_idx:self._wp_idx + 1], self.dgate, gs if loss_grads else 0.0, self.grads)
         ops.wgrad_flush()
+        ops.wgrad_join()
         if red is not None:
             red.finish()
 
