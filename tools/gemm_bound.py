@@ -96,10 +96,16 @@ def sample():
 stop = False
 th = threading.Thread(target=sample, daemon=True); th.start()
 print(f"{'GEMM':42s} {'normal':>8s} {'no feed':>8s} {'no store':>9s} {'no aux':>8s} {'none':>8s} {'mainloop':>9s} {'ml+feed':>8s}   (us)   [SM MHz during the row]")
+only = os.environ.get("OFB_BOUND_CASES")          # comma-separated substrings of the case names
+flag_sets = [int(f) for f in os.environ.get("OFB_BOUND_FLAGS", "0,1,2,4,7,15,14").split(",")]
+if only or "OFB_BOUND_FLAGS" in os.environ:
+    print("flags per column:", flag_sets)
 for name, fn in CASES.items():
+    if only and not any(o in name for o in only.split(",")):
+        continue
     row = []
     c0 = len(clk)
-    for flags in (0, 1, 2, 4, 7, 15, 14):
+    for flags in flag_sets:
         lib.ofb_debug_gemm_flags(flags)
         row.append(timeit(fn, iters=40))
     lib.ofb_debug_gemm_flags(0)
