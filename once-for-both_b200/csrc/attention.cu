@@ -250,15 +250,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     if (nj == 32) tmem_ld32(tS + col, v);
                     else tmem_ld16(tS + col, v);
                     tmem_ld_wait();
-                    if (col + nj <= a.T) {
+                    // packed fp32x2 scale / row-sum arithmetic (half the issue slots of the scalar form: 60.3 -> 57.2 us per launch)
+                    const float2 sl22 = splat2(sl2), nm2 = splat2(-mxs);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < nj) { v[j] = fast_ex2(fmaf(v[j], sl2, -mxs)); sum += v[j]; }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < nj) { v[j] = col + j < a.T ? fast_ex2(fmaf(v[j], sl2, -mxs)) : 0.f; sum += v[j]; }
+                    for (int k = 0; k < 16; ++k) {
+                        if (2 * k < nj) {
+                            const float2 e = fma2(make_float2(v[2 * k], v[2 * k + 1]), sl22, nm2);
+                            v[2 * k] = fast_ex2(e.x); v[2 * k + 1] = fast_ex2(e.y);
+                        }
                     }
+                    if (col + nj > a.T) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < nj) v[j] = col + j < a.T ? v[j] : 0.f;
+                    }
+                    float2 s2 = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int k = 0; k < 16; ++k)
+                        if (2 * k < nj) s2 = add2(s2, make_float2(v[2 * k], v[2 * k + 1]));
+                    sum += s2.x + s2.y;
 #pragma unroll
                     for (int q4 = 0; q4 < 4; ++q4) {
                         if (q4 * 8 < nj) {
@@ -557,8 +567,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                         if (i == 0) { const long long tw = TRC_NOW(); mbar_wait(bar(ACC_EMPTY), (n_acc & 1u) ^ 1u); ++n_acc; TRC_ACC(2, 9, tw); }   // previous dK / dV read out
                         tc_fence_after();
                         if (elect_one()) {
-#pragma unroll
-                            for (int k = 0; k < QT / 16; ++k)
+                            // reduction over the q rows of tile i: k steps whose 16 rows all lie past T would add 0 x 0
+                            const int kq = (min(QT, a.T - i * QT) + 15) >> 4;
+                            for (int k = 0; k < kq; ++k)
                                 umma_bf16(tDV, make_smem_desc_sw128(pbuf + k * 2048, TILE_B, 1024),
                                           make_smem_desc_sw128(doa + k * 2048, 0, 1024), IDESC_KV, (i > 0 || k > 0) ? 1u : 0u);
                             const uint32_t idesc = make_idesc_bf16(128, nj, 0, 0);
@@ -585,8 +596,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                             for (uint32_t k = 0; k < nj / 16; ++k)
                                 umma_bf16(tDQ + i * HD, make_smem_desc_sw128(pbuf + (k >> 2) * TILE_B + (k & 3) * 32, 0, 1024),
                                           make_smem_desc_sw128(kb + k * 2048, 0, 1024), IDESC_DQ, (j > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-                            for (int k = 0; k < QT / 16; ++k)
+                            const int kq = (min(QT, a.T - i * QT) + 15) >> 4;
+                            for (int k = 0; k < kq; ++k)
                                 umma_bf16(tDK, make_smem_desc_sw128(pbuf + k * 2048, TILE_B, 1024),
                                           make_smem_desc_sw128(qa + k * 2048, 0, 1024), IDESC_KV, (i > 0 || k > 0) ? 1u : 0u);
                             umma_commit(bar(PB_FREE + i));
@@ -708,6 +719,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     const int kv0 = j * QT + col;                 // kv index of the chunk
                     tmem_ld32(tR + col, v);
                     tmem_ld_wait();
+                    // (sending part of the exponentials through a polynomial on the fma / alu pipes instead of MUFU changes nothing: the
+                    // phase follows the 64 B/clk tcgen05.ld rate, profiles/r02b_attention.txt)
 #pragma unroll
                     for (int k = 0; k < 16; ++k) {
                         const float2 e = fma2(make_float2(v[2 * k], v[2 * k + 1]), sl22, nl2);
