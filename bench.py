@@ -323,10 +323,12 @@ def kernel_breakdown(run_steps, n):
     launches (the timed steps are CUDA-graph replays - an event pair around a host launch would time host gaps instead).
     Returns ({family: ms per step}, {kernel name: (ms per step, launches per step)}) or (None, why)."""
     import torch
+    ran = False
     try:
         from torch.profiler import ProfilerActivity, profile
         torch.cuda.synchronize()
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            ran = True
             run_steps(n)
             torch.cuda.synchronize()
         fam, kern = {}, {}
@@ -344,6 +346,9 @@ def kernel_breakdown(run_steps, n):
             return None, "torch.profiler returned no device activity records"
         return fam, kern
     except Exception as e:                      # noqa: BLE001
+        if not ran:
+            run_steps(n)        # N > 1: the steps hold collectives, every rank must run them exactly once whatever the profiler does
+            torch.cuda.synchronize()
         return None, f"{type(e).__name__}: {str(e)[:200]}"
 
 
@@ -567,10 +572,37 @@ def main():
     value = eff * args.steps / (ms / 1e3)
     scal = eng.scal.cpu().tolist()
 
+    # ---------------- N > 1: the gradient exchange in isolation (it is not overlapped by default, so this is what it adds to a step) ----------------
+    exchange = None
+    if world > 1 and hasattr(eng, "allreduce_grads"):
+        for _ in range(3):
+            eng.allreduce_grads()
+        sync_all()
+        n_ex = 20
+        e0.record()
+        for _ in range(n_ex):
+            eng.allreduce_grads()
+        e1.record()
+        sync_all()
+        t = torch.tensor([e0.elapsed_time(e1) / n_ex], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        nbytes = eng.grads.numel() * 4
+        mode = "captured in the step graph" if getattr(eng, "dp_in_graph", False) else (
+            "overlapped with backward" if getattr(eng, "dp_overlap", False) else "after the graph replay, before AdamW")
+        exchange = {"ms_per_step": float(t.item()), "bytes_per_rank": nbytes, "buckets": len(getattr(eng, "_dp_bounds", []) or []),
+                    "gbs_per_rank": nbytes / (float(t.item()) * 1e-3) / 1e9,
+                    "mode": mode, "note": "NCCL all-reduce (AVG) of the flat fp32 gradient arena, timed alone with CUDA events, max over ranks"}
+        eng.grads.zero_()
     # ---------------- per-kernel durations of the same replayed steps (CUPTI) ----------------
     n_prof = min(4, args.steps)
-    fam_ms, kern = (None, "skipped") if rank != 0 else kernel_breakdown(
-        lambda n: [step(dev_img[i % n_host], dev_lab[i % n_host]) for i in range(n)], n_prof)
+    def prof_steps(n):
+        for i in range(n):
+            step(dev_img[i % n_host], dev_lab[i % n_host])
+    if rank == 0:
+        fam_ms, kern = kernel_breakdown(prof_steps, n_prof)
+    else:
+        prof_steps(n_prof)          # the steps of an N > 1 run hold the gradient exchange: every rank runs them, rank 0 records
+        fam_ms, kern = None, "skipped"
     sync_all()
     mark("roofline pass done")
     # ---------------- end to end: host buffers -> step -> loss on host ----------------
@@ -691,6 +723,8 @@ def main():
                             for k, v in sorted(kern.items(), key=lambda kv: -kv[1][0])[:12]],
             "losses": {"base": scal[0], "arch": scal[1], "decoder": scal[2], "total": scal[3]},
         }
+        if exchange is not None:
+            line["exchange"] = exchange
         if world == 1:
             eng.release_graphs()
             del eng, step, eager_step, stage_img, dev_img
