@@ -357,7 +357,9 @@ class SearchStepEngine:
         self.att_pg, self.att_pb = torch.empty(B, Amax, **f32), torch.empty(B, 3 * Amax, **f32)
         self.e_gx, self.e_pos, self.e_mt = (torch.empty(T, D, **f32) for _ in range(3))
         self.rand_u = torch.empty(B * self.L + depth * 2 * B, **f32)
-        self._dp_bounds = dp.bucket_bounds(self.n_arena)
+        # the exchange that follows backward is ONE all-reduce of the arena: on 8 x B200 89.6 MB take 0.30 ms in one piece, 0.46 ms
+        # in four (profiles/r02b_allreduce_8gpu.txt); OFB_DP_BUCKETS restores a bucketed exchange
+        self._dp_bounds = dp.bucket_bounds(self.n_arena, max_buckets=int(os.environ.get("OFB_DP_BUCKETS", "1")))
         # exchange overlapped with backward (OFB_DP_OVERLAP=1): buckets of whole blocks' weight gradients (contiguous in the
         # decay group) are all-reduced as soon as backward has passed them. Default is the single exchange after backward:
         # measured on 2 x B200 (profiles/r01c_dp_overlap_ab.txt) the overlapped form is 0.1-0.2 ms/step SLOWER - every

@@ -135,7 +135,9 @@ class FinetuneStepEngine:
         self.cp0, self.cp1 = torch.empty(self.mlp_parts, hmax, **f32), torch.empty(self.mlp_parts, hmax, **f32)
         self.att_pg, self.att_pb = torch.empty(B, Amax, **f32), torch.empty(B, 3 * Amax, **f32)
         self.e_gx, self.e_pos, self.e_mt = (torch.empty(T, Dp, **f32) for _ in range(3))
-        self._dp_bounds = dp.bucket_bounds(self.n_arena)
+        # the exchange that follows backward is ONE all-reduce of the arena: on 8 x B200 89.6 MB take 0.30 ms in one piece, 0.46 ms
+        # in four (profiles/r02b_allreduce_8gpu.txt); OFB_DP_BUCKETS restores a bucketed exchange
+        self._dp_bounds = dp.bucket_bounds(self.n_arena, max_buckets=int(os.environ.get("OFB_DP_BUCKETS", "1")))
         self._graphs = {}
 
     # ------------------------------------------------------------------------------------------------------------
