@@ -130,6 +130,24 @@ def test_gemm_wgrad(cuda_dev, R, NO, KI):
     assert rel(dW, 1 + 0.5 * (dY.float().t() @ X.float())) < 1e-3
 
 
+@pytest.mark.parametrize("R,N,ld", [(50432, 768, 768), (1571, 384, 392), (256, 1000, 1000), (197, 250, 250)])
+def test_colsum_bf16(cuda_dev, R, N, ld):
+    """bias gradients as column sums of a bf16 matrix (decoder / head bias: engine.py:169 autograd of vt:723, 744): the
+    16-byte-load kernel (N % 8 == 0) and the 4-byte fallback, accumulating into `out`, bit-identical from run to run."""
+    from ofb_b200 import ops
+    torch.manual_seed(11)
+    x = torch.zeros(R, ld, device="cuda", dtype=torch.bfloat16)
+    x[:, :N] = rnd(R, N)
+    sc = torch.tensor([0.5], device="cuda")
+    out = torch.ones(N, device="cuda")
+    ops.colsum_bf16(x, R, N, out, scale=2.0, scale_dev=sc, ld=ld)
+    ref = 1 + x[:, :N].float().sum(0)
+    assert rel(out, ref) < 1e-5
+    out2 = torch.ones(N, device="cuda")
+    ops.colsum_bf16(x, R, N, out2, scale=2.0, scale_dev=sc, ld=ld)
+    assert torch.equal(out, out2)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # LayerNorm (layers.py:96-98)
 # ---------------------------------------------------------------------------------------------------------------------
