@@ -79,23 +79,55 @@ class ClockSampler:
         self.rows, self.proc, self.index = [], None, index
 
     def start(self):
+        # NVML from a thread (10 ms period: the default timed region is ~0.3 s); nvidia-smi -lms as the fallback
+        self.stop_flag = False
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.thr = threading.Thread(target=self._poll, daemon=True)
+            self.thr.start()
+            return
+        except Exception:
+            self.nv = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nv
+        bits = [("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)]
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                row = [str(self.index), str(sm), str(mx), "", ""] + ["Active" if (r & b) else "Not Active" for _, b in bits]
+                self.rows.append(row)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
-        if self.proc is None:
+        if getattr(self, "nv", None) is not None:
+            self.stop_flag = True
+            self.thr.join(timeout=1.0)
+        elif self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
+        else:
+            time.sleep(0.25)
+            self.proc.terminate()
         sm = sorted(int(r[1]) for r in self.rows if len(r) > 8 and r[1].isdigit())
         mx = [int(r[2]) for r in self.rows if len(r) > 8 and r[2].isdigit()]
         reasons = set()
@@ -106,7 +138,7 @@ class ClockSampler:
                     if v.lower().startswith("active"):
                         reasons.add(n)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "sm_mhz_min": sm[0] if sm else None}
 
 
 # BASELINE.json configs[4]: a searched OFB-DeiT-C-like subnet (README.md:23: 1.7 GFLOPs). The release checkpoints are not

@@ -96,7 +96,8 @@ def test_engine_prune_plan_matches_reference_compress(cuda_dev, path):
     plans = eng.plan_prune(0.2)
     pruned = eng.gather_pruned(plans)
     _check(g, cfg, P, plans, pruned)
-    # switch-only events can be applied in place; truncating ones are refused (post-prune shapes are not built yet)
+    # apply_prune() is the in-place path (switch-only events); truncating events change shapes and go through
+    # rebuild_pruned() / prune_event() (tests/test_pruned_step_golden.py), so apply_prune() refuses them
     if any(pl.truncated for pl in plans.values()):
         with pytest.raises(NotImplementedError):
             eng.apply_prune(plans)
