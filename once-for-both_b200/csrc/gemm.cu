@@ -33,7 +33,8 @@ static constexpr int PANEL_BYTES = BM * 128;              // one [128 rows][64 b
 // product): bit 0 = the producer stops issuing TMA loads once the operand ring has been filled (the MMAs then run on stale
 // shared memory: main loop + epilogue without any L2 -> SM operand feed), bit 1 = the epilogue skips its global / TMA stores,
 // bit 2 = the epilogue skips the TMA loads of residual / saved-activation panels, bit 3 = no epilogue at all (the accumulator
-// stage is handed straight back: pure main-loop rate).
+// stage is handed straight back: pure main-loop rate), bit 4 = the single-CTA kernels issue their MMAs in the TS form with the A
+// operand read from (arbitrary) tensor-memory columns instead of shared memory: what a weight-stationary A operand would cost.
 #ifdef OFB_GEMM_DEBUG
 __device__ int g_gemm_dbg = 0;
 #define GEMM_DBG(bit) ((g_gemm_dbg >> (bit)) & 1)
@@ -359,6 +360,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         if (rank == 0) {
             int stage = 0; uint32_t phase = 0;
             int it = 0;
+#ifdef OFB_GEMM_DEBUG
+            const bool dbg_ts = GEMM_DBG(4) != 0;
+#endif
             for (int t = cta_first; t < total_tiles; t += cta_stride) {
                 const int split = t / (mt * n_tiles);
                 const int kb0 = split * kb_per_split;
@@ -385,6 +389,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                             const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * 2048, BK * 128, 1024)
                                                      : make_smem_desc_sw128(sb + k * 32, 0, 1024);
                             if (CG == 2) umma_bf16_cg2(d_tmem, da, db, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+#ifdef OFB_GEMM_DEBUG
+                            else if (dbg_ts)
+                                umma_bf16_ts(d_tmem, tmem_base + uint32_t((acc ^ 1) * BN + (kb & 3) * 32 + k * 8), db,
+                                             make_idesc_bf16(BM, BN, 0, B_MN), (kb > kb0 || k > 0) ? 1u : 0u);
+#endif
                             else umma_bf16(d_tmem, da, db, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
                         }
                         if (CG == 2) {

@@ -174,6 +174,16 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same with the A operand in tensor memory (TS form): A[128 rows][16 k] = 128 lanes x 8 32-bit columns (two bf16 of consecutive k
+// per column) starting at `tmem_a`; only B streams through shared memory
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // One deterministic leader lane of a converged warp (elect.sync): the MMA-issuing warps run their loops warp-uniformly and
 // predicate only the tcgen05 instructions on it, so that descriptors / barrier addresses stay in uniform registers (a
 // `lane == 0` region makes the compiler broadcast every operand through an R2UR waterfall loop in front of each UTCHMMA).
