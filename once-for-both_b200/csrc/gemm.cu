@@ -1003,7 +1003,14 @@ int launch_gemm(int epi, int a_mn, int b_mn, int bn_hint, const void* A, int lda
     // data-gradient GEMMs read the weight as an MN-major B operand, whose half per CTA of a pair must be whole 64-wide atoms:
     // with a long reduction a 256-wide pair tile beats the 192-wide single-CTA tile even at 25 % column padding (measured in
     // situ at N = 384: K = 1536 94 -> 79 us, K = 1152 75 -> 65 us; K = 384 is epilogue-bound and stays on 192)
-    if (bn_hint <= 0 && epi == EPI_STORE && b_mn && g.K >= 768 && g.N > 128 && pair_ok(EPI_STORE, g.M, 256, true)) bn = 256;
+    // ... unless the padded 256-wide tiles also lose a wave: per k step a pair tile costs ~(128 + bn) / 2 operand-read clocks, so
+    // compare waves x (128 + bn) of the 256- and 128-wide pair tiles (N = 384, M = 50 432: 6 x 384 against 8 x 256 - measured
+    // tools/dgrad_bn_ab.py: K = 1536 80.6 -> 76.3 us, K = 1152 66.2 -> 60.2 us; N = 768 and N = 192 stay on 256)
+    if (bn_hint <= 0 && epi == EPI_STORE && b_mn && g.K >= 768 && g.N > 128 && pair_ok(EPI_STORE, g.M, 256, true)) {
+        const long mtp = ((g.M + BM - 1) / BM + 1) / 2, slots = num_sms() / 2;
+        auto cost = [&](int w) { return ((mtp * ((g.N + w - 1) / w) + slots - 1) / slots) * long(128 + w); };
+        bn = cost(128) < cost(256) ? 128 : 256;
+    }
     if (epi == EPI_WGRAD) {
         if (g.k_splits <= 0) g.k_splits = wgrad_plan(g.M, g.N, g.K, b_mn, bn_hint);
         if (g.splitk_ws != nullptr) {
