@@ -55,7 +55,7 @@ def parse():
 def gemm_traffic():
     """Measured DRAM traffic of the GEMM family per launch (ncu --set full capture of this workload, profiles/): only valid
     for the configuration it was captured on (DeiT-small, batch 256)."""
-    path = os.path.join(ROOT, "profiles", "r02b_gemm_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r02c_gemm_traffic.json")
     if os.path.exists(path):
         return json.load(open(path))
     return None
@@ -731,7 +731,7 @@ def main():
                          "traffic": (tr["dram_bytes_per_launch"] if tr and args.workload == "search" and args.model == "small"
                                      and B == 256 and args.depth == 12 else None),
                          "traffic_note": "DRAM bytes per GEMM launch (mean over the launches of a step), ncu --set full, "
-                                         "profiles/r02b_gemm_traffic.json",
+                                         "profiles/r02c_gemm_traffic.json",
                          "peak_source": pk["src"], "launches_per_step": work.get("gemm", [0, 0, 0])[2],
                          "ms_per_step": fam("gemm"), "share_of_step": fam("gemm") / step_ms if step_ms > 0 else None,
                          "timed_over": timed_over},
