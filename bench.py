@@ -631,7 +631,10 @@ def main():
         for i in range(n):
             step(dev_img[i % n_host], dev_lab[i % n_host])
     if rank == 0:
+        psampler = ClockSampler(local)          # the profiled replays are short: they may run at a higher clock than the timed region
+        psampler.start()
         fam_ms, kern = kernel_breakdown(prof_steps, n_prof)
+        clocks_profiled = psampler.stop()
     else:
         prof_steps(n_prof)          # the steps of an N > 1 run hold the gradient exchange: every rank runs them, rank 0 records
         fam_ms, kern = None, "skipped"
@@ -734,7 +737,8 @@ def main():
                                          "profiles/r02c_gemm_traffic.json",
                          "peak_source": pk["src"], "launches_per_step": work.get("gemm", [0, 0, 0])[2],
                          "ms_per_step": fam("gemm"), "share_of_step": fam("gemm") / step_ms if step_ms > 0 else None,
-                         "timed_over": timed_over},
+                         "share_of_kernel_time": fam("gemm") / ksum if ksum > 0 else None,
+                         "timed_over": timed_over, "clocks_profiled": clocks_profiled},
             # the whole step against the tensor roofline (north_star: >= 0.60): algorithmic FLOPs of the step / step time
             "roofline_step": {"bound": "tensor", "achieved": step_tf, "peak": pk["tflops"], "unit": "TFLOP/s",
                               "frac": step_tf / pk["tflops"], "target_frac": 0.60},
