@@ -1052,51 +1052,129 @@ __global__ void __launch_bounds__(512) embed_bwd_kernel(const __nv_bfloat16* __r
 
 // =============================================================================================
 // norm_targets (vision_transformer.py:121-141), evaluated only at masked patches, written patch-major in the
-// decoder's output order: tgt[(b*L + l), c*256 + i*16 + j].  One CTA per (patch, channel); window = 47.
+// decoder's output order: tgt[(b*L + l), c*256 + i*16 + j].  Window = 47; a CTA takes NT_PPC consecutive patches and skips the
+// unmasked ones (5-25 % are masked over the warm-up: one CTA per patch spent most of the launch on CTAs that exit at once).
+// The 16 window sums a row (then a column) of the 62-wide halo needs share their 32 middle elements:
+//     sum_j = [elements 15..30 + elements j..14] + [elements 31..46 + elements 47..j+46]
+// Two threads walk one line, each over 31 elements (16 shared + a running sum over its 15 outer elements, walking outwards),
+// on packed (x, x^2) pairs, and exchange their 8 + 8 partial sums by shuffle: 31 shared-memory reads and ~55 packed additions
+// per thread instead of 16 x 47 taps per line, in a fixed order.
 // =============================================================================================
 static constexpr int NT_P = 16, NT_K = 47, NT_R = 23, NT_W = NT_P + 2 * NT_R;  // 62
-__global__ void __launch_bounds__(256) norm_targets_kernel(const float* __restrict__ img, const float* __restrict__ mask,
-                                                           float* __restrict__ tgt, int HW) {
+static constexpr int NT_PPC = 4;              // patches per CTA
+static constexpr int NT_WS = 68;              // halo row pitch in floats: 64 columns [px - 24, px + 40) as 16 float4 + 4 of padding
+static_assert(NT_W == 2 * (NT_P - 1) + 32 && NT_K == NT_W - (NT_P - 1), "core / prefix / suffix split of the window sums");
+// f(e): packed (x, x^2) of element e of the line, e = 0 .. 61.  half 0 walks elements 30 .. 0, half 1 elements 31 .. 61.
+// Returns in t[n], n = 0 .. 7, the window sums of outputs j = n (half 0) or j = 15 - n (half 1); the two threads of a line are
+// neighbouring lanes.
+template <typename F>
+__device__ __forceinline__ void window_sums_half(F f, int half, float2 (&t)[8]) {
+    const int e0 = half ? 31 : 30, st = half ? 1 : -1;
+    float2 core = splat2(0.f);
+#pragma unroll
+    for (int m = 0; m < 16; ++m) core = add2(core, f(e0 + st * m));
+    float2 p[16];                             // p[n] = core + the n outer elements next to the core
+    p[0] = core;
+#pragma unroll
+    for (int n = 0; n < 15; ++n) p[n + 1] = add2(p[n], f(e0 + st * (16 + n)));
+    // output j = (elements 15..30 + j..14) + (elements 31..46 + 47..j+46) = p0[15 - j] + p1[j]; with mine / other for the two
+    // halves, t[n] = mine[15 - n] + other[n] is output n for half 0 and output 15 - n for half 1
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+        float2 o;
+        o.x = __shfl_xor_sync(0xffffffffu, p[n].x, 1);
+        o.y = __shfl_xor_sync(0xffffffffu, p[n].y, 1);
+        t[n] = add2(p[15 - n], o);
+    }
+}
+static constexpr int NT_THREADS = 128;        // the line sums keep 124 threads busy: 4-warp CTAs, four per SM (128 registers: spills cost 15 %)
+__global__ void __launch_bounds__(NT_THREADS, 4) norm_targets_kernel(const float* __restrict__ img, const float* __restrict__ mask,
+                                                                     float* __restrict__ tgt, int HW, int n_patches) {
     pdl_wait();          // programmatic dependent launch: inputs of the previous kernel are complete from here on (launch.cuh)
-    const int G = HW / NT_P;
-    const int patch = blockIdx.x;             // b*L + l
-    const int c = blockIdx.y;
-    if (mask[patch] == 0.f) return;
-    const int L = G * G;
-    const int b = patch / L, l = patch % L;
-    const int py = (l / G) * NT_P, px = (l % G) * NT_P;
-    __shared__ float win[NT_W][NT_W + 1];
-    __shared__ float h1[NT_W][NT_P + 1], h2[NT_W][NT_P + 1];
-    const float* plane = img + (size_t(b) * 3 + c) * HW * HW;
-    for (int idx = threadIdx.x; idx < NT_W * NT_W; idx += blockDim.x) {
-        const int wy = idx / NT_W, wx = idx % NT_W;
-        const int gy = py - NT_R + wy, gx = px - NT_R + wx;
-        win[wy][wx] = (gy >= 0 && gy < HW && gx >= 0 && gx < HW) ? __ldg(plane + size_t(gy) * HW + gx) : 0.f;
+    __shared__ __align__(16) float win[NT_W][NT_WS];
+    __shared__ float2 h[NT_W][NT_P + 1];      // horizontal window sums (x, x^2)
+    __shared__ float2 v[NT_P][NT_P + 1];      // full window sums
+    const int G = HW / NT_P, L = G * G;
+    const int tid = threadIdx.x;
+    const int oj = tid % NT_P, oi0 = tid / NT_P;                // this thread's two output pixels of every patch: rows oi0, oi0 + 8
+    constexpr int NLD = (NT_W * 16 + NT_THREADS - 1) / NT_THREADS;     // float4 loads per thread and channel (8)
+    float mk[NT_PPC];                                           // the CTA's mask values in one round trip
+#pragma unroll
+    for (int pp = 0; pp < NT_PPC; ++pp) {
+        const int patch = blockIdx.x * NT_PPC + pp;
+        mk[pp] = patch < n_patches ? __ldg(mask + patch) : 0.f;
     }
-    __syncthreads();
-    // horizontal box sums: for each window row, 16 outputs of width 47
-    for (int idx = threadIdx.x; idx < NT_W * NT_P; idx += blockDim.x) {
-        const int wy = idx / NT_P, j = idx % NT_P;
-        float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
-        for (int k = 0; k < NT_K; ++k) { const float v = win[wy][j + k]; s1 += v; s2 += v * v; }
-        h1[wy][j] = s1; h2[wy][j] = s2;
-    }
-    __syncthreads();
-    {
-        const int i = threadIdx.x / NT_P, j = threadIdx.x % NT_P;  // 256 threads = 16x16 outputs
-        float s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-        for (int k = 0; k < NT_K; ++k) { s1 += h1[i + k][j]; s2 += h2[i + k][j]; }
-        const int gy = py + i, gx = px + j;
-        const int cy = min(gy + NT_R, HW - 1) - max(gy - NT_R, 0) + 1;
-        const int cx = min(gx + NT_R, HW - 1) - max(gx - NT_R, 0) + 1;
-        const float cnt = float(cy * cx);
-        const float mu = s1 / cnt;
-        float var = (s2 / cnt - mu * mu) * (cnt / (cnt - 1.f));
-        var = fmaxf(var, 0.f);
-        const float xv = win[NT_R + i][NT_R + j];
-        tgt[size_t(patch) * (3 * NT_P * NT_P) + c * NT_P * NT_P + i * NT_P + j] = (xv - mu) / sqrtf(var + 1e-6f);
+    for (int pp = 0; pp < NT_PPC; ++pp) {
+        const int patch = blockIdx.x * NT_PPC + pp;             // b*L + l
+        if (mk[pp] == 0.f) continue;
+        const int b = patch / L, l = patch % L;
+        const int py = (l / G) * NT_P, px = (l % G) * NT_P;
+        // pixels of the (border-clipped) window around this thread's output pixels: the same for the three channels
+        float inv_cnt[2], bessel[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int gy = py + oi0 + 8 * k, gx = px + oj;
+            const int cy = min(gy + NT_R, HW - 1) - max(gy - NT_R, 0) + 1;
+            const int cx = min(gx + NT_R, HW - 1) - max(gx - NT_R, 0) + 1;
+            const float cnt = float(cy * cx);
+            inv_cnt[k] = 1.f / cnt;
+            bessel[k] = cnt / (cnt - 1.f);
+        }
+        // halo rows as 16 aligned float4 (image rows and px - 24 are multiples of 4 floats: a float4 lies inside or outside);
+        // a thread's loads are issued back to back, those of the next channel before the sums of the current one
+        float4 r[NLD];
+        auto load = [&](int c) {
+            const float* plane = img + (size_t(b) * 3 + c) * HW * HW;
+#pragma unroll
+            for (int i = 0; i < NLD; ++i) {
+                const int sl = tid + NT_THREADS * i, row = sl >> 4, vec = sl & 15;
+                const int gy = py - NT_R + row, gx = px - NT_R - 1 + 4 * vec;
+                const bool ok = sl < NT_W * 16 && gy >= 0 && gy < HW && gx >= 0 && gx < HW;
+                r[i] = ok ? __ldg(reinterpret_cast<const float4*>(plane + size_t(gy) * HW + gx)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        load(0);
+        for (int c = 0; c < 3; ++c) {
+#pragma unroll
+            for (int i = 0; i < NLD; ++i) {
+                const int sl = tid + NT_THREADS * i;
+                if (sl < NT_W * 16) *reinterpret_cast<float4*>(&win[sl >> 4][4 * (sl & 15)]) = r[i];
+            }
+            __syncthreads();
+            if (c + 1 < 3) load(c + 1);
+            // horizontal: threads (row, half); column e of the line is win[row][e + 1]; the shuffles name every lane, so
+            // threads 124 .. 127 repeat line 61 without storing
+            {
+                const int row = min(tid >> 1, NT_W - 1), half = tid & 1;
+                float2 t[8];
+                window_sums_half([&](int e) { const float x = win[row][e + 1]; return make_float2(x, x * x); }, half, t);
+                if (tid < 2 * NT_W) {
+#pragma unroll
+                    for (int n = 0; n < 8; ++n) h[row][half ? 15 - n : n] = t[n];
+                }
+            }
+            __syncthreads();
+            // vertical: threads (column, half) - one warp
+            if (tid < 2 * NT_P) {
+                const int j = tid >> 1, half = tid & 1;
+                float2 t[8];
+                window_sums_half([&](int e) { return h[e][j]; }, half, t);
+#pragma unroll
+                for (int n = 0; n < 8; ++n) v[half ? 15 - n : n][j] = t[n];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int oi = oi0 + 8 * k;
+                const float2 s12 = v[oi][oj];
+                const float mu = s12.x * inv_cnt[k];
+                const float var = fmaxf((s12.y * inv_cnt[k] - mu * mu) * bessel[k], 0.f);
+                const float xv = win[NT_R + oi][NT_R + 1 + oj];
+                tgt[size_t(patch) * (3 * NT_P * NT_P) + c * NT_P * NT_P + oi * NT_P + oj] = (xv - mu) * rsqrtf(var + 1e-6f);
+            }
+            __syncthreads();          // win / h / v are rewritten by the next channel / patch
+        }
     }
 }
 
@@ -1732,10 +1810,10 @@ int launch_embed_bwd(const void* g0, const void* x0, const float* gate, const fl
 }
 
 int launch_norm_targets(const float* img, const float* mask, float* tgt, int B, int HW, cudaStream_t s) {
-    if (HW % NT_P != 0) return 1012;
+    if (HW % NT_P != 0 || (reinterpret_cast<uintptr_t>(img) & 15u) != 0) return 1012;
     const int L = (HW / NT_P) * (HW / NT_P);
-    dim3 grid(B * L, 3);
-    OFB_LAUNCH(norm_targets_kernel, grid, 256, 0, s, img, mask, tgt, HW);
+    dim3 grid((B * L + NT_PPC - 1) / NT_PPC);
+    OFB_LAUNCH(norm_targets_kernel, grid, NT_THREADS, 0, s, img, mask, tgt, HW, B * L);
     return err();
 }
 
