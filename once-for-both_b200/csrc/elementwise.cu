@@ -792,8 +792,20 @@ __global__ void reduce_partials_multi_kernel(const ReduceJobs jobs) {
     const int ty = threadIdx.x >> 5, ny = blockDim.x >> 5;
     __shared__ float sm[32][33];
     float s = 0.f;
-    if (col < jb.N)
-        for (int r = ty; r < jb.R; r += ny) s += jb.part[size_t(r) * jb.N + col];
+    if (col < jb.N) {
+        // four independent row loads in flight per thread (the longest job - 788 partial rows of the fc2 data-gradient GEMM - was
+        // 25 dependent L2 round trips per thread); fixed addition order
+        const float* p = jb.part + col;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int r = ty;
+        for (; r + 3 * ny < jb.R; r += 4 * ny) {
+            const float v0 = __ldg(p + size_t(r) * jb.N), v1 = __ldg(p + size_t(r + ny) * jb.N),
+                        v2 = __ldg(p + size_t(r + 2 * ny) * jb.N), v3 = __ldg(p + size_t(r + 3 * ny) * jb.N);
+            s0 += v0; s1 += v1; s2 += v2; s3 += v3;
+        }
+        for (; r < jb.R; r += ny) s0 += __ldg(p + size_t(r) * jb.N);
+        s = (s0 + s1) + (s2 + s3);
+    }
     sm[ty][threadIdx.x & 31] = s;
     __syncthreads();
     if (ty == 0 && col < jb.N) {
@@ -819,7 +831,16 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const SplitkJobs job
     float4* out = reinterpret_cast<float4*>(jb.out);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < jb.n4; i += (long long)gridDim.x * blockDim.x) {
         float4 a = ws[i];
-        for (int s = 1; s < jb.splits; ++s) {
+        // ascending split order (bit-reproducible); the partial loads go out four at a time
+        int s = 1;
+        for (; s + 3 < jb.splits; s += 4) {
+            const float4 b0 = ws[s * jb.n4 + i], b1 = ws[(s + 1) * jb.n4 + i], b2 = ws[(s + 2) * jb.n4 + i], b3 = ws[(s + 3) * jb.n4 + i];
+            a.x += b0.x; a.y += b0.y; a.z += b0.z; a.w += b0.w;
+            a.x += b1.x; a.y += b1.y; a.z += b1.z; a.w += b1.w;
+            a.x += b2.x; a.y += b2.y; a.z += b2.z; a.w += b2.w;
+            a.x += b3.x; a.y += b3.y; a.z += b3.z; a.w += b3.w;
+        }
+        for (; s < jb.splits; ++s) {
             const float4 b = ws[s * jb.n4 + i];
             a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
         }
@@ -1310,8 +1331,29 @@ __global__ void __launch_bounds__(1024) loss_finalize_kernel(const float* __rest
     __shared__ float red[3][32];          // one CTA of 32 warps: the kernel sits on the critical path between forward and backward
     float a = 0.f, d = 0.f, m = 0.f;
     for (int i = threadIdx.x; i < B; i += blockDim.x) a += loss_rows[i];
-    for (int i = threadIdx.x; i < n_dec_part; i += blockDim.x) d += dec_part[i];
-    for (int i = threadIdx.x; i < n_mask; i += blockDim.x) m += mask[i];
+    // the two long vectors (decoder partials: ~10 k, PMIM mask: B * L = 50 k floats) as 16-byte loads, four in flight per thread:
+    // one CTA walking them one float at a time spent 49 dependent L2 round trips here (31 us on the critical path)
+    auto vsum = [&](const float* __restrict__ p, int n) {
+        float acc = 0.f;
+        if ((reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
+            const float4* p4 = reinterpret_cast<const float4*>(p);
+            const int n4 = n >> 2;
+            int i = threadIdx.x;
+            for (; i + 3 * int(blockDim.x) < n4; i += 4 * blockDim.x) {
+                const float4 v0 = __ldg(p4 + i), v1 = __ldg(p4 + i + blockDim.x), v2 = __ldg(p4 + i + 2 * blockDim.x),
+                             v3 = __ldg(p4 + i + 3 * blockDim.x);
+                acc += ((v0.x + v0.y) + (v0.z + v0.w)) + ((v1.x + v1.y) + (v1.z + v1.w)) + ((v2.x + v2.y) + (v2.z + v2.w)) +
+                       ((v3.x + v3.y) + (v3.z + v3.w));
+            }
+            for (; i < n4; i += blockDim.x) { const float4 v0 = __ldg(p4 + i); acc += (v0.x + v0.y) + (v0.z + v0.w); }
+            for (int j = (n4 << 2) + threadIdx.x; j < n; j += blockDim.x) acc += p[j];
+        } else {
+            for (int j = threadIdx.x; j < n; j += blockDim.x) acc += p[j];
+        }
+        return acc;
+    };
+    d = vsum(dec_part, n_dec_part);
+    m = vsum(mask, n_mask);
     a = warp_sum(a); d = warp_sum(d); m = warp_sum(m);
     if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a; red[1][threadIdx.x >> 5] = d; red[2][threadIdx.x >> 5] = m; }
     __syncthreads();
