@@ -760,7 +760,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         }
                         v[i] = s;
                     }
-                    if (row_ok && nvalid > 0) store_bf16x32(reinterpret_cast<__nv_bfloat16*>(g.out0) + size_t(row) * g.ld0 + col0, v, nvalid);
+                    // the sign matrix leaves through the staged panel + TMA store where the output allows it (one row per lane in a
+                    // direct global store costs 32 LSU wavefronts per instruction); rows >= M / columns >= N are clipped there
+                    if (TMA_OUT) stage_bf16x32(panel0, et, c & 1, v);
+                    else if (row_ok && nvalid > 0) store_bf16x32(reinterpret_cast<__nv_bfloat16*>(g.out0) + size_t(row) * g.ld0 + col0, v, nvalid);
                 }
 
                 if (TMA_OUT) {
@@ -1058,6 +1061,7 @@ int launch_gemm(int epi, int a_mn, int b_mn, int bn_hint, const void* A, int lda
             return launch_gemm_bn<0, 0, EPI_PATCH, 0>(bn, A, lda, B, ldb, g, stream);
         case EPI_DECODER:
             if (a_mn || b_mn) return 1003;
+            if (tma_out) return launch_gemm_bn<0, 0, EPI_DECODER, 1>(bn, A, lda, B, ldb, g, stream);
             return launch_gemm_bn<0, 0, EPI_DECODER, 0>(bn, A, lda, B, ldb, g, stream);
         default: return 1004;
     }
