@@ -1015,12 +1015,13 @@ __global__ void cls_rows_kernel(const float* __restrict__ cls, const float* __re
 __global__ void __launch_bounds__(512) embed_bwd_kernel(const __nv_bfloat16* __restrict__ g0, const __nv_bfloat16* __restrict__ x0,
                                  const float* __restrict__ gate, const float* __restrict__ mask, __nv_bfloat16* __restrict__ dconv,
                                  float* __restrict__ part_gx, float* __restrict__ part_pos, float* __restrict__ part_mt, int B, int T,
-                                 int D, int G) {
+                                 int D, int G, int VCc) {
     pdl_wait();          // programmatic dependent launch: inputs of the previous kernel are complete from here on (launch.cuh)
-    extern __shared__ float eb_red[];                  // [G][D]
+    extern __shared__ float eb_red[];                  // [G][Dc]
     const int t = blockIdx.x;
-    const int VC = D >> 3;
-    const int vc = threadIdx.x % VC, gq = threadIdx.x / VC;
+    // blockIdx.y: column slice of VCc 16-byte vectors (Dc = 8 VCc channels) - T CTAs alone are 1.33 per SM on 148 SMs
+    const int Dc = VCc << 3, c0 = blockIdx.y * Dc;
+    const int vl = threadIdx.x % VCc, vc = blockIdx.y * VCc + vl, gq = threadIdx.x / VCc;
     const int L = T - 1;
     float agx[8], apos[8], amt[8], gt[8];
 #pragma unroll
@@ -1060,13 +1061,13 @@ __global__ void __launch_bounds__(512) embed_bwd_kernel(const __nv_bfloat16* __r
         __syncthreads();
         if (gq < G) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) eb_red[gq * D + vc * 8 + j] = src[j];
+            for (int j = 0; j < 8; ++j) eb_red[gq * Dc + vl * 8 + j] = src[j];
         }
         __syncthreads();
-        for (int col = threadIdx.x; col < D; col += blockDim.x) {
+        for (int col = threadIdx.x; col < Dc; col += blockDim.x) {
             float a = 0.f;
-            for (int q2 = 0; q2 < G; ++q2) a += eb_red[q2 * D + col];
-            outs[k][size_t(t) * D + col] = a;
+            for (int q2 = 0; q2 < G; ++q2) a += eb_red[q2 * Dc + col];
+            outs[k][size_t(t) * D + c0 + col] = a;
         }
     }
 }
@@ -1841,13 +1842,25 @@ int launch_embed_bwd(const void* g0, const void* x0, const float* gate, const fl
                      float* part_mt, int B, int T, int D, cudaStream_t s) {
     if (D % 8 != 0 || D > 4096) return 1011;
     const int VC = D / 8;
-    int G = 512 / VC;
+    // column slices: the split (1 .. 4, a divisor of the row's 16-byte vectors, slices of at least 128 bytes) whose T x CS CTAs
+    // fill whole waves best (T = 197: 591 CTAs = 3.99 per SM)
+    int CS = 1;
+    double best = 1e30;
+    for (int cs = 1; cs <= 4; ++cs) {
+        if (VC % cs != 0 || VC / cs < 8) continue;
+        const double per_sm = double(T) * cs / num_sms();
+        const double cost = double(long(per_sm + 0.999999)) / per_sm;
+        if (cost < best - 1e-9) { best = cost; CS = cs; }
+    }
+    const int VCc = VC / CS;
+    int G = 512 / VCc;
     if (G > 16) G = 16;
     if (G > B) G = B;
     if (G < 1) return 1011;
-    const int threads = ((VC * G + 31) / 32) * 32;
-    OFB_LAUNCH(embed_bwd_kernel, T, threads, size_t(G) * D * sizeof(float), s, reinterpret_cast<const __nv_bfloat16*>(g0),
-        reinterpret_cast<const __nv_bfloat16*>(x0), gate, mask, reinterpret_cast<__nv_bfloat16*>(dconv), part_gx, part_pos, part_mt, B, T, D, G);
+    const int threads = ((VCc * G + 31) / 32) * 32;
+    OFB_LAUNCH(embed_bwd_kernel, dim3(T, CS), threads, size_t(G) * VCc * 8 * sizeof(float), s, reinterpret_cast<const __nv_bfloat16*>(g0),
+        reinterpret_cast<const __nv_bfloat16*>(x0), gate, mask, reinterpret_cast<__nv_bfloat16*>(dconv), part_gx, part_pos, part_mt, B, T, D, G,
+        VCc);
     return err();
 }
 
