@@ -143,7 +143,8 @@ int ofb_cls_rows(const float* cls, const float* pos, const float* gate, void* x_
 /* backward of the embed stage: d(conv out), and [T, D] partials of d gate (sum g*x), d pos_embed, d mask_token */
 int ofb_embed_bwd(const void* g0, const void* x0, const float* gate, const float* mask, void* dconv, float* part_gx,
                   float* part_pos, float* part_mt, int B, int T, int D, void* stream);
-/* norm_targets (vision_transformer.py:121-141, window 47) at masked patches only, patch-major [B*L, 768] fp32 */
+/* norm_targets (vision_transformer.py:121-141, window 47) at masked patches only, patch-major [B*L, 768] fp32;
+   img % 16 == 0 and a 16-byte aligned image base (the halo is read as float4), else 1012 */
 int ofb_norm_targets(const float* images, const float* mask, float* target, int B, int img, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
