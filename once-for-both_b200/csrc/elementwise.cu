@@ -793,18 +793,22 @@ __global__ void reduce_partials_multi_kernel(const ReduceJobs jobs) {
     __shared__ float sm[32][33];
     float s = 0.f;
     if (col < jb.N) {
-        // four independent row loads in flight per thread (the longest job - 788 partial rows of the fc2 data-gradient GEMM - was
-        // 25 dependent L2 round trips per thread); fixed addition order
+        // eight independent row loads in flight per thread (the longest job - 788 partial rows of the fc2 data-gradient GEMM - is
+        // 25 rows per thread, each a DRAM round trip); fixed addition order
         const float* p = jb.part + col;
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        float a[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = 0.f;
         int r = ty;
-        for (; r + 3 * ny < jb.R; r += 4 * ny) {
-            const float v0 = __ldg(p + size_t(r) * jb.N), v1 = __ldg(p + size_t(r + ny) * jb.N),
-                        v2 = __ldg(p + size_t(r + 2 * ny) * jb.N), v3 = __ldg(p + size_t(r + 3 * ny) * jb.N);
-            s0 += v0; s1 += v1; s2 += v2; s3 += v3;
+        for (; r + 7 * ny < jb.R; r += 8 * ny) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __ldg(p + size_t(r + i * ny) * jb.N);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] += v[i];
         }
-        for (; r < jb.R; r += ny) s0 += __ldg(p + size_t(r) * jb.N);
-        s = (s0 + s1) + (s2 + s3);
+        for (; r < jb.R; r += ny) a[0] += __ldg(p + size_t(r) * jb.N);
+        s = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
     }
     sm[ty][threadIdx.x & 31] = s;
     __syncthreads();
