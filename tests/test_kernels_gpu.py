@@ -335,6 +335,46 @@ def test_norm_targets(cuda_dev):
     assert tgt.cpu()[~m].abs().max() == 0                   # unmasked patches are never needed / never written
 
 
+@pytest.mark.parametrize("B,HW,frac", [(3, 48, 1.0), (5, 32, 0.5), (2, 64, 0.0), (1, 224, 1.0)])
+def test_norm_targets_edges(cuda_dev, B, HW, frac):
+    """Images smaller than the 47-pixel window (every window is clipped by the border on all sides: vt:121-141 divides by the
+    clipped pixel count), patch counts that are not a multiple of the 4 patches a CTA takes, everything / nothing masked."""
+    from ofb_b200 import ops
+    from ofb_oracle import norm_targets, patchify_pixel_shuffle
+    torch.manual_seed(23)
+    L = (HW // 16) ** 2
+    img = torch.randn(B, 3, HW, HW) * 1.5 + 0.3
+    mask = (torch.rand(B, L) < frac).float()
+    tgt = torch.zeros(B * L, 768, device="cuda")
+    ops.norm_targets(img.cuda(), mask.cuda(), tgt)
+    ref = patchify_pixel_shuffle(norm_targets(img, 47)).reshape(B * L, 768)
+    m = mask.reshape(-1).bool()
+    if m.any():
+        assert (tgt.cpu()[m] - ref[m]).abs().max() < 2e-4
+    if (~m).any():
+        assert tgt.cpu()[~m].abs().max() == 0
+
+
+@pytest.mark.parametrize("n_dec,n_mask", [(40, 37 * 196), (9457, 27), (1, 3), (4099, 50176)])
+def test_loss_finalize_vector_lengths(cuda_dev, n_dec, n_mask):
+    """The two long sums of loss_finalize (decoder partials, PMIM mask) at lengths around the 16-byte / four-in-flight chunks."""
+    from ofb_b200 import ops
+    torch.manual_seed(29)
+    rows = torch.rand(8, device="cuda") + 1.0
+    dec_part = torch.rand(n_dec, device="cuda")
+    mask = (torch.rand(n_mask, device="cuda") < 0.4).float()
+    mask[0] = 1.0
+    arch = torch.tensor([0.75], device="cuda")
+    scal = torch.zeros(8, device="cuda")
+    ops.loss_finalize(rows, dec_part, mask, arch, 1.0, scal)
+    base = rows.double().mean().item()
+    msum = mask.double().sum().item()
+    denom = (msum * 256 + 1e-5) * 3
+    dec = dec_part.double().sum().item() / denom
+    want = [base, 0.75, dec, base + 0.75 + base, base / dec, base / dec / denom, msum]
+    assert rel(scal[:7], torch.tensor(want, device="cuda", dtype=torch.float32)) < 1e-4
+
+
 def test_patch_embed_epilogue_and_embed_bwd(cuda_dev):
     from ofb_b200 import ops
     torch.manual_seed(8)
