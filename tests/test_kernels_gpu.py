@@ -375,10 +375,13 @@ def test_loss_finalize_vector_lengths(cuda_dev, n_dec, n_mask):
     assert rel(scal[:7], torch.tensor(want, device="cuda", dtype=torch.float32)) < 1e-4
 
 
-def test_patch_embed_epilogue_and_embed_bwd(cuda_dev):
+@pytest.mark.parametrize("B,D", [(3, 192), (5, 288), (2, 384), (17, 768), (3, 200)])
+def test_patch_embed_epilogue_and_embed_bwd(cuda_dev, B, D):
+    """D = 192 / 288 / 384 / 768: embed_bwd splits the embedding columns over three CTAs per token position (8 / 12 / 16 / 32
+    16-byte vectors each); D = 200 (25 vectors) has no admissible split and runs one CTA per position."""
     from ofb_b200 import ops
     torch.manual_seed(8)
-    B, D, L, T = 3, 192, 196, 197
+    L, T = 196, 197
     pat, W = rnd(B * L, 768), rnd(D, 768, s=0.05)
     bias, gate = torch.randn(D, device="cuda") * 0.1, torch.rand(D, device="cuda") * 0.5 + 0.5
     pos, mt = torch.randn(T, D, device="cuda") * 0.1, torch.randn(D, device="cuda") * 0.1
